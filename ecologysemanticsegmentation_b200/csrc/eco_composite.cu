@@ -1,0 +1,554 @@
+// Fused 3-organ composite loss (whole_body > ventral+dorsal > dorsal): 21 (a,b) leaves per pixel
+// from ONE read of x[:,0..2] and g[:,0..2].  Replaces ess/loss_composite.py:21-94 with
+// composite_set_theory=True, C == 3 (see include/ecoloss.h).
+//
+// Pass 1 (stats): per pixel, form p_c (= sigmoid(z_c) when from_logits), the pair operands
+//   d=|p_i-p_j|, m1=p_i p_j, m2=p_i d, m3=p_i (d p_i), u1=u(p_i,p_j), u2=u(p_i,d), u3=u(p_i,d p_i)
+//   and accumulate 84 fp32 sums per thread; every kFlushIters iterations the warp folds them
+//   (transposed butterfly, 31 shuffles per 32 sums) into per-warp fp64 slots in shared memory.
+//   Labels that are exactly 0/1 let the label-only transcendental sums collapse to counts; any other
+//   label value takes a rare slow path that accumulates exact corrections, so the result is right for
+//   arbitrary labels.
+// Pass 2 (grad): chain rule through the operands with 21 x 6 global coefficients.
+#include "eco_common.cuh"
+
+namespace eco {
+
+constexpr int kCThreads = 256;
+constexpr int kCWarps = kCThreads / 32;
+constexpr int kNAcc = 100;      // == ECO_C3_NACC
+constexpr int kNThreadAcc = 84; // indices 1..84 live in registers
+constexpr int kFlushIters = 8;
+constexpr int kMaxCompCtas = 148 * 4;
+
+static_assert(kNAcc == ECO_C3_NACC, "layout mismatch with ecoloss.h");
+
+// ---- accumulator layout ---------------------------------------------------------------------
+// 0            n (pixels)
+// 1..3         G_c   = sum g_c
+// 4..6         GD_p  = sum |g_i-g_j|           p = 0:(0,1) 1:(0,2) 2:(1,2)
+// 7+5c+k       channel leaf c: k = 0 X (sum x) 1 XX 2 GX 3 SPX 4 FLX(log2 units until flushed)
+// 22+21p+k     pair p: 0 M1 1 M1G 2 U1 3 UU1 4 GU1 5 SPU1 6 FLU1 | 7 M2 8 M2G 9 U2 10 UU2 11 GU2 12 SPU2 13 FLU2
+//                      | 14 M3 15 M3G 16 U3 17 UU3 18 GU3 19 SPU3 20 FLU3
+// 85+3L+k      label-b corrections (non-binary labels only), L = 0:g1 1:g2 2:gd01 3:gd02 4:gd12,
+//              k = 0 sum(b*b-b)  1 sum(SP(b)-lin)  2 sum(FL(b)-lin)
+constexpr int A_N = 0, A_G = 1, A_GD = 4, A_CH = 7, A_PAIR = 22, A_CORR = 85;
+
+__host__ __device__ constexpr int pair_i(int p) { return p == 2 ? 1 : 0; }
+__host__ __device__ constexpr int pair_j(int p) { return p == 0 ? 1 : 2; }
+
+// natural-log constants of the two label values
+constexpr double kSP0 = 0.6931471805599453094;       // softplus term at b = 0: log 2
+constexpr double kSP1 = 1.3132616875182228340;       // at b = 1: 1 + log(1 + e^-1)
+constexpr double kFL0 = 16.118095533458650;          // -(1-0)^1.5 log(0 + fp32(1e-7))
+
+// reference op order of ess/loss_composite.py:94, no FMA contraction across the ops
+__device__ __forceinline__ float union_operand(float sp, float p) {
+    return __fadd_rn(__fmul_rn(sp, __fsub_rn(1.0f, p)), __fmul_rn(__fadd_rn(__fmul_rn(sp, p), p), 0.5f));
+}
+
+struct CompArgs {
+    const void* x;
+    const void* g;
+    int64_t x_sn, x_sc, g_sn, g_sc;
+    int32_t N;
+    int64_t HW;
+    int64_t units_per_plane;  // HW / VEC
+    int64_t units_total;      // N * units_per_plane
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_vec(const T* p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) Vec4<T>::load(p, v);
+    else v[0] = Vec4<T>::load1(p);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) Vec4<T>::store(p, v);
+    else Vec4<T>::store1(p, v[0]);
+}
+
+// thread accumulators: acc[k] <-> layout index k+1
+template <bool UNIT>
+__device__ __forceinline__ void leaf_b_terms(float b, float& sp_acc, float& fl_acc) {
+    // SP in natural units; FL in log2 units with the sign folded (fl_acc accumulates (1-b)^1.5 log2(b+eps))
+    if (UNIT) sp_acc += fmaf(softplus_neg_abs_log2(b), kLn2, b);
+    else sp_acc += fmaf(softplus_neg_abs_log2(b), kLn2, fmaxf(b, 0.f));
+    fl_acc += focal_fg_log2(b);
+}
+
+template <bool UNIT>
+__device__ __forceinline__ void pixel_stats(const float (&x)[3], const float (&g)[3], float (&acc)[kNThreadAcc]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        acc[A_G - 1 + c] += g[c];
+        float* ch = &acc[A_CH - 1 + 5 * c];
+        ch[0] += x[c];
+        ch[1] = fmaf(x[c], x[c], ch[1]);
+        ch[2] = fmaf(g[c], x[c], ch[2]);
+        leaf_b_terms<UNIT>(x[c], ch[3], ch[4]);
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int i = pair_i(p), j = pair_j(p);
+        const float xi = x[i], xj = x[j], gi = g[i], gj = g[j];
+        const float d = fabsf(xi - xj);
+        const float gd = fabsf(gi - gj);
+        acc[A_GD - 1 + p] += gd;
+        float* pa = &acc[A_PAIR - 1 + 21 * p];
+        const float m1 = xi * xj;
+        const float m2 = xi * d;
+        const float q = d * xi;
+        const float m3 = xi * q;
+        const float u1 = union_operand(xi, xj);
+        const float u2 = union_operand(xi, d);
+        const float u3 = union_operand(xi, q);
+        pa[0] += m1;  pa[1] = fmaf(m1, gj, pa[1]);
+        pa[2] += u1;  pa[3] = fmaf(u1, u1, pa[3]);  pa[4] = fmaf(gi, u1, pa[4]);  leaf_b_terms<UNIT>(u1, pa[5], pa[6]);
+        pa[7] += m2;  pa[8] = fmaf(m2, gd, pa[8]);
+        pa[9] += u2;  pa[10] = fmaf(u2, u2, pa[10]); pa[11] = fmaf(gi, u2, pa[11]); leaf_b_terms<UNIT>(u2, pa[12], pa[13]);
+        pa[14] += m3; pa[15] = fmaf(m3, gd, pa[15]);
+        pa[16] += u3; pa[17] = fmaf(u3, u3, pa[17]); pa[18] = fmaf(gi, u3, pa[18]); leaf_b_terms<UNIT>(u3, pa[19], pa[20]);
+    }
+}
+
+// rare path: exact corrections for label values other than 0/1 (double math, shared atomics)
+__device__ __noinline__ void label_corrections(const float (&g)[3], double* corr /* smem [15] */) {
+    const float lb[5] = {g[1], g[2], fabsf(g[0] - g[1]), fabsf(g[0] - g[2]), fabsf(g[1] - g[2])};
+    for (int L = 0; L < 5; ++L) {
+        const double b = (double)lb[L];
+        if (b == 0.0 || b == 1.0) continue;
+        const double be = (double)(lb[L] + kEps);  // fp32 add like the reference
+        const double sp = fmax(b, 0.0) + log1p(exp(-fabs(b)));
+        const double fl = -pow(1.0 - b, 1.5) * log(be);
+        atomicAdd(&corr[3 * L + 0], b * b - b);
+        atomicAdd(&corr[3 * L + 1], sp - ((1.0 - b) * kSP0 + b * kSP1));
+        atomicAdd(&corr[3 * L + 2], fl - (1.0 - b) * kFL0);
+    }
+}
+
+// fold 32 per-lane values so that lane l ends up with the warp total of v[l]
+__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = lane & s;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void flush_thread_acc(float (&acc)[kNThreadAcc], double* warp_slot /* smem [96] */, int lane) {
+#pragma unroll
+    for (int grp = 0; grp < 3; ++grp) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int k = grp * 32 + i;
+            v[i] = (k < kNThreadAcc) ? acc[k] : 0.f;
+        }
+        const float tot = butterfly32(v, lane);
+        warp_slot[grp * 32 + lane] += (double)tot;
+    }
+#pragma unroll
+    for (int k = 0; k < kNThreadAcc; ++k) acc[k] = 0.f;
+}
+
+// is layout index `idx` accumulated in log2 units with the sign folded?  (FLX, FLU*)
+__host__ __device__ inline bool is_focal_slot(int idx) {
+    if (idx >= A_CH && idx < A_PAIR) return (idx - A_CH) % 5 == 4;
+    if (idx >= A_PAIR && idx < A_CORR) {
+        const int k = (idx - A_PAIR) % 21;
+        return k == 6 || k == 13 || k == 20;
+    }
+    return false;
+}
+
+template <typename TX, int VEC, bool LOGITS>
+__global__ void __launch_bounds__(kCThreads, 1)
+composite3_stats_kernel(CompArgs a, unsigned int* __restrict__ counter, double* __restrict__ partials,
+                        double* __restrict__ acc_out) {
+    __shared__ double warp_slots[kCWarps][96];
+    __shared__ double corr[15];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kCWarps * 96; i += kCThreads) (&warp_slots[0][0])[i] = 0.0;
+    if (threadIdx.x < 15) corr[threadIdx.x] = 0.0;
+    __syncthreads();
+
+    const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
+    const float* __restrict__ gb = reinterpret_cast<const float*>(a.g);
+
+    const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
+    const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
+    int64_t q = lo + threadIdx.x;
+    int64_t n = q / a.units_per_plane;
+    int64_t off = q - n * a.units_per_plane;
+
+    float acc[kNThreadAcc];
+#pragma unroll
+    for (int k = 0; k < kNThreadAcc; ++k) acc[k] = 0.f;
+    int since_flush = 0;
+
+    // warp-uniform trip count: the in-loop flush shuffles with a full mask
+    const int iters = (int)((hi - lo + kCThreads - 1) / kCThreads);
+    for (int it = 0; it < iters; ++it, q += kCThreads) {
+        if (q < hi) {
+            float xv[3][VEC], gv[3][VEC];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                load_vec<TX, VEC>(xb + n * a.x_sn + c * a.x_sc + off * VEC, xv[c]);
+                load_vec<float, VEC>(gb + n * a.g_sn + c * a.g_sc + off * VEC, gv[c]);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float x[3], g[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    x[c] = LOGITS ? sigmoid_exact(xv[c][v]) : xv[c][v];
+                    g[c] = gv[c][v];
+                }
+                pixel_stats<LOGITS>(x, g, acc);
+                const bool nonbin = (g[0] != 0.f && g[0] != 1.f) || (g[1] != 0.f && g[1] != 1.f) || (g[2] != 0.f && g[2] != 1.f);
+                if (nonbin) label_corrections(g, corr);
+            }
+            off += kCThreads;
+            while (off >= a.units_per_plane) {
+                off -= a.units_per_plane;
+                ++n;
+            }
+        }
+        if (++since_flush == kFlushIters) {
+            flush_thread_acc(acc, warp_slots[warp], lane);
+            since_flush = 0;
+        }
+    }
+    // every lane of a warp must take part in the shuffles: flush unconditionally
+    flush_thread_acc(acc, warp_slots[warp], lane);
+    __syncthreads();
+
+    double* mine = partials + (int64_t)blockIdx.x * kNAcc;
+    for (int idx = threadIdx.x; idx < kNAcc; idx += kCThreads) {
+        double v = 0.0;
+        if (idx == A_N) {
+            v = (double)(hi - lo) * VEC;
+        } else if (idx < A_CORR) {
+#pragma unroll
+            for (int w = 0; w < kCWarps; ++w) v += warp_slots[w][idx - 1];
+            if (is_focal_slot(idx)) v *= -kLn2d;
+        } else {
+            v = corr[idx - A_CORR];
+        }
+        mine[idx] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(counter, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int idx = warp; idx < kNAcc; idx += kCWarps) {
+        double v = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(partials + (int64_t)i * kNAcc + idx);
+        v = warp_sum(v);
+        if (lane == 0) acc_out[idx] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: 100 sums -> 21 leaves' stats -> losses[7], jac[21][7][7]
+// ---------------------------------------------------------------------------------------------
+__device__ inline void composite_leaf_sums(const double* A, int leaf, double* s /*[8]*/) {
+    const double n = A[A_N];
+    s[S_N] = n;
+    s[S_FLB] = 0.0;
+    if (leaf < 3) {
+        const double* ch = A + A_CH + 5 * leaf;
+        s[S_A] = A[A_G + leaf]; s[S_B] = ch[0]; s[S_BB] = ch[1]; s[S_AB] = ch[2]; s[S_SP] = ch[3]; s[S_FL] = ch[4];
+        return;
+    }
+    const int p = (leaf - 3) / 6, t = (leaf - 3) % 6;
+    const int i = pair_i(p), j = pair_j(p);
+    const double* pa = A + A_PAIR + 21 * p;
+    if (t & 1) {  // U-leaf: a = g_i, b = u_k
+        const double* u = pa + 2 + 7 * (t >> 1);
+        s[S_A] = A[A_G + i]; s[S_B] = u[0]; s[S_BB] = u[1]; s[S_AB] = u[2]; s[S_SP] = u[3]; s[S_FL] = u[4];
+    } else {  // I-leaf: a = m_k, b = label (g_j for I1, gd for I2/I3)
+        const double* m = pa + 7 * (t >> 1);
+        const int L = (t == 0) ? (j - 1) : (2 + p);
+        const double sb = (t == 0) ? A[A_G + j] : A[A_GD + p];
+        const double* co = A + A_CORR + 3 * L;
+        s[S_A] = m[0]; s[S_AB] = m[1]; s[S_B] = sb;
+        s[S_BB] = sb + co[0];
+        s[S_SP] = (n - sb) * kSP0 + sb * kSP1 + co[1];
+        s[S_FL] = (n - sb) * kFL0 + co[2];
+    }
+}
+
+struct CompFinArgs {
+    double scale[ECO_C3_NLEAF];
+};
+
+__global__ void composite3_finalize_kernel(const double* __restrict__ A, CompFinArgs fa, const double* scale_dev,
+                                           float* __restrict__ losses_out, double* __restrict__ jac_out,
+                                           double* __restrict__ leaf_sums_out) {
+    __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
+    const int leaf = threadIdx.x;
+    if (leaf < ECO_C3_NLEAF) {
+        double s[ECO_NSTAT];
+        composite_leaf_sums(A, leaf, s);
+        LeafOut o;
+        leaf_closed_form(s, 0.0, scale_dev ? scale_dev[leaf] : fa.scale[leaf], o);
+        for (int k = 0; k < ECO_NLOSS; ++k) {
+            sl[leaf][k] = o.loss[k];
+            if (jac_out)
+                for (int j = 0; j < ECO_NJAC; ++j) jac_out[(leaf * ECO_NLOSS + k) * ECO_NJAC + j] = o.jac[k][j];
+        }
+        if (leaf_sums_out)
+            for (int k = 0; k < ECO_NSTAT; ++k) leaf_sums_out[leaf * ECO_NSTAT + k] = s[k];
+    }
+    __syncthreads();
+    if (losses_out && threadIdx.x < ECO_NLOSS) {
+        double v = 0.0;
+        for (int l = 0; l < ECO_C3_NLEAF; ++l) v += sl[l][threadIdx.x];
+        losses_out[threadIdx.x] = (float)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient
+// ---------------------------------------------------------------------------------------------
+struct CompGradArgs {
+    CompArgs a;
+    void* gx;
+    int64_t gx_sn, gx_sc;
+};
+
+__device__ __forceinline__ float leaf_gb(const LeafCoef& c, float a, float b, bool need_sig, bool need_fl) {
+    float r = fmaf(c.sab, a, fmaf(c.sbb2, b, c.sb));
+    if (need_sig) r = fmaf(c.sp, sigmoid_fast(b), r);
+    if (need_fl) r = fmaf(c.fl, dfocal_fg(b), r);
+    return r;
+}
+
+__device__ __forceinline__ void pixel_grad(const float (&x)[3], const float (&g)[3], const LeafCoef* __restrict__ cf,
+                                           bool need_sig, bool need_fl, float (&gx)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gx[c] = leaf_gb(cf[c], g[c], x[c], need_sig, need_fl);
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int i = pair_i(p), j = pair_j(p);
+        const LeafCoef* L = cf + 3 + 6 * p;
+        const float xi = x[i], xj = x[j], gi = g[i], gj = g[j];
+        const float diff = xi - xj;
+        const float d = fabsf(diff);
+        const float s = (diff > 0.f ? 1.f : 0.f) - (diff < 0.f ? 1.f : 0.f);
+        const float gd = fabsf(gi - gj);
+        const float q = d * xi;
+        const float xis = xi * s;
+        const float dq_i = d + xis;  // d q / d x_i (also d m2 / d x_i)
+        const float hp = 0.5f * (1.0f - xi);  // d u / d p
+        float gi_acc = 0.f, gj_acc = 0.f;
+        // I1: a = xi*xj, b = gj
+        {
+            const float ga = fmaf(L[0].sab, gj, L[0].sa);
+            gi_acc = fmaf(ga, xj, gi_acc);
+            gj_acc = fmaf(ga, xi, gj_acc);
+        }
+        // U1: a = gi, b = u(xi, xj)
+        {
+            const float gb = leaf_gb(L[1], gi, union_operand(xi, xj), need_sig, need_fl);
+            gi_acc = fmaf(gb, 1.0f - 0.5f * xj, gi_acc);
+            gj_acc = fmaf(gb, hp, gj_acc);
+        }
+        // I2: a = xi*d, b = gd
+        {
+            const float ga = fmaf(L[2].sab, gd, L[2].sa);
+            gi_acc = fmaf(ga, dq_i, gi_acc);
+            gj_acc = fmaf(ga, -xis, gj_acc);
+        }
+        // U2: a = gi, b = u(xi, d)
+        {
+            const float gb = leaf_gb(L[3], gi, union_operand(xi, d), need_sig, need_fl);
+            gi_acc = fmaf(gb, fmaf(hp, s, 1.0f - 0.5f * d), gi_acc);
+            gj_acc = fmaf(gb, -hp * s, gj_acc);
+        }
+        // I3: a = xi*(d*xi), b = gd
+        {
+            const float ga = fmaf(L[4].sab, gd, L[4].sa);
+            gi_acc = fmaf(ga, fmaf(2.0f * xi, d, xi * xis), gi_acc);
+            gj_acc = fmaf(ga, -xi * xis, gj_acc);
+        }
+        // U3: a = gi, b = u(xi, q), q = d*xi
+        {
+            const float gb = leaf_gb(L[5], gi, union_operand(xi, q), need_sig, need_fl);
+            gi_acc = fmaf(gb, fmaf(hp, dq_i, 1.0f - 0.5f * q), gi_acc);
+            gj_acc = fmaf(gb, -hp * xis, gj_acc);
+        }
+        gx[i] += gi_acc;
+        gx[j] += gj_acc;
+    }
+}
+
+template <typename TX, int VEC, bool LOGITS>
+__global__ void __launch_bounds__(kCThreads, 2)
+composite3_grad_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+    const CompArgs& a = ga.a;
+    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
+    __syncthreads();
+    const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
+
+    const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
+    const float* __restrict__ gb = reinterpret_cast<const float*>(a.g);
+    TX* __restrict__ ob = reinterpret_cast<TX*>(ga.gx);
+
+    const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
+    const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
+    int64_t q = lo + threadIdx.x;
+    int64_t n = q / a.units_per_plane;
+    int64_t off = q - n * a.units_per_plane;
+
+    for (; q < hi; q += kCThreads) {
+        float xv[3][VEC], gv[3][VEC], ov[3][VEC];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            load_vec<TX, VEC>(xb + n * a.x_sn + c * a.x_sc + off * VEC, xv[c]);
+            load_vec<float, VEC>(gb + n * a.g_sn + c * a.g_sc + off * VEC, gv[c]);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float x[3], g[3], gx[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                x[c] = LOGITS ? sigmoid_exact(xv[c][v]) : xv[c][v];
+                g[c] = gv[c][v];
+            }
+            pixel_grad(x, g, cf, need_sig, need_fl, gx);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ov[c][v] = LOGITS ? gx[c] * ((1.0f - x[c]) * x[c]) : gx[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) store_vec<TX, VEC>(ob + n * ga.gx_sn + c * ga.gx_sc + off * VEC, ov[c]);
+        off += kCThreads;
+        while (off >= a.units_per_plane) {
+            off -= a.units_per_plane;
+            ++n;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static bool c_aligned(const void* ptr, int64_t sn, int64_t sc, int dtype, int64_t HW) {
+    const int64_t esz = dtype == ECO_BF16 ? 2 : 4;
+    return (reinterpret_cast<uintptr_t>(ptr) % (4 * esz) == 0) && (sn % 4 == 0) && (sc % 4 == 0) && (HW % 4 == 0);
+}
+
+static int fill_comp(CompArgs& a, const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int vec) {
+    a.x = x->ptr; a.g = g->ptr;
+    a.x_sn = x->sn; a.x_sc = x->sc; a.g_sn = g->sn; a.g_sc = g->sc;
+    a.N = N; a.HW = HW;
+    a.units_per_plane = HW / vec;
+    a.units_total = a.units_per_plane * N;
+    return 0;
+}
+
+static int check_comp(const EcoView* x, const EcoView* g, int32_t N, int64_t HW) {
+    if (!x || !g || !x->ptr || !g->ptr) { set_error("null input view"); return -1; }
+    if (N <= 0 || HW <= 0) { set_error("empty input (N=%d HW=%lld)", N, (long long)HW); return -2; }
+    if (x->dtype != ECO_F32 && x->dtype != ECO_BF16) { set_error("x dtype must be f32 or bf16"); return -4; }
+    if (g->dtype != ECO_F32) { set_error("composite3: labels must be f32"); return -4; }
+    return 0;
+}
+
+static int comp_grid(int device, int64_t units, int ctas_per_sm) {
+    const int sms = sm_count_cached(device);
+    if (sms <= 0) return -1;
+    int64_t g = (int64_t)sms * ctas_per_sm;
+    const int64_t need = (units + kCThreads - 1) / kCThreads;
+    if (g > need) g = need;
+    if (g > kMaxCompCtas) g = kMaxCompCtas;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace eco
+
+using namespace eco;
+
+extern "C" int64_t eco_composite3_ws_bytes(void) { return 256 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double); }
+
+#define ECO_DISPATCH_COMP(KERNEL, xdt, vec, logits, ...)                                         \
+    do {                                                                                          \
+        if (xdt == ECO_F32) {                                                                     \
+            if (vec == 4) { if (logits) KERNEL<float, 4, true> __VA_ARGS__; else KERNEL<float, 4, false> __VA_ARGS__; } \
+            else { if (logits) KERNEL<float, 1, true> __VA_ARGS__; else KERNEL<float, 1, false> __VA_ARGS__; }          \
+        } else {                                                                                  \
+            if (vec == 4) { if (logits) KERNEL<__nv_bfloat16, 4, true> __VA_ARGS__; else KERNEL<__nv_bfloat16, 4, false> __VA_ARGS__; } \
+            else { if (logits) KERNEL<__nv_bfloat16, 1, true> __VA_ARGS__; else KERNEL<__nv_bfloat16, 1, false> __VA_ARGS__; }          \
+        }                                                                                         \
+    } while (0)
+
+extern "C" int eco_composite3_stats(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                                    void* ws, int64_t ws_bytes, double* acc_out, int device, void* stream) {
+    int rc = check_comp(x, g, N, HW);
+    if (rc) return rc;
+    if (!ws || ws_bytes < eco_composite3_ws_bytes() || !acc_out) { set_error("workspace too small or null output"); return -5; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW)) ? 4 : 1;
+    CompArgs a{};
+    fill_comp(a, x, g, N, HW, vec);
+    const int grid = comp_grid(device, a.units_total, 1);
+    if (grid < 0) return -10;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ECO_DISPATCH_COMP(composite3_stats_kernel, x->dtype, vec, from_logits != 0, <<<grid, kCThreads, 0, st>>>(a, counter, partials, acc_out));
+    return check_cuda(cudaGetLastError(), "composite3_stats_kernel launch");
+}
+
+extern "C" int eco_composite3_finalize(const double* acc, const double* leaf_scale_host, const double* leaf_scale_dev,
+                                       float* losses_out, double* jac_out, double* leaf_sums_out, int device,
+                                       void* stream) {
+    if (!acc || (!leaf_scale_host && !leaf_scale_dev)) { set_error("null acc / scales"); return -1; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    CompFinArgs fa{};
+    if (leaf_scale_host)
+        for (int l = 0; l < ECO_C3_NLEAF; ++l) fa.scale[l] = leaf_scale_host[l];
+    composite3_finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        acc, fa, leaf_scale_host ? nullptr : leaf_scale_dev, losses_out, jac_out, leaf_sums_out);
+    return check_cuda(cudaGetLastError(), "composite3_finalize_kernel launch");
+}
+
+extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                                   const double* jac, const float* upstream, const EcoOut* gx, int device,
+                                   void* stream) {
+    int rc = check_comp(x, g, N, HW);
+    if (rc) return rc;
+    if (!jac || !upstream || !gx || !gx->ptr) { set_error("null jac/upstream/gx"); return -5; }
+    if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW) &&
+                     c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
+    CompGradArgs ga{};
+    fill_comp(ga.a, x, g, N, HW, vec);
+    ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
+    const int grid = comp_grid(device, ga.a.units_total, 2);
+    if (grid < 0) return -10;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ECO_DISPATCH_COMP(composite3_grad_kernel, x->dtype, vec, from_logits != 0, <<<grid, kCThreads, 0, st>>>(ga, jac, upstream));
+    return check_cuda(cudaGetLastError(), "composite3_grad_kernel launch");
+}

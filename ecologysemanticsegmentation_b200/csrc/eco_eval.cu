@@ -1,0 +1,291 @@
+// Evaluation scoring: sigmoid -> strict '>' threshold -> exact per-class pixel counts, plus the
+// un-thresholded soft-Dice sums, in ONE read of logits and labels (8 B/element, HBM-bound).
+// Replaces ess/test_multiclass.py:58,68-69,80-81 (see include/ecoloss.h).
+#include "eco_common.cuh"
+
+namespace eco {
+
+constexpr int kEvThreads = 256;
+constexpr int kEvUnroll = 4;
+constexpr int kEvCtasPerSm = 4;
+constexpr int kEvMaxCtas = 148 * kEvCtasPerSm * 2;  // per channel
+
+struct EvalArgs {
+    const void* z;
+    const void* l;
+    int64_t z_sn, z_sc, l_sn, l_sc;
+    int32_t N, C;
+    int64_t HW;
+    int32_t tiles_per_plane;
+    int64_t tiles_per_channel;
+    int32_t tiles_per_cta;
+    int32_t n_thr;
+    int32_t probs;  // inputs already are probabilities
+};
+
+// ws: counters u32[C] (padded to 256 B) | int64 partial counts [C][kEvMaxCtas][NT][2] ... laid out
+// generically as: per (c, cta): long long cnt[2*NT + 1] (last = label count), double soft[3].
+__host__ __device__ inline int64_t eval_rec_words(int nt) { return 2 * (int64_t)nt + 1 + 3; }  // 8-byte words
+__host__ __device__ inline int64_t eval_ws_off(int C) { return ((int64_t)C * 4 + 255) / 256 * 256; }
+
+template <typename TZ, typename TL, int VEC, int NT>
+__global__ void __launch_bounds__(kEvThreads, kEvCtasPerSm)
+dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
+                   long long* __restrict__ partials, long long* __restrict__ counts_out,
+                   double* __restrict__ soft_out) {
+    constexpr int kTile = kEvThreads * VEC * kEvUnroll;
+    constexpr int NTA = NT > 0 ? NT : 1;
+    const int c = blockIdx.y;
+    const TZ* __restrict__ zbase = reinterpret_cast<const TZ*>(p.z) + (int64_t)c * p.z_sc;
+    const TL* __restrict__ lbase = reinterpret_cast<const TL*>(p.l) + (int64_t)c * p.l_sc;
+
+    float thr[NTA];
+#pragma unroll
+    for (int k = 0; k < NTA; ++k) thr[k] = (k < p.n_thr) ? thresholds[k] : __int_as_float(0x7f800000);
+
+    // per-thread exact counters (a thread sees far fewer than 2^31 elements)
+    int cnt_o[NTA], cnt_i[NTA];
+    int cnt_l = 0;
+#pragma unroll
+    for (int k = 0; k < NTA; ++k) cnt_o[k] = cnt_i[k] = 0;
+    double dsoft[3] = {0.0, 0.0, 0.0};
+
+    int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+    int64_t tile_end = tile + p.tiles_per_cta;
+    if (tile_end > p.tiles_per_channel) tile_end = p.tiles_per_channel;
+    int64_t n = tile / p.tiles_per_plane;
+    int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
+
+    for (; tile < tile_end; ++tile) {
+        const TZ* zp = zbase + n * p.z_sn;
+        const TL* lp = lbase + n * p.l_sn;
+        const int64_t e0 = (int64_t)t * kTile + (int64_t)threadIdx.x * VEC;
+        float zv[kEvUnroll][VEC], lv[kEvUnroll][VEC];
+        bool ok[kEvUnroll];
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u) {
+            const int64_t e = e0 + (int64_t)u * kEvThreads * VEC;
+            ok[u] = e < p.HW;
+            if (ok[u]) {
+                if constexpr (VEC == 4) {
+                    Vec4<TZ>::load(zp + e, reinterpret_cast<float(&)[4]>(zv[u]));
+                    Vec4<TL>::load(lp + e, reinterpret_cast<float(&)[4]>(lv[u]));
+                } else {
+                    zv[u][0] = Vec4<TZ>::load1(zp + e);
+                    lv[u][0] = Vec4<TL>::load1(lp + e);
+                }
+            }
+        }
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u) {
+            if (!ok[u]) continue;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float pr = p.probs ? zv[u][v] : sigmoid_exact(zv[u][v]);
+                const float lab = lv[u][v];
+                const int li = fabsf(lab) >= 1.0f ? 1 : 0;
+                s0 = fmaf(pr, lab, s0);
+                s1 += pr;
+                s2 = fmaf(lab, lab, s2);
+                cnt_l += li;
+                if (NT > 0) {
+#pragma unroll
+                    for (int k = 0; k < NTA; ++k) {
+                        const bool on = pr > thr[k];
+                        cnt_o[k] += on ? 1 : 0;
+                        cnt_i[k] += on ? li : 0;
+                    }
+                }
+            }
+        }
+        dsoft[0] += (double)s0;
+        dsoft[1] += (double)s1;
+        dsoft[2] += (double)s2;
+        if (++t == p.tiles_per_plane) {
+            t = 0;
+            ++n;
+        }
+    }
+
+    // CTA reduction: integers via warp shuffles + shared atomics (exact, order-independent)
+    __shared__ long long sm_cnt[2 * NTA + 1];
+    __shared__ double sm_soft[kEvThreads / 32][3];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2 * NTA + 1) sm_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (NT > 0) {
+#pragma unroll
+        for (int k = 0; k < NTA; ++k) {
+            int o = __reduce_add_sync(0xffffffffu, cnt_o[k]);
+            int i = __reduce_add_sync(0xffffffffu, cnt_i[k]);
+            if (lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * k]), (unsigned long long)o);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * k + 1]), (unsigned long long)i);
+            }
+        }
+    }
+    {
+        int l = __reduce_add_sync(0xffffffffu, cnt_l);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * NTA]), (unsigned long long)l);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double v = warp_sum(dsoft[k]);
+        if (lane == 0) sm_soft[warp][k] = v;
+    }
+    __syncthreads();
+    const int64_t rec = eval_rec_words(NTA);
+    long long* mine = partials + ((int64_t)c * kEvMaxCtas + blockIdx.x) * rec;
+    if (threadIdx.x < 2 * NTA + 1) mine[threadIdx.x] = sm_cnt[threadIdx.x];
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kEvThreads / 32; ++w) v += sm_soft[w][threadIdx.x];
+        reinterpret_cast<double*>(mine)[2 * NTA + 1 + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&counters[c], 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const long long* base = partials + (int64_t)c * kEvMaxCtas * rec;
+    // counts: one warp per record word, lanes stride over CTAs
+    for (int w = warp; w < 2 * NTA + 1 + 3; w += kEvThreads / 32) {
+        if (w < 2 * NTA + 1) {
+            long long v = 0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(base + (int64_t)i * rec + w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+                if (w == 2 * NTA) {
+                    // label count goes to every threshold's third slot
+                    for (int k = 0; k < (p.n_thr > 0 ? p.n_thr : 1); ++k)
+                        counts_out[((int64_t)k * p.C + c) * 3 + 2] = v;
+                } else {
+                    const int k = w >> 1;
+                    // order in counts_out: (intersection, |out|, |lab|)
+                    if (k < p.n_thr) counts_out[((int64_t)k * p.C + c) * 3 + ((w & 1) ? 0 : 1)] = v;
+                }
+            }
+        } else {
+            const int s = w - (2 * NTA + 1);
+            double v = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32)
+                v += __ldcg(reinterpret_cast<const double*>(base + (int64_t)i * rec) + 2 * NTA + 1 + s);
+            v = warp_sum(v);
+            if (lane == 0) soft_out[c * 3 + s] = v;
+        }
+    }
+    if (threadIdx.x == 0) counters[c] = 0;
+}
+
+struct DiceFinArgs {
+    int C, n_thr;
+};
+__global__ void dice_finalize_kernel(const long long* __restrict__ counts, const double* __restrict__ soft,
+                                     DiceFinArgs a, float* __restrict__ dice_out, float* __restrict__ soft_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double eps = 1e-7;
+    if (dice_out && counts && i < a.n_thr * a.C) {
+        const long long* r = counts + (int64_t)i * 3;
+        dice_out[i] = (float)((2.0 * (double)r[0] + eps) / ((double)r[1] + (double)r[2] + eps));
+    }
+    if (soft_out && soft && i < a.C) {
+        const double* r = soft + (int64_t)i * 3;
+        soft_out[i] = (float)((2.0 * r[0] + eps) / ((r[1] + r[2]) + eps));
+    }
+}
+
+static bool ev_aligned(const EcoView* v, int64_t HW) {
+    const int64_t esz = v->dtype == ECO_BF16 ? 2 : 4;
+    return (reinterpret_cast<uintptr_t>(v->ptr) % (4 * esz) == 0) && (v->sn % 4 == 0) && (v->sc % 4 == 0) && (HW % 4 == 0);
+}
+
+template <int NT>
+static void launch_nt(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cudaStream_t st, const float* thr,
+                      unsigned int* counters, long long* partials, long long* counts_out, double* soft_out) {
+#define ECO_EV(TZ, TL, V) dice_counts_kernel<TZ, TL, V, NT><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out)
+    if (vec == 4) {
+        if (zd == ECO_F32 && ld == ECO_F32) ECO_EV(float, float, 4);
+        else if (zd == ECO_BF16 && ld == ECO_F32) ECO_EV(__nv_bfloat16, float, 4);
+        else if (zd == ECO_F32 && ld == ECO_BF16) ECO_EV(float, __nv_bfloat16, 4);
+        else ECO_EV(__nv_bfloat16, __nv_bfloat16, 4);
+    } else {
+        if (zd == ECO_F32 && ld == ECO_F32) ECO_EV(float, float, 1);
+        else if (zd == ECO_BF16 && ld == ECO_F32) ECO_EV(__nv_bfloat16, float, 1);
+        else if (zd == ECO_F32 && ld == ECO_BF16) ECO_EV(float, __nv_bfloat16, 1);
+        else ECO_EV(__nv_bfloat16, __nv_bfloat16, 1);
+    }
+#undef ECO_EV
+}
+
+static int nt_bucket(int n_thr) { return n_thr == 0 ? 0 : n_thr == 1 ? 1 : n_thr <= 4 ? 4 : 20; }
+
+}  // namespace eco
+
+using namespace eco;
+
+extern "C" int64_t eco_dice_ws_bytes(int32_t C, int32_t n_thr) {
+    if (C <= 0 || n_thr < 0 || n_thr > 20) return -1;
+    const int nta = nt_bucket(n_thr) > 0 ? nt_bucket(n_thr) : 1;
+    return eval_ws_off(C) + (int64_t)C * kEvMaxCtas * eval_rec_words(nta) * 8;
+}
+
+extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
+                               const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws,
+                               int64_t ws_bytes, int64_t* counts_out, double* soft_out, int device, void* stream) {
+    if (!logits || !labels || !logits->ptr || !labels->ptr) { set_error("null input view"); return -1; }
+    if (N <= 0 || C <= 0 || HW <= 0) { set_error("empty input (N=%d C=%d HW=%lld)", N, C, (long long)HW); return -2; }
+    if (C > 65535) { set_error("C too large"); return -3; }
+    if (n_thr < 0 || n_thr > 20) { set_error("n_thr must be in [0,20] per call (got %d)", n_thr); return -4; }
+    if (n_thr > 0 && !thresholds) { set_error("null thresholds"); return -4; }
+    if (!ws || ws_bytes < eco_dice_ws_bytes(C, n_thr) || !counts_out || !soft_out) { set_error("workspace too small or null output"); return -5; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    EvalArgs p{};
+    p.z = logits->ptr; p.l = labels->ptr;
+    p.z_sn = logits->sn; p.z_sc = logits->sc; p.l_sn = labels->sn; p.l_sc = labels->sc;
+    p.N = N; p.C = C; p.HW = HW; p.n_thr = n_thr; p.probs = logits_are_probs;
+    const int vec = (ev_aligned(logits, HW) && ev_aligned(labels, HW)) ? 4 : 1;
+    const int tile = kEvThreads * vec * kEvUnroll;
+    p.tiles_per_plane = (int32_t)((HW + tile - 1) / tile);
+    p.tiles_per_channel = (int64_t)p.tiles_per_plane * N;
+    const int sms = sm_count_cached(device);
+    if (sms <= 0) return -10;
+    int64_t max_ctas = (int64_t)sms * kEvCtasPerSm / C;
+    if (max_ctas < 1) max_ctas = 1;
+    if (max_ctas > kEvMaxCtas) max_ctas = kEvMaxCtas;
+    int64_t per = (p.tiles_per_channel + max_ctas - 1) / max_ctas;
+    p.tiles_per_cta = (int32_t)(per < 1 ? 1 : per);
+    int64_t ctas = (p.tiles_per_channel + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    dim3 grid((unsigned)(ctas < 1 ? 1 : ctas), (unsigned)C, 1);
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    long long* partials = reinterpret_cast<long long*>(reinterpret_cast<char*>(ws) + eval_ws_off(C));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    long long* co = reinterpret_cast<long long*>(counts_out);
+    switch (nt_bucket(n_thr)) {
+        case 0: launch_nt<0>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
+        case 1: launch_nt<1>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
+        case 4: launch_nt<4>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
+        default: launch_nt<20>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
+    }
+    return check_cuda(cudaGetLastError(), "dice_counts_kernel launch");
+}
+
+extern "C" int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
+                                 float* soft_dice_out, int device, void* stream) {
+    if (C <= 0 || n_thr < 0) { set_error("bad C/n_thr"); return -1; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    DiceFinArgs a{C, n_thr};
+    const int total = (n_thr > 0 ? n_thr : 1) * C;
+    dice_finalize_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(counts), soft, a, dice_out, soft_dice_out);
+    return check_cuda(cudaGetLastError(), "dice_finalize_kernel launch");
+}

@@ -1,0 +1,416 @@
+// Pair-leaf engine: C independent (a_c, b_c) leaves over N images, one streaming pass for the
+// statistics and one for the gradient.  See include/ecoloss.h for the contract.
+//
+// HBM-bound design (B200, 148 SMs): 256-thread CTAs, each thread keeps UNROLL independent 128-bit
+// loads per operand in flight, a contiguous run of tiles per CTA sized so the whole grid is one
+// resident wave, fp32 per-tile partials folded into fp64 thread accumulators, warp-shuffle +
+// shared-memory tree per CTA, deterministic last-CTA-per-channel reduction of the CTA partials.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "eco_common.cuh"
+
+namespace eco {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kCtasPerSm = 4;
+
+struct PairArgs {
+    const void* a;
+    const void* b;
+    int64_t a_sn, a_sc, b_sn, b_sc;
+    int32_t N, C;
+    int64_t HW;
+    uint32_t flags;
+    int32_t tiles_per_plane;
+    int64_t tiles_per_channel;
+    int32_t tiles_per_cta;
+};
+
+// ws layout: [0, 64*C) bytes: one uint32 arrival counter per channel (padded);
+//            then partials: double[C][max_ctas_per_channel][8]
+constexpr int kMaxCtasPerChannel = 148 * kCtasPerSm * 2;
+
+__host__ __device__ inline int64_t pair_ws_partials_offset(int C) { return ((int64_t)C * 4 + 255) / 256 * 256; }
+
+template <typename TA, typename TB, int VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __restrict__ partials,
+                  double* __restrict__ sums_out) {
+    constexpr int kTile = kThreads * VEC * kUnroll;
+    const int c = blockIdx.y;
+    const bool a_logit = p.flags & ECO_A_LOGIT, b_logit = p.flags & ECO_B_LOGIT;
+    const bool need_bg = p.flags & ECO_NEED_BG;
+    const TA* __restrict__ abase = reinterpret_cast<const TA*>(p.a) + (int64_t)c * p.a_sc;
+    const TB* __restrict__ bbase = reinterpret_cast<const TB*>(p.b) + (int64_t)c * p.b_sc;
+
+    double dacc[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dacc[k] = 0.0;
+
+    int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+    int64_t tile_end = tile + p.tiles_per_cta;
+    if (tile_end > p.tiles_per_channel) tile_end = p.tiles_per_channel;
+    int64_t n = tile / p.tiles_per_plane;
+    int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
+
+    for (; tile < tile_end; ++tile) {
+        const TA* ap = abase + n * p.a_sn;
+        const TB* bp = bbase + n * p.b_sn;
+        const int64_t e0 = (int64_t)t * kTile + (int64_t)threadIdx.x * VEC;
+        float av[kUnroll][VEC], bv[kUnroll][VEC];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t e = e0 + (int64_t)u * kThreads * VEC;
+            ok[u] = e < p.HW;
+            if (ok[u]) {
+                if constexpr (VEC == 4) {
+                    Vec4<TA>::load(ap + e, reinterpret_cast<float(&)[4]>(av[u]));
+                    Vec4<TB>::load(bp + e, reinterpret_cast<float(&)[4]>(bv[u]));
+                } else {
+                    av[u][0] = Vec4<TA>::load1(ap + e);
+                    bv[u][0] = Vec4<TB>::load1(bp + e);
+                }
+            }
+        }
+        float acc[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (ok[u]) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    float a = av[u][v], b = bv[u][v];
+                    if (a_logit) a = sigmoid_exact(a);
+                    if (b_logit) b = sigmoid_exact(b);
+                    acc[0] += a;
+                    acc[1] += b;
+                    acc[2] = fmaf(a, b, acc[2]);
+                    acc[3] = fmaf(b, b, acc[3]);
+                    acc[4] += fmaf(softplus_neg_abs_log2(b), kLn2, fmaxf(b, 0.f));
+                    acc[5] -= focal_fg_log2(b);
+                    if (need_bg) acc[6] -= focal_bg_log2(b);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) dacc[k] += (double)acc[k];
+        if (++t == p.tiles_per_plane) {
+            t = 0;
+            ++n;
+        }
+    }
+    // focal terms were accumulated in log2 units
+    dacc[5] *= kLn2d;
+    dacc[6] *= kLn2d;
+
+    // CTA reduction
+    __shared__ double sm[kThreads / 32][7];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        double v = warp_sum(dacc[k]);
+        if (lane == 0) sm[warp][k] = v;
+    }
+    __syncthreads();
+    double* my_partials = partials + ((int64_t)c * kMaxCtasPerChannel + blockIdx.x) * 8;
+    if (threadIdx.x < 7) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += sm[w][threadIdx.x];
+        my_partials[threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&counters[c], 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // deterministic final reduction by the last CTA of this channel: warp k sums stat k
+    if (warp < 7) {
+        const double* base = partials + (int64_t)c * kMaxCtasPerChannel * 8;
+        double v = 0.0;
+        for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(base + (int64_t)i * 8 + warp);
+        v = warp_sum(v);
+        if (lane == 0) sums_out[c * ECO_NSTAT + 1 + warp] = v;
+    }
+    if (threadIdx.x == 0) {
+        sums_out[c * ECO_NSTAT + S_N] = (double)p.N * (double)p.HW;
+        counters[c] = 0;  // re-arm for the next launch on this workspace
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: sums -> losses, Jacobian
+// ---------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+    double bw;
+    double scale[64];
+};
+
+__global__ void pair_finalize_kernel(const double* __restrict__ sums, int C, FinalizeArgs fa,
+                                     float* __restrict__ losses_out, float* __restrict__ total_out,
+                                     double* __restrict__ jac_out) {
+    __shared__ double sl[64][ECO_NLOSS];
+    const int c = threadIdx.x;
+    if (c < C) {
+        LeafOut o;
+        leaf_closed_form(sums + c * ECO_NSTAT, fa.bw, fa.scale[c], o);
+        for (int k = 0; k < ECO_NLOSS; ++k) {
+            sl[c][k] = o.loss[k];
+            if (losses_out) losses_out[c * ECO_NLOSS + k] = (float)o.loss[k];
+            if (jac_out)
+                for (int j = 0; j < ECO_NJAC; ++j) jac_out[(c * ECO_NLOSS + k) * ECO_NJAC + j] = o.jac[k][j];
+        }
+    }
+    __syncthreads();
+    if (total_out && threadIdx.x < ECO_NLOSS) {
+        double v = 0.0;
+        for (int i = 0; i < C; ++i) v += sl[i][threadIdx.x];
+        total_out[threadIdx.x] = (float)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient pass
+// ---------------------------------------------------------------------------------------------
+struct GradArgs {
+    PairArgs p;
+    void* ga;
+    void* gb;
+    int64_t ga_sn, ga_sc, gb_sn, gb_sc;
+    int32_t accumulate;
+};
+
+template <typename TA, typename TB, int VEC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    constexpr int kTile = kThreads * VEC * kUnroll;
+    const PairArgs& p = g.p;
+    const int c = blockIdx.y;
+    const bool a_logit = p.flags & ECO_A_LOGIT, b_logit = p.flags & ECO_B_LOGIT;
+    const TA* __restrict__ abase = reinterpret_cast<const TA*>(p.a) + (int64_t)c * p.a_sc;
+    const TB* __restrict__ bbase = reinterpret_cast<const TB*>(p.b) + (int64_t)c * p.b_sc;
+    TA* gabase = g.ga ? reinterpret_cast<TA*>(g.ga) + (int64_t)c * g.ga_sc : nullptr;
+    TB* gbbase = g.gb ? reinterpret_cast<TB*>(g.gb) + (int64_t)c * g.gb_sc : nullptr;
+
+    __shared__ LeafCoef coef_s;
+    if (threadIdx.x == 0) coef_s = make_coef(jac + (int64_t)c * ECO_NLOSS * ECO_NJAC, upstream);
+    __syncthreads();
+    const LeafCoef cf = coef_s;
+    const bool need_sig = cf.sp != 0.f, need_fl = cf.fl != 0.f, need_flb = cf.flb != 0.f;
+
+    int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+    int64_t tile_end = tile + p.tiles_per_cta;
+    if (tile_end > p.tiles_per_channel) tile_end = p.tiles_per_channel;
+    int64_t n = tile / p.tiles_per_plane;
+    int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
+
+    for (; tile < tile_end; ++tile) {
+        const TA* ap = abase + n * p.a_sn;
+        const TB* bp = bbase + n * p.b_sn;
+        TA* gap = gabase ? gabase + n * g.ga_sn : nullptr;
+        TB* gbp = gbbase ? gbbase + n * g.gb_sn : nullptr;
+        const int64_t e0 = (int64_t)t * kTile + (int64_t)threadIdx.x * VEC;
+        float av[kUnroll][VEC], bv[kUnroll][VEC];
+        bool ok[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t e = e0 + (int64_t)u * kThreads * VEC;
+            ok[u] = e < p.HW;
+            if (ok[u]) {
+                if constexpr (VEC == 4) {
+                    Vec4<TA>::load(ap + e, reinterpret_cast<float(&)[4]>(av[u]));
+                    Vec4<TB>::load(bp + e, reinterpret_cast<float(&)[4]>(bv[u]));
+                } else {
+                    av[u][0] = Vec4<TA>::load1(ap + e);
+                    bv[u][0] = Vec4<TB>::load1(bp + e);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!ok[u]) continue;
+            const int64_t e = e0 + (int64_t)u * kThreads * VEC;
+            float oa[VEC], ob[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float a = av[u][v], b = bv[u][v];
+                if (a_logit) a = sigmoid_exact(a);
+                if (b_logit) b = sigmoid_exact(b);
+                float da = fmaf(cf.sab, b, cf.sa);
+                float db = fmaf(cf.sab, a, fmaf(cf.sbb2, b, cf.sb));
+                if (need_sig) db = fmaf(cf.sp, sigmoid_fast(b), db);
+                if (need_fl) db = fmaf(cf.fl, dfocal_fg(b), db);
+                if (need_flb) db = fmaf(cf.flb, dfocal_bg(b), db);
+                if (a_logit) da *= (1.0f - a) * a;
+                if (b_logit) db *= (1.0f - b) * b;
+                oa[v] = da;
+                ob[v] = db;
+            }
+            if (gap) {
+                if constexpr (VEC == 4) {
+                    if (g.accumulate) {
+                        float old[4];
+                        Vec4<TA>::load(gap + e, old);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) oa[v] += old[v];
+                    }
+                    Vec4<TA>::store(gap + e, reinterpret_cast<float(&)[4]>(oa));
+                } else {
+                    if (g.accumulate) oa[0] += Vec4<TA>::load1(gap + e);
+                    Vec4<TA>::store1(gap + e, oa[0]);
+                }
+            }
+            if (gbp) {
+                if constexpr (VEC == 4) {
+                    if (g.accumulate) {
+                        float old[4];
+                        Vec4<TB>::load(gbp + e, old);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) ob[v] += old[v];
+                    }
+                    Vec4<TB>::store(gbp + e, reinterpret_cast<float(&)[4]>(ob));
+                } else {
+                    if (g.accumulate) ob[0] += Vec4<TB>::load1(gbp + e);
+                    Vec4<TB>::store1(gbp + e, ob[0]);
+                }
+            }
+        }
+        if (++t == p.tiles_per_plane) {
+            t = 0;
+            ++n;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool aligned_for_vec4(const void* ptr, int64_t sn, int64_t sc, int dtype, int64_t HW) {
+    const int64_t esz = dtype == ECO_BF16 ? 2 : 4;
+    const int64_t need = 4 * esz;  // bytes per 4-vector
+    return (reinterpret_cast<uintptr_t>(ptr) % need == 0) && (sn % 4 == 0) && (sc % 4 == 0) && (HW % 4 == 0);
+}
+
+static int plan(PairArgs& p, int vec, int device, dim3& grid) {
+    const int tile = kThreads * vec * kUnroll;
+    p.tiles_per_plane = (int32_t)((p.HW + tile - 1) / tile);
+    p.tiles_per_channel = (int64_t)p.tiles_per_plane * p.N;
+    const int sms = sm_count_cached(device);
+    if (sms <= 0) return -10;
+    int64_t max_ctas = (int64_t)sms * kCtasPerSm / p.C;
+    if (max_ctas < 1) max_ctas = 1;
+    if (max_ctas > kMaxCtasPerChannel) max_ctas = kMaxCtasPerChannel;
+    int64_t per = (p.tiles_per_channel + max_ctas - 1) / max_ctas;
+    if (per < 1) per = 1;
+    p.tiles_per_cta = (int32_t)per;
+    int64_t ctas = (p.tiles_per_channel + per - 1) / per;
+    if (ctas < 1) ctas = 1;
+    grid = dim3((unsigned)ctas, (unsigned)p.C, 1);
+    return 0;
+}
+
+static int fill_args(PairArgs& p, const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW,
+                     uint32_t flags) {
+    if (!a || !b || !a->ptr || !b->ptr) { set_error("null input view"); return -1; }
+    if (N <= 0 || C <= 0 || HW <= 0) { set_error("empty input (N=%d C=%d HW=%lld)", N, C, (long long)HW); return -2; }
+    if (C > 65535) { set_error("C=%d exceeds grid.y limit", C); return -3; }
+    if ((a->dtype != ECO_F32 && a->dtype != ECO_BF16) || (b->dtype != ECO_F32 && b->dtype != ECO_BF16)) {
+        set_error("unsupported dtype code");
+        return -4;
+    }
+    p.a = a->ptr; p.b = b->ptr;
+    p.a_sn = a->sn; p.a_sc = a->sc; p.b_sn = b->sn; p.b_sc = b->sc;
+    p.N = N; p.C = C; p.HW = HW; p.flags = flags;
+    return 0;
+}
+
+#define ECO_DISPATCH_PAIR(KERNEL, adt, bdt, vec, ...)                                              \
+    do {                                                                                            \
+        if (vec == 4) {                                                                             \
+            if (adt == ECO_F32 && bdt == ECO_F32) KERNEL<float, float, 4> __VA_ARGS__;              \
+            else if (adt == ECO_BF16 && bdt == ECO_F32) KERNEL<__nv_bfloat16, float, 4> __VA_ARGS__; \
+            else if (adt == ECO_F32 && bdt == ECO_BF16) KERNEL<float, __nv_bfloat16, 4> __VA_ARGS__; \
+            else KERNEL<__nv_bfloat16, __nv_bfloat16, 4> __VA_ARGS__;                                \
+        } else {                                                                                    \
+            if (adt == ECO_F32 && bdt == ECO_F32) KERNEL<float, float, 1> __VA_ARGS__;              \
+            else if (adt == ECO_BF16 && bdt == ECO_F32) KERNEL<__nv_bfloat16, float, 1> __VA_ARGS__; \
+            else if (adt == ECO_F32 && bdt == ECO_BF16) KERNEL<float, __nv_bfloat16, 1> __VA_ARGS__; \
+            else KERNEL<__nv_bfloat16, __nv_bfloat16, 1> __VA_ARGS__;                                \
+        }                                                                                           \
+    } while (0)
+
+}  // namespace eco
+
+using namespace eco;
+
+extern "C" int64_t eco_pair_ws_bytes(int32_t C) {
+    if (C <= 0) return -1;
+    return pair_ws_partials_offset(C) + (int64_t)C * kMaxCtasPerChannel * 8 * (int64_t)sizeof(double);
+}
+
+extern "C" int eco_pair_stats(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                              void* ws, int64_t ws_bytes, double* sums_out, int device, void* stream) {
+    PairArgs p{};
+    int rc = fill_args(p, a, b, N, C, HW, flags);
+    if (rc) return rc;
+    if (!ws || ws_bytes < eco_pair_ws_bytes(C) || !sums_out) { set_error("workspace too small or null output"); return -5; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    const int vec = (aligned_for_vec4(a->ptr, a->sn, a->sc, a->dtype, HW) &&
+                     aligned_for_vec4(b->ptr, b->sn, b->sc, b->dtype, HW)) ? 4 : 1;
+    dim3 grid;
+    rc = plan(p, vec, device, grid);
+    if (rc) return rc;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + pair_ws_partials_offset(C));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ECO_DISPATCH_PAIR(pair_stats_kernel, a->dtype, b->dtype, vec, <<<grid, kThreads, 0, st>>>(p, counters, partials, sums_out));
+    return check_cuda(cudaGetLastError(), "pair_stats_kernel launch");
+}
+
+extern "C" int eco_pair_finalize(const double* sums, int32_t C, double background_weight, const double* scale_host,
+                                 float* losses_out, float* total_out, double* jac_out, int device, void* stream) {
+    if (!sums || C <= 0 || C > 64) { set_error("eco_pair_finalize: C must be in [1,64] (got %d)", C); return -1; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    FinalizeArgs fa{};
+    fa.bw = background_weight;
+    for (int c = 0; c < C; ++c) fa.scale[c] = scale_host ? scale_host[c] : 1.0;
+    pair_finalize_kernel<<<1, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sums, C, fa, losses_out, total_out, jac_out);
+    return check_cuda(cudaGetLastError(), "pair_finalize_kernel launch");
+}
+
+extern "C" int eco_pair_grad(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                             const double* jac, const float* upstream, const EcoOut* ga, const EcoOut* gb,
+                             int32_t accumulate, int device, void* stream) {
+    GradArgs g{};
+    int rc = fill_args(g.p, a, b, N, C, HW, flags);
+    if (rc) return rc;
+    if (!jac || !upstream) { set_error("null jac/upstream"); return -5; }
+    const bool want_a = ga && ga->ptr, want_b = gb && gb->ptr;
+    if (!want_a && !want_b) return 0;
+    if (want_a && ga->dtype != a->dtype) { set_error("ga dtype must match slot a"); return -7; }
+    if (want_b && gb->dtype != b->dtype) { set_error("gb dtype must match slot b"); return -7; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    bool v4 = aligned_for_vec4(a->ptr, a->sn, a->sc, a->dtype, HW) && aligned_for_vec4(b->ptr, b->sn, b->sc, b->dtype, HW);
+    if (want_a) { g.ga = ga->ptr; g.ga_sn = ga->sn; g.ga_sc = ga->sc; v4 = v4 && aligned_for_vec4(ga->ptr, ga->sn, ga->sc, ga->dtype, HW); }
+    if (want_b) { g.gb = gb->ptr; g.gb_sn = gb->sn; g.gb_sc = gb->sc; v4 = v4 && aligned_for_vec4(gb->ptr, gb->sn, gb->sc, gb->dtype, HW); }
+    g.accumulate = accumulate;
+    const int vec = v4 ? 4 : 1;
+    dim3 grid;
+    rc = plan(g.p, vec, device, grid);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ECO_DISPATCH_PAIR(pair_grad_kernel, a->dtype, b->dtype, vec, <<<grid, kThreads, 0, st>>>(g, jac, upstream));
+    return check_cuda(cudaGetLastError(), "pair_grad_kernel launch");
+}

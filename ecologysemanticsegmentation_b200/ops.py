@@ -1,0 +1,298 @@
+"""Tensor-level wrappers over the C ABI and the autograd Functions built on them.
+
+Loss order everywhere: [ce, bce, focal, dice, generalized_dice, twersky, focal_dice]
+(ecology_semantic_segmentation/loss_composite.py:39).  "Slot a" is the reference's first positional
+argument, "slot b" the second.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+from . import distributed as dist_
+
+M_DICE = 10 * 0.33  # classification_dice_loss(factor=10), loss_functions.py:116
+
+
+# ------------------------------------------------------------------------------------------------
+# raw launches
+# ------------------------------------------------------------------------------------------------
+def _dev(t):
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def pair_stats(a, b, flags=0):
+    """a, b: [N,C,H,W] CUDA tensors -> float64 [C, 8] sums of the C (a_c, b_c) leaves of this shard."""
+    nat.require_cuda(a, b)
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError(f"pair_stats expects two [N,C,H,W] tensors of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+    a, a_sn, a_sc = nat.planes(a)
+    b, b_sn, b_sc = nat.planes(b)
+    n, c, h, w = a.shape
+    L = nat.lib()
+    ws = nat.workspace("pair", L.eco_pair_ws_bytes(c), a.device)
+    sums = torch.empty((c, nat.NSTAT), dtype=torch.float64, device=a.device)
+    va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
+    rc = L.eco_pair_stats(C.byref(va), C.byref(vb), n, c, h * w, flags, ws.data_ptr(), ws.numel(), sums.data_ptr(),
+                          _dev(a), nat.current_stream_ptr(a.device))
+    nat.check(rc, "eco_pair_stats")
+    return sums
+
+
+def pair_finalize(sums, background_weight, scales):
+    """sums float64 [C,8] -> (losses f32 [C,7], total f32 [7], jac f64 [C,7,7])."""
+    c = sums.shape[0]
+    dev = sums.device
+    losses = torch.empty((c, nat.NLOSS), dtype=torch.float32, device=dev)
+    total = torch.empty((nat.NLOSS,), dtype=torch.float32, device=dev)
+    jac = torch.empty((c, nat.NLOSS, nat.NJAC), dtype=torch.float64, device=dev)
+    sc = (C.c_double * c)(*[float(s) for s in scales])
+    rc = nat.lib().eco_pair_finalize(sums.data_ptr(), c, float(background_weight), sc, losses.data_ptr(), total.data_ptr(),
+                                     jac.data_ptr(), _dev(sums), nat.current_stream_ptr(dev))
+    nat.check(rc, "eco_pair_finalize")
+    return losses, total, jac
+
+
+def pair_grad(a, b, flags, jac, upstream, want_a, want_b):
+    a, a_sn, a_sc = nat.planes(a)
+    b, b_sn, b_sc = nat.planes(b)
+    n, c, h, w = a.shape
+    ga = torch.empty((n, c, h, w), dtype=a.dtype, device=a.device) if want_a else None
+    gb = torch.empty((n, c, h, w), dtype=b.dtype, device=b.device) if want_b else None
+    va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
+    oa, ob = nat.out_of(ga, c * h * w, h * w), nat.out_of(gb, c * h * w, h * w)
+    rc = nat.lib().eco_pair_grad(C.byref(va), C.byref(vb), n, c, h * w, flags, jac.data_ptr(), upstream.data_ptr(),
+                                 C.byref(oa), C.byref(ob), 0, _dev(a), nat.current_stream_ptr(a.device))
+    nat.check(rc, "eco_pair_grad")
+    return ga, gb
+
+
+def composite3_stats(x, g, from_logits):
+    nat.require_cuda(x, g)
+    if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"composite3 expects two [N,3,H,W] tensors, got {tuple(x.shape)} and {tuple(g.shape)}")
+    if g.dtype != torch.float32:
+        g = g.float()
+    x, x_sn, x_sc = nat.planes(x)
+    g, g_sn, g_sc = nat.planes(g)
+    n, _, h, w = x.shape
+    L = nat.lib()
+    ws = nat.workspace("comp3", L.eco_composite3_ws_bytes(), x.device)
+    acc = torch.empty((nat.C3_NACC,), dtype=torch.float64, device=x.device)
+    vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
+    rc = L.eco_composite3_stats(C.byref(vx), C.byref(vg), n, h * w, int(from_logits), ws.data_ptr(), ws.numel(),
+                                acc.data_ptr(), _dev(x), nat.current_stream_ptr(x.device))
+    nat.check(rc, "eco_composite3_stats")
+    return acc
+
+
+def composite3_finalize(acc, leaf_scales, want_leaf_sums=False):
+    dev = acc.device
+    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=dev)
+    jac = torch.empty((nat.C3_NLEAF, nat.NLOSS, nat.NJAC), dtype=torch.float64, device=dev)
+    leaf_sums = torch.empty((nat.C3_NLEAF, nat.NSTAT), dtype=torch.float64, device=dev) if want_leaf_sums else None
+    if isinstance(leaf_scales, torch.Tensor):
+        host, devp = None, leaf_scales.data_ptr()
+    else:
+        host, devp = (C.c_double * nat.C3_NLEAF)(*[float(s) for s in leaf_scales]), None
+    rc = nat.lib().eco_composite3_finalize(acc.data_ptr(), host, devp, losses.data_ptr(), jac.data_ptr(),
+                                           leaf_sums.data_ptr() if want_leaf_sums else None, _dev(acc),
+                                           nat.current_stream_ptr(dev))
+    nat.check(rc, "eco_composite3_finalize")
+    return losses, jac, leaf_sums
+
+
+def composite3_grad(x, g, from_logits, jac, upstream):
+    if g.dtype != torch.float32:
+        g = g.float()
+    x, x_sn, x_sc = nat.planes(x)
+    g, g_sn, g_sc = nat.planes(g)
+    n, c, h, w = x.shape
+    gx = torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+    vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
+    og = nat.out_of(gx, c * h * w, h * w)
+    rc = nat.lib().eco_composite3_grad(C.byref(vx), C.byref(vg), n, h * w, int(from_logits), jac.data_ptr(),
+                                       upstream.data_ptr(), C.byref(og), _dev(x), nat.current_stream_ptr(x.device))
+    nat.check(rc, "eco_composite3_grad")
+    return gx
+
+
+def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False):
+    """One pass over logits+labels -> (counts int64 [T,C,3] = (I, |out|, |lab|) per threshold,
+    soft float64 [C,3] = (sum p*lab, sum p, sum lab^2)).  thresholds: float32 CUDA tensor [T] or None."""
+    nat.require_cuda(logits, labels)
+    if logits.shape != labels.shape or logits.dim() != 4:
+        raise ValueError("dice_counts expects two [N,C,H,W] tensors of equal shape")
+    logits, z_sn, z_sc = nat.planes(logits)
+    labels, l_sn, l_sc = nat.planes(labels)
+    n, c, h, w = logits.shape
+    nthr = 0 if thresholds is None else int(thresholds.numel())
+    if nthr > 20:
+        raise ValueError("at most 20 thresholds per call")
+    if nthr:
+        if thresholds.dtype != torch.float32 or not thresholds.is_cuda:
+            raise ValueError("thresholds must be a float32 CUDA tensor")
+        thresholds = thresholds.contiguous()
+    L = nat.lib()
+    ws = nat.workspace("dice%d" % nthr, L.eco_dice_ws_bytes(c, nthr), logits.device)
+    counts = torch.zeros((max(nthr, 1), c, 3), dtype=torch.int64, device=logits.device)
+    soft = torch.empty((c, 3), dtype=torch.float64, device=logits.device)
+    vz, vl = nat.view_of(logits, z_sn, z_sc), nat.view_of(labels, l_sn, l_sc)
+    rc = L.eco_dice_counts(C.byref(vz), C.byref(vl), n, c, h * w, thresholds.data_ptr() if nthr else None, nthr,
+                           int(inputs_are_probs), ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),
+                           _dev(logits), nat.current_stream_ptr(logits.device))
+    nat.check(rc, "eco_dice_counts")
+    return counts, soft
+
+
+def dice_finalize(counts, soft, nthr):
+    c = soft.shape[0]
+    dev = soft.device
+    dice = torch.empty((max(nthr, 1), c), dtype=torch.float32, device=dev) if nthr else None
+    sdice = torch.empty((c,), dtype=torch.float32, device=dev)
+    rc = nat.lib().eco_dice_finalize(counts.data_ptr(), soft.data_ptr(), c, nthr, dice.data_ptr() if nthr else None,
+                                     sdice.data_ptr(), _dev(soft), nat.current_stream_ptr(dev))
+    nat.check(rc, "eco_dice_finalize")
+    return dice, sdice
+
+
+def softce_stats(a, b, need_bg):
+    nat.require_cuda(a, b)
+    a, a_sn, a_sc = nat.planes(a)
+    b, b_sn, b_sc = nat.planes(b)
+    n, c, h, w = a.shape
+    L = nat.lib()
+    ws = nat.workspace("softce", L.eco_softce_ws_bytes(), a.device)
+    sums = torch.zeros((2,), dtype=torch.float64, device=a.device)
+    va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
+    rc = L.eco_softce_stats(C.byref(va), C.byref(vb), n, c, h * w, int(need_bg), ws.data_ptr(), ws.numel(),
+                            sums.data_ptr(), _dev(a), nat.current_stream_ptr(a.device))
+    nat.check(rc, "eco_softce_stats")
+    return sums
+
+
+def softce_grad(a, b, bw, n_pix, upstream, want_a, want_b):
+    a, a_sn, a_sc = nat.planes(a)
+    b, b_sn, b_sc = nat.planes(b)
+    n, c, h, w = a.shape
+    ga = torch.empty((n, c, h, w), dtype=a.dtype, device=a.device) if want_a else None
+    gb = torch.empty((n, c, h, w), dtype=b.dtype, device=b.device) if want_b else None
+    va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
+    oa, ob = nat.out_of(ga, c * h * w, h * w), nat.out_of(gb, c * h * w, h * w)
+    rc = nat.lib().eco_softce_grad(C.byref(va), C.byref(vb), n, c, h * w, float(bw), float(n_pix),
+                                   upstream.data_ptr(), C.byref(oa), C.byref(ob), _dev(a),
+                                   nat.current_stream_ptr(a.device))
+    nat.check(rc, "eco_softce_grad")
+    return ga, gb
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------------
+def _stack_upstream(grads, like):
+    """7 optional 0-d grads -> one float32 [7] device tensor, without a host sync."""
+    zero = None
+    parts = []
+    for gr in grads:
+        if gr is None:
+            if zero is None:
+                zero = torch.zeros((), dtype=torch.float32, device=like.device)
+            parts.append(zero)
+        else:
+            parts.append(gr.reshape(()).to(torch.float32))
+    return torch.stack(parts)
+
+
+class PairLeaves(torch.autograd.Function):
+    """C independent 7-loss leaves over [N,C,H,W] slot tensors; returns the 7 totals over channels.
+
+    ``group``: optional torch.distributed process group -- the batch is sharded across its ranks and the
+    per-leaf sums are all-reduced before the closed forms."""
+
+    @staticmethod
+    def forward(ctx, a, b, background_weight, scale, flags, group):
+        c = a.shape[1]
+        sums = pair_stats(a.detach(), b.detach(), flags | (nat.FLAG_NEED_BG if background_weight != 0 else 0))
+        sums = dist_.allreduce_sums_(sums, group)
+        _, total, jac = pair_finalize(sums, background_weight, [scale] * c)
+        ctx.save_for_backward(a, b, jac)
+        ctx.flags = flags
+        ctx.set_materialize_grads(False)
+        return tuple(total.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        a, b, jac = ctx.saved_tensors
+        want_a, want_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (want_a or want_b) or all(g is None for g in grads):
+            return None, None, None, None, None, None
+        up = _stack_upstream(grads, a)
+        ga, gb = pair_grad(a.detach(), b.detach(), ctx.flags, jac, up, want_a, want_b)
+        return ga, gb, None, None, None, None
+
+
+class Composite3(torch.autograd.Function):
+    """Fused 21-leaf composite loss for C == 3 (loss_composite.py:21-94, composite_set_theory=True)."""
+
+    @staticmethod
+    def forward(ctx, x, g, leaf_scales, from_logits, group):
+        acc = composite3_stats(x.detach(), g.detach(), from_logits)
+        acc = dist_.allreduce_sums_(acc, group)
+        losses, jac, _ = composite3_finalize(acc, leaf_scales)
+        ctx.save_for_backward(x, g, jac)
+        ctx.from_logits = from_logits
+        ctx.set_materialize_grads(False)
+        return tuple(losses.unbind(0))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, g, jac = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("the fused composite kernel produces gradients for the predictions only; "
+                                      "labels that require grad are not supported on this path")
+        if not ctx.needs_input_grad[0] or all(gr is None for gr in grads):
+            return None, None, None, None, None
+        up = _stack_upstream(grads, x)
+        gx = composite3_grad(x.detach(), g.detach(), ctx.from_logits, jac, up)
+        return gx, None, None, None, None
+
+
+class SoftCE(torch.autograd.Function):
+    """F.cross_entropy(b, a) + bw * F.cross_entropy(1-b, 1-a) with float targets (loss_functions.py:29-30)."""
+
+    @staticmethod
+    def forward(ctx, a, b, background_weight):
+        sums = softce_stats(a.detach(), b.detach(), background_weight != 0)
+        n_pix = a.shape[0] * a.shape[2] * a.shape[3]
+        ctx.save_for_backward(a, b)
+        ctx.bw, ctx.n_pix = float(background_weight), n_pix
+        return (-(sums[0] + background_weight * sums[1]) / n_pix).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, b = ctx.saved_tensors
+        want_a, want_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        up = grad.reshape(1).to(torch.float32)
+        ga, gb = softce_grad(a.detach(), b.detach(), ctx.bw, ctx.n_pix, up, want_a, want_b)
+        return ga, gb, None
+
+
+# ------------------------------------------------------------------------------------------------
+# shape plumbing for the stand-alone primitives (reduce over the WHOLE tensor pair)
+# ------------------------------------------------------------------------------------------------
+def as_single_leaf(a, b):
+    """Two equal-shape tensors -> [N,1,H,W]-shaped views describing ONE leaf over all their elements."""
+    nat.require_cuda(a, b)
+    if a.shape != b.shape:
+        a, b = torch.broadcast_tensors(a, b)
+    if a.dim() == 4 and a.shape[1] == 1:
+        return a, b  # the reference's usual case: channel slices; planes() handles the strides
+    return a.contiguous().view(1, 1, 1, -1), b.contiguous().view(1, 1, 1, -1)
+
+
+def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None):
+    """The 7 losses of ONE leaf over all elements of (a, b), each times ``scale``."""
+    a4, b4 = as_single_leaf(a, b)
+    return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group)

@@ -1,0 +1,172 @@
+/*
+ * ecoloss.h -- C ABI of the B200-native per-pixel loss / Dice-scoring path.
+ *
+ * The reference (hansk0812/EcologySemanticSegmentation) has no FFI layer: its seam is plain
+ * Python.  Each entry point below names the reference code it replaces
+ * (paths relative to the reference root, `ess/` = `ecology_semantic_segmentation/`); the
+ * Python side of this repo (`ecologysemanticsegmentation_b200/`) binds them with ctypes and
+ * re-exposes the reference's own function names and signatures.  INTEGRATION.md shows the stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the library allocates nothing: the caller owns all buffers, including the workspace;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*) of device
+ *     `device`; entry points are re-entrant (PyTorch calls backward from its autograd thread);
+ *   - return value 0 = success, >0 = cudaError_t, <0 = argument error; `eco_last_error()`
+ *     returns a thread-local description;
+ *   - tensors are NCHW; a "plane" is the H*W contiguous elements of one (n, c).  A tensor is
+ *     described by its base pointer and two element strides: `sn` between images and `sc`
+ *     between channels, so `x[:, c:c+1]` slices of a contiguous tensor need no copy;
+ *   - dtype codes: ECO_F32 = 0, ECO_BF16 = 1 (logits / probabilities / labels / gradients);
+ *   - "slots": `a` is the reference's FIRST positional argument ("gt"), `b` the SECOND ("pred").
+ *     Which one is really the label depends on the caller.
+ *
+ * Statistics vector of one (a, b) leaf (float64[ECO_NSTAT]), additive across shards:
+ *   [0] n  [1] sum a  [2] sum b  [3] sum a*b  [4] sum b*b
+ *   [5] sum max(b,0)+log(1+exp(-|b|))  [6] sum -(1-b)^1.5 log(b+1e-7)  [7] sum -b^1.5 log(1-b+1e-7)
+ * Loss order everywhere (ess/loss_composite.py:39):
+ *   [ce, bce, focal, dice, generalized_dice, twersky, focal_dice]
+ */
+#ifndef ECOLOSS_H
+#define ECOLOSS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECO_F32 0
+#define ECO_BF16 1
+
+#define ECO_NSTAT 8
+#define ECO_NLOSS 7
+#define ECO_NJAC 7 /* d loss_k / d stat[1..7] */
+
+/* flags for eco_pair_* */
+#define ECO_A_LOGIT 1      /* slot a holds logits: sigmoid applied on load, gradient chained to the logit */
+#define ECO_B_LOGIT 2      /* same for slot b */
+#define ECO_NEED_BG 4      /* background_weight != 0: also accumulate stat [7] */
+#define ECO_UNIT_RANGE_B 8 /* caller guarantees b in [0,1] (e.g. b = sigmoid(.)): lets max(b,0) collapse to b */
+
+/* A strided view of C planes-per-image over N images. */
+typedef struct EcoView {
+    const void* ptr;
+    int64_t sn; /* element stride between images   */
+    int64_t sc; /* element stride between channels */
+    int32_t dtype;
+    int32_t _pad;
+} EcoView;
+
+/* Mutable flavour for gradient outputs (ptr may be NULL = not requested). */
+typedef struct EcoOut {
+    void* ptr;
+    int64_t sn;
+    int64_t sc;
+    int32_t dtype;
+    int32_t _pad;
+} EcoOut;
+
+const char* eco_version(void);
+const char* eco_last_error(void);
+/* Number of SMs of `device` (grid sizing is a multiple of it); <0 on error. */
+int eco_sm_count(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Pair-leaf engine: C independent (a_c, b_c) leaves in one pass.
+ * Replaces, per leaf, the 7 calls of ess/loss_composite.py:32-39 (= ess/train_multiclass.py:269-272):
+ *   cross_entropy_loss(bce=True) (ess/loss_functions.py:26,34 + ess/__init__.py:24), cross_entropy_loss
+ *   (bce=False, :29-30, identically 0 on one channel), focal_loss (:46), classification_dice_loss (:110)
+ *   -> dice_loss (:52), twersky_loss (:82), focal_dice_coefficient (:96);
+ * and, used one statistic at a time, each of those primitives when called on its own.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Workspace bytes needed by eco_pair_stats for C channels (partials + arrival counters). */
+int64_t eco_pair_ws_bytes(int32_t C);
+
+/* Pass 1.  sums_out: float64[C][ECO_NSTAT] (this shard's sums; n = N*HW).  Deterministic. */
+int eco_pair_stats(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                   void* ws, int64_t ws_bytes, double* sums_out, int device, void* stream);
+
+/* sums -> losses and Jacobian.  `sums` may have been all-reduced across shards first (its [0] is the
+ * global n).  scale_host[c] multiplies leaf c's 7 losses (2.0 for ess/loss_composite.py:40's doubling).
+ * losses_out: float32[C][7]; total_out: float32[7] = sum over c (may be NULL);
+ * jac_out: float64[C][7][ECO_NJAC] = d(scale*loss_k)/d stat[1+s]. */
+int eco_pair_finalize(const double* sums, int32_t C, double background_weight, const double* scale_host,
+                      float* losses_out, float* total_out, double* jac_out, int device, void* stream);
+
+/* Pass 2.  upstream: float32[7] device (dT/dloss_k, shared by all channels; ce's entry is ignored).
+ * ga/gb: gradient w.r.t. slot a / slot b (w.r.t. the logit where the slot is flagged as logit);
+ * either may have ptr == NULL.  accumulate != 0 adds into the outputs instead of overwriting. */
+int eco_pair_grad(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                  const double* jac, const float* upstream, const EcoOut* ga, const EcoOut* gb, int32_t accumulate,
+                  int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3-organ composite loss: ess/loss_composite.py:21-94 `losses_fn(x, g, composite_set_theory=True)`
+ * with C == 3 (whole_body, ventral+dorsal, dorsal): the 3 per-channel leaves (:28) plus, per organ
+ * pair i<j, the six intersection_loss / union_loss leaves (:56-81, :87-94) = 21 leaves, fused.
+ * x: probabilities, or logits when from_logits != 0 (then sigmoid of ess/train_multiclass.py:134 is
+ * fused and the gradient is w.r.t. the logits).  g: labels.  Gradient is produced for x only.
+ * ------------------------------------------------------------------------------------------ */
+#define ECO_C3_NLEAF 21
+#define ECO_C3_NACC 100 /* accumulated sums per shard (see csrc/eco_composite.cu for the layout) */
+
+int64_t eco_composite3_ws_bytes(void);
+
+/* acc_out: float64[ECO_C3_NACC], additive across shards (acc_out[0] = this shard's pixel count). */
+int eco_composite3_stats(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits, void* ws,
+                         int64_t ws_bytes, double* acc_out, int device, void* stream);
+
+/* leaf scales: scale of each leaf's 7 losses, order = 3 channel leaves then, per pair
+ * (0,1),(0,2),(1,2): I1,U1,I2,U2,I3,U3 (the host computes 2, 2, 2 and per pair 2*w_j, 2*w_i, 2*w_d, 2*w_i,
+ * 2*w_d, 2*w_i*w_i*w_j with the numpy RNG stream of :49-52).  Given either as a host array (copied into
+ * the launch) or, if leaf_scale_host is NULL, as a device array.
+ * losses_out: float32[7]; jac_out: float64[21][7][ECO_NJAC]; leaf_sums_out: float64[21][ECO_NSTAT] (may be NULL). */
+int eco_composite3_finalize(const double* acc, const double* leaf_scale_host, const double* leaf_scale_dev,
+                            float* losses_out, double* jac_out, double* leaf_sums_out, int device, void* stream);
+
+int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                        const double* jac, const float* upstream, const EcoOut* gx, int device, void* stream);
+
+/* Single cooperative launch: stats -> grid barrier -> finalize -> gradient, for one GPU (no shard
+ * exchange).  upstream is known up front (the weights of ess/train_multiclass.py:145). */
+int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                         const double* leaf_scale_dev, const float* upstream, void* ws,
+                         int64_t ws_bytes, float* losses_out, const EcoOut* gx, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation scoring: ess/test_multiclass.py:58 (sigmoid), :68-69 (threshold rule, strict '>' in fp32),
+ * :80-81 (per-class dice_loss(out_c, lab_c, background_weight=0)).
+ * counts_out: int64[C][3] = (sum out*lab, sum out, sum lab) over pixels with out = (sigmoid(z) > T) and
+ *             lab counted where lab != 0 after truncation to integer (exact);
+ * soft_out:   float64[C][3] = (sum p*lab, sum p, sum lab^2) with p = sigmoid(z), the un-thresholded live path.
+ * Both additive across shards.  thresholds: float32[n_thr] device (n_thr may be 0); counts_out is then
+ * int64[n_thr][C][3] -- one read of logits+labels serves every threshold of the beam search (:64-77).
+ * ------------------------------------------------------------------------------------------ */
+int64_t eco_dice_ws_bytes(int32_t C, int32_t n_thr);
+int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
+                    const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws, int64_t ws_bytes,
+                    int64_t* counts_out, double* soft_out, int device, void* stream);
+/* dice_out: float32[n_thr][C] thresholded and soft_dice_out: float32[C], each (2I+eps)/(U+eps); either may be NULL. */
+int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
+                      float* soft_dice_out, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Soft-label cross entropy over the channel dim: ess/loss_functions.py:29-30
+ * `F.cross_entropy(pred, gt) + bw * F.cross_entropy(1-pred, 1-gt)` with float targets.
+ * a = gt (targets), b = pred (softmax input).  sums_out: float64[2] = (sum_pix sum_c a_c*logsoftmax(b)_c,
+ * same for (1-a, 1-b)); loss = -(s0 + bw*s1)/n_pix.  Gradients w.r.t. both slots.
+ * ------------------------------------------------------------------------------------------ */
+int64_t eco_softce_ws_bytes(void);
+int eco_softce_stats(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, int32_t need_bg, void* ws,
+                     int64_t ws_bytes, double* sums_out, int device, void* stream);
+int eco_softce_grad(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, double background_weight,
+                    double n_pix_total, const float* upstream, const EcoOut* ga, const EcoOut* gb, int device,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECOLOSS_H */

@@ -1,0 +1,148 @@
+"""Parity of the CUDA path against the oracle (= the reference, see oracle/__init__.py) on identical
+seeded inputs.  Tolerances: loss scalars 1e-5 relative, gradients 1e-5 in max-norm and rel-L2 (fp32),
+thresholded pixel counts bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from parity import assert_grad_close, assert_losses_close, TOL
+
+pytestmark = pytest.mark.gpu
+
+UP = [0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 1.0]          # bce + gdice + twersky + focal_dice (cfg2 combination)
+UP_ALL = [0.3, 1.0, 0.7, 0.2, 1.0, 0.5, 1.0]      # every output carries gradient
+
+
+def _inputs(n, c, s, seed, **kw):
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    return make_inputs(n, c, s, seed, **kw)
+
+
+def _combine(losses, up):
+    return sum(float(w) * l for w, l in zip(up, losses) if w != 0.0)
+
+
+def _oracle(fn, x_cpu, g_cpu, up, *args, device="cpu", **kw):
+    from oracle import torch_port as tp
+    x = x_cpu.to(device).clone().requires_grad_(True)
+    g = g_cpu.to(device)
+    losses = getattr(tp, fn)(x, g, *args, **kw)
+    _combine(losses, up).backward()
+    return [float(v) for v in losses], x.grad.detach().cpu()
+
+
+def _ours(x_cpu, g_cpu, up, *args, **kw):
+    import ecologysemanticsegmentation_b200 as eco
+    x = x_cpu.cuda().requires_grad_(True)
+    g = g_cpu.cuda()
+    losses = eco.losses_fn(x, g, *args, **kw)
+    assert isinstance(losses, eco.LossList) and len(losses) == 7
+    _combine(losses, up).backward()
+    return [float(v) for v in losses], x.grad.detach().cpu()
+
+
+@pytest.mark.parametrize("bw", [0, 0.5])
+@pytest.mark.parametrize("shape", [(2, 1, 16, 16), (3, 1, 17, 19), (54, 1, 256, 256)])
+def test_single_channel_leaf(shape, bw):
+    z, g = _inputs(*shape[:2], shape[2], 101) if shape[2] == shape[3] else (torch.randn(shape), (torch.rand(shape) > 0.5).float())
+    p = torch.sigmoid(z)
+    ref_l, ref_g = _oracle("losses_composite", p, g, UP_ALL, False, bw)
+    our_l, our_g = _ours(p, g, UP_ALL, False, bw)
+    assert_losses_close(our_l, ref_l, what=f"leaf{shape} bw={bw}")
+    assert_grad_close(our_g, ref_g, what=f"leaf{shape} bw={bw}")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (2, 2, 8, 24), (5, 4, 33, 7), (54, 3, 256, 256)])
+def test_multichannel_plain(shape):
+    torch.manual_seed(7)
+    z = torch.randn(shape)
+    g = (torch.rand(shape) > 0.5).float()
+    p = torch.sigmoid(z)
+    ref_l, ref_g = _oracle("losses_composite", p, g, UP_ALL, False, 0)
+    our_l, our_g = _ours(p, g, UP_ALL, False, 0)
+    assert_losses_close(our_l, ref_l, what=f"plain{shape}")
+    assert_grad_close(our_g, ref_g, what=f"plain{shape}")
+
+
+@pytest.mark.parametrize("up", [UP, UP_ALL])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 3, 17, 19), (54, 3, 256, 256)])
+def test_composite_on_probabilities(shape, up):
+    if shape[2] == shape[3]:
+        z, g = _inputs(shape[0], 3, shape[2], 102)
+    else:
+        torch.manual_seed(3)
+        z, g = torch.randn(shape), (torch.rand(shape) > 0.5).float()
+    p = torch.sigmoid(z)
+    np.random.seed(0)
+    ref_l, ref_g = _oracle("losses_composite", p, g, up, True)
+    np.random.seed(0)
+    our_l, our_g = _ours(p, g, up, True)
+    assert_losses_close(our_l, ref_l, what=f"composite{shape}")
+    assert_grad_close(our_g, ref_g, what=f"composite{shape}")
+
+
+def test_composite_early_stopped_rng_stream():
+    z, g = _inputs(4, 3, 32, 5)
+    p = torch.sigmoid(z)
+    np.random.seed(123)
+    ref_l, ref_g = _oracle("losses_composite", p, g, UP, True, 0, True)
+    state_ref = np.random.get_state()[1].copy()
+    np.random.seed(123)
+    our_l, our_g = _ours(p, g, UP, True, 0, True)
+    state_ours = np.random.get_state()[1].copy()
+    assert (state_ref == state_ours).all(), "numpy RNG stream consumed differently from the reference"
+    assert_losses_close(our_l, ref_l)
+    assert_grad_close(our_g, ref_g)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (54, 3, 256, 256)])
+def test_composite_from_logits_same_device_oracle(shape):
+    """from_logits: the oracle's sigmoid runs on the SAME device (torch CUDA) so that the |x_i-x_j| kink sees
+    identical probability bits (SURVEY.md section 7 'abs() kink')."""
+    import ecologysemanticsegmentation_b200 as eco
+    from oracle import torch_port as tp
+    z_cpu, g_cpu = _inputs(shape[0], 3, shape[2], 102)
+    z = z_cpu.cuda().requires_grad_(True)
+    np.random.seed(0)
+    ref = tp.losses_composite(torch.sigmoid(z), g_cpu.cuda(), True)
+    _combine(ref, UP).backward()
+    ref_g = z.grad.detach().cpu()
+    z2 = z_cpu.cuda().requires_grad_(True)
+    np.random.seed(0)
+    ours = eco.losses_fn(z2, g_cpu.cuda(), True, from_logits=True)
+    _combine(ours, UP).backward()
+    assert_losses_close(ours, ref, what="from_logits")
+    assert_grad_close(z2.grad.cpu(), ref_g, what="from_logits")
+
+
+def test_nonbinary_labels_take_exact_slow_path():
+    torch.manual_seed(11)
+    p = torch.rand(2, 3, 16, 16) * 0.98 + 0.01
+    g = (torch.rand(2, 3, 16, 16) > 0.5).float()
+    g[0, 1, 3, 4] = 0.25
+    g[1, 2, 0, 0] = 0.6
+    g[1, 0, 5, 5] = 0.5
+    np.random.seed(0)
+    ref_l, ref_g = _oracle("losses_composite", p, g, UP_ALL, True)
+    np.random.seed(0)
+    our_l, our_g = _ours(p, g, UP_ALL, True)
+    assert_losses_close(our_l, ref_l, what="nonbinary labels")
+    assert_grad_close(our_g, ref_g, what="nonbinary labels")
+
+
+@pytest.mark.parametrize("thr", [None, 0.8, 0.9])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 2, 17, 19), (8, 3, 256, 256)])
+def test_eval_counts_bit_exact(shape, thr):
+    from ecologysemanticsegmentation_b200 import ops
+    from oracle import counts as oc
+    torch.manual_seed(5)
+    z = torch.randn(shape) * 2
+    lab = (torch.rand(shape) > 0.6).float()
+    zc, lc = z.cuda(), lab.cuda()
+    thr_t = None if thr is None else torch.tensor([thr], dtype=torch.float32, device="cuda")
+    counts, soft = ops.dice_counts(zc, lc, thr_t)
+    soft_ref = oc.batch_soft_sums(zc, lc)
+    np.testing.assert_allclose(soft.cpu().numpy(), soft_ref, rtol=1e-6)
+    if thr is not None:
+        ref = oc.batch_counts(zc, lc, thr)  # same-device sigmoid bits
+        assert (counts[0].cpu().numpy() == ref).all(), (counts[0].cpu().numpy(), ref)
