@@ -10,6 +10,8 @@
 //   label value takes a rare slow path that accumulates exact corrections, so the result is right for
 //   arbitrary labels.
 // Pass 2 (grad): chain rule through the operands with 21 x 6 global coefficients.
+#include <cooperative_groups.h>
+
 #include "eco_common.cuh"
 
 namespace eco {
@@ -168,13 +170,20 @@ __host__ __device__ inline bool is_focal_slot(int idx) {
     return false;
 }
 
+struct StatsSmem {
+    double warp_slots[kCWarps][96];
+    double corr[15];
+    bool is_last;
+};
+
+// Phase 1 body, shared by the stand-alone stats kernel and the fused cooperative kernel.  On return the
+// LAST CTA to arrive has written acc_out[0..100) (visible device-wide after a grid barrier / kernel end).
 template <typename TX, int VEC, bool LOGITS>
-__global__ void __launch_bounds__(kCThreads, 1)
-composite3_stats_kernel(CompArgs a, unsigned int* __restrict__ counter, double* __restrict__ partials,
-                        double* __restrict__ acc_out) {
-    __shared__ double warp_slots[kCWarps][96];
-    __shared__ double corr[15];
-    __shared__ bool is_last;
+__device__ __forceinline__ void stats_phase(const CompArgs& a, StatsSmem& sm, unsigned int* __restrict__ counter,
+                                            double* __restrict__ partials, double* __restrict__ acc_out) {
+    double (*warp_slots)[96] = sm.warp_slots;
+    double* corr = sm.corr;
+    bool& is_last = sm.is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kCWarps * 96; i += kCThreads) (&warp_slots[0][0])[i] = 0.0;
     if (threadIdx.x < 15) corr[threadIdx.x] = 0.0;
@@ -252,46 +261,61 @@ composite3_stats_kernel(CompArgs a, unsigned int* __restrict__ counter, double* 
         is_last = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int idx = warp; idx < kNAcc; idx += kCWarps) {
-        double v = 0.0;
-        for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(partials + (int64_t)i * kNAcc + idx);
-        v = warp_sum(v);
-        if (lane == 0) acc_out[idx] = v;
+    if (is_last) {
+        __threadfence();
+        for (int idx = warp; idx < kNAcc; idx += kCWarps) {
+            double v = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(partials + (int64_t)i * kNAcc + idx);
+            v = warp_sum(v);
+            if (lane == 0) acc_out[idx] = v;
+        }
+        if (threadIdx.x == 0) *counter = 0;
     }
-    if (threadIdx.x == 0) *counter = 0;
+}
+
+template <typename TX, int VEC, bool LOGITS>
+__global__ void __launch_bounds__(kCThreads, 1)
+composite3_stats_kernel(CompArgs a, unsigned int* __restrict__ counter, double* __restrict__ partials,
+                        double* __restrict__ acc_out) {
+    __shared__ StatsSmem sm;
+    stats_phase<TX, VEC, LOGITS>(a, sm, counter, partials, acc_out);
 }
 
 // ---------------------------------------------------------------------------------------------
 // finalize: 100 sums -> 21 leaves' stats -> losses[7], jac[21][7][7]
 // ---------------------------------------------------------------------------------------------
-__device__ inline void composite_leaf_sums(const double* A, int leaf, double* s /*[8]*/) {
+template <bool CG>
+__device__ inline void composite_leaf_sums_t(const double* A_, int leaf, double* s /*[8]*/) {
+    struct Rd { const double* p; __device__ double operator[](int i) const { return CG ? __ldcg(p + i) : p[i]; } };
+    const Rd A{A_};
     const double n = A[A_N];
     s[S_N] = n;
     s[S_FLB] = 0.0;
     if (leaf < 3) {
-        const double* ch = A + A_CH + 5 * leaf;
+        const Rd ch{A_ + A_CH + 5 * leaf};
         s[S_A] = A[A_G + leaf]; s[S_B] = ch[0]; s[S_BB] = ch[1]; s[S_AB] = ch[2]; s[S_SP] = ch[3]; s[S_FL] = ch[4];
         return;
     }
     const int p = (leaf - 3) / 6, t = (leaf - 3) % 6;
     const int i = pair_i(p), j = pair_j(p);
-    const double* pa = A + A_PAIR + 21 * p;
+    const double* pa = A_ + A_PAIR + 21 * p;
     if (t & 1) {  // U-leaf: a = g_i, b = u_k
-        const double* u = pa + 2 + 7 * (t >> 1);
+        const Rd u{pa + 2 + 7 * (t >> 1)};
         s[S_A] = A[A_G + i]; s[S_B] = u[0]; s[S_BB] = u[1]; s[S_AB] = u[2]; s[S_SP] = u[3]; s[S_FL] = u[4];
     } else {  // I-leaf: a = m_k, b = label (g_j for I1, gd for I2/I3)
-        const double* m = pa + 7 * (t >> 1);
+        const Rd m{pa + 7 * (t >> 1)};
         const int L = (t == 0) ? (j - 1) : (2 + p);
         const double sb = (t == 0) ? A[A_G + j] : A[A_GD + p];
-        const double* co = A + A_CORR + 3 * L;
+        const Rd co{A_ + A_CORR + 3 * L};
         s[S_A] = m[0]; s[S_AB] = m[1]; s[S_B] = sb;
         s[S_BB] = sb + co[0];
         s[S_SP] = (n - sb) * kSP0 + sb * kSP1 + co[1];
         s[S_FL] = (n - sb) * kFL0 + co[2];
     }
 }
+
+__device__ inline void composite_leaf_sums(const double* A, int leaf, double* s) { composite_leaf_sums_t<false>(A, leaf, s); }
+__device__ inline void composite_leaf_sums_ldcg(const double* A, int leaf, double* s) { composite_leaf_sums_t<true>(A, leaf, s); }
 
 struct CompFinArgs {
     double scale[ECO_C3_NLEAF];
@@ -399,14 +423,9 @@ __device__ __forceinline__ void pixel_grad(const float (&x)[3], const float (&g)
 }
 
 template <typename TX, int VEC, bool LOGITS>
-__global__ void __launch_bounds__(kCThreads, 2)
-composite3_grad_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
-    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+__device__ __forceinline__ void grad_phase(const CompGradArgs& ga, const LeafCoef* __restrict__ cf, bool need_sig,
+                                           bool need_fl) {
     const CompArgs& a = ga.a;
-    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
-    __syncthreads();
-    const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
-
     const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
     const float* __restrict__ gb = reinterpret_cast<const float*>(a.g);
     TX* __restrict__ ob = reinterpret_cast<TX*>(ga.gx);
@@ -444,6 +463,51 @@ composite3_grad_kernel(CompGradArgs ga, const double* __restrict__ jac, const fl
             ++n;
         }
     }
+}
+
+template <typename TX, int VEC, bool LOGITS>
+__global__ void __launch_bounds__(kCThreads, 2)
+composite3_grad_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
+    __syncthreads();
+    grad_phase<TX, VEC, LOGITS>(ga, cf, upstream[1] != 0.f, upstream[2] != 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused: stats -> grid barrier -> closed forms (redundantly per CTA) -> gradient, ONE cooperative launch
+// ---------------------------------------------------------------------------------------------
+template <typename TX, int VEC, bool LOGITS>
+__global__ void __launch_bounds__(kCThreads, 1)
+composite3_fused_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
+                        unsigned int* __restrict__ counter,
+                        double* __restrict__ partials, double* __restrict__ acc_glob, float* __restrict__ losses_out) {
+    __shared__ StatsSmem sm;
+    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+    __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
+    stats_phase<TX, VEC, LOGITS>(ga.a, sm, counter, partials, acc_glob);
+
+    // grid barrier (all CTAs are co-resident: cooperative launch); also orders the last CTA's acc_glob writes
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+
+    const int leaf = threadIdx.x;
+    if (leaf < ECO_C3_NLEAF) {
+        // each of the 21 threads needs only a handful of the 100 sums; read straight from L2
+        double s[ECO_NSTAT];
+        composite_leaf_sums_ldcg(acc_glob, leaf, s);
+        LeafOut o;
+        leaf_closed_form(s, 0.0, scale_dev[leaf], o);
+        cf[leaf] = make_coef(&o.jac[0][0], upstream);
+        for (int k = 0; k < ECO_NLOSS; ++k) sl[leaf][k] = o.loss[k];
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < ECO_NLOSS) {
+        double v = 0.0;
+        for (int l = 0; l < ECO_C3_NLEAF; ++l) v += sl[l][threadIdx.x];
+        losses_out[threadIdx.x] = (float)v;
+    }
+    grad_phase<TX, VEC, LOGITS>(ga, cf, upstream[1] != 0.f, upstream[2] != 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -486,7 +550,7 @@ static int comp_grid(int device, int64_t units, int ctas_per_sm) {
 
 using namespace eco;
 
-extern "C" int64_t eco_composite3_ws_bytes(void) { return 256 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double); }
+extern "C" int64_t eco_composite3_ws_bytes(void) { return 256 + 128 * 8 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double); }
 
 #define ECO_DISPATCH_COMP(KERNEL, xdt, vec, logits, ...)                                         \
     do {                                                                                          \
@@ -551,4 +615,40 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ECO_DISPATCH_COMP(composite3_grad_kernel, x->dtype, vec, from_logits != 0, <<<grid, kCThreads, 0, st>>>(ga, jac, upstream));
     return check_cuda(cudaGetLastError(), "composite3_grad_kernel launch");
+}
+
+extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                                    const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
+                                    float* losses_out, const EcoOut* gx, int device, void* stream) {
+    int rc = check_comp(x, g, N, HW);
+    if (rc) return rc;
+    if (!leaf_scale_dev || !upstream || !losses_out || !gx || !gx->ptr) { set_error("null scale/upstream/output"); return -5; }
+    if (!ws || ws_bytes < eco_composite3_ws_bytes()) { set_error("workspace too small"); return -5; }
+    if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW) &&
+                     c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
+    CompGradArgs ga{};
+    fill_comp(ga.a, x, g, N, HW, vec);
+    ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
+    const int grid = comp_grid(device, ga.a.units_total, 1);  // one CTA per SM: co-resident by construction
+    if (grid < 0) return -10;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+    double* partials = acc_glob + 128;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out};
+    const void* fn = nullptr;
+#define ECO_PICK(TX, V, LG) fn = (const void*)composite3_fused_kernel<TX, V, LG>
+    const bool lg = from_logits != 0;
+    if (x->dtype == ECO_F32) {
+        if (vec == 4) { if (lg) ECO_PICK(float, 4, true); else ECO_PICK(float, 4, false); }
+        else { if (lg) ECO_PICK(float, 1, true); else ECO_PICK(float, 1, false); }
+    } else {
+        if (vec == 4) { if (lg) ECO_PICK(__nv_bfloat16, 4, true); else ECO_PICK(__nv_bfloat16, 4, false); }
+        else { if (lg) ECO_PICK(__nv_bfloat16, 1, true); else ECO_PICK(__nv_bfloat16, 1, false); }
+    }
+#undef ECO_PICK
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCThreads), args, 0, st), "composite3_fused_kernel launch");
 }

@@ -296,3 +296,32 @@ def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None):
     """The 7 losses of ONE leaf over all elements of (a, b), each times ``scale``."""
     a4, b4 = as_single_leaf(a, b)
     return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group)
+
+
+def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None):
+    """ONE cooperative launch: statistics -> grid barrier -> closed forms -> gradient of
+    sum_k upstream[k] * loss_k.  leaf_scales: float64 CUDA [21]; upstream: float32 CUDA [7].
+    Returns (losses f32 [7], grad w.r.t. x -- w.r.t. the logits when from_logits)."""
+    nat.require_cuda(x, g, leaf_scales, upstream)
+    if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"composite3 expects two [N,3,H,W] tensors, got {tuple(x.shape)} and {tuple(g.shape)}")
+    if leaf_scales.dtype != torch.float64 or leaf_scales.numel() != nat.C3_NLEAF:
+        raise ValueError("leaf_scales must be float64 [21]")
+    if upstream.dtype != torch.float32 or upstream.numel() != nat.NLOSS:
+        raise ValueError("upstream must be float32 [7]")
+    if g.dtype != torch.float32:
+        g = g.float()
+    x, x_sn, x_sc = nat.planes(x)
+    g, g_sn, g_sc = nat.planes(g)
+    n, c, h, w = x.shape
+    L = nat.lib()
+    ws = nat.workspace("comp3", L.eco_composite3_ws_bytes(), x.device)
+    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
+    gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+    vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
+    og = nat.out_of(gx, c * h * w, h * w)
+    rc = L.eco_composite3_fused(C.byref(vx), C.byref(vg), n, h * w, int(from_logits), leaf_scales.data_ptr(),
+                                upstream.data_ptr(), ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og),
+                                _dev(x), nat.current_stream_ptr(x.device))
+    nat.check(rc, "eco_composite3_fused")
+    return losses, gx

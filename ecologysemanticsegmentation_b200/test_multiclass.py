@@ -1,0 +1,109 @@
+"""Drop-in for the scoring of ``ecology_semantic_segmentation/test_multiclass.py``.
+
+The reference's ``test()`` (test_multiclass.py:30-108) does, per batch: ``out = F.sigmoid(net(x))`` (:58),
+optionally the threshold rule ``out[out > T] = 1; out[out != 1] = 0`` (:68-69, commented there; live in
+test_multiclass_sequential_densenetloss.py:88-89), then per class
+``dice_loss(out_c, lab_c, background_weight=0)`` (:80-81) accumulated as a running sum and divided by the
+number of batches (:82, :104) -- a mean of per-batch Dice, not a dataset-global Dice.
+
+Here the sigmoid, the threshold, the integer pixel counts and the soft sums come from ONE kernel pass over
+logits and labels (8 B/element), the counts are exact int64, and nothing syncs with the host until the end.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+from . import distributed as dist_
+
+
+def get_env_variable(name, default_value):
+    """dataset/fish/__init__.py:10-14."""
+    return os.environ.get(name, default_value)
+
+
+ORGANS = [o for o in get_env_variable("ORGANS", "whole_body").split(",")]
+
+
+def score_batch(logits, labels, threshold=None, *, group=None, inputs_are_probs=False, return_counts=False):
+    """Per-class Dice of one batch, float32 [C] on the device.
+
+    threshold=None: the live path of the reference -- soft Dice ``(2 sum p*lab + eps) / (sum (p + lab^2) + eps)``.
+    threshold=T (float) or a sequence of up to 20 Ts: ``out = sigmoid(z) > float32(T)`` (strict), Dice from exact
+    counts; a sequence returns [T, C].  ``group``: batch sharded across a process group, counts all-reduced.
+    """
+    ops.nat.require_cuda(logits, labels)
+    thr_t = None
+    many = False
+    if threshold is not None:
+        if isinstance(threshold, torch.Tensor):
+            thr_t = threshold.to(device=logits.device, dtype=torch.float32).reshape(-1)
+            many = threshold.dim() > 0
+        else:
+            many = hasattr(threshold, "__len__")
+            vals = list(threshold) if many else [threshold]
+            thr_t = torch.tensor([float(v) for v in vals], dtype=torch.float32, device=logits.device)
+    counts, soft = ops.dice_counts(logits, labels, thr_t, inputs_are_probs=inputs_are_probs)
+    counts = dist_.allreduce_sums_(counts, group)
+    soft = dist_.allreduce_sums_(soft, group)
+    nthr = 0 if thr_t is None else thr_t.numel()
+    dice, sdice = ops.dice_finalize(counts, soft, nthr)
+    out = sdice if thr_t is None else (dice if many else dice[0])
+    if return_counts:
+        return out, counts, soft
+    return out
+
+
+class DiceAccumulator:
+    """Running ``test_dice = [[sum of per-batch Dice per class], number of batches]`` of test_multiclass.py:32,82,104,
+    kept on the device."""
+
+    def __init__(self):
+        self.total = None
+        self.count = 0
+
+    def update(self, dice):
+        self.total = dice.clone() if self.total is None else self.total + dice
+        self.count += 1
+
+    def mean(self):
+        return self.total / float(self.count)
+
+
+def score_stream(batches, threshold=None, *, group=None):
+    """Mean over batches of the per-batch per-class Dice (test_multiclass.py:104).  ``batches`` yields
+    (logits, labels) CUDA tensor pairs."""
+    acc = DiceAccumulator()
+    for logits, labels in batches:
+        acc.update(score_batch(logits, labels, threshold, group=group))
+    return acc.mean()
+
+
+def test(net, dataloader, models_dir="models/vgg", results_dir="test_results/", batch_size=1, saved_epoch=-1,
+         single_model=False, threshold=None):
+    """Same call signature and return value as the reference ``test()`` (test_multiclass.py:30): a float32
+    CPU tensor [C] with the mean per-batch Dice per organ, or None when the results directory of this epoch
+    already exists.  ``net`` maps images to logits; the sigmoid is fused into the scoring kernel.  Image dumping
+    (``single_model``) is outside this path and not performed."""
+    label_dirs = ORGANS
+    dir_name = os.path.join(results_dir, "%s" % str(saved_epoch).zfill(4), ",".join(label_dirs))
+    try:
+        os.makedirs(dir_name)
+    except Exception:
+        if os.path.isdir(dir_name):
+            print("Skipping epoch %d! Test already done!" % saved_epoch)
+            return None
+    net = net.eval()
+    acc = DiceAccumulator()
+    with torch.no_grad():
+        for j, batch in enumerate(dataloader, 0):
+            test_images, test_labels, image_ids = batch
+            test_images = test_images.cuda()
+            test_labels = test_labels.cuda()
+            acc.update(score_batch(net(test_images), test_labels, threshold))
+    dice_loss_val = acc.mean().cpu()
+    print("Epoch %d: \n\t Test Dice Score: " % saved_epoch, dice_loss_val)
+    print('Finished Testing')
+    return dice_loss_val

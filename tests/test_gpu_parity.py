@@ -146,3 +146,23 @@ def test_eval_counts_bit_exact(shape, thr):
     if thr is not None:
         ref = oc.batch_counts(zc, lc, thr)  # same-device sigmoid bits
         assert (counts[0].cpu().numpy() == ref).all(), (counts[0].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 3, 17, 19), (54, 3, 256, 256)])
+def test_fused_single_launch_matches_split_path(shape):
+    """The cooperative single-launch kernel must agree with the stats/finalize/grad path bit for bit on the
+    gradient coefficients' inputs (same sums, same closed forms) and to 1e-6 on outputs."""
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    torch.manual_seed(3)
+    z = torch.randn(shape).cuda()
+    g = (torch.rand(shape) > 0.5).float().cuda()
+    np.random.seed(0)
+    step = CompositeLossStep(UP)
+    losses, dz = step(z, g)
+    z2 = z.clone().requires_grad_(True)
+    np.random.seed(0)
+    ref = eco.losses_fn(z2, g, True, from_logits=True)
+    _combine(ref, UP).backward()
+    assert_losses_close(losses, ref, tol=1e-6, what="fused vs split")
+    assert_grad_close(dz.cpu(), z2.grad.cpu(), tol=1e-6, what="fused vs split")
