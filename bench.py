@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: fused per-pixel loss forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+Workload (N=1 and per GPU for N>1, weak scaling): BASELINE.json configs[1] = "cfg2": 3-organ composite
+multiclass loss (loss_composite.losses_fn, composite_set_theory=True) on synthetic logits/masks
+54 x 3 x 256 x 256 fp32, loss = bce + generalized_dice + twersky + focal_dice, forward AND backward
+(d loss / d logits).  One "step" = one pass of that path over one batch.
+
+Prints ONE JSON line (rank 0).  `value` = Gpixel/s with inputs resident in HBM; `e2e` = the same metric
+through the public API with pinned HOST buffers (H2D of logits+masks and D2H of the 7 losses inside the
+timed region); `roofline` = algorithmic bytes (12 B/element) / kernel time against the measured HBM peak;
+`cpu_baseline` = the CPU oracle port of the reference path timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WEIGHTS = dict(bce=1.0, generalized_dice=1.0, twersky=1.0, focal_dice=1.0)  # BASELINE.md cfg2 combination
+N_BUFFER_SETS = 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------
+def workload_shape(name):
+    from ecologysemanticsegmentation_b200.synthetic import CONFIGS
+    seed, n, c, s = CONFIGS[name]
+    if name == "cfg4":
+        n = 54  # per-GPU shard of the 432-image batch
+    return seed, n, c, s
+
+
+def cpu_reference_step(z, g, weights):
+    """The reference path on the CPU (oracle port = op-for-op restatement of the reference's eager ops):
+    sigmoid -> losses_fn(composite) -> weighted sum -> backward."""
+    import numpy as np
+    import torch
+    from oracle import torch_port as tp
+    zz = z.clone().requires_grad_(True)
+    np.random.seed(0)
+    comp = z.shape[1] == 3
+    losses = tp.losses_composite(torch.sigmoid(zz), g, comp)
+    total = sum(w * l for w, l in zip(weights, losses) if w != 0.0)
+    total.backward()
+    return [float(l) for l in losses], zz.grad
+
+
+def time_cpu_baseline(name, budget_s=20.0, n_images=None, steps=None, warmup=1):
+    """Bounded CPU sample: `n_images` images of the workload per step."""
+    import torch
+    from ecologysemanticsegmentation_b200 import fused
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    seed, n, c, s = workload_shape(name)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    weights = fused.loss_weights(**WEIGHTS)
+    if n_images is None:
+        n_images = n
+    z, g = make_inputs(n_images, c, s, seed)
+    for _ in range(warmup):
+        cpu_reference_step(z, g, weights)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        cpu_reference_step(z, g, weights)
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif len(times) >= 3 and (time.perf_counter() - t_start) > budget_s or len(times) >= 10:
+            break
+    pixels = n_images * s * s
+    return {"times": times, "pixels": pixels, "cores": torch.get_num_threads(), "n_images": n_images, "shape": (n_images, c, s, s)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (its eager ops, restated op for op in
+    oracle/torch_port.py because /root/reference does not travel to the GPU box), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seed, n, c, s = workload_shape(args.workload)
+    # size the per-step sample so the whole run ends within ~2 minutes
+    probe = time_cpu_baseline(args.workload, n_images=2, steps=1, warmup=1)
+    per_image = probe["times"][0] / 2
+    total_steps = args.steps + args.warmup
+    n_images = int(max(1, min(n, 100.0 / max(per_image * total_steps, 1e-9))))
+    res = time_cpu_baseline(args.workload, n_images=n_images, steps=args.steps, warmup=args.warmup)
+    t = sum(res["times"]) / len(res["times"])
+    value = res["pixels"] / t / 1e9
+    sample = f"{n_images} of {n} images of {args.workload} ({n_images}x{c}x{s}x{s}) per step, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "Gpixel/s fused loss fwd+bwd", "value": value, "unit": "Gpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: composite 3-organ loss fwd+bwd from logits, {n}x{c}x{s}x{s} f32",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": res["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ecologysemanticsegmentation_b200 import fused
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    seed, n, c, s = workload_shape(args.workload)
+    weights = fused.loss_weights(**WEIGHTS)
+    import numpy as np
+    np.random.seed(0)
+    if world > 1:
+        step = fused.ShardedCompositeLossStep(weights, group="world", device=dev)
+    else:
+        step = fused.CompositeLossStep(weights, device=dev)
+
+    # each rank owns its own 54-image shard (distinct seeds): weak scaling, global batch = 54 * world
+    host_sets = []
+    for k in range(N_BUFFER_SETS):
+        z, g = make_inputs(n, c, s, seed + 1000 * rank + 17 * k, pin=True)
+        host_sets.append((z, g))
+    dev_sets = [(z.to(dev), g.to(dev)) for z, g in host_sets]
+    grads = [torch.empty_like(z) for z, _ in dev_sets]
+    pixels_per_step = n * s * s * world
+    elems_per_gpu = n * c * s * s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(i):
+        z, g = dev_sets[i % N_BUFFER_SETS]
+        return step(z, g, out=grads[i % N_BUFFER_SETS])
+
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        losses, _ = one(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = pixels_per_step / (ms_per_step * 1e-3) / 1e9
+    launches_per_step = 1 if world == 1 else 3
+
+    # ---- end to end: pinned host buffers in, 7 losses out, every step --------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(3, min(args.steps, 50))
+        zd, gd = torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])
+
+        def one_e2e(i):
+            zh, gh = host_sets[i % N_BUFFER_SETS]
+            zd.copy_(zh, non_blocking=True)
+            gd.copy_(gh, non_blocking=True)
+            l, _ = step(zd, gd, out=grads[0])
+            return l.cpu()  # device -> host read of the step's result (synchronises)
+
+        for i in range(3):
+            one_e2e(i)
+        barrier()
+        ev0.record()
+        for i in range(e_steps):
+            one_e2e(i)
+        ev1.record()
+        barrier()
+        te = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te.item()) / e_steps
+        e2e = {"value": pixels_per_step / (e_ms * 1e-3) / 1e9, "unit": "Gpixel/s",
+               "h2d_bytes_per_step": 2 * elems_per_gpu * 4 * world, "d2h_bytes_per_step": 7 * 4 * world,
+               "ms_per_step": e_ms, "steps": e_steps}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = 12.0 * elems_per_gpu  # read logits 4 + read masks 4 + write grad 4 per element, per GPU
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload if world == 1 else args.workload + "_sharded")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "composite3_fused_kernel" if world == 1 else "composite3_stats+allreduce+finalize+grad",
+                    "algorithmic_bytes_per_launch": alg_bytes}
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            res = time_cpu_baseline(args.workload, budget_s=15.0)
+            tb = min(res["times"])
+            cpu_baseline = {"value": res["pixels"] / tb / 1e9, "unit": "Gpixel/s", "cores": res["cores"],
+                            "kind": "port", "sample": f"{len(res['times'])} full steps of {args.workload} "
+                            f"({res['shape'][0]}x{c}x{s}x{s}), best of; oracle/torch_port.py (op-for-op restatement of the reference's eager path)",
+                            "ms_per_step": tb * 1e3}
+        line = {
+            "metric": "Gpixel/s fused loss fwd+bwd", "value": value, "unit": "Gpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: ORGANS=whole_body,ventral_side,dorsal_side composite multiclass loss "
+                                   f"fwd+bwd from logits, {n}x{c}x{s}x{s} f32 per GPU, loss=bce+gdice+twersky+focal_dice",
+                       "global_batch": n * world, "parallelism": f"dp{world} (batch sharded, 800 B sums all-reduced)" if world > 1 else "single GPU, one cooperative launch per step",
+                       "l2": f"rotating {N_BUFFER_SETS} buffer sets ({N_BUFFER_SETS * 3 * elems_per_gpu * 4 / 1e6:.0f} MB) > 126 MB L2 between timed iterations"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps * world,
+            "losses": [float(v) for v in losses.cpu()],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,3 +50,21 @@ class CompositeLossStep:
 
     def as_losslist(self, losses):
         return LossList(losses.unbind(0))
+
+
+class ShardedCompositeLossStep(CompositeLossStep):
+    """Batch sharded over a process group (one process per GPU): statistics kernel -> ONE all-reduce of the
+    100 float64 sums (800 B) over NCCL/NVLink -> closed forms -> gradient kernel for this rank's shard.
+    The result equals the single-device loss of the concatenated batch."""
+
+    def __init__(self, weights, group="world", **kw):
+        super().__init__(weights, **kw)
+        self.group = group
+
+    def __call__(self, logits, labels, out=None):
+        from . import distributed as dist_
+        acc = ops.composite3_stats(logits, labels, self.from_logits)
+        acc = dist_.allreduce_sums_(acc, self.group)
+        losses, jac, _ = ops.composite3_finalize(acc, self.scales)
+        grad = ops.composite3_grad(logits, labels, self.from_logits, jac, self.upstream, out=out)
+        return losses, grad

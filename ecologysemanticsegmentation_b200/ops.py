@@ -104,13 +104,13 @@ def composite3_finalize(acc, leaf_scales, want_leaf_sums=False):
     return losses, jac, leaf_sums
 
 
-def composite3_grad(x, g, from_logits, jac, upstream):
+def composite3_grad(x, g, from_logits, jac, upstream, out=None):
     if g.dtype != torch.float32:
         g = g.float()
     x, x_sn, x_sc = nat.planes(x)
     g, g_sn, g_sc = nat.planes(g)
     n, c, h, w = x.shape
-    gx = torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+    gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
     vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
     og = nat.out_of(gx, c * h * w, h * w)
     rc = nat.lib().eco_composite3_grad(C.byref(vx), C.byref(vg), n, h * w, int(from_logits), jac.data_ptr(),
