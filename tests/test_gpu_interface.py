@@ -1,0 +1,204 @@
+"""Behaviour of the drop-in interface on the GPU: layouts, dtypes, edge cases, the scoring loop."""
+import numpy as np
+import pytest
+import torch
+
+from parity import assert_grad_close, assert_losses_close, TOL, TOL_BF16
+
+pytestmark = pytest.mark.gpu
+UP = [0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 1.0]
+UP_ALL = [0.3, 1.0, 0.7, 0.2, 1.0, 0.5, 1.0]
+
+
+def _combine(losses, up):
+    return sum(float(w) * l for w, l in zip(up, losses) if w != 0.0)
+
+
+def _ref(fn_name, x, g, up, *args):
+    from oracle import torch_port as tp
+    x = x.detach().clone().requires_grad_(True)
+    losses = getattr(tp, fn_name)(x, g, *args)
+    _combine(losses, up).backward()
+    return [float(v) for v in losses], x.grad
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1, 1), (2, 3, 5, 3), (1, 3, 7, 9), (3, 3, 1, 130)])
+def test_ragged_and_tiny_shapes_composite(shape):
+    """H*W not a multiple of 4 -> scalar path; single pixel; one image."""
+    import ecologysemanticsegmentation_b200 as eco
+    torch.manual_seed(shape[2] * 100 + shape[3])
+    p = (torch.rand(shape) * 0.9 + 0.05).cuda()
+    g = (torch.rand(shape) > 0.5).float().cuda()
+    np.random.seed(0)
+    rl, rg = _ref("losses_composite", p, g, UP_ALL, True)
+    x = p.clone().requires_grad_(True)
+    np.random.seed(0)
+    ours = eco.losses_fn(x, g, True)
+    _combine(ours, UP_ALL).backward()
+    assert_losses_close(ours, rl, what=f"ragged {shape}")
+    assert_grad_close(x.grad.cpu(), rg.cpu(), what=f"ragged {shape}")
+
+
+def test_noncontiguous_channel_slices_and_offsets():
+    """The reference slices x[:, c:c+1]; odd storage offsets force the unaligned scalar path."""
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200 import loss_functions as lf
+    from oracle import torch_port as tp
+    torch.manual_seed(9)
+    big = (torch.rand(3, 5, 12, 10) * 0.9 + 0.05).cuda()
+    lab = (torch.rand(3, 5, 12, 10) > 0.5).float().cuda()
+    for c in (0, 3):
+        xs, gs = big[:, c:c + 1], lab[:, c:c + 1]
+        assert not xs.is_contiguous()
+        ours = eco.losses_fn(xs, gs, False, 0.5)
+        ref = tp.losses_composite(xs, gs, False, 0.5)
+        assert_losses_close(ours, ref, what="channel slice")
+        assert_losses_close([lf.dice_loss(gs, xs)], [tp.pair_dice(gs, xs)])
+    flat = torch.rand(1001, device="cuda")
+    a, b = flat[1:1000].view(1, 1, 27, 37), flat[2:1001].view(1, 1, 27, 37)   # 4-byte aligned only
+    assert_losses_close(eco.losses_fn(a, b), tp.losses_composite(a, b), what="unaligned views")
+    sub = big[:, 1:4, 2:9, 1:7]   # planes themselves strided -> one contiguous copy
+    np.random.seed(0)
+    ref = tp.losses_composite(sub, lab[:, 1:4, 2:9, 1:7], True)
+    np.random.seed(0)
+    assert_losses_close(eco.losses_fn(sub, lab[:, 1:4, 2:9, 1:7], True), ref, what="strided planes")
+
+
+def test_generic_organ_count_composite():
+    """composite_set_theory with C != 3 (ratios supplied by the caller): composed from per-leaf kernel passes."""
+    import ecologysemanticsegmentation_b200 as eco
+    torch.manual_seed(4)
+    for C, ratios in ((2, [1.0, 0.4]), (4, [1.0, 0.6, 0.3, 0.1])):
+        p = (torch.rand(2, C, 8, 8) * 0.9 + 0.05).cuda()
+        g = (torch.rand(2, C, 8, 8) > 0.5).float().cuda()
+        np.random.seed(1)
+        rl, rg = _ref("losses_composite", p, g, UP_ALL, True, 0, False, ratios)
+        x = p.clone().requires_grad_(True)
+        np.random.seed(1)
+        ours = eco.losses_fn(x, g, True, relative_set_ratios=ratios)
+        _combine(ours, UP_ALL).backward()
+        assert_losses_close(ours, rl, what=f"C={C}")
+        assert_grad_close(x.grad.cpu(), rg.cpu(), what=f"C={C}")
+
+
+def test_intersection_and_union_loss():
+    import ecologysemanticsegmentation_b200 as eco
+    from oracle import torch_port as tp
+    torch.manual_seed(6)
+    sp, p = torch.rand(2, 1, 8, 8).cuda(), torch.rand(2, 1, 8, 8).cuda()
+    g = (torch.rand(2, 1, 8, 8) > 0.5).float().cuda()
+    assert_losses_close(eco.intersection_loss(sp, p, g), tp.leaf7(sp * p, g, 0, True))
+    assert_losses_close(eco.union_loss(sp, p, g), tp.leaf7(g, tp.union_operand(sp, p), 0, True))
+    assert isinstance(eco.union_loss(sp, p, g), eco.LossList)
+
+
+def test_labels_that_require_grad_on_leaf_path():
+    """Both arguments may carry grad."""
+    import ecologysemanticsegmentation_b200 as eco
+    from oracle import torch_port as tp
+    torch.manual_seed(8)
+    x0, g0 = torch.rand(2, 3, 8, 8) * 0.9 + 0.05, torch.rand(2, 3, 8, 8) * 0.9 + 0.05
+    xr, gr = x0.clone().requires_grad_(True), g0.clone().requires_grad_(True)
+    _combine(tp.losses_composite(xr, gr), UP_ALL).backward()
+    x, g = x0.cuda().requires_grad_(True), g0.cuda().requires_grad_(True)
+    _combine(eco.losses_fn(x, g), UP_ALL).backward()
+    assert_grad_close(x.grad.cpu(), xr.grad, what="d/dx")
+    assert_grad_close(g.grad.cpu(), gr.grad, what="d/dg")
+
+
+def test_bf16_inputs_within_1e2():
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(4, 3, 64, 77)
+    p16 = torch.sigmoid(z).to(torch.bfloat16)
+    np.random.seed(0)
+    rl, rg = _ref("losses_composite", p16.float(), g, UP, True)
+    x = p16.cuda().requires_grad_(True)
+    np.random.seed(0)
+    ours = eco.losses_fn(x, g.cuda(), True)
+    _combine(ours, UP).backward()
+    assert x.grad.dtype == torch.bfloat16
+    assert_losses_close(ours, rl, tol=TOL_BF16, what="bf16")
+    assert_grad_close(x.grad.float().cpu(), rg, tol=TOL_BF16, what="bf16")
+    # plain per-channel path with bf16 predictions
+    rl, rg = _ref("losses_composite", p16.float(), g, UP, False)
+    x = p16.cuda().requires_grad_(True)
+    ours = eco.losses_fn(x, g.cuda(), False)
+    _combine(ours, UP).backward()
+    assert_losses_close(ours, rl, tol=TOL_BF16, what="bf16 plain")
+    assert_grad_close(x.grad.float().cpu(), rg, tol=TOL_BF16, what="bf16 plain")
+
+
+def test_unused_outputs_and_partial_backward():
+    """train() weights some of the 7 outputs by 0 and .item()s the rest (train_multiclass.py:145-156)."""
+    import ecologysemanticsegmentation_b200 as eco
+    p = torch.rand(2, 3, 8, 8, device="cuda").requires_grad_(True)
+    g = (torch.rand(2, 3, 8, 8, device="cuda") > 0.5).float()
+    ce, bce, fl, dice, gdice, tw, fd = eco.losses_fn(p, g)
+    assert float(ce) == 0.0
+    (0 * fd + 1 * bce + 1 * (gdice + tw)).backward()
+    assert p.grad is not None and torch.isfinite(p.grad).all()
+    vals = [v.item() for v in (ce, bce, fl, dice, gdice, tw, fd)]
+    assert all(np.isfinite(vals))
+
+
+def test_empty_input_is_an_error():
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200 import _native
+    with pytest.raises(_native.EcoLossError, match="empty"):
+        eco.losses_fn(torch.zeros(0, 3, 4, 4, device="cuda"), torch.zeros(0, 3, 4, 4, device="cuda"))
+
+
+def test_multi_threshold_beam_in_one_pass():
+    """np.arange(0.8, 0.99, 0.01) (test_multiclass.py:64): 19 thresholds from one read == 19 single calls."""
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    torch.manual_seed(12)
+    z = (torch.randn(4, 3, 64, 64) * 3).cuda()
+    lab = (torch.rand(4, 3, 64, 64) > 0.5).float().cuda()
+    thrs = np.arange(0.8, 0.99, step=0.01)
+    assert len(thrs) == 19
+    many, counts, _ = tmc.score_batch(z, lab, list(thrs), return_counts=True)
+    assert many.shape == (19, 3)
+    for k, t in enumerate(thrs):
+        one, c1, _ = tmc.score_batch(z, lab, float(t), return_counts=True)
+        assert torch.equal(c1[0], counts[k])
+        assert torch.equal(one, many[k])
+
+
+def test_reference_test_loop_semantics(tmp_path):
+    """test(): mean over batches of per-batch Dice, returns None when the epoch directory exists."""
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    from oracle import torch_port as tp
+    torch.manual_seed(2)
+    C = len(tmc.ORGANS)
+    batches = [(torch.rand(2, 3, 16, 16), (torch.rand(2, C, 16, 16) > 0.5).float(), ["a", "b"]) for _ in range(3)]
+    net = torch.nn.Conv2d(3, C, 3, padding=1).cuda()
+    out = tmc.test(net, batches, results_dir=str(tmp_path), saved_epoch=7)
+    with torch.no_grad():
+        ref = tp.eval_stream_dice([(net(x.cuda()), y.cuda()) for x, y, _ in batches])
+    assert out.device.type == "cpu" and out.shape == (C,)
+    assert_losses_close(out.numpy(), ref.numpy(), what="test() mean dice")
+    assert tmc.test(net, batches, results_dir=str(tmp_path), saved_epoch=7) is None
+
+
+def test_stats_are_additive_over_batch_shards_full_size():
+    """Size-independent property at cfg2 size: sums of the two half-batches add up to the full-batch sums, and
+    the gradient of shard k from the all-reduced sums equals rows k of the full-batch gradient."""
+    from ecologysemanticsegmentation_b200 import ops
+    from ecologysemanticsegmentation_b200.loss_composite import DEFAULT_RATIOS, composite3_leaf_scales, draw_pair_weights
+    from ecologysemanticsegmentation_b200.synthetic import make_config
+    z, g = make_config("cfg2")
+    z, g = z.cuda(), g.cuda()
+    full = ops.composite3_stats(z, g, True)
+    a, b = ops.composite3_stats(z[:27], g[:27], True), ops.composite3_stats(z[27:], g[27:], True)
+    rel = ((a + b) - full).abs() / full.abs().clamp_min(1e-30)
+    assert float(rel.max()) < 1e-12, float(rel.max())
+    np.random.seed(0)
+    scales = composite3_leaf_scales(draw_pair_weights(DEFAULT_RATIOS, False))
+    up = torch.tensor(UP, dtype=torch.float32, device="cuda")
+    l_full, jac_full, _ = ops.composite3_finalize(full, scales)
+    l_sum, jac_sum, _ = ops.composite3_finalize(a + b, scales)
+    assert torch.allclose(l_full, l_sum, rtol=1e-6)
+    g_full = ops.composite3_grad(z, g, True, jac_full, up)
+    g_b = ops.composite3_grad(z[27:], g[27:], True, jac_sum, up)
+    assert_grad_close(g_b.cpu(), g_full[27:].cpu(), tol=1e-6, what="shard gradient from global sums")
