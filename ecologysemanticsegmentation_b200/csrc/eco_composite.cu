@@ -528,8 +528,8 @@ static int fill_comp(CompArgs& a, const EcoView* x, const EcoView* g, int32_t N,
 }
 
 static int check_comp(const EcoView* x, const EcoView* g, int32_t N, int64_t HW) {
-    if (!x || !g || !x->ptr || !g->ptr) { set_error("null input view"); return -1; }
     if (N <= 0 || HW <= 0) { set_error("empty input (N=%d HW=%lld)", N, (long long)HW); return -2; }
+    if (!x || !g || !x->ptr || !g->ptr) { set_error("null input view"); return -1; }
     if (x->dtype != ECO_F32 && x->dtype != ECO_BF16) { set_error("x dtype must be f32 or bf16"); return -4; }
     if (g->dtype != ECO_F32) { set_error("composite3: labels must be f32"); return -4; }
     return 0;

@@ -240,8 +240,8 @@ extern "C" int64_t eco_dice_ws_bytes(int32_t C, int32_t n_thr) {
 extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
                                const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws,
                                int64_t ws_bytes, int64_t* counts_out, double* soft_out, int device, void* stream) {
-    if (!logits || !labels || !logits->ptr || !labels->ptr) { set_error("null input view"); return -1; }
     if (N <= 0 || C <= 0 || HW <= 0) { set_error("empty input (N=%d C=%d HW=%lld)", N, C, (long long)HW); return -2; }
+    if (!logits || !labels || !logits->ptr || !labels->ptr) { set_error("null input view"); return -1; }
     if (C > 65535) { set_error("C too large"); return -3; }
     if (n_thr < 0 || n_thr > 20) { set_error("n_thr must be in [0,20] per call (got %d)", n_thr); return -4; }
     if (n_thr > 0 && !thresholds) { set_error("null thresholds"); return -4; }

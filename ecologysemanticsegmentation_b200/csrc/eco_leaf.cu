@@ -320,8 +320,8 @@ static int plan(PairArgs& p, int vec, int device, dim3& grid) {
 
 static int fill_args(PairArgs& p, const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW,
                      uint32_t flags) {
-    if (!a || !b || !a->ptr || !b->ptr) { set_error("null input view"); return -1; }
     if (N <= 0 || C <= 0 || HW <= 0) { set_error("empty input (N=%d C=%d HW=%lld)", N, C, (long long)HW); return -2; }
+    if (!a || !b || !a->ptr || !b->ptr) { set_error("null input view"); return -1; }
     if (C > 65535) { set_error("C=%d exceeds grid.y limit", C); return -3; }
     if ((a->dtype != ECO_F32 && a->dtype != ECO_BF16) || (b->dtype != ECO_F32 && b->dtype != ECO_BF16)) {
         set_error("unsupported dtype code");

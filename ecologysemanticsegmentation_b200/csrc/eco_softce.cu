@@ -120,8 +120,8 @@ softce_grad_kernel(SceGradArgs g, const float* __restrict__ upstream) {
 }
 
 static int sce_fill(SceArgs& p, const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, int need_bg) {
-    if (!a || !b || !a->ptr || !b->ptr) { set_error("null input view"); return -1; }
     if (N <= 0 || C <= 0 || HW <= 0) { set_error("empty input"); return -2; }
+    if (!a || !b || !a->ptr || !b->ptr) { set_error("null input view"); return -1; }
     p.a = a->ptr; p.b = b->ptr; p.a_sn = a->sn; p.a_sc = a->sc; p.b_sn = b->sn; p.b_sc = b->sc;
     p.N = N; p.C = C; p.HW = HW; p.need_bg = need_bg;
     return 0;

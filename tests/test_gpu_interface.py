@@ -191,8 +191,11 @@ def test_stats_are_additive_over_batch_shards_full_size():
     z, g = z.cuda(), g.cuda()
     full = ops.composite3_stats(z, g, True)
     a, b = ops.composite3_stats(z[:27], g[:27], True), ops.composite3_stats(z[27:], g[27:], True)
-    rel = ((a + b) - full).abs() / full.abs().clamp_min(1e-30)
-    assert float(rel.max()) < 1e-12, float(rel.max())
+    # per-thread partials are fp32 (folded into fp64 every 8 iterations), so additivity holds to fp32-partial
+    # rounding, far inside the 1e-5 budget; pixel counts and label counts are exact
+    rel = ((a + b) - full).abs() / full.abs().clamp_min(1.0)
+    assert float(rel.max()) < 1e-7, float(rel.max())
+    assert torch.equal((a + b)[:7], full[:7])
     np.random.seed(0)
     scales = composite3_leaf_scales(draw_pair_weights(DEFAULT_RATIOS, False))
     up = torch.tensor(UP, dtype=torch.float32, device="cuda")
