@@ -435,8 +435,9 @@ __device__ __forceinline__ void grad_phase(const CompGradArgs& ga, const LeafCoe
     int64_t q = lo + threadIdx.x;
     int64_t n = q / a.units_per_plane;
     int64_t off = q - n * a.units_per_plane;
+    const int nthreads = blockDim.x;
 
-    for (; q < hi; q += kCThreads) {
+    for (; q < hi; q += nthreads) {
         float xv[3][VEC], gv[3][VEC], ov[3][VEC];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -457,7 +458,7 @@ __device__ __forceinline__ void grad_phase(const CompGradArgs& ga, const LeafCoe
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) store_vec<TX, VEC>(ob + n * ga.gx_sn + c * ga.gx_sc + off * VEC, ov[c]);
-        off += kCThreads;
+        off += nthreads;
         while (off >= a.units_per_plane) {
             off -= a.units_per_plane;
             ++n;
@@ -510,6 +511,97 @@ composite3_fused_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, c
     grad_phase<TX, VEC, LOGITS>(ga, cf, upstream[1] != 0.f, upstream[2] != 0.f);
 }
 
+// rare path of the packed kernels: one role's share of the label corrections for a pixel pair
+__device__ __noinline__ void label_corrections_role(float2 gi, float2 gj, int role, double* corr) {
+    const float gis[2] = {gi.x, gi.y}, gjs[2] = {gj.x, gj.y};
+    for (int h = 0; h < 2; ++h) {
+        float lb[2];
+        int L[2];
+        int n = 0;
+        if (role != 2) { lb[n] = gjs[h]; L[n] = role; ++n; }       // g1 (role 0) / g2 (role 1); role 2 shares g2
+        lb[n] = fabsf(gis[h] - gjs[h]); L[n] = 2 + role; ++n;       // gd01 / gd02 / gd12
+        for (int k = 0; k < n; ++k) {
+            const double b = (double)lb[k];
+            if (b == 0.0 || b == 1.0) continue;
+            const double be = (double)(lb[k] + kEps);
+            const double sp = fmax(b, 0.0) + log1p(exp(-fabs(b)));
+            const double fl = -pow(1.0 - b, 1.5) * log(be);
+            atomicAdd(&corr[3 * L[k] + 0], b * b - b);
+            atomicAdd(&corr[3 * L[k] + 1], sp - ((1.0 - b) * kSP0 + b * kSP1));
+            atomicAdd(&corr[3 * L[k] + 2], fl - (1.0 - b) * kFL0);
+        }
+    }
+}
+
+}  // namespace eco
+
+#include "eco_composite_packed.cuh"
+
+namespace eco {
+
+template <typename TX, bool LOGITS>
+__global__ void __launch_bounds__(kPThreads, 1)
+composite3_stats_packed_kernel(CompArgs a, unsigned int* __restrict__ counter, double* __restrict__ partials,
+                               double* __restrict__ acc_out) {
+    __shared__ PStatsSmem sm;
+    stats_phase_packed<TX, LOGITS>(a, sm, counter, partials, acc_out);
+}
+
+// shared tail of the packed gradient kernels: coefficients -> (packed | scalar focal fallback) gradient pass
+template <typename TX, bool LOGITS>
+__device__ __forceinline__ void grad_dispatch_packed(const CompGradArgs& ga, LeafCoef* cf, PCoef& pc,
+                                                     const float* __restrict__ upstream, bool reverse) {
+    const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
+    if (need_fl) {  // focal-loss gradient requested: general scalar pass (rare: train() weights it 0 at :145)
+        grad_phase<TX, 4, LOGITS>(ga, cf, need_sig, true);
+        return;
+    }
+    fill_pcoef<LOGITS>(pc, cf, threadIdx.x);
+    __syncthreads();
+    if (need_sig) grad_phase_packed<TX, LOGITS, true>(ga, pc, reverse);
+    else grad_phase_packed<TX, LOGITS, false>(ga, pc, reverse);
+}
+
+template <typename TX, bool LOGITS>
+__global__ void __launch_bounds__(kPThreads, 1)
+composite3_grad_packed_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+    __shared__ PCoef pc;
+    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
+    __syncthreads();
+    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, upstream, false);
+}
+
+template <typename TX, bool LOGITS>
+__global__ void __launch_bounds__(kPThreads, 1)
+composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
+                               unsigned int* __restrict__ counter, double* __restrict__ partials,
+                               double* __restrict__ acc_glob, float* __restrict__ losses_out) {
+    __shared__ PStatsSmem sm;
+    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+    __shared__ PCoef pc;
+    __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
+    stats_phase_packed<TX, LOGITS>(ga.a, sm, counter, partials, acc_glob);
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const int leaf = threadIdx.x;
+    if (leaf < ECO_C3_NLEAF) {
+        double s[ECO_NSTAT];
+        composite_leaf_sums_ldcg(acc_glob, leaf, s);
+        LeafOut o;
+        leaf_closed_form(s, 0.0, scale_dev[leaf], o);
+        cf[leaf] = make_coef(&o.jac[0][0], upstream);
+        for (int k = 0; k < ECO_NLOSS; ++k) sl[leaf][k] = o.loss[k];
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < ECO_NLOSS) {
+        double v = 0.0;
+        for (int l = 0; l < ECO_C3_NLEAF; ++l) v += sl[l][threadIdx.x];
+        losses_out[threadIdx.x] = (float)v;
+    }
+    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, upstream, true);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
@@ -535,11 +627,11 @@ static int check_comp(const EcoView* x, const EcoView* g, int32_t N, int64_t HW)
     return 0;
 }
 
-static int comp_grid(int device, int64_t units, int ctas_per_sm) {
+static int comp_grid(int device, int64_t units, int ctas_per_sm, int threads_per_unit_stride) {
     const int sms = sm_count_cached(device);
     if (sms <= 0) return -1;
     int64_t g = (int64_t)sms * ctas_per_sm;
-    const int64_t need = (units + kCThreads - 1) / kCThreads;
+    const int64_t need = (units + threads_per_unit_stride - 1) / threads_per_unit_stride;
     if (g > need) g = need;
     if (g > kMaxCompCtas) g = kMaxCompCtas;
     if (g < 1) g = 1;
@@ -552,15 +644,16 @@ using namespace eco;
 
 extern "C" int64_t eco_composite3_ws_bytes(void) { return 256 + 128 * 8 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double); }
 
-#define ECO_DISPATCH_COMP(KERNEL, xdt, vec, logits, ...)                                         \
+// scalar kernels serve the unaligned / ragged path (VEC == 1); the aligned path runs the packed kernels
+#define ECO_DISPATCH_SCALAR(KERNEL, xdt, logits, ...)                                            \
     do {                                                                                          \
-        if (xdt == ECO_F32) {                                                                     \
-            if (vec == 4) { if (logits) KERNEL<float, 4, true> __VA_ARGS__; else KERNEL<float, 4, false> __VA_ARGS__; } \
-            else { if (logits) KERNEL<float, 1, true> __VA_ARGS__; else KERNEL<float, 1, false> __VA_ARGS__; }          \
-        } else {                                                                                  \
-            if (vec == 4) { if (logits) KERNEL<__nv_bfloat16, 4, true> __VA_ARGS__; else KERNEL<__nv_bfloat16, 4, false> __VA_ARGS__; } \
-            else { if (logits) KERNEL<__nv_bfloat16, 1, true> __VA_ARGS__; else KERNEL<__nv_bfloat16, 1, false> __VA_ARGS__; }          \
-        }                                                                                         \
+        if (xdt == ECO_F32) { if (logits) KERNEL<float, 1, true> __VA_ARGS__; else KERNEL<float, 1, false> __VA_ARGS__; } \
+        else { if (logits) KERNEL<__nv_bfloat16, 1, true> __VA_ARGS__; else KERNEL<__nv_bfloat16, 1, false> __VA_ARGS__; } \
+    } while (0)
+#define ECO_DISPATCH_PACKED(KERNEL, xdt, logits, ...)                                            \
+    do {                                                                                          \
+        if (xdt == ECO_F32) { if (logits) KERNEL<float, true> __VA_ARGS__; else KERNEL<float, false> __VA_ARGS__; } \
+        else { if (logits) KERNEL<__nv_bfloat16, true> __VA_ARGS__; else KERNEL<__nv_bfloat16, false> __VA_ARGS__; } \
     } while (0)
 
 extern "C" int eco_composite3_stats(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
@@ -573,13 +666,14 @@ extern "C" int eco_composite3_stats(const EcoView* x, const EcoView* g, int32_t 
     const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW)) ? 4 : 1;
     CompArgs a{};
     fill_comp(a, x, g, N, HW, vec);
-    const int grid = comp_grid(device, a.units_total, 1);
+    const int grid = comp_grid(device, a.units_total, 1, vec == 4 ? kRoleThreads : kCThreads);
     if (grid < 0) return -10;
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
-    double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256 + 128 * 8);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    ECO_DISPATCH_COMP(composite3_stats_kernel, x->dtype, vec, from_logits != 0, <<<grid, kCThreads, 0, st>>>(a, counter, partials, acc_out));
-    return check_cuda(cudaGetLastError(), "composite3_stats_kernel launch");
+    if (vec == 4) ECO_DISPATCH_PACKED(composite3_stats_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, 0, st>>>(a, counter, partials, acc_out));
+    else ECO_DISPATCH_SCALAR(composite3_stats_kernel, x->dtype, from_logits != 0, <<<grid, kCThreads, 0, st>>>(a, counter, partials, acc_out));
+    return check_cuda(cudaGetLastError(), "composite3_stats kernel launch");
 }
 
 extern "C" int eco_composite3_finalize(const double* acc, const double* leaf_scale_host, const double* leaf_scale_dev,
@@ -610,11 +704,12 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     CompGradArgs ga{};
     fill_comp(ga.a, x, g, N, HW, vec);
     ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
-    const int grid = comp_grid(device, ga.a.units_total, 2);
+    const int grid = comp_grid(device, ga.a.units_total, vec == 4 ? 1 : 2, vec == 4 ? kPThreads : kCThreads);
     if (grid < 0) return -10;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    ECO_DISPATCH_COMP(composite3_grad_kernel, x->dtype, vec, from_logits != 0, <<<grid, kCThreads, 0, st>>>(ga, jac, upstream));
-    return check_cuda(cudaGetLastError(), "composite3_grad_kernel launch");
+    if (vec == 4) ECO_DISPATCH_PACKED(composite3_grad_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, 0, st>>>(ga, jac, upstream));
+    else ECO_DISPATCH_SCALAR(composite3_grad_kernel, x->dtype, from_logits != 0, <<<grid, kCThreads, 0, st>>>(ga, jac, upstream));
+    return check_cuda(cudaGetLastError(), "composite3_grad kernel launch");
 }
 
 extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
@@ -632,7 +727,7 @@ extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t 
     CompGradArgs ga{};
     fill_comp(ga.a, x, g, N, HW, vec);
     ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
-    const int grid = comp_grid(device, ga.a.units_total, 1);  // one CTA per SM: co-resident by construction
+    const int grid = comp_grid(device, ga.a.units_total, 1, vec == 4 ? kRoleThreads : kCThreads);  // one CTA per SM: co-resident
     if (grid < 0) return -10;
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
@@ -640,15 +735,15 @@ extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out};
     const void* fn = nullptr;
-#define ECO_PICK(TX, V, LG) fn = (const void*)composite3_fused_kernel<TX, V, LG>
     const bool lg = from_logits != 0;
-    if (x->dtype == ECO_F32) {
-        if (vec == 4) { if (lg) ECO_PICK(float, 4, true); else ECO_PICK(float, 4, false); }
-        else { if (lg) ECO_PICK(float, 1, true); else ECO_PICK(float, 1, false); }
+    int threads = kCThreads;
+    if (vec == 4) {
+        threads = kPThreads;
+        if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_packed_kernel<float, true> : (const void*)composite3_fused_packed_kernel<float, false>;
+        else fn = lg ? (const void*)composite3_fused_packed_kernel<__nv_bfloat16, true> : (const void*)composite3_fused_packed_kernel<__nv_bfloat16, false>;
     } else {
-        if (vec == 4) { if (lg) ECO_PICK(__nv_bfloat16, 4, true); else ECO_PICK(__nv_bfloat16, 4, false); }
-        else { if (lg) ECO_PICK(__nv_bfloat16, 1, true); else ECO_PICK(__nv_bfloat16, 1, false); }
+        if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_kernel<float, 1, true> : (const void*)composite3_fused_kernel<float, 1, false>;
+        else fn = lg ? (const void*)composite3_fused_kernel<__nv_bfloat16, 1, true> : (const void*)composite3_fused_kernel<__nv_bfloat16, 1, false>;
     }
-#undef ECO_PICK
-    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCThreads), args, 0, st), "composite3_fused_kernel launch");
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, st), "composite3_fused kernel launch");
 }

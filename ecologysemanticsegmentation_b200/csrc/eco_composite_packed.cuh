@@ -1,0 +1,468 @@
+// Packed-fp32x2 (FFMA2/FADD2/FMUL2) implementation of the 3-organ composite kernels for the aligned
+// 128-bit path.  Included by eco_composite.cu after the shared layout / helper definitions.
+//
+// Why this shape (measured on B200, profiles/microbench/pipes.cu): the FMA pipe sustains 128 fp32 lanes
+// /clk/SM with scalar FFMA *or* with FFMA2, but FFMA2 needs half the issue slots, and MUFU (16 lanes/clk/SM)
+// overlaps fully with an FFMA2 stream.  The composite loss is ~420 FMA-class ops and ~40 MUFU per pixel, far
+// above what 12 B/element of HBM traffic can hide, so the kernel is built to keep the FMA and XU pipes busy:
+//   * two pixels per instruction (float2 lanes);
+//   * sigmoid = ex2.approx + rcp.approx; the exact (ATen-bit-compatible) sigmoid is recomputed only where
+//     |p_i - p_j| < 4e-6, i.e. where the sign of the |.| kink could depend on the last bits;
+//   * on the from-logits path every b operand lies in [0,1], so log(1+exp(-b)) and sigmoid(b) are short
+//     even polynomials in b^2 on the FMA pipe instead of two MUFU each; the linear and quadratic parts of the
+//     softplus series fold into sums that are accumulated anyway (sum b, sum b^2);
+//   * u(sp, p) = sp + p * (0.5 - 0.5 sp): one FFMA2, and sum u follows algebraically from other sums;
+//   * pass 1 is role-split: warps 0-3 / 4-7 / 8-11 of a 384-thread CTA each own one organ pair (26 packed
+//     accumulators instead of 84), all three roles walk the same pixels so the second read of a plane hits L1;
+//   * pass 2 walks each CTA's range backwards so that it starts on the lines pass 1 left in L2.
+#pragma once
+
+namespace eco {
+
+constexpr int kPThreads = 384;
+constexpr int kPWarps = kPThreads / 32;
+constexpr int kRoleWarps = kPWarps / 3;
+constexpr int kRoleThreads = kRoleWarps * 32;
+constexpr int kRAcc = 26;
+constexpr int kPFlushIters = 8;
+constexpr float kTieEps = 4e-6f;
+
+// per-role accumulator indices
+enum : int {
+    R_G = 0, R_GD, R_DS, R_X, R_XX, R_GX, R_RX, R_FLX, R_M1, R_M1G, R_M2, R_M2G, R_M3, R_M3G,
+    R_U = 14  // + 4k + {0 UU, 1 GU, 2 RU, 3 FLU}, k = 0..2
+};
+
+typedef float2 f2;
+__device__ __forceinline__ f2 splat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 abs2(f2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+
+// softplus(-b) = ln2 - b/2 + t/8 + t^2 r(t), t = b^2, b in [0,1]   (max abs err 7e-9)
+constexpr float kSpR0 = -5.2077806842e-03f, kSpR1 = 3.4455654967e-04f, kSpR2 = -2.2275527791e-05f;
+// sigmoid(b) = 1/2 + b s(t), b in [0,1]                               (max abs err 7e-8)
+constexpr float kSgS0 = 2.4999950727e-01f, kSgS1 = -2.0825986369e-02f, kSgS2 = 2.054964847e-03f,
+                kSgS3 = -1.6997672007e-04f;
+
+__device__ __forceinline__ f2 sigmoid_fast2(f2 z) {
+    const f2 t = mul2(z, splat(-kLog2e));
+    const f2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+    const f2 d = add2(e, splat(1.0f));
+    return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+}
+
+// accumulate the b-only terms of a leaf: the softplus remainder (or the whole term) and the focal term
+template <bool UNIT>
+__device__ __forceinline__ void leaf_b_terms2(f2 b, f2 t, f2& r_acc, f2& fl_acc) {
+    if (UNIT) {
+        const f2 t2 = mul2(t, t);
+        f2 r = fma2(splat(kSpR2), t, splat(kSpR1));
+        r = fma2(r, t, splat(kSpR0));
+        r_acc = fma2(t2, r, r_acc);
+    } else {
+        r_acc.x += fmaf(softplus_neg_abs_log2(b.x), kLn2, fmaxf(b.x, 0.f));
+        r_acc.y += fmaf(softplus_neg_abs_log2(b.y), kLn2, fmaxf(b.y, 0.f));
+    }
+    const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
+    const f2 s = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
+    const f2 w = mul2(om, s);
+    const f2 be = add2(b, splat(kEps));
+    const f2 l = make_float2(lg2_approx(be.x), lg2_approx(be.y));
+    fl_acc = fma2(w, l, fl_acc);
+}
+
+// one pixel pair of one organ pair (i, j); `pc`/`gc` = the channel whose plain leaf this role owns
+template <bool UNIT>
+__device__ __forceinline__ void role_pair_stats(f2 pi, f2 pj, f2 gi, f2 gj, f2 pc, f2 gc, f2 d, f2 (&acc)[kRAcc]) {
+    const f2 hh = fma2(pi, splat(-0.5f), splat(0.5f));
+    const f2 m1 = mul2(pi, pj);
+    const f2 q = mul2(pi, d);
+    const f2 m3 = mul2(pi, q);
+    const f2 u1 = fma2(pj, hh, pi);
+    const f2 u2 = fma2(d, hh, pi);
+    const f2 u3 = fma2(q, hh, pi);
+    const f2 gd = abs2(fma2(gj, splat(-1.0f), gi));
+    acc[R_G] = add2(acc[R_G], gc);
+    acc[R_GD] = add2(acc[R_GD], gd);
+    acc[R_DS] = add2(acc[R_DS], d);
+    // plain leaf (a = g_c, b = p_c)
+    {
+        const f2 t = mul2(pc, pc);
+        acc[R_X] = add2(acc[R_X], pc);
+        acc[R_XX] = add2(acc[R_XX], t);
+        acc[R_GX] = fma2(gc, pc, acc[R_GX]);
+        leaf_b_terms2<UNIT>(pc, t, acc[R_RX], acc[R_FLX]);
+    }
+    // intersection leaves (a = m_k, b = label)
+    acc[R_M1] = add2(acc[R_M1], m1);
+    acc[R_M1G] = fma2(m1, gj, acc[R_M1G]);
+    acc[R_M2] = add2(acc[R_M2], q);
+    acc[R_M2G] = fma2(q, gd, acc[R_M2G]);
+    acc[R_M3] = add2(acc[R_M3], m3);
+    acc[R_M3G] = fma2(m3, gd, acc[R_M3G]);
+    // union leaves (a = g_i, b = u_k)
+    const f2 us[3] = {u1, u2, u3};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const f2 u = us[k];
+        const f2 t = mul2(u, u);
+        acc[R_U + 4 * k + 0] = add2(acc[R_U + 4 * k + 0], t);
+        acc[R_U + 4 * k + 1] = fma2(gi, u, acc[R_U + 4 * k + 1]);
+        leaf_b_terms2<UNIT>(u, t, acc[R_U + 4 * k + 2], acc[R_U + 4 * k + 3]);
+    }
+}
+
+__device__ __forceinline__ void flush_role_acc(f2 (&acc)[kRAcc], double* warp_slot /* smem [32] */, int lane) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (i < kRAcc) ? acc[i].x + acc[i].y : 0.f;
+    const float tot = butterfly32(v, lane);
+    warp_slot[lane] += (double)tot;
+#pragma unroll
+    for (int k = 0; k < kRAcc; ++k) acc[k] = splat(0.f);
+}
+
+struct PStatsSmem {
+    double warp_slots[kPWarps][32];
+    double role_sums[3][32];
+    double corr[15];
+    bool is_last;
+};
+
+// organ channel -> role that owns its plain leaf; role -> (i, j, c)
+__host__ __device__ constexpr int role_of_channel(int c) { return c == 0 ? 1 : (c == 1 ? 0 : 2); }
+__host__ __device__ constexpr int role_channel(int r) { return r == 0 ? 1 : (r == 1 ? 0 : 2); }
+
+// block-level conversion of the three roles' sums into the shared 100-slot layout (see eco_composite.cu)
+template <bool UNIT>
+__device__ inline double packed_to_layout(const double (*R)[32], const double* corr, int idx, double n_blk) {
+    auto X = [&](int c) { return R[role_of_channel(c)][R_X]; };
+    auto sp_of = [&](double sb, double sbb, double r) { return UNIT ? n_blk * kLn2d + 0.5 * sb + 0.125 * sbb + r : r; };
+    if (idx == A_N) return n_blk;
+    if (idx < A_GD) return R[role_of_channel(idx - A_G)][R_G];
+    if (idx < A_CH) return R[idx - A_GD][R_GD];
+    if (idx < A_PAIR) {
+        const int c = (idx - A_CH) / 5, k = (idx - A_CH) % 5;
+        const double* r = R[role_of_channel(c)];
+        switch (k) {
+            case 0: return r[R_X];
+            case 1: return r[R_XX];
+            case 2: return r[R_GX];
+            case 3: return sp_of(r[R_X], r[R_XX], r[R_RX]);
+            default: return -kLn2d * r[R_FLX];
+        }
+    }
+    if (idx < A_CORR) {
+        const int p = (idx - A_PAIR) / 21, k = (idx - A_PAIR) % 21;
+        const double* r = R[p];
+        const int i = pair_i(p), j = pair_j(p);
+        const int grp = k / 7, kk = k % 7;  // grp 0: (M1, U1) 1: (M2, U2) 2: (M3, U3)
+        const double m = r[R_M1 + 2 * grp], mg = r[R_M1G + 2 * grp];
+        // sum u_k = X_i + 0.5 (sum p_k - sum x_i p_k): p_1 = x_j, p_2 = d, p_3 = q = x_i d
+        const double psum = grp == 0 ? X(j) : (grp == 1 ? r[R_DS] : r[R_M2]);
+        const double usum = X(i) + 0.5 * (psum - m);
+        const double* ul = r + R_U + 4 * grp;
+        switch (kk) {
+            case 0: return m;
+            case 1: return mg;
+            case 2: return usum;
+            case 3: return ul[0];
+            case 4: return ul[1];
+            case 5: return sp_of(usum, ul[0], ul[2]);
+            default: return -kLn2d * ul[3];
+        }
+    }
+    return corr[idx - A_CORR];
+}
+
+template <typename TX, bool LOGITS>
+__device__ __forceinline__ void load_x4(const TX* p, float (&v)[4]) { Vec4<TX>::load(p, v); }
+
+// default-cached 128-bit load (the three roles of a CTA read each plane twice: keep it in L1)
+template <typename T>
+__device__ __forceinline__ void ld4_cached(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void ld4_cached<float>(const float* p, float (&v)[4]) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <>
+__device__ __forceinline__ void ld4_cached<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(r.x << 16);
+    v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16);
+    v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+
+// Pass 1 (packed, role-split).  Same contract as stats_phase(): the LAST CTA leaves acc_out[0..100).
+template <typename TX, bool LOGITS>
+__device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem& sm, unsigned int* __restrict__ counter,
+                                                   double* __restrict__ partials, double* __restrict__ acc_out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int role = warp / kRoleWarps;
+    const int rtid = threadIdx.x - role * kRoleThreads;
+    for (int i = threadIdx.x; i < kPWarps * 32; i += kPThreads) (&sm.warp_slots[0][0])[i] = 0.0;
+    if (threadIdx.x < 15) sm.corr[threadIdx.x] = 0.0;
+    __syncthreads();
+
+    const int ci = pair_i(role), cj = pair_j(role);
+    const bool chan_is_i = role_channel(role) == ci;
+    const TX* __restrict__ xi_b = reinterpret_cast<const TX*>(a.x) + (int64_t)ci * a.x_sc;
+    const TX* __restrict__ xj_b = reinterpret_cast<const TX*>(a.x) + (int64_t)cj * a.x_sc;
+    const float* __restrict__ gi_b = reinterpret_cast<const float*>(a.g) + (int64_t)ci * a.g_sc;
+    const float* __restrict__ gj_b = reinterpret_cast<const float*>(a.g) + (int64_t)cj * a.g_sc;
+
+    const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
+    const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
+    int64_t q = lo + rtid;
+    int64_t n = q / a.units_per_plane;
+    int64_t off = q - n * a.units_per_plane;
+
+    f2 acc[kRAcc];
+#pragma unroll
+    for (int k = 0; k < kRAcc; ++k) acc[k] = splat(0.f);
+    int since_flush = 0;
+    const int iters = (int)((hi - lo + kRoleThreads - 1) / kRoleThreads);
+    for (int it = 0; it < iters; ++it, q += kRoleThreads) {
+        if (q < hi) {
+            float xi4[4], xj4[4], gi4[4], gj4[4];
+            ld4_cached<TX>(xi_b + n * a.x_sn + off * 4, xi4);
+            ld4_cached<TX>(xj_b + n * a.x_sn + off * 4, xj4);
+            ld4_cached<float>(gi_b + n * a.g_sn + off * 4, gi4);
+            ld4_cached<float>(gj_b + n * a.g_sn + off * 4, gj4);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                f2 pi = make_float2(xi4[2 * h], xi4[2 * h + 1]), pj = make_float2(xj4[2 * h], xj4[2 * h + 1]);
+                const f2 gi = make_float2(gi4[2 * h], gi4[2 * h + 1]), gj = make_float2(gj4[2 * h], gj4[2 * h + 1]);
+                f2 d;
+                if (LOGITS) {
+                    const f2 zi = pi, zj = pj;
+                    pi = sigmoid_fast2(zi);
+                    pj = sigmoid_fast2(zj);
+                    d = abs2(fma2(pj, splat(-1.0f), pi));
+                    if (fminf(d.x, d.y) < kTieEps) {  // rare: the sign of (p_i - p_j) must match ATen's bits
+                        if (d.x < kTieEps) { pi.x = sigmoid_exact(zi.x); pj.x = sigmoid_exact(zj.x); d.x = fabsf(pi.x - pj.x); }
+                        if (d.y < kTieEps) { pi.y = sigmoid_exact(zi.y); pj.y = sigmoid_exact(zj.y); d.y = fabsf(pi.y - pj.y); }
+                    }
+                } else {
+                    d = abs2(fma2(pj, splat(-1.0f), pi));
+                }
+                const f2 pc = chan_is_i ? pi : pj;
+                const f2 gc = chan_is_i ? gi : gj;
+                role_pair_stats<LOGITS>(pi, pj, gi, gj, pc, gc, d, acc);
+                const bool nb = (gi.x != 0.f && gi.x != 1.f) || (gi.y != 0.f && gi.y != 1.f) ||
+                                (gj.x != 0.f && gj.x != 1.f) || (gj.y != 0.f && gj.y != 1.f);
+                if (nb) label_corrections_role(gi, gj, role, sm.corr);
+            }
+            off += kRoleThreads;
+            while (off >= a.units_per_plane) {
+                off -= a.units_per_plane;
+                ++n;
+            }
+        }
+        if (++since_flush == kPFlushIters) {
+            flush_role_acc(acc, sm.warp_slots[warp], lane);
+            since_flush = 0;
+        }
+    }
+    flush_role_acc(acc, sm.warp_slots[warp], lane);
+    __syncthreads();
+    if (threadIdx.x < 96) {
+        const int r = threadIdx.x >> 5, k = threadIdx.x & 31;
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kRoleWarps; ++w) v += sm.warp_slots[r * kRoleWarps + w][k];
+        sm.role_sums[r][k] = v;
+    }
+    __syncthreads();
+    double* mine = partials + (int64_t)blockIdx.x * kNAcc;
+    if (threadIdx.x < kNAcc)
+        mine[threadIdx.x] = packed_to_layout<LOGITS>(sm.role_sums, sm.corr, threadIdx.x, (double)(hi - lo) * 4.0);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counter, 1u);
+        sm.is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sm.is_last) {
+        __threadfence();
+        // 100 sums x gridDim partials: 3 threads per sum, each a strided third, fixed order -> deterministic
+        double* scratch = &sm.warp_slots[0][0];  // 384 doubles
+        const int idx = threadIdx.x / 3, part = threadIdx.x % 3;
+        double v = 0.0;
+        if (idx < kNAcc)
+            for (int i = part; i < (int)gridDim.x; i += 3) v += __ldcg(partials + (int64_t)i * kNAcc + idx);
+        __syncthreads();
+        scratch[threadIdx.x] = v;
+        __syncthreads();
+        if (threadIdx.x < kNAcc) acc_out[threadIdx.x] = scratch[3 * threadIdx.x] + scratch[3 * threadIdx.x + 1] + scratch[3 * threadIdx.x + 2];
+        if (threadIdx.x == 0) *counter = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2
+// ---------------------------------------------------------------------------------------------
+struct PCoef {
+    f2 u[12][4];  // plain c (0..2), then 3 + 3p + k for U_k of pair p: {sb', sab, sbb2, sp}
+    f2 i[9][2];   // 3p + k for I_k of pair p: {sa, sab}
+};
+
+// fill from the 21 LeafCoef of the leaf order (3 channel leaves, then per pair I1,U1,I2,U2,I3,U3)
+template <bool UNIT>
+__device__ __forceinline__ void fill_pcoef(PCoef& pc, const LeafCoef* cf, int t) {
+    if (t >= ECO_C3_NLEAF) return;
+    const LeafCoef c = cf[t];
+    int ul = -1, il = -1;
+    if (t < 3) ul = t;
+    else {
+        const int p = (t - 3) / 6, k = (t - 3) % 6;
+        if (k & 1) ul = 3 + 3 * p + (k >> 1);
+        else il = 3 * p + (k >> 1);
+    }
+    if (ul >= 0) {
+        pc.u[ul][0] = splat(UNIT ? c.sb + 0.5f * c.sp : c.sb);
+        pc.u[ul][1] = splat(c.sab);
+        pc.u[ul][2] = splat(c.sbb2);
+        pc.u[ul][3] = splat(c.sp);
+    } else {
+        pc.i[il][0] = splat(c.sa);
+        pc.i[il][1] = splat(c.sab);
+    }
+}
+
+// d T / d b of a leaf with a = label, b in slot 2 (plain and union leaves)
+template <bool UNIT, bool SIG>
+__device__ __forceinline__ f2 leaf_gb2(const f2 (&c)[4], f2 a, f2 b) {
+    if (!SIG) return fma2(c[1], a, fma2(c[2], b, c[0]));
+    if (UNIT) {
+        const f2 t = mul2(b, b);
+        f2 s = fma2(splat(kSgS3), t, splat(kSgS2));
+        s = fma2(s, t, splat(kSgS1));
+        s = fma2(s, t, splat(kSgS0));
+        const f2 w = fma2(c[3], s, c[2]);
+        return fma2(c[1], a, fma2(b, w, c[0]));
+    }
+    const f2 sg = make_float2(sigmoid_fast(b.x), sigmoid_fast(b.y));
+    return fma2(c[3], sg, fma2(c[1], a, fma2(c[2], b, c[0])));
+}
+
+__device__ __forceinline__ float sign0(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+
+template <bool UNIT, bool SIG>
+__device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[3], const PCoef& pc, f2 (&gx)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gx[c] = leaf_gb2<UNIT, SIG>(pc.u[c], g[c], x[c]);
+    f2 hh[2];
+    hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
+    hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int i = pair_i(p), j = pair_j(p);
+        const f2 xi = x[i], xj = x[j], gi = g[i], gj = g[j], h = hh[i];
+        const f2 diff = fma2(xj, splat(-1.0f), xi);
+        const f2 d = abs2(diff);
+        const f2 ns = make_float2(-sign0(diff.x), -sign0(diff.y));  // -sign(x_i - x_j), sign(0) = 0
+        const f2 gd = abs2(fma2(gj, splat(-1.0f), gi));
+        const f2 q = mul2(d, xi);
+        const f2 nxis = mul2(xi, ns);                    // -x_i s   = d q / d x_j
+        const f2 dq = fma2(nxis, splat(-1.0f), d);       // d + x_i s = d q / d x_i
+        f2 gi_acc, gj_acc;
+        {   // I1: a = x_i x_j, b = g_j
+            const f2 ga = fma2(pc.i[3 * p + 0][1], gj, pc.i[3 * p + 0][0]);
+            gi_acc = mul2(ga, xj);
+            gj_acc = mul2(ga, xi);
+        }
+        {   // U1: b = u(x_i, x_j) = x_i + x_j h
+            const f2 gb = leaf_gb2<UNIT, SIG>(pc.u[3 + 3 * p + 0], gi, fma2(xj, h, xi));
+            gi_acc = fma2(gb, fma2(xj, splat(-0.5f), splat(1.0f)), gi_acc);
+            gj_acc = fma2(gb, h, gj_acc);
+        }
+        {   // I2: a = x_i d, b = gd
+            const f2 ga = fma2(pc.i[3 * p + 1][1], gd, pc.i[3 * p + 1][0]);
+            gi_acc = fma2(ga, dq, gi_acc);
+            gj_acc = fma2(ga, nxis, gj_acc);
+        }
+        {   // U2: b = u(x_i, d): du/dx_i = 1 - d/2 + h s, du/dx_j = -h s
+            const f2 gb = leaf_gb2<UNIT, SIG>(pc.u[3 + 3 * p + 1], gi, fma2(d, h, xi));
+            const f2 nhs = mul2(h, ns);
+            const f2 dui = fma2(nhs, splat(-1.0f), fma2(d, splat(-0.5f), splat(1.0f)));
+            gi_acc = fma2(gb, dui, gi_acc);
+            gj_acc = fma2(gb, nhs, gj_acc);
+        }
+        {   // I3: a = x_i^2 d: da/dx_i = x_i (d + dq), da/dx_j = x_i (-x_i s)
+            const f2 ga = fma2(pc.i[3 * p + 2][1], gd, pc.i[3 * p + 2][0]);
+            gi_acc = fma2(ga, mul2(xi, add2(d, dq)), gi_acc);
+            gj_acc = fma2(ga, mul2(xi, nxis), gj_acc);
+        }
+        {   // U3: b = u(x_i, q): du/dx_i = 1 - q/2 + h dq, du/dx_j = h (-x_i s)
+            const f2 gb = leaf_gb2<UNIT, SIG>(pc.u[3 + 3 * p + 2], gi, fma2(q, h, xi));
+            const f2 dui = fma2(h, dq, fma2(q, splat(-0.5f), splat(1.0f)));
+            gi_acc = fma2(gb, dui, gi_acc);
+            gj_acc = fma2(gb, mul2(h, nxis), gj_acc);
+        }
+        gx[i] = add2(gx[i], gi_acc);
+        gx[j] = add2(gx[j], gj_acc);
+    }
+}
+
+template <typename TX, bool LOGITS, bool SIG>
+__device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const PCoef& pc, bool reverse) {
+    const CompArgs& a = ga.a;
+    const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
+    const float* __restrict__ gb = reinterpret_cast<const float*>(a.g);
+    TX* __restrict__ ob = reinterpret_cast<TX*>(ga.gx);
+    const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
+    const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
+    const int iters = (int)((hi - lo + kPThreads - 1) / kPThreads);
+    for (int it = 0; it < iters; ++it) {
+        const int step = reverse ? (iters - 1 - it) : it;
+        const int64_t q = lo + (int64_t)step * kPThreads + threadIdx.x;
+        if (q >= hi) continue;
+        const int64_t n = q / a.units_per_plane;
+        const int64_t off = (q - n * a.units_per_plane) * 4;
+        float xv[3][4], gv[3][4], ov[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Vec4<TX>::load(xb + n * a.x_sn + c * a.x_sc + off, xv[c]);
+            Vec4<float>::load(gb + n * a.g_sn + c * a.g_sc + off, gv[c]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            f2 x[3], g[3], gx[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                x[c] = make_float2(xv[c][2 * h], xv[c][2 * h + 1]);
+                g[c] = make_float2(gv[c][2 * h], gv[c][2 * h + 1]);
+            }
+            if (LOGITS) {
+                const f2 z0 = x[0], z1 = x[1], z2 = x[2];
+                x[0] = sigmoid_fast2(z0);
+                x[1] = sigmoid_fast2(z1);
+                x[2] = sigmoid_fast2(z2);
+                const float dx = fminf(fminf(fabsf(x[0].x - x[1].x), fabsf(x[0].x - x[2].x)), fabsf(x[1].x - x[2].x));
+                const float dy = fminf(fminf(fabsf(x[0].y - x[1].y), fabsf(x[0].y - x[2].y)), fabsf(x[1].y - x[2].y));
+                if (fminf(dx, dy) < kTieEps) {
+                    if (dx < kTieEps) { x[0].x = sigmoid_exact(z0.x); x[1].x = sigmoid_exact(z1.x); x[2].x = sigmoid_exact(z2.x); }
+                    if (dy < kTieEps) { x[0].y = sigmoid_exact(z0.y); x[1].y = sigmoid_exact(z1.y); x[2].y = sigmoid_exact(z2.y); }
+                }
+            }
+            pixel_pair_grad<LOGITS, SIG>(x, g, pc, gx);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                f2 o = gx[c];
+                if (LOGITS) o = mul2(o, mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
+                ov[c][2 * h] = o.x;
+                ov[c][2 * h + 1] = o.y;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Vec4<TX>::store(ob + n * ga.gx_sn + c * ga.gx_sc + off, ov[c]);
+    }
+}
+
+}  // namespace eco
