@@ -182,69 +182,120 @@ struct LeafOut {
     double jac[ECO_NLOSS][ECO_NJAC];  // d loss_k / d (Sa, Sb, Sab, Sbb, SP, FL, FLB)
 };
 
-__device__ __forceinline__ double phi_fd(double t) { return -pow(1.0 - t, 1.8) * log(t + 1e-7); }
-__device__ __forceinline__ double dphi_fd(double t) {
-    return 1.8 * pow(1.0 - t, 0.8) * log(t + 1e-7) - pow(1.0 - t, 1.8) / (t + 1e-7);
+// phi(t) = -(1-t)^1.8 log(t+eps) and its derivative (focal_dice_coefficient, loss_functions.py:101).
+// `omt` = 1-t and `te` = t+eps are formed in float64 (1-t cancels when the Dice coefficient is near 1); the
+// transcendentals themselves run in fp32 (rel. error ~1e-7, two orders inside the 1e-5 budget) because a
+// float64 pow/log chain here sits on the critical path between the two passes of the fused kernel.
+__device__ __forceinline__ void phi_fd(double omt, double te, double& phi, double& dphi) {
+    const float l = logf((float)te);
+    const float p08 = powf((float)omt, 0.8f);
+    const double p18 = (double)p08 * omt;
+    phi = -p18 * (double)l;
+    dphi = 1.8 * (double)p08 * (double)l - p18 / te;
+}
+
+struct LeafMoments {
+    double n, I, D, Ib, Db, FN, FP;
+};
+__device__ __forceinline__ LeafMoments leaf_moments(const double* s) {
+    LeafMoments m;
+    m.n = s[S_N];
+    m.I = s[S_AB];
+    m.D = s[S_A] + s[S_BB];
+    m.Ib = m.n - s[S_A] - s[S_B] + s[S_AB];
+    m.Db = (m.n - s[S_A]) + (m.n - 2 * s[S_B] + s[S_BB]);
+    m.FN = s[S_A] - s[S_AB];
+    m.FP = s[S_B] - s[S_AB];
+    return m;
+}
+
+// One of the 7 losses of a leaf (k = 0..6) and its row of the Jacobian, both times `scale`.
+// Rows are independent, so the fused kernel spreads them over threads.
+__device__ inline void leaf_closed_form_row(const double* s, double bw, double scale, int k, double& loss,
+                                            double (&jrow)[ECO_NJAC]) {
+    const double eps = 1e-7, m = 10 * 0.33, alpha = 0.5, beta = 0.3;
+    const LeafMoments M = leaf_moments(s);
+    const double n = M.n, I = M.I, D = M.D, Ib = M.Ib, Db = M.Db, FN = M.FN, FP = M.FP;
+#pragma unroll
+    for (int j = 0; j < ECO_NJAC; ++j) jrow[j] = 0.0;
+    double dI = 0, dD = 0, dIb = 0, dDb = 0, dFN = 0, dFP = 0;
+    loss = 0.0;
+    switch (k) {
+        case 1:  // bce
+            loss = (s[S_SP] - s[S_AB]) / n;
+            jrow[2] = -1.0 / n;
+            jrow[4] = 1.0 / n;
+            break;
+        case 2:  // focal
+            loss = (s[S_FL] + bw * s[S_FLB]) / n;
+            jrow[5] = 1.0 / n;
+            jrow[6] = bw / n;
+            break;
+        case 3: {  // dice
+            const double r = 1.0 / (D + eps), rb = 1.0 / (2 * Db + eps);
+            loss = m * (-(2 * I + eps) * r - bw * (2 * Ib + eps) * rb);
+            dI = -m * 2 * r;
+            dD = m * (2 * I + eps) * r * r;
+            dIb = -m * bw * 2 * rb;
+            dDb = m * bw * (2 * Ib + eps) * 2 * rb * rb;
+            break;
+        }
+        case 4: {  // generalized dice
+            const double r = 1.0 / (D + eps), rb = 1.0 / (Db + eps);
+            loss = m * (-((I + eps) * r + bw * (Ib + eps) * rb));
+            dI = -m * r;
+            dD = m * (I + eps) * r * r;
+            dIb = -m * bw * rb;
+            dDb = m * bw * (Ib + eps) * rb * rb;
+            break;
+        }
+        case 5: {  // tversky
+            const double r1 = 1.0 / (I + alpha * FN + beta * FP + eps);
+            const double r2 = 1.0 / (Ib + alpha * FP + beta * FN + eps);
+            loss = m * (-(I + eps) * r1 + bw * (-(Ib + eps) * r2));
+            // -1/t1 + (I+eps)/t1^2 = -(alpha FN + beta FP)/t1^2: no cancellation
+            dI = -m * (alpha * FN + beta * FP) * r1 * r1;
+            dIb = -m * bw * (alpha * FP + beta * FN) * r2 * r2;
+            dFN = m * ((I + eps) * alpha * r1 * r1 + bw * (Ib + eps) * beta * r2 * r2);
+            dFP = m * ((I + eps) * beta * r1 * r1 + bw * (Ib + eps) * alpha * r2 * r2);
+            break;
+        }
+        case 6: {  // focal dice
+            const double r = 1.0 / (D + eps);
+            const double dc = (2 * I + eps) * r;
+            double phi, dphi;
+            phi_fd((D - 2 * I) * r, dc + eps, phi, dphi);  // 1 - dc = (D - 2I)/(D + eps)
+            loss = m * phi;
+            dI = m * dphi * 2 * r;
+            dD = -m * dphi * dc * r;
+            if (bw != 0.0) {
+                const double rb = 1.0 / (Db + eps);
+                const double dcb = (2 * Ib + eps) * rb;
+                double phib, dphib;
+                phi_fd((Db - 2 * Ib) * rb, dcb + eps, phib, dphib);
+                loss += m * bw * phib;
+                dIb = m * bw * dphib * 2 * rb;
+                dDb = -m * bw * dphib * dcb * rb;
+            }
+            break;
+        }
+        default:
+            break;
+    }
+    if (k >= 3) {
+        // chain to the sums: Sa: +D -Ib -Db +FN ; Sb: -Ib -2Db +FP ; Sab: +I +Ib -FN -FP ; Sbb: +D +Db
+        jrow[0] = dD - dIb - dDb + dFN;
+        jrow[1] = -dIb - 2 * dDb + dFP;
+        jrow[2] = dI + dIb - dFN - dFP;
+        jrow[3] = dD + dDb;
+    }
+    loss *= scale;
+#pragma unroll
+    for (int j = 0; j < ECO_NJAC; ++j) jrow[j] *= scale;
 }
 
 __device__ inline void leaf_closed_form(const double* s, double bw, double scale, LeafOut& o) {
-    const double eps = 1e-7, m = 10 * 0.33, alpha = 0.5, beta = 0.3;
-    const double n = s[S_N];
-    const double I = s[S_AB], D = s[S_A] + s[S_BB];
-    const double Ib = n - s[S_A] - s[S_B] + s[S_AB];
-    const double Db = (n - s[S_A]) + (n - 2 * s[S_B] + s[S_BB]);
-    const double FN = s[S_A] - s[S_AB], FP = s[S_B] - s[S_AB];
-    const double t1 = I + alpha * FN + beta * FP + eps;
-    const double t2 = Ib + alpha * FP + beta * FN + eps;
-    const double dc = (2 * I + eps) / (D + eps), dcb = (2 * Ib + eps) / (Db + eps);
-
-    for (int k = 0; k < ECO_NLOSS; ++k)
-        for (int j = 0; j < ECO_NJAC; ++j) o.jac[k][j] = 0.0;
-
-    o.loss[0] = 0.0;
-    o.loss[1] = (s[S_SP] - s[S_AB]) / n;
-    o.loss[2] = (s[S_FL] + bw * s[S_FLB]) / n;
-    o.loss[3] = m * (-(2 * I + eps) / (D + eps) - bw * (2 * Ib + eps) / (2 * Db + eps));
-    o.loss[4] = m * (-((I + eps) / (D + eps) + bw * (Ib + eps) / (Db + eps)));
-    o.loss[5] = m * (-(I + eps) / t1 + bw * (-(Ib + eps) / t2));
-    const double phi_b = (bw != 0.0) ? phi_fd(dcb) : 0.0;
-    o.loss[6] = m * (phi_fd(dc) + bw * phi_b);
-
-    // partials w.r.t. the intermediate moments (I, D, Ib, Db, FN, FP), then chained to the sums.
-    // chain: Sa: +D -Ib -Db +FN ; Sb: -Ib -2Db +FP ; Sab: +I +Ib -FN -FP ; Sbb: +D +Db
-    auto chain = [&](int k, double dI, double dD, double dIb, double dDb, double dFN, double dFP) {
-        o.jac[k][0] = dD - dIb - dDb + dFN;
-        o.jac[k][1] = -dIb - 2 * dDb + dFP;
-        o.jac[k][2] = dI + dIb - dFN - dFP;
-        o.jac[k][3] = dD + dDb;
-    };
-    // bce
-    o.jac[1][2] = -1.0 / n;
-    o.jac[1][4] = 1.0 / n;
-    // focal
-    o.jac[2][5] = 1.0 / n;
-    o.jac[2][6] = bw / n;
-    // dice
-    chain(3, -m * 2 / (D + eps), m * (2 * I + eps) / ((D + eps) * (D + eps)), -m * bw * 2 / (2 * Db + eps),
-          m * bw * (2 * Ib + eps) * 2 / ((2 * Db + eps) * (2 * Db + eps)), 0.0, 0.0);
-    // generalized dice
-    chain(4, -m / (D + eps), m * (I + eps) / ((D + eps) * (D + eps)), -m * bw / (Db + eps),
-          m * bw * (Ib + eps) / ((Db + eps) * (Db + eps)), 0.0, 0.0);
-    // tversky
-    chain(5, m * (-1 / t1 + (I + eps) / (t1 * t1)), 0.0, m * bw * (-1 / t2 + (Ib + eps) / (t2 * t2)), 0.0,
-          m * ((I + eps) * alpha / (t1 * t1) + bw * (Ib + eps) * beta / (t2 * t2)),
-          m * ((I + eps) * beta / (t1 * t1) + bw * (Ib + eps) * alpha / (t2 * t2)));
-    // focal dice
-    {
-        const double p1 = dphi_fd(dc);
-        const double p2 = (bw != 0.0) ? dphi_fd(dcb) : 0.0;
-        chain(6, m * p1 * 2 / (D + eps), -m * p1 * (2 * I + eps) / ((D + eps) * (D + eps)),
-              m * bw * p2 * 2 / (Db + eps), -m * bw * p2 * (2 * Ib + eps) / ((Db + eps) * (Db + eps)), 0.0, 0.0);
-    }
-    for (int k = 0; k < ECO_NLOSS; ++k) {
-        o.loss[k] *= scale;
-        for (int j = 0; j < ECO_NJAC; ++j) o.jac[k][j] *= scale;
-    }
+    for (int k = 0; k < ECO_NLOSS; ++k) leaf_closed_form_row(s, bw, scale, k, o.loss[k], o.jac[k]);
 }
 
 // coefficient vector c[j] = sum_k upstream[k] * jac[k][j]  (7 values), as floats for the per-pixel pass.

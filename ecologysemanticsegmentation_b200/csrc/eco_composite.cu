@@ -511,25 +511,22 @@ composite3_fused_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, c
     grad_phase<TX, VEC, LOGITS>(ga, cf, upstream[1] != 0.f, upstream[2] != 0.f);
 }
 
-// rare path of the packed kernels: one role's share of the label corrections for a pixel pair
-__device__ __noinline__ void label_corrections_role(float2 gi, float2 gj, int role, double* corr) {
-    const float gis[2] = {gi.x, gi.y}, gjs[2] = {gj.x, gj.y};
-    for (int h = 0; h < 2; ++h) {
-        float lb[2];
-        int L[2];
-        int n = 0;
-        if (role != 2) { lb[n] = gjs[h]; L[n] = role; ++n; }       // g1 (role 0) / g2 (role 1); role 2 shares g2
-        lb[n] = fabsf(gis[h] - gjs[h]); L[n] = 2 + role; ++n;       // gd01 / gd02 / gd12
-        for (int k = 0; k < n; ++k) {
-            const double b = (double)lb[k];
-            if (b == 0.0 || b == 1.0) continue;
-            const double be = (double)(lb[k] + kEps);
-            const double sp = fmax(b, 0.0) + log1p(exp(-fabs(b)));
-            const double fl = -pow(1.0 - b, 1.5) * log(be);
-            atomicAdd(&corr[3 * L[k] + 0], b * b - b);
-            atomicAdd(&corr[3 * L[k] + 1], sp - ((1.0 - b) * kSP0 + b * kSP1));
-            atomicAdd(&corr[3 * L[k] + 2], fl - (1.0 - b) * kFL0);
-        }
+// rare path of the packed kernels: one role's share of the transcendental label corrections for one pixel
+// (sum(b^2 - b) comes from the second-moment accumulators)
+__device__ __noinline__ void label_corrections_role(float gi, float gj, int role, double* corr) {
+    float lb[2];
+    int L[2];
+    int n = 0;
+    if (role != 2) { lb[n] = gj; L[n] = role; ++n; }       // g1 (role 0) / g2 (role 1); role 2 shares g2
+    lb[n] = fabsf(gi - gj); L[n] = 2 + role; ++n;           // gd01 / gd02 / gd12
+    for (int k = 0; k < n; ++k) {
+        const double b = (double)lb[k];
+        if (b == 0.0 || b == 1.0) continue;
+        const double be = (double)(lb[k] + kEps);
+        const double sp = fmax(b, 0.0) + log1p(exp(-fabs(b)));
+        const double fl = -pow(1.0 - b, 1.5) * log(be);
+        atomicAdd(&corr[3 * L[k] + 1], sp - ((1.0 - b) * kSP0 + b * kSP1));
+        atomicAdd(&corr[3 * L[k] + 2], fl - (1.0 - b) * kFL0);
     }
 }
 
@@ -552,14 +549,16 @@ template <typename TX, bool LOGITS>
 __device__ __forceinline__ void grad_dispatch_packed(const CompGradArgs& ga, LeafCoef* cf, PCoef& pc,
                                                      const float* __restrict__ upstream, bool reverse) {
     const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
-    if (need_fl) {  // focal-loss gradient requested: general scalar pass (rare: train() weights it 0 at :145)
-        grad_phase<TX, 4, LOGITS>(ga, cf, need_sig, true);
-        return;
-    }
     fill_pcoef<LOGITS>(pc, cf, threadIdx.x);
     __syncthreads();
-    if (need_sig) grad_phase_packed<TX, LOGITS, true>(ga, pc, reverse);
-    else grad_phase_packed<TX, LOGITS, false>(ga, pc, reverse);
+    // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
+    if (need_fl) {
+        if (need_sig) grad_phase_packed<TX, LOGITS, true, true>(ga, pc, reverse);
+        else grad_phase_packed<TX, LOGITS, false, true>(ga, pc, reverse);
+    } else {
+        if (need_sig) grad_phase_packed<TX, LOGITS, true, false>(ga, pc, reverse);
+        else grad_phase_packed<TX, LOGITS, false, false>(ga, pc, reverse);
+    }
 }
 
 template <typename TX, bool LOGITS>
@@ -581,24 +580,25 @@ composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale
     __shared__ LeafCoef cf[ECO_C3_NLEAF];
     __shared__ PCoef pc;
     __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
+    __shared__ double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
     stats_phase_packed<TX, LOGITS>(ga.a, sm, counter, partials, acc_glob);
     __threadfence();
     cooperative_groups::this_grid().sync();
-    const int leaf = threadIdx.x;
-    if (leaf < ECO_C3_NLEAF) {
+    // closed forms, redundantly per CTA (no second grid barrier): one thread per (leaf, loss) row
+    if (threadIdx.x < ECO_C3_NLEAF * ECO_NLOSS) {
+        const int leaf = threadIdx.x / ECO_NLOSS, k = threadIdx.x % ECO_NLOSS;
         double s[ECO_NSTAT];
         composite_leaf_sums_ldcg(acc_glob, leaf, s);
-        LeafOut o;
-        leaf_closed_form(s, 0.0, scale_dev[leaf], o);
-        cf[leaf] = make_coef(&o.jac[0][0], upstream);
-        for (int k = 0; k < ECO_NLOSS; ++k) sl[leaf][k] = o.loss[k];
+        leaf_closed_form_row(s, 0.0, scale_dev[leaf], k, sl[leaf][k], jac_s[leaf][k]);
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x < ECO_NLOSS) {
+    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(&jac_s[threadIdx.x][0][0], upstream);
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + ECO_NLOSS) {
         double v = 0.0;
-        for (int l = 0; l < ECO_C3_NLEAF; ++l) v += sl[l][threadIdx.x];
-        losses_out[threadIdx.x] = (float)v;
+        for (int l = 0; l < ECO_C3_NLEAF; ++l) v += sl[l][threadIdx.x - 32];
+        losses_out[threadIdx.x - 32] = (float)v;
     }
+    __syncthreads();
     grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, upstream, true);
 }
 

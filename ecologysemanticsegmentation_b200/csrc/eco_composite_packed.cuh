@@ -23,14 +23,15 @@ constexpr int kPThreads = 384;
 constexpr int kPWarps = kPThreads / 32;
 constexpr int kRoleWarps = kPWarps / 3;
 constexpr int kRoleThreads = kRoleWarps * 32;
-constexpr int kRAcc = 26;
+constexpr int kRAcc = 29;
 constexpr int kPFlushIters = 8;
 constexpr float kTieEps = 4e-6f;
 
 // per-role accumulator indices
 enum : int {
     R_G = 0, R_GD, R_DS, R_X, R_XX, R_GX, R_RX, R_FLX, R_M1, R_M1G, R_M2, R_M2G, R_M3, R_M3G,
-    R_U = 14  // + 4k + {0 UU, 1 GU, 2 RU, 3 FLU}, k = 0..2
+    R_U = 14,  // + 4k + {0 UU, 1 GU, 2 RU, 3 FLU}, k = 0..2
+    R_GJ = 26, R_GGJ = 27, R_GDD = 28  // sum g_j, sum g_j^2, sum gd^2: label-b second moments (binary <=> GG == G)
 };
 
 typedef float2 f2;
@@ -87,6 +88,9 @@ __device__ __forceinline__ void role_pair_stats(f2 pi, f2 pj, f2 gi, f2 gj, f2 p
     acc[R_G] = add2(acc[R_G], gc);
     acc[R_GD] = add2(acc[R_GD], gd);
     acc[R_DS] = add2(acc[R_DS], d);
+    acc[R_GJ] = add2(acc[R_GJ], gj);
+    acc[R_GGJ] = fma2(gj, gj, acc[R_GGJ]);
+    acc[R_GDD] = fma2(gd, gd, acc[R_GDD]);
     // plain leaf (a = g_c, b = p_c)
     {
         const f2 t = mul2(pc, pc);
@@ -114,7 +118,9 @@ __device__ __forceinline__ void role_pair_stats(f2 pi, f2 pj, f2 gi, f2 gj, f2 p
     }
 }
 
-__device__ __forceinline__ void flush_role_acc(f2 (&acc)[kRAcc], double* warp_slot /* smem [32] */, int lane) {
+__device__ __forceinline__ bool flush_role_acc(f2 (&acc)[kRAcc], double* warp_slot /* smem [32] */, int lane) {
+    const bool nonbinary = acc[R_GGJ].x != acc[R_GJ].x || acc[R_GGJ].y != acc[R_GJ].y ||
+                           acc[R_GDD].x != acc[R_GD].x || acc[R_GDD].y != acc[R_GD].y;
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = (i < kRAcc) ? acc[i].x + acc[i].y : 0.f;
@@ -122,6 +128,7 @@ __device__ __forceinline__ void flush_role_acc(f2 (&acc)[kRAcc], double* warp_sl
     warp_slot[lane] += (double)tot;
 #pragma unroll
     for (int k = 0; k < kRAcc; ++k) acc[k] = splat(0.f);
+    return nonbinary;
 }
 
 struct PStatsSmem {
@@ -174,11 +181,13 @@ __device__ inline double packed_to_layout(const double (*R)[32], const double* c
             default: return -kLn2d * ul[3];
         }
     }
-    return corr[idx - A_CORR];
+    // label-b corrections: sum(b^2 - b) follows from the second-moment accumulators, the transcendental
+    // corrections from the (rare) slow pass over non-binary labels
+    const int L = (idx - A_CORR) / 3, k = (idx - A_CORR) % 3;
+    if (k != 0) return corr[idx - A_CORR];
+    if (L < 2) return R[L][R_GGJ] - R[L][R_GJ];          // g1 via role 0 (j = 1), g2 via role 1 (j = 2)
+    return R[L - 2][R_GDD] - R[L - 2][R_GD];              // gd of pair L-2
 }
-
-template <typename TX, bool LOGITS>
-__device__ __forceinline__ void load_x4(const TX* p, float (&v)[4]) { Vec4<TX>::load(p, v); }
 
 // default-cached 128-bit load (the three roles of a CTA read each plane twice: keep it in L1)
 template <typename T>
@@ -196,6 +205,23 @@ __device__ __forceinline__ void ld4_cached<__nv_bfloat16>(const __nv_bfloat16* p
     v[2] = __uint_as_float(r.y << 16);
     v[3] = __uint_as_float(r.y & 0xffff0000u);
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// walks the float4 units [lo, hi) of a CTA with a fixed thread stride, tracking (image, offset) incrementally
+struct UnitWalker {
+    int64_t q, n, off, upp;
+    __device__ __forceinline__ void init(int64_t q0, int64_t units_per_plane) {
+        q = q0; upp = units_per_plane;
+        n = q / upp;
+        off = q - n * upp;
+    }
+    __device__ __forceinline__ void advance(int stride) {
+        q += stride;
+        off += stride;
+        while (off >= upp) { off -= upp; ++n; }
+    }
+};
 
 // Pass 1 (packed, role-split).  Same contract as stats_phase(): the LAST CTA leaves acc_out[0..100).
 template <typename TX, bool LOGITS>
@@ -217,22 +243,31 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
 
     const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
     const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
-    int64_t q = lo + rtid;
-    int64_t n = q / a.units_per_plane;
-    int64_t off = q - n * a.units_per_plane;
+    UnitWalker w;
+    w.init(lo + rtid, a.units_per_plane);
 
     f2 acc[kRAcc];
 #pragma unroll
     for (int k = 0; k < kRAcc; ++k) acc[k] = splat(0.f);
     int since_flush = 0;
+    bool any_nonbinary = false;
     const int iters = (int)((hi - lo + kRoleThreads - 1) / kRoleThreads);
-    for (int it = 0; it < iters; ++it, q += kRoleThreads) {
-        if (q < hi) {
+    for (int it = 0; it < iters; ++it) {
+        if (w.q < hi) {
+            const int64_t ex = w.n * a.x_sn + w.off * 4, eg = w.n * a.g_sn + w.off * 4;
             float xi4[4], xj4[4], gi4[4], gj4[4];
-            ld4_cached<TX>(xi_b + n * a.x_sn + off * 4, xi4);
-            ld4_cached<TX>(xj_b + n * a.x_sn + off * 4, xj4);
-            ld4_cached<float>(gi_b + n * a.g_sn + off * 4, gi4);
-            ld4_cached<float>(gj_b + n * a.g_sn + off * 4, gj4);
+            ld4_cached<TX>(xi_b + ex, xi4);
+            ld4_cached<TX>(xj_b + ex, xj4);
+            ld4_cached<float>(gi_b + eg, gi4);
+            ld4_cached<float>(gj_b + eg, gj4);
+            w.advance(kRoleThreads);
+            if (w.q < hi) {  // pull the next unit's lines towards the SM while this one is being processed
+                const int64_t nx = w.n * a.x_sn + w.off * 4, ng = w.n * a.g_sn + w.off * 4;
+                prefetch_l1(xi_b + nx);
+                prefetch_l1(xj_b + nx);
+                prefetch_l1(gi_b + ng);
+                prefetch_l1(gj_b + ng);
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 f2 pi = make_float2(xi4[2 * h], xi4[2 * h + 1]), pj = make_float2(xj4[2 * h], xj4[2 * h + 1]);
@@ -253,28 +288,30 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
                 const f2 pc = chan_is_i ? pi : pj;
                 const f2 gc = chan_is_i ? gi : gj;
                 role_pair_stats<LOGITS>(pi, pj, gi, gj, pc, gc, d, acc);
-                const bool nb = (gi.x != 0.f && gi.x != 1.f) || (gi.y != 0.f && gi.y != 1.f) ||
-                                (gj.x != 0.f && gj.x != 1.f) || (gj.y != 0.f && gj.y != 1.f);
-                if (nb) label_corrections_role(gi, gj, role, sm.corr);
-            }
-            off += kRoleThreads;
-            while (off >= a.units_per_plane) {
-                off -= a.units_per_plane;
-                ++n;
             }
         }
         if (++since_flush == kPFlushIters) {
-            flush_role_acc(acc, sm.warp_slots[warp], lane);
+            any_nonbinary |= flush_role_acc(acc, sm.warp_slots[warp], lane);
             since_flush = 0;
         }
     }
-    flush_role_acc(acc, sm.warp_slots[warp], lane);
-    __syncthreads();
+    any_nonbinary |= flush_role_acc(acc, sm.warp_slots[warp], lane);
+    if (__syncthreads_or(any_nonbinary)) {
+        // rare slow pass: some label is not exactly 0 or 1 -> exact transcendental corrections for this CTA's range
+        const float* gi_s = reinterpret_cast<const float*>(a.g) + (int64_t)ci * a.g_sc;
+        const float* gj_s = reinterpret_cast<const float*>(a.g) + (int64_t)cj * a.g_sc;
+        for (int64_t q = lo + rtid; q < hi; q += kRoleThreads) {
+            const int64_t n = q / a.units_per_plane, off = (q - n * a.units_per_plane) * 4;
+            for (int e = 0; e < 4; ++e)
+                label_corrections_role(gi_s[n * a.g_sn + off + e], gj_s[n * a.g_sn + off + e], role, sm.corr);
+        }
+        __syncthreads();
+    }
     if (threadIdx.x < 96) {
         const int r = threadIdx.x >> 5, k = threadIdx.x & 31;
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kRoleWarps; ++w) v += sm.warp_slots[r * kRoleWarps + w][k];
+        for (int wq = 0; wq < kRoleWarps; ++wq) v += sm.warp_slots[r * kRoleWarps + wq][k];
         sm.role_sums[r][k] = v;
     }
     __syncthreads();
@@ -308,7 +345,7 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
 // pass 2
 // ---------------------------------------------------------------------------------------------
 struct PCoef {
-    f2 u[12][4];  // plain c (0..2), then 3 + 3p + k for U_k of pair p: {sb', sab, sbb2, sp}
+    f2 u[12][6];  // plain c (0..2), then 3 + 3p + k for U_k of pair p: {sb', sab, sbb2, sp, fl, -}
     f2 i[9][2];   // 3p + k for I_k of pair p: {sa, sab}
 };
 
@@ -329,6 +366,8 @@ __device__ __forceinline__ void fill_pcoef(PCoef& pc, const LeafCoef* cf, int t)
         pc.u[ul][1] = splat(c.sab);
         pc.u[ul][2] = splat(c.sbb2);
         pc.u[ul][3] = splat(c.sp);
+        pc.u[ul][4] = splat(c.fl);
+        pc.u[ul][5] = splat(0.f);
     } else {
         pc.i[il][0] = splat(c.sa);
         pc.i[il][1] = splat(c.sab);
@@ -336,27 +375,45 @@ __device__ __forceinline__ void fill_pcoef(PCoef& pc, const LeafCoef* cf, int t)
 }
 
 // d T / d b of a leaf with a = label, b in slot 2 (plain and union leaves)
-template <bool UNIT, bool SIG>
-__device__ __forceinline__ f2 leaf_gb2(const f2 (&c)[4], f2 a, f2 b) {
-    if (!SIG) return fma2(c[1], a, fma2(c[2], b, c[0]));
-    if (UNIT) {
+template <bool UNIT, bool SIG, bool FL>
+__device__ __forceinline__ f2 leaf_gb2(const f2 (&c)[6], f2 a, f2 b) {
+    f2 r;
+    if (!SIG) {
+        r = fma2(c[1], a, fma2(c[2], b, c[0]));
+    } else if (UNIT) {
         const f2 t = mul2(b, b);
         f2 s = fma2(splat(kSgS3), t, splat(kSgS2));
         s = fma2(s, t, splat(kSgS1));
         s = fma2(s, t, splat(kSgS0));
         const f2 w = fma2(c[3], s, c[2]);
-        return fma2(c[1], a, fma2(b, w, c[0]));
+        r = fma2(c[1], a, fma2(b, w, c[0]));
+    } else {
+        const f2 sg = make_float2(sigmoid_fast(b.x), sigmoid_fast(b.y));
+        r = fma2(c[3], sg, fma2(c[1], a, fma2(c[2], b, c[0])));
     }
-    const f2 sg = make_float2(sigmoid_fast(b.x), sigmoid_fast(b.y));
-    return fma2(c[3], sg, fma2(c[1], a, fma2(c[2], b, c[0])));
+    if (FL) {  // + c_fl * d/db[-(1-b)^1.5 log(b+eps)]
+        const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
+        const f2 s = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
+        const f2 be = add2(b, splat(kEps));
+        const f2 l = make_float2(lg2_approx(be.x), lg2_approx(be.y));
+        const f2 rc = make_float2(rcp_approx(be.x), rcp_approx(be.y));
+        const f2 v = fma2(mul2(s, splat(1.5f * kLn2)), l, mul2(mul2(om, s), mul2(rc, splat(-1.0f))));
+        r = fma2(c[4], v, r);
+    }
+    return r;
 }
 
-__device__ __forceinline__ float sign0(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+// -sign(v) with sign(0) = 0 (torch.abs backward), as +-1.0f / 0.0f
+__device__ __forceinline__ float neg_sign0(float v) {
+    const float s = __uint_as_float((__float_as_uint(v) & 0x80000000u) ^ 0xbf800000u);  // -copysign(1, v)
+    return v == 0.f ? 0.f : s;
+}
 
-template <bool UNIT, bool SIG>
-__device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[3], const PCoef& pc, f2 (&gx)[3]) {
+template <bool UNIT, bool SIG, bool FL>
+__device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[3], const f2 (&diffs)[3],
+                                                const PCoef& pc, f2 (&gx)[3]) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gx[c] = leaf_gb2<UNIT, SIG>(pc.u[c], g[c], x[c]);
+    for (int c = 0; c < 3; ++c) gx[c] = leaf_gb2<UNIT, SIG, FL>(pc.u[c], g[c], x[c]);
     f2 hh[2];
     hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
     hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
@@ -364,9 +421,9 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
     for (int p = 0; p < 3; ++p) {
         const int i = pair_i(p), j = pair_j(p);
         const f2 xi = x[i], xj = x[j], gi = g[i], gj = g[j], h = hh[i];
-        const f2 diff = fma2(xj, splat(-1.0f), xi);
+        const f2 diff = diffs[p];
         const f2 d = abs2(diff);
-        const f2 ns = make_float2(-sign0(diff.x), -sign0(diff.y));  // -sign(x_i - x_j), sign(0) = 0
+        const f2 ns = make_float2(neg_sign0(diff.x), neg_sign0(diff.y));
         const f2 gd = abs2(fma2(gj, splat(-1.0f), gi));
         const f2 q = mul2(d, xi);
         const f2 nxis = mul2(xi, ns);                    // -x_i s   = d q / d x_j
@@ -378,7 +435,7 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
             gj_acc = mul2(ga, xi);
         }
         {   // U1: b = u(x_i, x_j) = x_i + x_j h
-            const f2 gb = leaf_gb2<UNIT, SIG>(pc.u[3 + 3 * p + 0], gi, fma2(xj, h, xi));
+            const f2 gb = leaf_gb2<UNIT, SIG, FL>(pc.u[3 + 3 * p + 0], gi, fma2(xj, h, xi));
             gi_acc = fma2(gb, fma2(xj, splat(-0.5f), splat(1.0f)), gi_acc);
             gj_acc = fma2(gb, h, gj_acc);
         }
@@ -388,7 +445,7 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
             gj_acc = fma2(ga, nxis, gj_acc);
         }
         {   // U2: b = u(x_i, d): du/dx_i = 1 - d/2 + h s, du/dx_j = -h s
-            const f2 gb = leaf_gb2<UNIT, SIG>(pc.u[3 + 3 * p + 1], gi, fma2(d, h, xi));
+            const f2 gb = leaf_gb2<UNIT, SIG, FL>(pc.u[3 + 3 * p + 1], gi, fma2(d, h, xi));
             const f2 nhs = mul2(h, ns);
             const f2 dui = fma2(nhs, splat(-1.0f), fma2(d, splat(-0.5f), splat(1.0f)));
             gi_acc = fma2(gb, dui, gi_acc);
@@ -400,7 +457,7 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
             gj_acc = fma2(ga, mul2(xi, nxis), gj_acc);
         }
         {   // U3: b = u(x_i, q): du/dx_i = 1 - q/2 + h dq, du/dx_j = h (-x_i s)
-            const f2 gb = leaf_gb2<UNIT, SIG>(pc.u[3 + 3 * p + 2], gi, fma2(q, h, xi));
+            const f2 gb = leaf_gb2<UNIT, SIG, FL>(pc.u[3 + 3 * p + 2], gi, fma2(q, h, xi));
             const f2 dui = fma2(h, dq, fma2(q, splat(-0.5f), splat(1.0f)));
             gi_acc = fma2(gb, dui, gi_acc);
             gj_acc = fma2(gb, mul2(h, nxis), gj_acc);
@@ -410,7 +467,7 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
     }
 }
 
-template <typename TX, bool LOGITS, bool SIG>
+template <typename TX, bool LOGITS, bool SIG, bool FL>
 __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const PCoef& pc, bool reverse) {
     const CompArgs& a = ga.a;
     const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
@@ -425,15 +482,29 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
         if (q >= hi) continue;
         const int64_t n = q / a.units_per_plane;
         const int64_t off = (q - n * a.units_per_plane) * 4;
+        const TX* xp = xb + n * a.x_sn + off;
+        const float* gp = gb + n * a.g_sn + off;
         float xv[3][4], gv[3][4], ov[3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            Vec4<TX>::load(xb + n * a.x_sn + c * a.x_sc + off, xv[c]);
-            Vec4<float>::load(gb + n * a.g_sn + c * a.g_sc + off, gv[c]);
+            Vec4<TX>::load(xp + c * a.x_sc, xv[c]);
+            Vec4<float>::load(gp + c * a.g_sc, gv[c]);
+        }
+        {   // L2 prefetch of the unit this thread handles next
+            const int64_t qn = q + (reverse ? -(int64_t)kPThreads : (int64_t)kPThreads);
+            if (qn >= lo && qn < hi) {
+                const int64_t nn = qn / a.units_per_plane;
+                const int64_t on = (qn - nn * a.units_per_plane) * 4;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    prefetch_l2(xb + nn * a.x_sn + on + c * a.x_sc);
+                    prefetch_l2(gb + nn * a.g_sn + on + c * a.g_sc);
+                }
+            }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            f2 x[3], g[3], gx[3];
+            f2 x[3], g[3], gx[3], diffs[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 x[c] = make_float2(xv[c][2 * h], xv[c][2 * h + 1]);
@@ -444,14 +515,21 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
                 x[0] = sigmoid_fast2(z0);
                 x[1] = sigmoid_fast2(z1);
                 x[2] = sigmoid_fast2(z2);
-                const float dx = fminf(fminf(fabsf(x[0].x - x[1].x), fabsf(x[0].x - x[2].x)), fabsf(x[1].x - x[2].x));
-                const float dy = fminf(fminf(fabsf(x[0].y - x[1].y), fabsf(x[0].y - x[2].y)), fabsf(x[1].y - x[2].y));
-                if (fminf(dx, dy) < kTieEps) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) diffs[p] = fma2(x[pair_j(p)], splat(-1.0f), x[pair_i(p)]);
+                const float dx = fminf(fminf(fabsf(diffs[0].x), fabsf(diffs[1].x)), fabsf(diffs[2].x));
+                const float dy = fminf(fminf(fabsf(diffs[0].y), fabsf(diffs[1].y)), fabsf(diffs[2].y));
+                if (fminf(dx, dy) < kTieEps) {  // rare: exact ATen sigmoid bits decide the sign of the kink
                     if (dx < kTieEps) { x[0].x = sigmoid_exact(z0.x); x[1].x = sigmoid_exact(z1.x); x[2].x = sigmoid_exact(z2.x); }
                     if (dy < kTieEps) { x[0].y = sigmoid_exact(z0.y); x[1].y = sigmoid_exact(z1.y); x[2].y = sigmoid_exact(z2.y); }
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) diffs[p] = fma2(x[pair_j(p)], splat(-1.0f), x[pair_i(p)]);
                 }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) diffs[p] = fma2(x[pair_j(p)], splat(-1.0f), x[pair_i(p)]);
             }
-            pixel_pair_grad<LOGITS, SIG>(x, g, pc, gx);
+            pixel_pair_grad<LOGITS, SIG, FL>(x, g, diffs, pc, gx);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 f2 o = gx[c];
