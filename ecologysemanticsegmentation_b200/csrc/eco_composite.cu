@@ -325,19 +325,15 @@ __global__ void composite3_finalize_kernel(const double* __restrict__ A, CompFin
                                            float* __restrict__ losses_out, double* __restrict__ jac_out,
                                            double* __restrict__ leaf_sums_out) {
     __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
-    const int leaf = threadIdx.x;
-    if (leaf < ECO_C3_NLEAF) {
-        double s[ECO_NSTAT];
+    if (threadIdx.x < ECO_C3_NLEAF * ECO_NLOSS) {
+        const int leaf = threadIdx.x / ECO_NLOSS, k = threadIdx.x % ECO_NLOSS;
+        double s[ECO_NSTAT], jrow[ECO_NJAC];
         composite_leaf_sums(A, leaf, s);
-        LeafOut o;
-        leaf_closed_form(s, 0.0, scale_dev ? scale_dev[leaf] : fa.scale[leaf], o);
-        for (int k = 0; k < ECO_NLOSS; ++k) {
-            sl[leaf][k] = o.loss[k];
-            if (jac_out)
-                for (int j = 0; j < ECO_NJAC; ++j) jac_out[(leaf * ECO_NLOSS + k) * ECO_NJAC + j] = o.jac[k][j];
-        }
-        if (leaf_sums_out)
-            for (int k = 0; k < ECO_NSTAT; ++k) leaf_sums_out[leaf * ECO_NSTAT + k] = s[k];
+        leaf_closed_form_row(s, 0.0, scale_dev ? scale_dev[leaf] : fa.scale[leaf], k, sl[leaf][k], jrow);
+        if (jac_out)
+            for (int j = 0; j < ECO_NJAC; ++j) jac_out[(leaf * ECO_NLOSS + k) * ECO_NJAC + j] = jrow[j];
+        if (leaf_sums_out && k == 0)
+            for (int j = 0; j < ECO_NSTAT; ++j) leaf_sums_out[leaf * ECO_NSTAT + j] = s[j];
     }
     __syncthreads();
     if (losses_out && threadIdx.x < ECO_NLOSS) {
@@ -540,35 +536,37 @@ template <typename TX, bool LOGITS>
 __global__ void __launch_bounds__(kPThreads, 1)
 composite3_stats_packed_kernel(CompArgs a, unsigned int* __restrict__ counter, double* __restrict__ partials,
                                double* __restrict__ acc_out) {
+    extern __shared__ __align__(16) char stage_smem[];
     __shared__ PStatsSmem sm;
-    stats_phase_packed<TX, LOGITS>(a, sm, counter, partials, acc_out);
+    stats_phase_packed<TX, LOGITS>(a, sm, stage_smem, counter, partials, acc_out);
 }
 
 // shared tail of the packed gradient kernels: coefficients -> (packed | scalar focal fallback) gradient pass
 template <typename TX, bool LOGITS>
-__device__ __forceinline__ void grad_dispatch_packed(const CompGradArgs& ga, LeafCoef* cf, PCoef& pc,
+__device__ __forceinline__ void grad_dispatch_packed(const CompGradArgs& ga, LeafCoef* cf, PCoef& pc, char* stage_smem,
                                                      const float* __restrict__ upstream, bool reverse) {
     const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
     fill_pcoef<LOGITS>(pc, cf, threadIdx.x);
     __syncthreads();
     // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
     if (need_fl) {
-        if (need_sig) grad_phase_packed<TX, LOGITS, true, true>(ga, pc, reverse);
-        else grad_phase_packed<TX, LOGITS, false, true>(ga, pc, reverse);
+        if (need_sig) grad_phase_packed<TX, LOGITS, true, true>(ga, pc, stage_smem, reverse);
+        else grad_phase_packed<TX, LOGITS, false, true>(ga, pc, stage_smem, reverse);
     } else {
-        if (need_sig) grad_phase_packed<TX, LOGITS, true, false>(ga, pc, reverse);
-        else grad_phase_packed<TX, LOGITS, false, false>(ga, pc, reverse);
+        if (need_sig) grad_phase_packed<TX, LOGITS, true, false>(ga, pc, stage_smem, reverse);
+        else grad_phase_packed<TX, LOGITS, false, false>(ga, pc, stage_smem, reverse);
     }
 }
 
 template <typename TX, bool LOGITS>
 __global__ void __launch_bounds__(kPThreads, 1)
 composite3_grad_packed_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    extern __shared__ __align__(16) char stage_smem[];
     __shared__ LeafCoef cf[ECO_C3_NLEAF];
     __shared__ PCoef pc;
     if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
     __syncthreads();
-    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, upstream, false);
+    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, stage_smem, upstream, false);
 }
 
 template <typename TX, bool LOGITS>
@@ -576,12 +574,13 @@ __global__ void __launch_bounds__(kPThreads, 1)
 composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
                                unsigned int* __restrict__ counter, double* __restrict__ partials,
                                double* __restrict__ acc_glob, float* __restrict__ losses_out) {
+    extern __shared__ __align__(16) char stage_smem[];
     __shared__ PStatsSmem sm;
     __shared__ LeafCoef cf[ECO_C3_NLEAF];
     __shared__ PCoef pc;
     __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
     __shared__ double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
-    stats_phase_packed<TX, LOGITS>(ga.a, sm, counter, partials, acc_glob);
+    stats_phase_packed<TX, LOGITS>(ga.a, sm, stage_smem, counter, partials, acc_glob);
     __threadfence();
     cooperative_groups::this_grid().sync();
     // closed forms, redundantly per CTA (no second grid barrier): one thread per (leaf, loss) row
@@ -599,7 +598,7 @@ composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale
         losses_out[threadIdx.x - 32] = (float)v;
     }
     __syncthreads();
-    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, upstream, true);
+    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, stage_smem, upstream, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -625,6 +624,31 @@ static int check_comp(const EcoView* x, const EcoView* g, int32_t N, int64_t HW)
     if (x->dtype != ECO_F32 && x->dtype != ECO_BF16) { set_error("x dtype must be f32 or bf16"); return -4; }
     if (g->dtype != ECO_F32) { set_error("composite3: labels must be f32"); return -4; }
     return 0;
+}
+
+// opt in to > 48 KB of dynamic shared memory once per process and device (the attribute is per device)
+template <typename K>
+static int set_smem_attr(K kernel) {
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes), "cudaFuncSetAttribute(smem)");
+}
+static int ensure_packed_smem() {
+    static thread_local int done_for_device[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -6;
+    if (done_for_device[dev]) return 0;
+    int rc = 0;
+#define ECO_SMEM_ALL(TX)                                                                           \
+    rc = rc ? rc : set_smem_attr(composite3_stats_packed_kernel<TX, true>);                        \
+    rc = rc ? rc : set_smem_attr(composite3_stats_packed_kernel<TX, false>);                       \
+    rc = rc ? rc : set_smem_attr(composite3_grad_packed_kernel<TX, true>);                         \
+    rc = rc ? rc : set_smem_attr(composite3_grad_packed_kernel<TX, false>);                        \
+    rc = rc ? rc : set_smem_attr(composite3_fused_packed_kernel<TX, true>);                        \
+    rc = rc ? rc : set_smem_attr(composite3_fused_packed_kernel<TX, false>);
+    ECO_SMEM_ALL(float)
+    ECO_SMEM_ALL(__nv_bfloat16)
+#undef ECO_SMEM_ALL
+    if (!rc) done_for_device[dev] = 1;
+    return rc;
 }
 
 static int comp_grid(int device, int64_t units, int ctas_per_sm, int threads_per_unit_stride) {
@@ -671,7 +695,11 @@ extern "C" int eco_composite3_stats(const EcoView* x, const EcoView* g, int32_t 
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256 + 128 * 8);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (vec == 4) ECO_DISPATCH_PACKED(composite3_stats_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, 0, st>>>(a, counter, partials, acc_out));
+    if (vec == 4) {
+        rc = ensure_packed_smem();
+        if (rc) return rc;
+        ECO_DISPATCH_PACKED(composite3_stats_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, kStageBytes, st>>>(a, counter, partials, acc_out));
+    }
     else ECO_DISPATCH_SCALAR(composite3_stats_kernel, x->dtype, from_logits != 0, <<<grid, kCThreads, 0, st>>>(a, counter, partials, acc_out));
     return check_cuda(cudaGetLastError(), "composite3_stats kernel launch");
 }
@@ -685,7 +713,7 @@ extern "C" int eco_composite3_finalize(const double* acc, const double* leaf_sca
     CompFinArgs fa{};
     if (leaf_scale_host)
         for (int l = 0; l < ECO_C3_NLEAF; ++l) fa.scale[l] = leaf_scale_host[l];
-    composite3_finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    composite3_finalize_kernel<<<1, 160, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         acc, fa, leaf_scale_host ? nullptr : leaf_scale_dev, losses_out, jac_out, leaf_sums_out);
     return check_cuda(cudaGetLastError(), "composite3_finalize_kernel launch");
 }
@@ -707,7 +735,11 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     const int grid = comp_grid(device, ga.a.units_total, vec == 4 ? 1 : 2, vec == 4 ? kPThreads : kCThreads);
     if (grid < 0) return -10;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (vec == 4) ECO_DISPATCH_PACKED(composite3_grad_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, 0, st>>>(ga, jac, upstream));
+    if (vec == 4) {
+        rc = ensure_packed_smem();
+        if (rc) return rc;
+        ECO_DISPATCH_PACKED(composite3_grad_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, kStageBytes, st>>>(ga, jac, upstream));
+    }
     else ECO_DISPATCH_SCALAR(composite3_grad_kernel, x->dtype, from_logits != 0, <<<grid, kCThreads, 0, st>>>(ga, jac, upstream));
     return check_cuda(cudaGetLastError(), "composite3_grad kernel launch");
 }
@@ -737,13 +769,17 @@ extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t 
     const void* fn = nullptr;
     const bool lg = from_logits != 0;
     int threads = kCThreads;
+    size_t dyn_smem = 0;
     if (vec == 4) {
+        rc = ensure_packed_smem();
+        if (rc) return rc;
         threads = kPThreads;
+        dyn_smem = kStageBytes;
         if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_packed_kernel<float, true> : (const void*)composite3_fused_packed_kernel<float, false>;
         else fn = lg ? (const void*)composite3_fused_packed_kernel<__nv_bfloat16, true> : (const void*)composite3_fused_packed_kernel<__nv_bfloat16, false>;
     } else {
         if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_kernel<float, 1, true> : (const void*)composite3_fused_kernel<float, 1, false>;
         else fn = lg ? (const void*)composite3_fused_kernel<__nv_bfloat16, 1, true> : (const void*)composite3_fused_kernel<__nv_bfloat16, 1, false>;
     }
-    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, 0, st), "composite3_fused kernel launch");
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, dyn_smem, st), "composite3_fused kernel launch");
 }

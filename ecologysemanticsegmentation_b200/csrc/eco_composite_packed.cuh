@@ -76,7 +76,18 @@ __device__ __forceinline__ void leaf_b_terms2(f2 b, f2 t, f2& r_acc, f2& fl_acc)
 
 // one pixel pair of one organ pair (i, j); `pc`/`gc` = the channel whose plain leaf this role owns
 template <bool UNIT>
-__device__ __forceinline__ void role_pair_stats(f2 pi, f2 pj, f2 gi, f2 gj, f2 pc, f2 gc, f2 d, f2 (&acc)[kRAcc]) {
+__device__ __forceinline__ void role_plain_stats(f2 pc, f2 gc, f2 (&acc)[kRAcc]) {
+    // plain leaf (a = g_c, b = p_c)
+    const f2 t = mul2(pc, pc);
+    acc[R_G] = add2(acc[R_G], gc);
+    acc[R_X] = add2(acc[R_X], pc);
+    acc[R_XX] = add2(acc[R_XX], t);
+    acc[R_GX] = fma2(gc, pc, acc[R_GX]);
+    leaf_b_terms2<UNIT>(pc, t, acc[R_RX], acc[R_FLX]);
+}
+
+template <bool UNIT>
+__device__ __forceinline__ void role_pair_stats(f2 pi, f2 pj, f2 gi, f2 gj, f2 d, f2 (&acc)[kRAcc]) {
     const f2 hh = fma2(pi, splat(-0.5f), splat(0.5f));
     const f2 m1 = mul2(pi, pj);
     const f2 q = mul2(pi, d);
@@ -85,20 +96,11 @@ __device__ __forceinline__ void role_pair_stats(f2 pi, f2 pj, f2 gi, f2 gj, f2 p
     const f2 u2 = fma2(d, hh, pi);
     const f2 u3 = fma2(q, hh, pi);
     const f2 gd = abs2(fma2(gj, splat(-1.0f), gi));
-    acc[R_G] = add2(acc[R_G], gc);
     acc[R_GD] = add2(acc[R_GD], gd);
     acc[R_DS] = add2(acc[R_DS], d);
     acc[R_GJ] = add2(acc[R_GJ], gj);
     acc[R_GGJ] = fma2(gj, gj, acc[R_GGJ]);
     acc[R_GDD] = fma2(gd, gd, acc[R_GDD]);
-    // plain leaf (a = g_c, b = p_c)
-    {
-        const f2 t = mul2(pc, pc);
-        acc[R_X] = add2(acc[R_X], pc);
-        acc[R_XX] = add2(acc[R_XX], t);
-        acc[R_GX] = fma2(gc, pc, acc[R_GX]);
-        leaf_b_terms2<UNIT>(pc, t, acc[R_RX], acc[R_FLX]);
-    }
     // intersection leaves (a = m_k, b = label)
     acc[R_M1] = add2(acc[R_M1], m1);
     acc[R_M1G] = fma2(m1, gj, acc[R_M1G]);
@@ -208,6 +210,42 @@ __device__ __forceinline__ void ld4_cached<__nv_bfloat16>(const __nv_bfloat16* p
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// cp.async (LDGSTS): BYTES = 16 (4 x f32) or 8 (4 x bf16), L1-allocating so the second role's copy of a plane hits
+// streaming flavour (L2 only; 16-byte copies only): pass 2 reads every line once
+template <int BYTES>
+__device__ __forceinline__ void cp_async_cg(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T>
+__device__ __forceinline__ void lds_x4(const void* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void lds_x4<float>(const void* p, float (&v)[4]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <>
+__device__ __forceinline__ void lds_x4<__nv_bfloat16>(const void* p, float (&v)[4]) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(r.x << 16);
+    v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16);
+    v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+
+// dynamic shared memory of the packed kernels: 2 stages x 6 planes x kPThreads x 16 B (pass 2 uses all 6 planes)
+constexpr int kStageBytes = 2 * 6 * kPThreads * 16;
+
 // walks the float4 units [lo, hi) of a CTA with a fixed thread stride, tracking (image, offset) incrementally
 struct UnitWalker {
     int64_t q, n, off, upp;
@@ -225,8 +263,9 @@ struct UnitWalker {
 
 // Pass 1 (packed, role-split).  Same contract as stats_phase(): the LAST CTA leaves acc_out[0..100).
 template <typename TX, bool LOGITS>
-__device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem& sm, unsigned int* __restrict__ counter,
-                                                   double* __restrict__ partials, double* __restrict__ acc_out) {
+__device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem& sm, char* stage_smem,
+                                                   unsigned int* __restrict__ counter, double* __restrict__ partials,
+                                                   double* __restrict__ acc_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int role = warp / kRoleWarps;
     const int rtid = threadIdx.x - role * kRoleThreads;
@@ -246,48 +285,73 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
     UnitWalker w;
     w.init(lo + rtid, a.units_per_plane);
 
+    // per-thread staging slots: [stage][plane 0..3 = x_i, x_j, g_i, g_j][thread] x 16 B, filled by cp.async
+    // one iteration ahead, so the global-load latency is off the critical path without costing registers
+    constexpr int kXB = sizeof(TX) * 4;  // bytes of 4 elements of x
+    char* my_stage = stage_smem + (size_t)threadIdx.x * 16;
+    auto slot = [&](int st, int plane) { return my_stage + ((size_t)(st * 4 + plane) * kPThreads) * 16; };
+    auto issue = [&](int st) {
+        const int64_t ex = w.n * a.x_sn + w.off * 4, eg = w.n * a.g_sn + w.off * 4;
+        cp_async<kXB>(slot(st, 0), xi_b + ex);
+        cp_async<kXB>(slot(st, 1), xj_b + ex);
+        cp_async<16>(slot(st, 2), gi_b + eg);
+        cp_async<16>(slot(st, 3), gj_b + eg);
+    };
+
     f2 acc[kRAcc];
 #pragma unroll
     for (int k = 0; k < kRAcc; ++k) acc[k] = splat(0.f);
     int since_flush = 0;
     bool any_nonbinary = false;
     const int iters = (int)((hi - lo + kRoleThreads - 1) / kRoleThreads);
+    if (w.q < hi) issue(0);
+    cp_async_commit();
     for (int it = 0; it < iters; ++it) {
-        if (w.q < hi) {
-            const int64_t ex = w.n * a.x_sn + w.off * 4, eg = w.n * a.g_sn + w.off * 4;
-            float xi4[4], xj4[4], gi4[4], gj4[4];
-            ld4_cached<TX>(xi_b + ex, xi4);
-            ld4_cached<TX>(xj_b + ex, xj4);
-            ld4_cached<float>(gi_b + eg, gi4);
-            ld4_cached<float>(gj_b + eg, gj4);
-            w.advance(kRoleThreads);
-            if (w.q < hi) {  // pull the next unit's lines towards the SM while this one is being processed
-                const int64_t nx = w.n * a.x_sn + w.off * 4, ng = w.n * a.g_sn + w.off * 4;
-                prefetch_l1(xi_b + nx);
-                prefetch_l1(xj_b + nx);
-                prefetch_l1(gi_b + ng);
-                prefetch_l1(gj_b + ng);
+        const bool active = w.q < hi;
+        w.advance(kRoleThreads);
+        if (w.q < hi) issue((it + 1) & 1);
+        cp_async_commit();
+        cp_async_wait<1>();  // this iteration's copies (committed one iteration ago) have landed
+        if (active) {
+            const int st = it & 1;
+            float xi4[4], xj4[4];
+            lds_x4<TX>(slot(st, 0), xi4);
+            lds_x4<TX>(slot(st, 1), xj4);
+            const float4 gi4 = *reinterpret_cast<const float4*>(slot(st, 2));
+            const float4 gj4 = *reinterpret_cast<const float4*>(slot(st, 3));
+            f2 pi[2] = {make_float2(xi4[0], xi4[1]), make_float2(xi4[2], xi4[3])};
+            f2 pj[2] = {make_float2(xj4[0], xj4[1]), make_float2(xj4[2], xj4[3])};
+            const f2 gi[2] = {make_float2(gi4.x, gi4.y), make_float2(gi4.z, gi4.w)};
+            const f2 gj[2] = {make_float2(gj4.x, gj4.y), make_float2(gj4.z, gj4.w)};
+            f2 d[2];
+            if (LOGITS) {
+                const f2 zi[2] = {pi[0], pi[1]}, zj[2] = {pj[0], pj[1]};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    pi[h] = sigmoid_fast2(zi[h]);
+                    pj[h] = sigmoid_fast2(zj[h]);
+                    d[h] = abs2(fma2(pj[h], splat(-1.0f), pi[h]));
+                }
+                if (fminf(fminf(d[0].x, d[0].y), fminf(d[1].x, d[1].y)) < kTieEps) {
+                    // rare: the sign of (p_i - p_j) must come from ATen's exact sigmoid bits
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (d[h].x < kTieEps) { pi[h].x = sigmoid_exact(zi[h].x); pj[h].x = sigmoid_exact(zj[h].x); d[h].x = fabsf(pi[h].x - pj[h].x); }
+                        if (d[h].y < kTieEps) { pi[h].y = sigmoid_exact(zi[h].y); pj[h].y = sigmoid_exact(zj[h].y); d[h].y = fabsf(pi[h].y - pj[h].y); }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) d[h] = abs2(fma2(pj[h], splat(-1.0f), pi[h]));
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                f2 pi = make_float2(xi4[2 * h], xi4[2 * h + 1]), pj = make_float2(xj4[2 * h], xj4[2 * h + 1]);
-                const f2 gi = make_float2(gi4[2 * h], gi4[2 * h + 1]), gj = make_float2(gj4[2 * h], gj4[2 * h + 1]);
-                f2 d;
-                if (LOGITS) {
-                    const f2 zi = pi, zj = pj;
-                    pi = sigmoid_fast2(zi);
-                    pj = sigmoid_fast2(zj);
-                    d = abs2(fma2(pj, splat(-1.0f), pi));
-                    if (fminf(d.x, d.y) < kTieEps) {  // rare: the sign of (p_i - p_j) must match ATen's bits
-                        if (d.x < kTieEps) { pi.x = sigmoid_exact(zi.x); pj.x = sigmoid_exact(zj.x); d.x = fabsf(pi.x - pj.x); }
-                        if (d.y < kTieEps) { pi.y = sigmoid_exact(zi.y); pj.y = sigmoid_exact(zj.y); d.y = fabsf(pi.y - pj.y); }
-                    }
-                } else {
-                    d = abs2(fma2(pj, splat(-1.0f), pi));
-                }
-                const f2 pc = chan_is_i ? pi : pj;
-                const f2 gc = chan_is_i ? gi : gj;
-                role_pair_stats<LOGITS>(pi, pj, gi, gj, pc, gc, d, acc);
+            for (int h = 0; h < 2; ++h) role_pair_stats<LOGITS>(pi[h], pj[h], gi[h], gj[h], d[h], acc);
+            if (chan_is_i) {  // warp-uniform: which of the two channels' plain leaf this role owns
+#pragma unroll
+                for (int h = 0; h < 2; ++h) role_plain_stats<LOGITS>(pi[h], gi[h], acc);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) role_plain_stats<LOGITS>(pj[h], gj[h], acc);
             }
         }
         if (++since_flush == kPFlushIters) {
@@ -295,6 +359,7 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
             since_flush = 0;
         }
     }
+    cp_async_wait<0>();
     any_nonbinary |= flush_role_acc(acc, sm.warp_slots[warp], lane);
     if (__syncthreads_or(any_nonbinary)) {
         // rare slow pass: some label is not exactly 0 or 1 -> exact transcendental corrections for this CTA's range
@@ -468,7 +533,7 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
 }
 
 template <typename TX, bool LOGITS, bool SIG, bool FL>
-__device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const PCoef& pc, bool reverse) {
+__device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const PCoef& pc, char* stage_smem, bool reverse) {
     const CompArgs& a = ga.a;
     const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
     const float* __restrict__ gb = reinterpret_cast<const float*>(a.g);
@@ -476,31 +541,38 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
     const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
     const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
     const int iters = (int)((hi - lo + kPThreads - 1) / kPThreads);
+    constexpr int kXB = sizeof(TX) * 4;
+    char* my_stage = stage_smem + (size_t)threadIdx.x * 16;
+    auto slot = [&](int st, int plane) { return my_stage + ((size_t)(st * 6 + plane) * kPThreads) * 16; };
+    auto unit_of = [&](int it) { return lo + (int64_t)(reverse ? (iters - 1 - it) : it) * kPThreads + threadIdx.x; };
+    auto issue = [&](int it) {
+        const int64_t q = unit_of(it);
+        if (it < iters && q < hi) {
+            const int64_t n = q / a.units_per_plane;
+            const int64_t off = (q - n * a.units_per_plane) * 4;
+            const TX* xp = xb + n * a.x_sn + off;
+            const float* gp = gb + n * a.g_sn + off;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                cp_async_cg<kXB>(slot(it & 1, c), xp + c * a.x_sc);
+                cp_async_cg<16>(slot(it & 1, 3 + c), gp + c * a.g_sc);
+            }
+        }
+        cp_async_commit();
+    };
+    issue(0);
     for (int it = 0; it < iters; ++it) {
-        const int step = reverse ? (iters - 1 - it) : it;
-        const int64_t q = lo + (int64_t)step * kPThreads + threadIdx.x;
+        issue(it + 1);
+        cp_async_wait<1>();
+        const int64_t q = unit_of(it);
         if (q >= hi) continue;
         const int64_t n = q / a.units_per_plane;
         const int64_t off = (q - n * a.units_per_plane) * 4;
-        const TX* xp = xb + n * a.x_sn + off;
-        const float* gp = gb + n * a.g_sn + off;
         float xv[3][4], gv[3][4], ov[3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            Vec4<TX>::load(xp + c * a.x_sc, xv[c]);
-            Vec4<float>::load(gp + c * a.g_sc, gv[c]);
-        }
-        {   // L2 prefetch of the unit this thread handles next
-            const int64_t qn = q + (reverse ? -(int64_t)kPThreads : (int64_t)kPThreads);
-            if (qn >= lo && qn < hi) {
-                const int64_t nn = qn / a.units_per_plane;
-                const int64_t on = (qn - nn * a.units_per_plane) * 4;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    prefetch_l2(xb + nn * a.x_sn + on + c * a.x_sc);
-                    prefetch_l2(gb + nn * a.g_sn + on + c * a.g_sc);
-                }
-            }
+            lds_x4<TX>(slot(it & 1, c), xv[c]);
+            lds_x4<float>(slot(it & 1, 3 + c), gv[c]);
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -541,6 +613,7 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
 #pragma unroll
         for (int c = 0; c < 3; ++c) Vec4<TX>::store(ob + n * ga.gx_sn + c * ga.gx_sc + off, ov[c]);
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace eco
