@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: all-reduce of the sums inside the fused kernel over peer memory, or NCCL between kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -206,7 +208,9 @@ def main():
     weights = fused.loss_weights(**WEIGHTS)
     import numpy as np
     np.random.seed(0)
-    if world > 1:
+    if world > 1 and args.exchange == "p2p":
+        step = fused.PeerShardedCompositeLossStep(weights, group="world", device=dev)
+    elif world > 1:
         step = fused.ShardedCompositeLossStep(weights, group="world", device=dev)
     else:
         step = fused.CompositeLossStep(weights, device=dev)
@@ -252,7 +256,7 @@ def main():
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = pixels_per_step / (ms_per_step * 1e-3) / 1e9
-    launches_per_step = 1 if world == 1 else 3
+    launches_per_step = 1 if (world == 1 or args.exchange == "p2p") else 3
 
     # ---- end to end: pinned host buffers in, 7 losses out, every step --------------------------------
     e2e = None
@@ -300,7 +304,7 @@ def main():
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
-                    "kernel": "composite3_fused_kernel" if world == 1 else "composite3_stats+allreduce+finalize+grad",
+                    "kernel": "composite3_fused_packed_kernel" if (world == 1 or args.exchange == "p2p") else "composite3_stats+allreduce+finalize+grad",
                     "algorithmic_bytes_per_launch": alg_bytes}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
@@ -316,7 +320,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: ORGANS=whole_body,ventral_side,dorsal_side composite multiclass loss "
                                    f"fwd+bwd from logits, {n}x{c}x{s}x{s} f32 per GPU, loss=bce+gdice+twersky+focal_dice",
-                       "global_batch": n * world, "parallelism": f"dp{world} (batch sharded, 800 B sums all-reduced)" if world > 1 else "single GPU, one cooperative launch per step",
+                       "global_batch": n * world, "parallelism": (f"dp{world} (batch sharded, 800 B of sums all-reduced " + ("in-kernel over NVLink peer memory, one launch per rank)" if args.exchange == "p2p" else "by NCCL between the two kernels)")) if world > 1 else "single GPU, one cooperative launch per step",
                        "l2": f"rotating {N_BUFFER_SETS} buffer sets ({N_BUFFER_SETS * 3 * elems_per_gpu * 4 / 1e6:.0f} MB) > 126 MB L2 between timed iterations"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps * world,
@@ -324,6 +328,8 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        if hasattr(step, "close"):
+            step.close()
         dist.destroy_process_group()
 
 

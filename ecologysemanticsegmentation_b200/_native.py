@@ -52,6 +52,13 @@ SIGNATURES = {
     "eco_composite3_finalize": (C.c_int, [_vp, C.POINTER(_f64), _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "eco_composite3_grad": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _OUT, C.c_int, _vp]),
     "eco_composite3_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
+    "eco_composite3_fused_sharded": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, _vp, _i32, _i32,
+                                               _u32, C.c_int, _vp]),
+    "eco_xch_bytes": (_i64, [_i32]),
+    "eco_xch_alloc": (C.c_int, [_i32, C.POINTER(_vp), C.c_char_p, C.c_int]),
+    "eco_xch_open": (C.c_int, [C.c_char_p, C.POINTER(_vp), C.c_int]),
+    "eco_xch_close": (C.c_int, [_vp, C.c_int]),
+    "eco_xch_free": (C.c_int, [_vp, C.c_int]),
     "eco_dice_ws_bytes": (_i64, [_i32, _i32]),
     "eco_dice_counts": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp, C.c_int, _vp]),
     "eco_dice_finalize": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),

@@ -11,6 +11,7 @@
 //   arbitrary labels.
 // Pass 2 (grad): chain rule through the operands with 21 x 6 global coefficients.
 #include <cooperative_groups.h>
+#include <string.h>
 
 #include "eco_common.cuh"
 
@@ -573,14 +574,14 @@ template <typename TX, bool LOGITS>
 __global__ void __launch_bounds__(kPThreads, 1)
 composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
                                unsigned int* __restrict__ counter, double* __restrict__ partials,
-                               double* __restrict__ acc_glob, float* __restrict__ losses_out) {
+                               double* __restrict__ acc_glob, float* __restrict__ losses_out, XchArgs xch) {
     extern __shared__ __align__(16) char stage_smem[];
     __shared__ PStatsSmem sm;
     __shared__ LeafCoef cf[ECO_C3_NLEAF];
     __shared__ PCoef pc;
     __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
     __shared__ double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
-    stats_phase_packed<TX, LOGITS>(ga.a, sm, stage_smem, counter, partials, acc_glob);
+    stats_phase_packed<TX, LOGITS>(ga.a, sm, stage_smem, counter, partials, acc_glob, &xch);
     __threadfence();
     cooperative_groups::this_grid().sync();
     // closed forms, redundantly per CTA (no second grid barrier): one thread per (leaf, loss) row
@@ -744,9 +745,9 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     return check_cuda(cudaGetLastError(), "composite3_grad kernel launch");
 }
 
-extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
-                                    const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
-                                    float* losses_out, const EcoOut* gx, int device, void* stream) {
+static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                        const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
+                        float* losses_out, const EcoOut* gx, XchArgs xch, int device, void* stream) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
     if (!leaf_scale_dev || !upstream || !losses_out || !gx || !gx->ptr) { set_error("null scale/upstream/output"); return -5; }
@@ -756,6 +757,7 @@ extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t 
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW) &&
                      c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
+    if (xch.world > 1 && vec != 4) { set_error("the peer-exchange fused step needs 16-byte aligned planes with H*W %% 4 == 0"); return -8; }
     CompGradArgs ga{};
     fill_comp(ga.a, x, g, N, HW, vec);
     ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
@@ -764,22 +766,90 @@ extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t 
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
     double* partials = acc_glob + 128;
+    xch.status = counter + 32;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out};
-    const void* fn = nullptr;
     const bool lg = from_logits != 0;
-    int threads = kCThreads;
-    size_t dyn_smem = 0;
     if (vec == 4) {
         rc = ensure_packed_smem();
         if (rc) return rc;
-        threads = kPThreads;
-        dyn_smem = kStageBytes;
+        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out, &xch};
+        const void* fn;
         if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_packed_kernel<float, true> : (const void*)composite3_fused_packed_kernel<float, false>;
         else fn = lg ? (const void*)composite3_fused_packed_kernel<__nv_bfloat16, true> : (const void*)composite3_fused_packed_kernel<__nv_bfloat16, false>;
-    } else {
-        if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_kernel<float, 1, true> : (const void*)composite3_fused_kernel<float, 1, false>;
-        else fn = lg ? (const void*)composite3_fused_kernel<__nv_bfloat16, 1, true> : (const void*)composite3_fused_kernel<__nv_bfloat16, 1, false>;
+        return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPThreads), args, kStageBytes, st), "composite3_fused_packed_kernel launch");
     }
-    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, dyn_smem, st), "composite3_fused kernel launch");
+    void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out};
+    const void* fn;
+    if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_kernel<float, 1, true> : (const void*)composite3_fused_kernel<float, 1, false>;
+    else fn = lg ? (const void*)composite3_fused_kernel<__nv_bfloat16, 1, true> : (const void*)composite3_fused_kernel<__nv_bfloat16, 1, false>;
+    return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCThreads), args, 0, st), "composite3_fused_kernel launch");
+}
+
+extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                                    const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
+                                    float* losses_out, const EcoOut* gx, int device, void* stream) {
+    XchArgs xch{};
+    xch.world = 1;
+    return launch_fused(x, g, N, HW, from_logits, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+}
+
+extern "C" int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                                            const double* leaf_scale_dev, const float* upstream, void* ws,
+                                            int64_t ws_bytes, float* losses_out, const EcoOut* gx,
+                                            void* const* peer_xch_dev, int32_t rank, int32_t world, uint32_t epoch,
+                                            int device, void* stream) {
+    if (!peer_xch_dev || world < 1 || world > 64 || rank < 0 || rank >= world || epoch == 0) {
+        set_error("bad exchange arguments (world=%d rank=%d epoch=%u)", world, rank, epoch);
+        return -9;
+    }
+    XchArgs xch{};
+    xch.peers = reinterpret_cast<double* const*>(peer_xch_dev);
+    xch.rank = rank;
+    xch.world = world;
+    xch.epoch = epoch;
+    return launch_fused(x, g, N, HW, from_logits, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+}
+
+// ---- peer exchange buffers (CUDA IPC).  The one place the library allocates: IPC needs a cudaMalloc base pointer. ----
+extern "C" int64_t eco_xch_bytes(int32_t world) {
+    if (world < 1 || world > 64) return -1;
+    return (int64_t)xch_flags_offset_doubles(world) * 8 + 256;
+}
+
+extern "C" int eco_xch_alloc(int32_t world, void** ptr_out, unsigned char* handle_out /*[64]*/, int device) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ptr_out || !handle_out || eco_xch_bytes(world) < 0) { set_error("bad eco_xch_alloc arguments"); return -1; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    void* p = nullptr;
+    ECO_CUDA(cudaMalloc(&p, (size_t)eco_xch_bytes(world)));
+    ECO_CUDA(cudaMemset(p, 0, (size_t)eco_xch_bytes(world)));
+    ECO_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    int rc = check_cuda(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle");
+    if (rc) { cudaFree(p); return rc; }
+    memcpy(handle_out, &h, 64);
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int eco_xch_open(const unsigned char* handle /*[64]*/, void** ptr_out, int device) {
+    if (!handle || !ptr_out) { set_error("bad eco_xch_open arguments"); return -1; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return check_cuda(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+extern "C" int eco_xch_close(void* peer_ptr, int device) {
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    return check_cuda(cudaIpcCloseMemHandle(peer_ptr), "cudaIpcCloseMemHandle");
+}
+
+extern "C" int eco_xch_free(void* ptr, int device) {
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    return check_cuda(cudaFree(ptr), "cudaFree");
 }

@@ -68,3 +68,81 @@ class ShardedCompositeLossStep(CompositeLossStep):
         losses, jac, _ = ops.composite3_finalize(acc, self.scales)
         grad = ops.composite3_grad(logits, labels, self.from_logits, jac, self.upstream, out=out)
         return losses, grad
+
+
+class PeerShardedCompositeLossStep(CompositeLossStep):
+    """The data-parallel step as ONE cooperative launch per rank: statistics of the local shard -> in-kernel
+    all-reduce of the 100 sums over NVLink peer memory (P2P stores into every peer's exchange buffer, release /
+    acquire flags, fixed-order sum) -> closed forms -> gradient of the local shard.  No NCCL call on the step.
+
+    torch.distributed is used once, at construction, to swap the 64-byte CUDA IPC handles of the exchange buffers.
+    Every rank must call the step the same number of times (it is a collective).  Needs 16-byte aligned planes
+    with H*W % 4 == 0 (otherwise use ShardedCompositeLossStep)."""
+
+    def __init__(self, weights, group="world", **kw):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import distributed as dist_
+        super().__init__(weights, **kw)
+        self.pg = dist_._resolve(group)
+        self.world = dist.get_world_size(self.pg)
+        self.rank = dist.get_rank(self.pg)
+        self.epoch = 0
+        L = ops.nat.lib()
+        dev = self.device.index
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ops.nat.check(L.eco_xch_alloc(self.world, C.byref(own), handle, dev), "eco_xch_alloc")
+        self._own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.pg)
+        self._peers = []
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self._own)
+                continue
+            p = C.c_void_p()
+            ops.nat.check(L.eco_xch_open(h, C.byref(p), dev), f"eco_xch_open(rank {r})")
+            self._peers.append(p.value)
+            ptrs.append(p.value)
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        dist.barrier(group=self.pg)
+
+    def __call__(self, logits, labels, out=None):
+        import ctypes as C
+        x, g = logits, labels
+        ops.nat.require_cuda(x, g)
+        if g.dtype != torch.float32:
+            g = g.float()
+        x, x_sn, x_sc = ops.nat.planes(x)
+        g, g_sn, g_sc = ops.nat.planes(g)
+        n, c, h, w = x.shape
+        L = ops.nat.lib()
+        ws = ops.nat.workspace("comp3", L.eco_composite3_ws_bytes(), x.device)
+        losses = torch.empty((ops.nat.NLOSS,), dtype=torch.float32, device=x.device)
+        gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+        vx, vg = ops.nat.view_of(x, x_sn, x_sc), ops.nat.view_of(g, g_sn, g_sc)
+        og = ops.nat.out_of(gx, c * h * w, h * w)
+        self.epoch += 1
+        rc = L.eco_composite3_fused_sharded(C.byref(vx), C.byref(vg), n, h * w, int(self.from_logits),
+                                            self.scales.data_ptr(), self.upstream.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            losses.data_ptr(), C.byref(og), self.peer_ptrs.data_ptr(), self.rank,
+                                            self.world, self.epoch & 0xFFFFFFFF or 1, x.device.index,
+                                            ops.nat.current_stream_ptr(x.device))
+        ops.nat.check(rc, "eco_composite3_fused_sharded")
+        return losses, gx
+
+    def close(self):
+        """Unmap the peers' buffers and free the own one (collective: all ranks should call it)."""
+        import torch.distributed as dist
+        if self._own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.pg)
+        L = ops.nat.lib()
+        for p in self._peers:
+            L.eco_xch_close(p, self.device.index)
+        dist.barrier(group=self.pg)
+        L.eco_xch_free(self._own, self.device.index)
+        self._own, self._peers = None, []

@@ -136,6 +136,26 @@ int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t 
                          const double* leaf_scale_dev, const float* upstream, void* ws,
                          int64_t ws_bytes, float* losses_out, const EcoOut* gx, int device, void* stream);
 
+/* Sharded flavour of eco_composite3_fused: one process per GPU, each with its batch shard; the 100 sums are
+ * all-reduced INSIDE the kernel over NVLink peer memory (P2P stores + release/acquire flags), so the whole
+ * data-parallel step -- ess/train_multiclass.py:133-147 on a sharded batch -- stays one launch per rank.
+ * peer_xch_dev: device array of `world` pointers to every rank's exchange buffer as mapped into THIS process
+ * (entry [rank] = own buffer).  epoch: 1, 2, 3, ... incremented by the caller on every call, identical on all
+ * ranks.  Every rank must make the same sequence of calls (as with any collective). */
+int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+                                 const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
+                                 float* losses_out, const EcoOut* gx, void* const* peer_xch_dev, int32_t rank,
+                                 int32_t world, uint32_t epoch, int device, void* stream);
+
+/* Exchange buffers for the call above (CUDA IPC needs a cudaMalloc base pointer, so this is the one place the
+ * library allocates).  alloc: zeroed buffer of eco_xch_bytes(world) + its 64-byte IPC handle to send to the peers;
+ * open/close: map / unmap a peer's buffer from its handle; free: release the own buffer. */
+int64_t eco_xch_bytes(int32_t world);
+int eco_xch_alloc(int32_t world, void** ptr_out, unsigned char* handle_out, int device);
+int eco_xch_open(const unsigned char* handle, void** ptr_out, int device);
+int eco_xch_close(void* peer_ptr, int device);
+int eco_xch_free(void* ptr, int device);
+
 /* ------------------------------------------------------------------------------------------
  * Evaluation scoring: ess/test_multiclass.py:58 (sigmoid), :68-69 (threshold rule, strict '>' in fp32),
  * :80-81 (per-class dice_loss(out_c, lab_c, background_weight=0)).

@@ -48,6 +48,16 @@ def _worker(rank, world, port, q):
         step = fused.ShardedCompositeLossStep(up, group=D.WORLD)
         l2, dz = step(zs.detach(), gs)
         e_step = float((dz - zr.grad[lo:hi]).abs().max() / zr.grad.abs().max())
+        # ONE-launch step with the all-reduce done in-kernel over NVLink peer memory (several calls: epochs, parity)
+        np.random.seed(0)
+        pstep = fused.PeerShardedCompositeLossStep(up, group=D.WORLD)
+        e_peer = 0.0
+        for _ in range(5):
+            l3, dz3 = pstep(zs.detach(), gs)
+            e_peer = max(e_peer, float((dz3 - zr.grad[lo:hi]).abs().max() / zr.grad.abs().max()),
+                         max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-30) for a, b in zip(l3[1:], ref[1:])))
+        pstep.close()
+        e_step = max(e_step, e_peer)
         # plain per-channel path and scoring
         zr2 = zf.clone().requires_grad_(True)
         r2 = eco.losses_fn(torch.sigmoid(zr2), gf)
