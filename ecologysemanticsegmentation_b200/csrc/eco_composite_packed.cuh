@@ -305,6 +305,66 @@ __device__ __forceinline__ void lds_x4<__nv_bfloat16>(const void* p, float (&v)[
     v[3] = __uint_as_float(r.y & 0xffff0000u);
 }
 
+// 32-bit shared-window addressing: generic char* arithmetic costs several 64-bit IMADs per access
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int BYTES, bool STREAM>
+__device__ __forceinline__ void cp_async_s(uint32_t dst, const void* gmem_src) {
+    if (STREAM && BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+// staged unit of x (4 elements) at shared address a -> 4 floats
+template <typename TX>
+__device__ __forceinline__ float4 lds_unit(uint32_t a);
+template <>
+__device__ __forceinline__ float4 lds_unit<float>(uint32_t a) { return lds_f4(a); }
+template <>
+__device__ __forceinline__ float4 lds_unit<__nv_bfloat16>(uint32_t a) {
+    const uint2 r = lds_u2(a);
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+}
+
+// running global cursor over the float4 units of one CTA range for a fixed thread stride: byte offsets of the
+// current unit inside plane 0 of x and of g, advanced without multiplications (one compare per step)
+struct UnitCursor {
+    int64_t q, off, upp, n;
+    int64_t xoff, goff;          // element offsets n * sn + off * 4
+    int64_t x_sn, g_sn;
+    __device__ __forceinline__ void init(int64_t q0, const CompArgs& a) {
+        q = q0; upp = a.units_per_plane; x_sn = a.x_sn; g_sn = a.g_sn;
+        n = q / upp;
+        off = q - n * upp;
+        xoff = n * x_sn + off * 4;
+        goff = n * g_sn + off * 4;
+    }
+    __device__ __forceinline__ void advance(int stride) {
+        q += stride; off += stride; xoff += (int64_t)stride * 4; goff += (int64_t)stride * 4;
+        while (off >= upp) {   // next image: planes of one image are sn apart, not upp * 4
+            off -= upp; ++n;
+            xoff += x_sn - upp * 4;
+            goff += g_sn - upp * 4;
+        }
+    }
+    __device__ __forceinline__ void retreat(int stride) {
+        q -= stride; off -= stride; xoff -= (int64_t)stride * 4; goff -= (int64_t)stride * 4;
+        while (off < 0) {
+            off += upp; --n;
+            xoff -= x_sn - upp * 4;
+            goff -= g_sn - upp * 4;
+        }
+    }
+};
+
 // dynamic shared memory of the packed kernels: 2 stages x 6 planes x kPThreads x 16 B (pass 2 uses all 6 planes)
 constexpr int kStageBytes = 2 * 6 * kPThreads * 16;
 
@@ -344,21 +404,22 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
 
     const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
     const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
-    UnitWalker w;
-    w.init(lo + rtid, a.units_per_plane);
+    UnitCursor w;
+    w.init(lo + rtid, a);
 
     // per-thread staging slots: [stage][plane 0..3 = x_i, x_j, g_i, g_j][thread] x 16 B, filled by cp.async
     // one iteration ahead, so the global-load latency is off the critical path without costing registers
     constexpr int kXB = sizeof(TX) * 4;  // bytes of 4 elements of x
-    char* my_stage = stage_smem + (size_t)threadIdx.x * 16;
-    auto slot = [&](int st, int plane) { return my_stage + ((size_t)(st * 4 + plane) * kPThreads) * 16; };
-    auto issue = [&](int st) {
-        const int64_t ex = w.n * a.x_sn + w.off * 4, eg = w.n * a.g_sn + w.off * 4;
-        cp_async<kXB>(slot(st, 0), xi_b + ex);
-        cp_async<kXB>(slot(st, 1), xj_b + ex);
-        cp_async<16>(slot(st, 2), gi_b + eg);
-        cp_async<16>(slot(st, 3), gj_b + eg);
-    };
+    constexpr uint32_t kPlaneStride = kPThreads * 16;
+    const uint32_t my_stage = smem_u32(stage_smem) + threadIdx.x * 16;
+#define ECO_SLOT(st, plane) (my_stage + (uint32_t)((st) * 4 + (plane)) * kPlaneStride)
+#define ECO_ISSUE(st)                                              \
+    do {                                                           \
+        cp_async_s<kXB, false>(ECO_SLOT(st, 0), xi_b + w.xoff);    \
+        cp_async_s<kXB, false>(ECO_SLOT(st, 1), xj_b + w.xoff);    \
+        cp_async_s<16, false>(ECO_SLOT(st, 2), gi_b + w.goff);     \
+        cp_async_s<16, false>(ECO_SLOT(st, 3), gj_b + w.goff);     \
+    } while (0)
 
     f2 acc[kRAcc];
 #pragma unroll
@@ -366,23 +427,24 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
     int since_flush = 0;
     bool any_nonbinary = false;
     const int iters = (int)((hi - lo + kRoleThreads - 1) / kRoleThreads);
-    if (w.q < hi) issue(0);
+    if (w.q < hi) ECO_ISSUE(0);
     cp_async_commit();
     for (int it = 0; it < iters; ++it) {
         const bool active = w.q < hi;
         w.advance(kRoleThreads);
-        if (w.q < hi) issue((it + 1) & 1);
+        const int st = it & 1;
+        if (w.q < hi) {
+            if (st) ECO_ISSUE(0);
+            else ECO_ISSUE(1);
+        }
         cp_async_commit();
         cp_async_wait<1>();  // this iteration's copies (committed one iteration ago) have landed
         if (active) {
-            const int st = it & 1;
-            float xi4[4], xj4[4];
-            lds_x4<TX>(slot(st, 0), xi4);
-            lds_x4<TX>(slot(st, 1), xj4);
-            const float4 gi4 = *reinterpret_cast<const float4*>(slot(st, 2));
-            const float4 gj4 = *reinterpret_cast<const float4*>(slot(st, 3));
-            f2 pi[2] = {make_float2(xi4[0], xi4[1]), make_float2(xi4[2], xi4[3])};
-            f2 pj[2] = {make_float2(xj4[0], xj4[1]), make_float2(xj4[2], xj4[3])};
+            const uint32_t sbase = my_stage + (uint32_t)st * 4 * kPlaneStride;
+            const float4 xi4 = lds_unit<TX>(sbase), xj4 = lds_unit<TX>(sbase + kPlaneStride);
+            const float4 gi4 = lds_f4(sbase + 2 * kPlaneStride), gj4 = lds_f4(sbase + 3 * kPlaneStride);
+            f2 pi[2] = {make_float2(xi4.x, xi4.y), make_float2(xi4.z, xi4.w)};
+            f2 pj[2] = {make_float2(xj4.x, xj4.y), make_float2(xj4.z, xj4.w)};
             const f2 gi[2] = {make_float2(gi4.x, gi4.y), make_float2(gi4.z, gi4.w)};
             const f2 gj[2] = {make_float2(gj4.x, gj4.y), make_float2(gj4.z, gj4.w)};
             f2 d[2];
@@ -422,6 +484,8 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
         }
     }
     cp_async_wait<0>();
+#undef ECO_ISSUE
+#undef ECO_SLOT
     any_nonbinary |= flush_role_acc(acc, sm.warp_slots[warp], lane);
     if (__syncthreads_or(any_nonbinary)) {
         // rare slow pass: some label is not exactly 0 or 1 -> exact transcendental corrections for this CTA's range
@@ -613,37 +677,46 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
     const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
     const int iters = (int)((hi - lo + kPThreads - 1) / kPThreads);
     constexpr int kXB = sizeof(TX) * 4;
-    char* my_stage = stage_smem + (size_t)threadIdx.x * 16;
-    auto slot = [&](int st, int plane) { return my_stage + ((size_t)(st * 6 + plane) * kPThreads) * 16; };
-    auto unit_of = [&](int it) { return lo + (int64_t)(reverse ? (iters - 1 - it) : it) * kPThreads + threadIdx.x; };
-    auto issue = [&](int it) {
-        const int64_t q = unit_of(it);
-        if (it < iters && q < hi) {
-            const int64_t n = q / a.units_per_plane;
-            const int64_t off = (q - n * a.units_per_plane) * 4;
-            const TX* xp = xb + n * a.x_sn + off;
-            const float* gp = gb + n * a.g_sn + off;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                cp_async_cg<kXB>(slot(it & 1, c), xp + c * a.x_sc);
-                cp_async_cg<16>(slot(it & 1, 3 + c), gp + c * a.g_sc);
-            }
-        }
-        cp_async_commit();
-    };
-    issue(0);
+    constexpr uint32_t kPlaneStride = kPThreads * 16;
+    const uint32_t my_stage = smem_u32(stage_smem) + threadIdx.x * 16;
+    // cursor of the unit being STAGED (one iteration ahead of the one being processed); pass 2 may walk backwards
+    UnitCursor w;
+    w.init(lo + (int64_t)(reverse ? (iters - 1) : 0) * kPThreads + threadIdx.x, a);
+#define ECO_ISSUE2(st)                                                                                     \
+    do {                                                                                                   \
+        if (w.q >= lo && w.q < hi) {                                                                       \
+            _Pragma("unroll") for (int c = 0; c < 3; ++c) {                                                \
+                cp_async_s<kXB, true>(my_stage + (uint32_t)((st) * 6 + c) * kPlaneStride, xb + w.xoff + c * a.x_sc);     \
+                cp_async_s<16, true>(my_stage + (uint32_t)((st) * 6 + 3 + c) * kPlaneStride, gb + w.goff + c * a.g_sc); \
+            }                                                                                              \
+        }                                                                                                  \
+        cp_async_commit();                                                                                 \
+    } while (0)
+    ECO_ISSUE2(0);
     for (int it = 0; it < iters; ++it) {
-        issue(it + 1);
+        const int64_t q = w.q;            // unit processed in this iteration
+        const int64_t xoff = w.xoff;      // = n * x_sn + off * 4; the gradient is written with gx_sn, see below
+        const int64_t n = w.n, off4 = w.off * 4;
+        if (reverse) w.retreat(kPThreads);
+        else w.advance(kPThreads);
+        const int st = it & 1;
+        if (it + 1 < iters) {
+            if (st) ECO_ISSUE2(0);
+            else ECO_ISSUE2(1);
+        } else {
+            cp_async_commit();
+        }
         cp_async_wait<1>();
-        const int64_t q = unit_of(it);
+        (void)xoff;
         if (q >= hi) continue;
-        const int64_t n = q / a.units_per_plane;
-        const int64_t off = (q - n * a.units_per_plane) * 4;
+        const int64_t off = off4;
         float xv[3][4], gv[3][4], ov[3][4];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            lds_x4<TX>(slot(it & 1, c), xv[c]);
-            lds_x4<float>(slot(it & 1, 3 + c), gv[c]);
+            const float4 xq = lds_unit<TX>(my_stage + (uint32_t)(st * 6 + c) * kPlaneStride);
+            const float4 gq = lds_f4(my_stage + (uint32_t)(st * 6 + 3 + c) * kPlaneStride);
+            xv[c][0] = xq.x; xv[c][1] = xq.y; xv[c][2] = xq.z; xv[c][3] = xq.w;
+            gv[c][0] = gq.x; gv[c][1] = gq.y; gv[c][2] = gq.z; gv[c][3] = gq.w;
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -685,6 +758,7 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
         for (int c = 0; c < 3; ++c) Vec4<TX>::store(ob + n * ga.gx_sn + c * ga.gx_sc + off, ov[c]);
     }
     cp_async_wait<0>();
+#undef ECO_ISSUE2
 }
 
 }  // namespace eco
