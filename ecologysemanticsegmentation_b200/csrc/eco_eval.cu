@@ -28,8 +28,15 @@ struct EvalArgs {
 __host__ __device__ inline int64_t eval_rec_words(int nt) { return 2 * (int64_t)nt + 1 + 3; }  // 8-byte words
 __host__ __device__ inline int64_t eval_ws_off(int C) { return ((int64_t)C * 4 + 255) / 256 * 256; }
 
+// Per-thread counters are packed: low 16 bits = |out| count, high 16 bits = intersection count of one threshold
+// (one FSETP + one predicated IADD per threshold and element); a thread folds them into 32-bit counters before
+// either half can overflow.  For NT <= 4 the sigmoid is the 4-instruction MUFU form and the exact
+// (ATen-bit-compatible) one is recomputed only within 4e-6 of a threshold, which keeps the counts bit-exact.
+constexpr int kPackFlushElems = 32768;
+constexpr float kThrEps = 4e-6f;
+
 template <typename TZ, typename TL, int VEC, int NT>
-__global__ void __launch_bounds__(kEvThreads, kEvCtasPerSm)
+__global__ void __launch_bounds__(kEvThreads, NT > 4 ? 2 : kEvCtasPerSm)
 dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
                    long long* __restrict__ partials, long long* __restrict__ counts_out,
                    double* __restrict__ soft_out) {
@@ -44,10 +51,14 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
     for (int k = 0; k < NTA; ++k) thr[k] = (k < p.n_thr) ? thresholds[k] : __int_as_float(0x7f800000);
 
     // per-thread exact counters (a thread sees far fewer than 2^31 elements)
-    int cnt_o[NTA], cnt_i[NTA];
+    unsigned int cnt_pk[NTA];
     int cnt_l = 0;
+    int since_fold = 0;
 #pragma unroll
-    for (int k = 0; k < NTA; ++k) cnt_o[k] = cnt_i[k] = 0;
+    for (int k = 0; k < NTA; ++k) cnt_pk[k] = 0u;
+    __shared__ long long sm_cnt[2 * NTA + 1];
+    if (threadIdx.x < 2 * NTA + 1) sm_cnt[threadIdx.x] = 0;
+    __syncthreads();
     double dsoft[3] = {0.0, 0.0, 0.0};
 
     int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
@@ -82,26 +93,45 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
             if (!ok[u]) continue;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float pr = p.probs ? zv[u][v] : sigmoid_exact(zv[u][v]);
+                float pr;
+                if (p.probs) {
+                    pr = zv[u][v];
+                } else if (NT > 4) {
+                    pr = sigmoid_exact(zv[u][v]);
+                } else {
+                    pr = sigmoid_fast(zv[u][v]);
+                    if (NT > 0) {
+                        bool near = false;
+#pragma unroll
+                        for (int k = 0; k < NTA; ++k) near |= fabsf(pr - thr[k]) < kThrEps;
+                        if (near) pr = sigmoid_exact(zv[u][v]);  // rare: the strict '>' must see ATen's bits
+                    }
+                }
                 const float lab = lv[u][v];
                 const int li = fabsf(lab) >= 1.0f ? 1 : 0;
+                const unsigned int inc = 1u + ((unsigned int)li << 16);
                 s0 = fmaf(pr, lab, s0);
                 s1 += pr;
                 s2 = fmaf(lab, lab, s2);
                 cnt_l += li;
                 if (NT > 0) {
 #pragma unroll
-                    for (int k = 0; k < NTA; ++k) {
-                        const bool on = pr > thr[k];
-                        cnt_o[k] += on ? 1 : 0;
-                        cnt_i[k] += on ? li : 0;
-                    }
+                    for (int k = 0; k < NTA; ++k) cnt_pk[k] += (pr > thr[k]) ? inc : 0u;
                 }
             }
         }
         dsoft[0] += (double)s0;
         dsoft[1] += (double)s1;
         dsoft[2] += (double)s2;
+        if (NT > 0 && (since_fold += kEvUnroll * VEC) >= kPackFlushElems) {  // rare: before a 16-bit half can overflow
+#pragma unroll
+            for (int k = 0; k < NTA; ++k) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * k]), (unsigned long long)(cnt_pk[k] & 0xffffu));
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * k + 1]), (unsigned long long)(cnt_pk[k] >> 16));
+                cnt_pk[k] = 0u;
+            }
+            since_fold = 0;
+        }
         if (++t == p.tiles_per_plane) {
             t = 0;
             ++n;
@@ -109,17 +139,14 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
     }
 
     // CTA reduction: integers via warp shuffles + shared atomics (exact, order-independent)
-    __shared__ long long sm_cnt[2 * NTA + 1];
     __shared__ double sm_soft[kEvThreads / 32][3];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 2 * NTA + 1) sm_cnt[threadIdx.x] = 0;
-    __syncthreads();
     if (NT > 0) {
 #pragma unroll
         for (int k = 0; k < NTA; ++k) {
-            int o = __reduce_add_sync(0xffffffffu, cnt_o[k]);
-            int i = __reduce_add_sync(0xffffffffu, cnt_i[k]);
+            int o = __reduce_add_sync(0xffffffffu, (int)(cnt_pk[k] & 0xffffu));
+            int i = __reduce_add_sync(0xffffffffu, (int)(cnt_pk[k] >> 16));
             if (lane == 0) {
                 atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * k]), (unsigned long long)o);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&sm_cnt[2 * k + 1]), (unsigned long long)i);
