@@ -12,6 +12,14 @@ from .loss_functions import (binary_cross_entropy_list, classification_dice_list
                              focal_list)
 
 
+def return_union_sets_descending_order(ann, exclude_indices=[0]):
+    """train_multiclass.py:32-45 -- the twin ``train()`` calls on every label batch (:110).  It walks
+    ``ann.shape[0]``, i.e. the BATCH dimension of the [N,C,H,W] labels (the class-dim version lives in
+    utils/subsets_union.py); kept as is, in place, as one CUDA pass."""
+    from .subsets_union import _union_inplace
+    return _union_inplace(ann, 0, exclude_indices, False)
+
+
 def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopped=False, *, group=None,
               from_logits=False):
     """train_multiclass.py:253-303: like ``loss_composite.losses_fn`` but WITHOUT the doubling (:274), returning

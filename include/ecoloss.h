@@ -186,6 +186,17 @@ int eco_softce_grad(const EcoView* a, const EcoView* b, int32_t N, int32_t C, in
                     double n_pix_total, const float* upstream, const EcoOut* ga, const EcoOut* gb, int device,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Label union / un-union adjacent to the path, IN PLACE: ess/utils/subsets_union.py:8-32
+ * `return_union_sets_descending_order(ann, exclude_indices=[0], reverse=False)` (along the class dim) and its
+ * batch-dim twin ess/train_multiclass.py:32-45 that train() calls at :110.  The tensor is viewed as
+ * [outer][K][inner] (inner contiguous, element strides stride_outer / stride_k); bit k of exclude_mask = index k is
+ * left alone.  forward: entry k (not excluded, not last) <- sum of entries k..K-1, then everything > 1 is set to 1;
+ * reverse: from the back, entry k <- |entry k - entry k+1|.  K <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int eco_union_sets(void* data, int32_t dtype, int64_t outer, int32_t K, int64_t inner, int64_t stride_outer,
+                   int64_t stride_k, uint64_t exclude_mask, int32_t reverse, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -225,3 +225,52 @@ def eval_stream_dice(batches, threshold=None):
         acc = [0 - (-v) for v in d] if acc is None else [s - (-v) for s, v in zip(acc, d)]
         count += 1
     return torch.tensor([float(v) for v in acc]) / float(count)
+
+
+# ----------------------------------------------------------------------------------------------
+# steps adjacent to the path
+# ----------------------------------------------------------------------------------------------
+def union_sets_descending(ann, exclude_indices=(0,), reverse=False):
+    """ess/utils/subsets_union.py:8-32 -- in place, along the CLASS dim (dim 1) of [N,C,H,W].
+    forward: every non-excluded channel but the last becomes the sum of itself and all later channels, then
+    everything above 1 is clamped to 1; reverse: from the back, channel c becomes |c - (c+1)|."""
+    C = ann.shape[1]
+    if not reverse:
+        for c in range(C - 1):
+            if c in exclude_indices:
+                continue
+            ann[:, c] = torch.sum(ann[:, c:], axis=1)
+        ann[ann > 1] = 1
+    else:
+        for c in range(C - 2, -1, -1):
+            if c in exclude_indices:
+                continue
+            ann[:, c] = torch.abs(ann[:, c] - ann[:, c + 1])
+    return ann
+
+
+def union_sets_descending_batchdim(ann, exclude_indices=(0,)):
+    """ess/train_multiclass.py:32-45 -- the twin that train() really calls (:110): same recipe but along dim 0
+    (the batch dimension of the [N,C,H,W] labels; a bug of the reference that a drop-in has to keep)."""
+    for i in range(ann.shape[0] - 1):
+        if i in exclude_indices:
+            continue
+        ann[i] = sum(x for x in ann[i:])
+    ann[ann > 1] = 1
+    return ann
+
+
+def losses_sequential_densenet(x, g, composite_set_theory=False, background_weight=0, early_stopped=False):
+    """ess/train_multiclass_sequential_densenetloss.py:272-362 ``losses_fn``: per-channel leaves without doubling,
+    plus -- for C>1 -- the extra leaf(a = g_1 - g_2, b = |x_1 - x_2|) added to channel 1 (:285).  The composite
+    branch is unreachable for C>1 and hits an undefined name for C=1."""
+    if g.shape[1] > 1:
+        per_c = [leaf7(g[:, c:c + 1, :, :], x[:, c:c + 1, :, :], 0, False) for c in range(g.shape[1])]
+        extra = leaf7(g[:, 1:2, :, :] - g[:, 2:3, :, :], torch.abs(x[:, 1:2, :, :] - x[:, 2:3, :, :]), 0, False)
+        per_c[1] = [a + b for a, b in zip(extra, per_c[1])]
+        return [sum(col) for col in zip(*per_c)]
+    out = leaf7(x, g, background_weight, False)
+    if composite_set_theory:
+        # :304-320 slice channels 1 and 2 of a 1-channel tensor; the first leaf on them raises inside BCEWithLogits
+        raise ValueError("Target size must be the same as input size")
+    return out

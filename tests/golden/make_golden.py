@@ -129,6 +129,21 @@ def main():
                 [[int((out[:, c].long() * le[:, c].long()).sum()), int(out[:, c].long().sum()), int(le[:, c].long().sum())]
                  for c in range(3)], dtype=np.int64)
 
+    # ---- adjacent steps: label union / un-union, sequential-variant losses_fn ---------------------------------
+    union_cls, union_bat, seq = ref_loader.load_adjacent()
+    torch.manual_seed(31)
+    ann = (torch.rand(5, 4, 6, 6) > 0.6).float()
+    prob = torch.rand(5, 4, 6, 6)
+    small["union_ann"], small["union_prob"] = ann.numpy(), prob.numpy()
+    for tag, ex in (("e0", [0]), ("e02", [0, 2]), ("none", [])):
+        small[f"union_cls_fwd_{tag}"] = union_cls(ann.clone(), ex).numpy()
+        small[f"union_cls_rev_{tag}"] = union_cls(prob.clone(), ex, reverse=True).numpy()
+        small[f"union_bat_fwd_{tag}"] = union_bat(ann.clone(), ex).numpy()
+    l, gr = run_losses(seq, p, g_nested, UP_ALL)
+    small["seq_losses"], small["seq_grad"] = np.array(l), gr.numpy()
+    l, gr = run_losses(seq, p[:, :1], g_iid[:, :1], UP_ALL, False, 0.5)
+    small["seq_c1_losses"], small["seq_c1_grad"] = np.array(l), gr.numpy()
+
     # ---- SURVEY.md 8(c) known-answer values (seed 0, 4x3x64x64) -----------------------------------------
     torch.manual_seed(0)
     pk = torch.sigmoid(torch.randn(4, 3, 64, 64))

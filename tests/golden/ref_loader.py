@@ -59,3 +59,29 @@ def load():
         ns[k] = getattr(lf, k)
     exec(compile(ast.Module(body=[fn_node], type_ignores=[]), "train_multiclass.py[losses_fn]", "exec"), ns)
     return lf, lc, ns["losses_fn"]
+
+
+def load_adjacent():
+    """Functions next to the path, pulled out of their files by AST because importing
+    those modules drags in datasets: (class-dim union from utils/subsets_union.py:8-32, batch-dim twin from
+    train_multiclass.py:32-45, losses_fn of train_multiclass_sequential_densenetloss.py:272-362)."""
+    import numpy as np
+    import torch
+    lf, lc, tm = load()
+
+    def extract(rel, name, ns):
+        path = os.path.join(PKG_DIR, rel)
+        tree = ast.parse(open(path).read())
+        node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+        exec(compile(ast.Module(body=[node], type_ignores=[]), rel + "[" + name + "]", "exec"), ns)
+        return ns[name]
+
+    base = {"np": np, "torch": torch}
+    union_cls = extract(os.path.join("utils", "subsets_union.py"), "return_union_sets_descending_order", dict(base))
+    union_bat = extract("train_multiclass.py", "return_union_sets_descending_order", dict(base))
+    ns = dict(base)
+    for k in ("cross_entropy_loss", "focal_loss", "classification_dice_loss", "cross_entropy_list",
+              "binary_cross_entropy_list", "focal_list", "classification_dice_list", "dice_loss"):
+        ns[k] = getattr(lf, k)
+    seq = extract("train_multiclass_sequential_densenetloss.py", "losses_fn", ns)
+    return union_cls, union_bat, seq

@@ -202,3 +202,39 @@ def test_cfg3_scoring_counts_and_properties():
         assert torch.equal(halves[0] + halves[1], counts)
     if same_bits:
         assert_losses_close(tmc.score_batch(zc, gc).cpu().numpy(), c["dice_None"], what="cfg3 soft dice")
+
+
+def test_label_union_and_unun_vs_reference_outputs():
+    """utils/subsets_union.py:8-32 (class dim, forward + reverse) and train_multiclass.py:32-45 (batch-dim twin)."""
+    from ecologysemanticsegmentation_b200 import subsets_union as su, train_multiclass as tm
+    for tag, ex in (("e0", [0]), ("e02", [0, 2]), ("none", [])):
+        a = _c("union_ann")
+        out = su.return_union_sets_descending_order(a, ex)
+        assert out.data_ptr() == a.data_ptr(), "must work in place like the reference"
+        assert np.array_equal(a.cpu().numpy(), G[f"union_cls_fwd_{tag}"])
+        pr = _c("union_prob")
+        su.return_union_sets_descending_order(pr, ex, reverse=True)
+        np.testing.assert_allclose(pr.cpu().numpy(), G[f"union_cls_rev_{tag}"], rtol=1e-6)
+        b = _c("union_ann")
+        tm.return_union_sets_descending_order(b, ex)
+        assert np.array_equal(b.cpu().numpy(), G[f"union_bat_fwd_{tag}"])
+    # full-size property: forward union then reverse un-union gives back nested binary labels
+    from ecologysemanticsegmentation_b200.synthetic import make_config
+    _, g = make_config("cfg2")
+    parts = torch.stack([g[:, 0], g[:, 1] - g[:, 2], g[:, 2]], 1).contiguous().cuda()   # disjoint ventral / dorsal
+    u = su.return_union_sets_descending_order(parts.clone())
+    assert torch.equal(u, g.cuda())
+    back = su.return_union_sets_descending_order(u.clone(), reverse=True)
+    assert torch.equal(back[:, 1:], parts[:, 1:])
+
+
+def test_sequential_variant_losses_fn_vs_reference_outputs():
+    from ecologysemanticsegmentation_b200 import train_multiclass_sequential_densenetloss as seq
+    l, gr = _run(seq.losses_fn, _c("p"), _c("g_nested"), UP_ALL)
+    assert_losses_close(l, G["seq_losses"], what="sequential C=3")
+    assert_grad_close(gr.cpu(), G["seq_grad"], what="sequential C=3")
+    l, gr = _run(seq.losses_fn, _c("p")[:, :1], _c("g_iid")[:, :1], UP_ALL, False, 0.5)
+    assert_losses_close(l, G["seq_c1_losses"], what="sequential C=1")
+    assert_grad_close(gr.cpu(), G["seq_c1_grad"], what="sequential C=1")
+    with pytest.raises(ValueError):
+        seq.losses_fn(_c("p")[:, :1], _c("g_iid")[:, :1], True)

@@ -131,3 +131,19 @@ def test_survey_known_answers():
     # the survey's printed values
     np.testing.assert_allclose(kat["lc_c1"], [0, 1.51038, 16.11810, -3.28321, -1.64160, -3.65241, 1.33557], rtol=1e-5)
     np.testing.assert_allclose(kat["lc_c3_composite"], [0, 111.96028, 462.16394, -222.08194, -111.04097, -215.71408, 201.62666], rtol=1e-5)
+
+
+def test_adjacent_steps_against_golden():
+    """Label union / un-union (utils/subsets_union.py:8-32, train_multiclass.py:32-45) and the sequential-variant
+    losses_fn (train_multiclass_sequential_densenetloss.py:272-362)."""
+    from oracle import torch_port as tp
+    ann, prob = _t("union_ann"), _t("union_prob")
+    for tag, ex in (("e0", [0]), ("e02", [0, 2]), ("none", [])):
+        assert np.array_equal(tp.union_sets_descending(ann.clone(), ex).numpy(), G[f"union_cls_fwd_{tag}"])
+        np.testing.assert_allclose(tp.union_sets_descending(prob.clone(), ex, True).numpy(), G[f"union_cls_rev_{tag}"], rtol=1e-6)
+        assert np.array_equal(tp.union_sets_descending_batchdim(ann.clone(), ex).numpy(), G[f"union_bat_fwd_{tag}"])
+    l, gr = _run(tp.losses_sequential_densenet, _t("p"), _t("g_nested"), UP_ALL)
+    np.testing.assert_allclose(l, G["seq_losses"], rtol=RT)
+    np.testing.assert_allclose(gr, G["seq_grad"], rtol=1e-4, atol=1e-9)
+    l, gr = _run(tp.losses_sequential_densenet, _t("p")[:, :1], _t("g_iid")[:, :1], UP_ALL, False, 0.5)
+    np.testing.assert_allclose(l, G["seq_c1_losses"], rtol=RT)

@@ -93,3 +93,24 @@ def test_eval_matches_reference_lines(ref):
         want = [float(-lf.dice_loss(out[:, c:c + 1], lab[:, c:c + 1], background_weight=0)) for c in range(3)]
         got = [float(v) for v in tp.eval_batch_dice(z, lab, thr)]
         assert want == got
+
+
+def test_adjacent_steps_bit_identical(ref):
+    from oracle import torch_port as tp
+    union_cls, union_bat, seq = ref_loader.load_adjacent()
+    torch.manual_seed(4)
+    ann = (torch.rand(4, 5, 6, 6) > 0.6).float()
+    prob = torch.rand(4, 5, 6, 6)
+    for ex in ([0], [0, 3], []):
+        assert torch.equal(union_cls(ann.clone(), ex), tp.union_sets_descending(ann.clone(), ex))
+        assert torch.equal(union_cls(prob.clone(), ex, reverse=True), tp.union_sets_descending(prob.clone(), ex, True))
+        assert torch.equal(union_bat(ann.clone(), ex), tp.union_sets_descending_batchdim(ann.clone(), ex))
+    z = torch.randn(3, 3, 8, 8)
+    u = torch.rand(3, 1, 8, 8)
+    g = torch.cat([u < 0.6, u < 0.4, u < 0.2], 1).float()   # nested, so g_1 - g_2 stays in {0, 1}
+    a, b = _run(seq, z, g), _run(tp.losses_sequential_densenet, z, g)
+    assert a[0] == b[0] and torch.equal(a[1], b[1])
+    with pytest.raises(ValueError):
+        seq(torch.rand(2, 1, 4, 4), torch.rand(2, 1, 4, 4), True)
+    with pytest.raises(ValueError):
+        tp.losses_sequential_densenet(torch.rand(2, 1, 4, 4), torch.rand(2, 1, 4, 4), True)
