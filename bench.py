@@ -41,6 +41,7 @@ def parse():
                     help="N>1: all-reduce of the sums inside the fused kernel over peer memory, or NCCL between kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     return ap.parse_args()
 
 
@@ -183,6 +184,41 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def measure_aux(dev):
+    """Other kernels of the path on BASELINE.json's other single-GPU configs, for context next to the headline:
+    cfg3 = per-class thresholded Dice scoring at 54x3x1024x1024 (8 B/element), cfg1 = single-class leaf fwd+bwd.
+    Inputs are larger than L2 (cfg3: 1.36 GB) or rotated (cfg1)."""
+    import torch
+    from ecologysemanticsegmentation_b200 import ops
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(iters):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / iters * 1e-3
+
+    n, c, s = 54, 3, 1024
+    z, g = make_inputs(n, c, s, 103)
+    z, g = z.to(dev), g.to(dev)
+    for label, thr in (("soft", None), ("threshold_0.8", torch.tensor([0.8], dtype=torch.float32, device=dev))):
+        t = timed(lambda: ops.dice_counts(z, g, thr), 20)
+        gbs = 8.0 * n * c * s * s / t / 1e9
+        out["dice_eval_cfg3_" + label] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
+                                          "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 8}
+    del z, g
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -287,6 +323,11 @@ def main():
                "h2d_bytes_per_step": 2 * elems_per_gpu * 4 * world, "d2h_bytes_per_step": 7 * 4 * world,
                "ms_per_step": e_ms, "steps": e_steps}
 
+    # ---- auxiliary line items (not the headline): the Dice-scoring kernel and the un-fused leaf path ----------
+    aux = None
+    if world == 1 and not args.no_aux:
+        aux = measure_aux(dev)
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -325,6 +366,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps * world,
             "losses": [float(v) for v in losses.cpu()],
+            "aux": aux,
         }
         print(json.dumps(line))
     if world > 1:

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libecoloss.so")
 
-ECO_F32, ECO_BF16 = 0, 1
+ECO_F32, ECO_BF16, ECO_U8 = 0, 1, 2
 NSTAT, NLOSS, NJAC = 8, 7, 7
 C3_NLEAF, C3_NACC = 21, 100
 FLAG_A_LOGIT, FLAG_B_LOGIT, FLAG_NEED_BG = 1, 2, 4
@@ -95,11 +95,13 @@ def check(rc: int, what: str):
         raise EcoLossError(f"{what} failed (rc={rc}): {msg}")
 
 
-def dtype_code(t: torch.Tensor) -> int:
+def dtype_code(t: torch.Tensor, allow_u8: bool = False) -> int:
     if t.dtype == torch.float32:
         return ECO_F32
     if t.dtype == torch.bfloat16:
         return ECO_BF16
+    if allow_u8 and t.dtype == torch.uint8:
+        return ECO_U8
     raise EcoLossError(f"unsupported dtype {t.dtype}: the kernels take float32 or bfloat16")
 
 
@@ -130,8 +132,8 @@ def planes(t: torch.Tensor):
     return t, (st[0] if n > 1 else c * h * w), (st[1] if c > 1 else h * w)
 
 
-def view_of(t: torch.Tensor, sn: int, sc: int) -> EcoView:
-    return EcoView(t.data_ptr(), sn, sc, dtype_code(t), 0)
+def view_of(t: torch.Tensor, sn: int, sc: int, allow_u8: bool = False) -> EcoView:
+    return EcoView(t.data_ptr(), sn, sc, dtype_code(t, allow_u8), 0)
 
 
 def out_of(t, sn: int = 0, sc: int = 0) -> EcoOut:

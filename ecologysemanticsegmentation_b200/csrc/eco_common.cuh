@@ -103,6 +103,19 @@ struct Vec4<__nv_bfloat16> {
     static __device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// uint8 masks (labels stored as bytes: 1 B instead of 4 B per element)
+template <>
+struct Vec4<uint8_t> {
+    static __device__ __forceinline__ void load(const uint8_t* p, float (&v)[4]) {
+        uint32_t r;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+        // byte k -> float without I2F: 0x4b000000 | byte is 8388608 + byte exactly
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __uint_as_float(0x4b000000u | ((r >> (8 * k)) & 0xffu)) - 8388608.0f;
+    }
+    static __device__ __forceinline__ float load1(const uint8_t* p) { return (float)__ldg(p); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // per-element math
 // ---------------------------------------------------------------------------------------------

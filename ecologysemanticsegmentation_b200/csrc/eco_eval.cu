@@ -230,7 +230,7 @@ __global__ void dice_finalize_kernel(const long long* __restrict__ counts, const
 }
 
 static bool ev_aligned(const EcoView* v, int64_t HW) {
-    const int64_t esz = v->dtype == ECO_BF16 ? 2 : 4;
+    const int64_t esz = v->dtype == ECO_BF16 ? 2 : (v->dtype == ECO_U8 ? 1 : 4);
     return (reinterpret_cast<uintptr_t>(v->ptr) % (4 * esz) == 0) && (v->sn % 4 == 0) && (v->sc % 4 == 0) && (HW % 4 == 0);
 }
 
@@ -238,7 +238,10 @@ template <int NT>
 static void launch_nt(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cudaStream_t st, const float* thr,
                       unsigned int* counters, long long* partials, long long* counts_out, double* soft_out) {
 #define ECO_EV(TZ, TL, V) dice_counts_kernel<TZ, TL, V, NT><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out)
-    if (vec == 4) {
+    if (ld == ECO_U8) {
+        if (vec == 4) { if (zd == ECO_F32) ECO_EV(float, uint8_t, 4); else ECO_EV(__nv_bfloat16, uint8_t, 4); }
+        else { if (zd == ECO_F32) ECO_EV(float, uint8_t, 1); else ECO_EV(__nv_bfloat16, uint8_t, 1); }
+    } else if (vec == 4) {
         if (zd == ECO_F32 && ld == ECO_F32) ECO_EV(float, float, 4);
         else if (zd == ECO_BF16 && ld == ECO_F32) ECO_EV(__nv_bfloat16, float, 4);
         else if (zd == ECO_F32 && ld == ECO_BF16) ECO_EV(float, __nv_bfloat16, 4);
@@ -272,6 +275,11 @@ extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int
     if (C > 65535) { set_error("C too large"); return -3; }
     if (n_thr < 0 || n_thr > 20) { set_error("n_thr must be in [0,20] per call (got %d)", n_thr); return -4; }
     if (n_thr > 0 && !thresholds) { set_error("null thresholds"); return -4; }
+    if ((logits->dtype != ECO_F32 && logits->dtype != ECO_BF16) ||
+        (labels->dtype != ECO_F32 && labels->dtype != ECO_BF16 && labels->dtype != ECO_U8)) {
+        set_error("dice_counts: logits must be f32/bf16, labels f32/bf16/u8");
+        return -4;
+    }
     if (!ws || ws_bytes < eco_dice_ws_bytes(C, n_thr) || !counts_out || !soft_out) { set_error("workspace too small or null output"); return -5; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }

@@ -125,6 +125,8 @@ def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False):
     nat.require_cuda(logits, labels)
     if logits.shape != labels.shape or logits.dim() != 4:
         raise ValueError("dice_counts expects two [N,C,H,W] tensors of equal shape")
+    if labels.dtype == torch.bool:
+        labels = labels.view(torch.uint8)   # byte masks: 5 B/element instead of 8
     logits, z_sn, z_sc = nat.planes(logits)
     labels, l_sn, l_sc = nat.planes(labels)
     n, c, h, w = logits.shape
@@ -139,7 +141,7 @@ def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False):
     ws = nat.workspace("dice%d" % nthr, L.eco_dice_ws_bytes(c, nthr), logits.device)
     counts = torch.zeros((max(nthr, 1), c, 3), dtype=torch.int64, device=logits.device)
     soft = torch.empty((c, 3), dtype=torch.float64, device=logits.device)
-    vz, vl = nat.view_of(logits, z_sn, z_sc), nat.view_of(labels, l_sn, l_sc)
+    vz, vl = nat.view_of(logits, z_sn, z_sc), nat.view_of(labels, l_sn, l_sc, allow_u8=True)
     rc = L.eco_dice_counts(C.byref(vz), C.byref(vl), n, c, h * w, thresholds.data_ptr() if nthr else None, nthr,
                            int(inputs_are_probs), ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),
                            _dev(logits), nat.current_stream_ptr(logits.device))

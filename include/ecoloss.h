@@ -18,7 +18,8 @@
  *   - tensors are NCHW; a "plane" is the H*W contiguous elements of one (n, c).  A tensor is
  *     described by its base pointer and two element strides: `sn` between images and `sc`
  *     between channels, so `x[:, c:c+1]` slices of a contiguous tensor need no copy;
- *   - dtype codes: ECO_F32 = 0, ECO_BF16 = 1 (logits / probabilities / labels / gradients);
+ *   - dtype codes: ECO_F32 = 0, ECO_BF16 = 1 (logits / probabilities / labels / gradients), ECO_U8 = 2 (byte
+ *     masks, accepted for the labels of eco_dice_counts);
  *   - "slots": `a` is the reference's FIRST positional argument ("gt"), `b` the SECOND ("pred").
  *     Which one is really the label depends on the caller.
  *
@@ -39,6 +40,7 @@ extern "C" {
 
 #define ECO_F32 0
 #define ECO_BF16 1
+#define ECO_U8 2 /* labels only, eco_dice_counts: masks stored as bytes */
 
 #define ECO_NSTAT 8
 #define ECO_NLOSS 7

@@ -205,3 +205,19 @@ def test_stats_are_additive_over_batch_shards_full_size():
     g_full = ops.composite3_grad(z, g, True, jac_full, up)
     g_b = ops.composite3_grad(z[27:], g[27:], True, jac_sum, up)
     assert_grad_close(g_b.cpu(), g_full[27:].cpu(), tol=1e-6, what="shard gradient from global sums")
+
+
+def test_scoring_accepts_byte_and_bool_masks():
+    """uint8 / bool masks: same counts and Dice as the float32 masks of the reference."""
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    torch.manual_seed(21)
+    z = (torch.randn(3, 3, 64, 64) * 2).cuda()
+    lab = (torch.rand(3, 3, 64, 64) > 0.55).cuda()
+    d_f, c_f, s_f = tmc.score_batch(z, lab.float(), 0.8, return_counts=True)
+    for masks in (lab, lab.to(torch.uint8)):
+        d, c, s = tmc.score_batch(z, masks, 0.8, return_counts=True)
+        assert torch.equal(c, c_f) and torch.equal(d, d_f)
+        assert torch.allclose(s, s_f, rtol=1e-12)
+    # odd plane size -> scalar path
+    z2, l2 = z[:, :, :7, :9].contiguous(), lab[:, :, :7, :9].contiguous()
+    assert torch.equal(tmc.score_batch(z2, l2, 0.8, return_counts=True)[1], tmc.score_batch(z2, l2.float(), 0.8, return_counts=True)[1])
