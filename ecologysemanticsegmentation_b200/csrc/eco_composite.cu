@@ -543,7 +543,7 @@ composite3_stats_packed_kernel(CompArgs a, unsigned int* __restrict__ counter, d
 }
 
 // shared tail of the packed gradient kernels: coefficients -> (packed | scalar focal fallback) gradient pass
-template <typename TX, bool LOGITS>
+template <typename TX, bool LOGITS, int THREADS>
 __device__ __forceinline__ void grad_dispatch_packed(const CompGradArgs& ga, LeafCoef* cf, PCoef& pc, char* stage_smem,
                                                      const float* __restrict__ upstream, bool reverse) {
     const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
@@ -551,23 +551,24 @@ __device__ __forceinline__ void grad_dispatch_packed(const CompGradArgs& ga, Lea
     __syncthreads();
     // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
     if (need_fl) {
-        if (need_sig) grad_phase_packed<TX, LOGITS, true, true>(ga, pc, stage_smem, reverse);
-        else grad_phase_packed<TX, LOGITS, false, true>(ga, pc, stage_smem, reverse);
+        if (need_sig) grad_phase_packed<TX, LOGITS, true, true, THREADS>(ga, pc, stage_smem, reverse);
+        else grad_phase_packed<TX, LOGITS, false, true, THREADS>(ga, pc, stage_smem, reverse);
     } else {
-        if (need_sig) grad_phase_packed<TX, LOGITS, true, false>(ga, pc, stage_smem, reverse);
-        else grad_phase_packed<TX, LOGITS, false, false>(ga, pc, stage_smem, reverse);
+        if (need_sig) grad_phase_packed<TX, LOGITS, true, false, THREADS>(ga, pc, stage_smem, reverse);
+        else grad_phase_packed<TX, LOGITS, false, false, THREADS>(ga, pc, stage_smem, reverse);
     }
 }
 
+constexpr int kGThreads = 256;   // stand-alone pass 2: fewer, fatter threads (255 registers, no spills)
 template <typename TX, bool LOGITS>
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kGThreads, 1)
 composite3_grad_packed_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
     extern __shared__ __align__(16) char stage_smem[];
     __shared__ LeafCoef cf[ECO_C3_NLEAF];
     __shared__ PCoef pc;
     if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
     __syncthreads();
-    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, stage_smem, upstream, false);
+    grad_dispatch_packed<TX, LOGITS, kGThreads>(ga, cf, pc, stage_smem, upstream, false);
 }
 
 template <typename TX, bool LOGITS>
@@ -599,7 +600,7 @@ composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale
         losses_out[threadIdx.x - 32] = (float)v;
     }
     __syncthreads();
-    grad_dispatch_packed<TX, LOGITS>(ga, cf, pc, stage_smem, upstream, true);
+    grad_dispatch_packed<TX, LOGITS, kPThreads>(ga, cf, pc, stage_smem, upstream, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -733,13 +734,13 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     CompGradArgs ga{};
     fill_comp(ga.a, x, g, N, HW, vec);
     ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
-    const int grid = comp_grid(device, ga.a.units_total, vec == 4 ? 1 : 2, vec == 4 ? kPThreads : kCThreads);
+    const int grid = comp_grid(device, ga.a.units_total, vec == 4 ? 1 : 2, vec == 4 ? kGThreads : kCThreads);
     if (grid < 0) return -10;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (vec == 4) {
         rc = ensure_packed_smem();
         if (rc) return rc;
-        ECO_DISPATCH_PACKED(composite3_grad_packed_kernel, x->dtype, from_logits != 0, <<<grid, kPThreads, kStageBytes, st>>>(ga, jac, upstream));
+        ECO_DISPATCH_PACKED(composite3_grad_packed_kernel, x->dtype, from_logits != 0, <<<grid, kGThreads, kStageBytes, st>>>(ga, jac, upstream));
     }
     else ECO_DISPATCH_SCALAR(composite3_grad_kernel, x->dtype, from_logits != 0, <<<grid, kCThreads, 0, st>>>(ga, jac, upstream));
     return check_cuda(cudaGetLastError(), "composite3_grad kernel launch");

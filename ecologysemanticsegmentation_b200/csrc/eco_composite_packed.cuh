@@ -667,7 +667,7 @@ __device__ __forceinline__ void pixel_pair_grad(const f2 (&x)[3], const f2 (&g)[
     }
 }
 
-template <typename TX, bool LOGITS, bool SIG, bool FL>
+template <typename TX, bool LOGITS, bool SIG, bool FL, int THREADS>
 __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const PCoef& pc, char* stage_smem, bool reverse) {
     const CompArgs& a = ga.a;
     const TX* __restrict__ xb = reinterpret_cast<const TX*>(a.x);
@@ -675,13 +675,13 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
     TX* __restrict__ ob = reinterpret_cast<TX*>(ga.gx);
     const int64_t lo = a.units_total * blockIdx.x / gridDim.x;
     const int64_t hi = a.units_total * (blockIdx.x + 1) / gridDim.x;
-    const int iters = (int)((hi - lo + kPThreads - 1) / kPThreads);
+    const int iters = (int)((hi - lo + THREADS - 1) / THREADS);
     constexpr int kXB = sizeof(TX) * 4;
-    constexpr uint32_t kPlaneStride = kPThreads * 16;
+    constexpr uint32_t kPlaneStride = THREADS * 16;
     const uint32_t my_stage = smem_u32(stage_smem) + threadIdx.x * 16;
     // cursor of the unit being STAGED (one iteration ahead of the one being processed); pass 2 may walk backwards
     UnitCursor w;
-    w.init(lo + (int64_t)(reverse ? (iters - 1) : 0) * kPThreads + threadIdx.x, a);
+    w.init(lo + (int64_t)(reverse ? (iters - 1) : 0) * THREADS + threadIdx.x, a);
 #define ECO_ISSUE2(st)                                                                                     \
     do {                                                                                                   \
         if (w.q >= lo && w.q < hi) {                                                                       \
@@ -697,8 +697,8 @@ __device__ __forceinline__ void grad_phase_packed(const CompGradArgs& ga, const 
         const int64_t q = w.q;            // unit processed in this iteration
         const int64_t xoff = w.xoff;      // = n * x_sn + off * 4; the gradient is written with gx_sn, see below
         const int64_t n = w.n, off4 = w.off * 4;
-        if (reverse) w.retreat(kPThreads);
-        else w.advance(kPThreads);
+        if (reverse) w.retreat(THREADS);
+        else w.advance(THREADS);
         const int st = it & 1;
         if (it + 1 < iters) {
             if (st) ECO_ISSUE2(0);

@@ -221,3 +221,48 @@ def test_scoring_accepts_byte_and_bool_masks():
     # odd plane size -> scalar path
     z2, l2 = z[:, :, :7, :9].contiguous(), lab[:, :, :7, :9].contiguous()
     assert torch.equal(tmc.score_batch(z2, l2, 0.8, return_counts=True)[1], tmc.score_batch(z2, l2.float(), 0.8, return_counts=True)[1])
+
+
+def test_cfg4_sharding_property_on_one_gpu():
+    """BASELINE configs[3]: 432 x 3 x 512 x 512 split into 8 shards of 54.  On one GPU the 8 shards are processed
+    one after the other: the shard sums add up to the full-batch sums, and each shard's gradient from the global sums
+    equals the matching rows of the single-launch full-batch gradient (the multi-process version of this, over NCCL /
+    peer memory, is tests/test_gpu_distributed.py)."""
+    from ecologysemanticsegmentation_b200 import fused, ops
+    from ecologysemanticsegmentation_b200.distributed import shard_bounds
+    from ecologysemanticsegmentation_b200.synthetic import make_config
+    free, _ = torch.cuda.mem_get_info()
+    if free < 8e9:
+        pytest.skip("needs ~6 GB of device memory")
+    z, g = make_config("cfg4")
+    z, g = z.cuda(), g.cuda()
+    np.random.seed(0)
+    step = fused.CompositeLossStep(UP)
+    losses_full, dz_full = step(z, g)
+    acc = None
+    for r in range(8):
+        lo, hi = shard_bounds(432, 8, r)
+        a = ops.composite3_stats(z[lo:hi], g[lo:hi], True)
+        acc = a if acc is None else acc + a
+    losses, jac, _ = ops.composite3_finalize(acc, step.scales)
+    assert_losses_close(losses.cpu().numpy(), losses_full.cpu().numpy(), tol=1e-6, what="cfg4 sharded sums")
+    for r in (0, 3, 7):
+        lo, hi = shard_bounds(432, 8, r)
+        dz = ops.composite3_grad(z[lo:hi], g[lo:hi], True, jac, step.upstream)
+        assert_grad_close(dz.cpu(), dz_full[lo:hi].cpu(), tol=1e-6, what=f"cfg4 shard {r}")
+
+
+def test_cfg5_frame_stream_scoring():
+    """BASELINE configs[4]: a stream of 64 x 3 x 512 x 512 batches, sigmoid -> threshold -> per-class Dice per batch,
+    mean over batches (test_multiclass.py:104), against the reference ops on the same device."""
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    from oracle import torch_port as tp
+    batches = []
+    for k in range(4):
+        z, g = make_inputs(64, 3, 512, 105 + k)
+        batches.append((z.cuda(), g.cuda()))
+    for thr in (None, 0.8):
+        ours = tmc.score_stream(batches, thr)
+        ref = tp.eval_stream_dice(batches, thr)
+        assert_losses_close(ours.cpu().numpy(), ref.numpy(), what=f"cfg5 stream thr={thr}")
