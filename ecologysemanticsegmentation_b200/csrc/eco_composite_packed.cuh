@@ -429,6 +429,7 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
     const int iters = (int)((hi - lo + kRoleThreads - 1) / kRoleThreads);
     if (w.q < hi) ECO_ISSUE(0);
     cp_async_commit();
+
     for (int it = 0; it < iters; ++it) {
         const bool active = w.q < hi;
         w.advance(kRoleThreads);
