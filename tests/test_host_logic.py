@@ -132,3 +132,16 @@ def test_synthetic_configs_are_nested_and_seeded():
     assert set(g1.unique().tolist()) <= {0.0, 1.0}
     assert bool((g1[:, 0] >= g1[:, 1]).all()) and bool((g1[:, 1] >= g1[:, 2]).all())
     assert CONFIGS["cfg2"][1:] == (54, 3, 256) and CONFIGS["cfg3"][1:] == (54, 3, 1024)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may import, call or execute it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ecologysemanticsegmentation_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+                assert "torch_port" not in src and "closed_form" not in src, f
