@@ -530,6 +530,7 @@ __device__ __noinline__ void label_corrections_role(float gi, float gj, int role
 }  // namespace eco
 
 #include "eco_composite_packed.cuh"
+#include "eco_composite_v2.cuh"
 
 namespace eco {
 
@@ -649,6 +650,8 @@ static int ensure_packed_smem() {
     ECO_SMEM_ALL(float)
     ECO_SMEM_ALL(__nv_bfloat16)
 #undef ECO_SMEM_ALL
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, fused v2)");
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
     if (!rc) done_for_device[dev] = 1;
     return rc;
 }
@@ -664,11 +667,27 @@ static int comp_grid(int device, int64_t units, int ctas_per_sm, int threads_per
     return (int)g;
 }
 
+// second-generation kernels: fp32 logits, 16-byte aligned planes, sums inside the fixed-point range of V2Ws
+static bool v2_eligible(const EcoView* x, int32_t from_logits, int vec, int32_t N, int64_t HW) {
+    return vec == 4 && from_logits != 0 && x->dtype == ECO_F32 && (int64_t)N * HW <= ((int64_t)1 << 31);
+}
+static int v2_grid(int device, int32_t N, int64_t HW) {
+    const int sms = sm_count_cached(device);
+    if (sms <= 0) return -1;
+    const int64_t tiles = (int64_t)N * ((HW + v2::kTP - 1) / v2::kTP);
+    int64_t g = sms;   // one CTA per SM: co-resident, the grid-wide hand-over spins
+    if (g > tiles) g = tiles;
+    if (g > v2::kMaxGrid) g = v2::kMaxGrid;
+    return (int)(g < 1 ? 1 : g);
+}
+
 }  // namespace eco
 
 using namespace eco;
 
-extern "C" int64_t eco_composite3_ws_bytes(void) { return 256 + 128 * 8 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double); }
+// workspace: [0,256) arrival counters / status | 128 doubles of totals | per-CTA partials | v2 integer accumulators
+static constexpr int64_t kWsV2Offset = 256 + 128 * 8 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double);
+extern "C" int64_t eco_composite3_ws_bytes(void) { return kWsV2Offset + (int64_t)sizeof(v2::V2Ws); }
 
 // scalar kernels serve the unaligned / ragged path (VEC == 1); the aligned path runs the packed kernels
 #define ECO_DISPATCH_SCALAR(KERNEL, xdt, logits, ...)                                            \
@@ -737,6 +756,14 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     const int grid = comp_grid(device, ga.a.units_total, vec == 4 ? 1 : 2, vec == 4 ? kGThreads : kCThreads);
     if (grid < 0) return -10;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (v2_eligible(x, from_logits, vec, N, HW)) {
+        rc = ensure_packed_smem();
+        if (rc) return rc;
+        const int g2 = v2_grid(device, N, HW);
+        if (g2 < 0) return -10;
+        v2::composite3_grad_v2_kernel<<<g2, v2::kThreads, v2::kSmemBytes, st>>>(ga, jac, upstream);
+        return check_cuda(cudaGetLastError(), "composite3_grad_v2_kernel launch");
+    }
     if (vec == 4) {
         rc = ensure_packed_smem();
         if (rc) return rc;
@@ -770,6 +797,17 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
     xch.status = counter + 32;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool lg = from_logits != 0;
+    if (v2_eligible(x, from_logits, vec, N, HW)) {
+        rc = ensure_packed_smem();
+        if (rc) return rc;
+        const int g2 = v2_grid(device, N, HW);
+        if (g2 < 0) return -10;
+        v2::V2Ws* ws2 = reinterpret_cast<v2::V2Ws*>(reinterpret_cast<char*>(ws) + kWsV2Offset);
+        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws2, &acc_glob, &losses_out, &xch};
+        return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v2_kernel, dim3(g2), dim3(v2::kThreads), args,
+                                                      v2::kSmemBytes, st),
+                          "composite3_fused_v2_kernel launch");
+    }
     if (vec == 4) {
         rc = ensure_packed_smem();
         if (rc) return rc;
@@ -814,7 +852,7 @@ extern "C" int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, 
 // ---- peer exchange buffers (CUDA IPC).  The one place the library allocates: IPC needs a cudaMalloc base pointer. ----
 extern "C" int64_t eco_xch_bytes(int32_t world) {
     if (world < 1 || world > 64) return -1;
-    return (int64_t)xch_flags_offset_doubles(world) * 8 + 256;
+    return (int64_t)xch_flags_offset_doubles(world) * 8 + 512;  // two flag arrays of 64 u32
 }
 
 extern "C" int eco_xch_alloc(int32_t world, void** ptr_out, unsigned char* handle_out /*[64]*/, int device) {

@@ -1,0 +1,826 @@
+// Second-generation 3-organ composite kernels (fp32, from-logits, 16-byte aligned planes).
+// Included by eco_composite.cu after eco_composite_packed.cuh.
+//
+// Design notes (all numbers measured on B200; profiles/microbench/regbw2.cu, profiles/README.md):
+//   * An SM sub-partition issues one warp instruction per clock and an instruction holds the issue path for
+//     max(1, its register-file read cycles): FFMA2/FMUL2/FADD2 take 2 cycles with <= 2 distinct vector-register
+//     operands (immediates, ".F32" scalar pairs and reuse-cache hits are free) and 3 cycles with 3; MUFU, ALU, LDS
+//     and branches take one cycle each and do NOT overlap with FMA issue.  The kernel's time is therefore the SUM of
+//     those cycles, and the loops below are written to minimise it rather than to "balance pipes":
+//     universal polynomial constants are immediates, per-leaf coefficients are scalars, the chain rule is factored
+//     through the intermediates d = |x_i - x_j| and q = x_i d (17 instead of 32 FMA-class instructions per pair).
+//   * Pass 1 is SCALAR and not role-split: one thread owns all 59 sums of its pixels, so each sigmoid is computed
+//     once (the role-split packed kernel computes it twice) and the float2 packing, which buys no issue cycles,
+//     is dropped where it would cost 2x the accumulator registers.
+//   * BCE and focal are LINEAR in their per-pixel sums, so those sums do not feed the gradient coefficients: they
+//     are accumulated in pass 2, where the union operands u_k and their squares are formed anyway, as two scalars
+//     already weighted by the leaf scales.  Pass 1 is left with 6 MUFU and ~100 FMA-class instructions per pixel
+//     and runs close to the HBM roofline of its 8 B/element.
+//   * Both passes read their input through a ring of shared-memory stages filled by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp; 16 consumer warps (4 per
+//     sub-partition, 120 registers) do nothing but math.  Pass 2 walks the CTA's tiles backwards so that it starts
+//     on the lines pass 1 left in L2.
+//   * Tied pixels (|x_i - x_j| < 4e-6, ~2e-5 of all pixels) are recomputed in pass 2 by a scalar slow path with
+//     ATen's exact sigmoid bits and sign(0) = 0; the sign of the |.| kink is otherwise one LOP3 per lane.
+#pragma once
+
+namespace eco {
+namespace v2 {
+
+#ifdef ECO_V2_TIMELINE
+__device__ unsigned long long g_timeline[1024 * 16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ECO_TL(slot) do { if (threadIdx.x == 0) g_timeline[blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+#else
+#define ECO_TL(slot) do { } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ f2 lds_f2(uint32_t a) {
+    f2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void stg_stream_f2(float* p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile pipeline.  A tile = kTP consecutive pixels of one image x 6 planes (x0 x1 x2 g0 g1 g2); it never straddles
+// two images and the last tile of a plane may be short.  One consumer thread owns one pixel PAIR of a tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCWarps = 16;                       // consumer warps (4 per SM sub-partition)
+constexpr int kCThreads = kCWarps * 32;           // 512
+constexpr int kThreads = kCThreads + 32;          // + the producer warp
+constexpr int kTP = kCThreads * 2;                // pixels per tile
+#ifndef ECO_V2_STAGES
+#define ECO_V2_STAGES 5
+#endif
+constexpr int kStages = ECO_V2_STAGES;
+constexpr int kStageBytes = 6 * kTP * 4;          // 24 KB
+constexpr int kSmemBytes = kStages * kStageBytes; // 120 KB of dynamic shared memory
+
+// barrier over the consumer warps only (the producer warp runs free after the prologue)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(kCThreads) : "memory"); }
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct TileRange {
+    int tpp;         // tiles per plane
+    int t_lo, t_hi;  // this CTA's tiles (global tile index = n * tpp + k)
+};
+__device__ __forceinline__ TileRange tile_range(const CompArgs& a) {
+    TileRange r;
+    r.tpp = (int)((a.HW + kTP - 1) / kTP);
+    const int64_t total = (int64_t)a.N * r.tpp;
+    r.t_lo = (int)(total * blockIdx.x / gridDim.x);
+    r.t_hi = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    return r;
+}
+
+struct PipeSmem {
+    unsigned long long full[kStages];
+    unsigned long long empty[kStages];
+};
+
+__device__ __forceinline__ void pipe_init(PipeSmem& ps) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&ps.full[s]), 1);
+            mbar_init(smem_u32(&ps.empty[s]), kCWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// producer: ONE lane of the producer warp.  `k0` = tiles this CTA has pushed through the ring before this call
+// (the mbarrier phases run on across the two passes of the fused kernel).
+__device__ __forceinline__ void produce_tiles(const CompArgs& a, const TileRange& tr, bool reverse, uint32_t stage_base,
+                                              PipeSmem& ps, int k0) {
+    const float* xb = reinterpret_cast<const float*>(a.x);
+    const float* gb = reinterpret_cast<const float*>(a.g);
+    const int ntiles = tr.t_hi - tr.t_lo;
+    if (ntiles <= 0) return;
+    int t = reverse ? tr.t_hi - 1 : tr.t_lo;
+    int n = t / tr.tpp, kk = t - n * tr.tpp;
+    for (int k = 0; k < ntiles; ++k) {
+        const int kg = k0 + k;
+        const int s = kg % kStages;
+        const uint32_t full = smem_u32(&ps.full[s]), empty = smem_u32(&ps.empty[s]);
+        if (kg >= kStages) mbar_wait(empty, ((kg / kStages) - 1) & 1);
+        const int64_t p0 = (int64_t)kk * kTP;
+        const int valid = (int)((a.HW - p0 < kTP) ? (a.HW - p0) : kTP);
+        const uint32_t bytes = (uint32_t)valid * 4u;
+        mbar_expect_tx(full, 6u * bytes);
+        const uint32_t dst = stage_base + (uint32_t)s * kStageBytes;
+        const float* xs = xb + n * a.x_sn + p0;
+        const float* gs = gb + n * a.g_sn + p0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            bulk_g2s(dst + (uint32_t)c * (kTP * 4), xs + c * a.x_sc, bytes, full);
+            bulk_g2s(dst + (uint32_t)(3 + c) * (kTP * 4), gs + c * a.g_sc, bytes, full);
+        }
+        if (reverse) { if (--kk < 0) { kk = tr.tpp - 1; --n; } }
+        else { if (++kk == tr.tpp) { kk = 0; ++n; } }
+    }
+}
+
+// consumer side of one tile: wait, copy this thread's pixel pair of all six planes to registers, release the stage
+__device__ __forceinline__ void consume_tile(uint32_t my_base, PipeSmem& ps, int kg, int lane, f2 (&z)[3], f2 (&g)[3]) {
+    const int s = kg % kStages;
+    mbar_wait(smem_u32(&ps.full[s]), (kg / kStages) & 1);
+    const uint32_t sb = my_base + (uint32_t)s * kStageBytes;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        z[c] = lds_f2(sb + (uint32_t)c * (kTP * 4));
+        g[c] = lds_f2(sb + (uint32_t)(3 + c) * (kTP * 4));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ps.empty[s]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: scalar, all 59 sums of a pixel in one thread
+// ---------------------------------------------------------------------------------------------
+enum : int {
+    F_G = 0,     // + c           sum g_c
+    F_GG = 3,    // + c - 1       sum g_c^2, c = 1, 2 (labels that appear as the b of an intersection leaf)
+    F_X = 5,     // + c
+    F_XX = 8,    // + c
+    F_GX = 11,   // + c
+    F_PAIR = 14, // + 15 p + {0 GD, 1 GDD, 2 DS, 3 M1, 4 M1G, 5 M2, 6 M2G, 7 M3, 8 M3G, 9 UU1, 10 GU1, 11 UU2, 12 GU2, 13 UU3, 14 GU3}
+    F_NACC = 59
+};
+constexpr int kFlushTiles = 16;   // 32 pixels per fp32 accumulator between folds into fp64
+
+struct StatsSmem {
+    double warp_slots[kCWarps][64];
+    double sums[64];
+    double corr[15];
+    bool flag;
+};
+
+__device__ __forceinline__ void stats_pixel(float z0, float z1, float z2, float g0, float g1, float g2, float (&acc)[F_NACC]) {
+    const float x[3] = {sigmoid_fast(z0), sigmoid_fast(z1), sigmoid_fast(z2)};
+    const float g[3] = {g0, g1, g2};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        acc[F_G + c] += g[c];
+        acc[F_X + c] += x[c];
+        acc[F_XX + c] = fmaf(x[c], x[c], acc[F_XX + c]);
+        acc[F_GX + c] = fmaf(g[c], x[c], acc[F_GX + c]);
+    }
+    acc[F_GG + 0] = fmaf(g1, g1, acc[F_GG + 0]);
+    acc[F_GG + 1] = fmaf(g2, g2, acc[F_GG + 1]);
+    const float hh[2] = {fmaf(x[0], -0.5f, 0.5f), fmaf(x[1], -0.5f, 0.5f)};
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int i = pair_i(p), j = pair_j(p);
+        float* pa = &acc[F_PAIR + 15 * p];
+        const float xi = x[i], xj = x[j], gi = g[i], gj = g[j], h = hh[i];
+        const float d = fabsf(xi - xj);
+        const float gd = fabsf(gi - gj);
+        const float m1 = xi * xj;
+        const float q = xi * d;
+        const float m3 = xi * q;
+        const float u1 = fmaf(xj, h, xi);
+        const float u2 = fmaf(d, h, xi);
+        const float u3 = fmaf(q, h, xi);
+        pa[0] += gd;
+        pa[1] = fmaf(gd, gd, pa[1]);
+        pa[2] += d;
+        pa[3] += m1;
+        pa[4] = fmaf(m1, gj, pa[4]);
+        pa[5] += q;
+        pa[6] = fmaf(q, gd, pa[6]);
+        pa[7] += m3;
+        pa[8] = fmaf(m3, gd, pa[8]);
+        pa[9] = fmaf(u1, u1, pa[9]);
+        pa[10] = fmaf(gi, u1, pa[10]);
+        pa[11] = fmaf(u2, u2, pa[11]);
+        pa[12] = fmaf(gi, u2, pa[12]);
+        pa[13] = fmaf(u3, u3, pa[13]);
+        pa[14] = fmaf(gi, u3, pa[14]);
+    }
+}
+
+__device__ __forceinline__ bool flush_flat_acc(float (&acc)[F_NACC], double* warp_slot /* smem [64] */, int lane) {
+    bool nonbinary = acc[F_GG + 0] != acc[F_G + 1] || acc[F_GG + 1] != acc[F_G + 2];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) nonbinary |= acc[F_PAIR + 15 * p + 1] != acc[F_PAIR + 15 * p + 0];
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (grp * 32 + i < F_NACC) ? acc[grp * 32 + i] : 0.f;
+        const float tot = butterfly32(v, lane);
+        warp_slot[grp * 32 + lane] += (double)tot;
+    }
+#pragma unroll
+    for (int k = 0; k < F_NACC; ++k) acc[k] = 0.f;
+    return nonbinary;
+}
+
+// flat sums -> the shared 100-slot layout of eco_composite.cu.  The SP slots of the real-b leaves hold only the
+// algebraic part n ln2 + sum b / 2 + sum b^2 / 8 and their FL slots are 0: the fused kernel adds the weighted
+// remainder / focal sums of pass 2 to the loss totals.
+__device__ inline double flat_to_layout(const double* S, const double* corr, int idx, double n_blk) {
+    auto sp_of = [&](double sb, double sbb) { return n_blk * kLn2d + 0.5 * sb + 0.125 * sbb; };
+    if (idx == A_N) return n_blk;
+    if (idx < A_GD) return S[F_G + idx - A_G];
+    if (idx < A_CH) return S[F_PAIR + 15 * (idx - A_GD) + 0];
+    if (idx < A_PAIR) {
+        const int c = (idx - A_CH) / 5, k = (idx - A_CH) % 5;
+        switch (k) {
+            case 0: return S[F_X + c];
+            case 1: return S[F_XX + c];
+            case 2: return S[F_GX + c];
+            case 3: return sp_of(S[F_X + c], S[F_XX + c]);
+            default: return 0.0;
+        }
+    }
+    if (idx < A_CORR) {
+        const int p = (idx - A_PAIR) / 21, k = (idx - A_PAIR) % 21;
+        const double* r = S + F_PAIR + 15 * p;
+        const int i = pair_i(p), j = pair_j(p);
+        const int grp = k / 7, kk = k % 7;
+        const double m = r[3 + 2 * grp], mg = r[4 + 2 * grp];
+        const double psum = grp == 0 ? S[F_X + j] : (grp == 1 ? r[2] : r[5]);
+        const double usum = S[F_X + i] + 0.5 * (psum - m);
+        switch (kk) {
+            case 0: return m;
+            case 1: return mg;
+            case 2: return usum;
+            case 3: return r[9 + 2 * grp];
+            case 4: return r[10 + 2 * grp];
+            case 5: return sp_of(usum, r[9 + 2 * grp]);
+            default: return 0.0;
+        }
+    }
+    const int L = (idx - A_CORR) / 3, k = (idx - A_CORR) % 3;
+    if (k != 0) return corr[idx - A_CORR];
+    if (L < 2) return S[F_GG + L] - S[F_G + 1 + L];                                   // g1, g2
+    return S[F_PAIR + 15 * (L - 2) + 1] - S[F_PAIR + 15 * (L - 2) + 0];               // gd of pair L-2
+}
+
+__device__ __forceinline__ void stats_smem_init(StatsSmem& sm) {
+    for (int i = threadIdx.x; i < kCWarps * 64; i += blockDim.x) (&sm.warp_slots[0][0])[i] = 0.0;
+    if (threadIdx.x < 15) sm.corr[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) sm.flag = false;
+}
+
+__device__ __forceinline__ void stats_consume(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem& ps,
+                                              int k0, StatsSmem& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntiles = tr.t_hi - tr.t_lo;
+    int kk = ntiles > 0 ? tr.t_lo % tr.tpp : 0;
+    float acc[F_NACC];
+#pragma unroll
+    for (int k = 0; k < F_NACC; ++k) acc[k] = 0.f;
+    int since_flush = 0;
+    bool any_nonbinary = false;
+    const uint32_t my = stage_base + threadIdx.x * 8;
+    for (int k = 0; k < ntiles; ++k) {
+        f2 z[3], g[3];
+        consume_tile(my, ps, k0 + k, lane, z, g);
+        if ((int64_t)kk * kTP + 2 * (int)threadIdx.x < a.HW) {
+#ifdef ECO_V2_EXP_NOCOMPUTE
+            acc[0] += z[0].x + z[1].x + z[2].x + g[0].x + g[1].x + g[2].x + z[0].y + z[1].y + z[2].y + g[0].y + g[1].y + g[2].y;
+#else
+            stats_pixel(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, acc);
+            stats_pixel(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
+#endif
+        }
+        if (++kk == tr.tpp) kk = 0;
+        if (++since_flush == kFlushTiles) {
+            any_nonbinary |= flush_flat_acc(acc, sm.warp_slots[warp], lane);
+            since_flush = 0;
+        }
+    }
+    any_nonbinary |= flush_flat_acc(acc, sm.warp_slots[warp], lane);
+    if (any_nonbinary) sm.flag = true;
+}
+
+constexpr int kMaxGrid = 192;   // CTAs of one cooperative launch (one per SM)
+// peer all-reduce of `count` doubles starting at slot `slot0` of this rank's row, flags at u32 offset `flag0`
+// (see peer_allreduce() in eco_composite_packed.cuh for the protocol); called by all CONSUMER threads of ONE CTA
+__device__ inline double peer_allreduce_c(const XchArgs& x, double mine, int slot0, int count, int flag0, double* bcast) {
+    const int par = x.epoch & 1u;
+    if ((int)threadIdx.x < count) {
+        for (int r = 0; r < x.world; ++r) {
+            double* slot = x.peers[r] + ((size_t)(par * x.world + x.rank)) * 128 + slot0;
+            slot[threadIdx.x] = mine;
+        }
+    }
+    __threadfence_system();
+    csync();
+    if ((int)threadIdx.x < x.world) {
+        unsigned int* flag = reinterpret_cast<unsigned int*>(x.peers[threadIdx.x] + xch_flags_offset_doubles(x.world)) + flag0 + x.rank;
+        st_release_sys(flag, x.epoch);
+        const unsigned int* own = reinterpret_cast<const unsigned int*>(x.peers[x.rank] + xch_flags_offset_doubles(x.world)) + flag0 + threadIdx.x;
+        unsigned int spins = 0;
+        while ((int)(ld_acquire_sys(own) - x.epoch) < 0) {
+            __nanosleep(40);
+            if (++spins > (1u << 26)) {  // seconds: a peer is gone; poison instead of hanging the GPU
+                *x.status = 1u;
+                bcast[0] = __longlong_as_double(0x7ff8000000000000ll);
+                break;
+            }
+        }
+    }
+    csync();
+    double tot = 0.0;
+    if ((int)threadIdx.x < count) {
+        const double* own = x.peers[x.rank] + (size_t)(par * x.world) * 128 + slot0;
+        for (int r = 0; r < x.world; ++r) tot += ld_volatile_f64(own + (size_t)r * 128 + threadIdx.x);
+    }
+    return tot;
+}
+
+// Deterministic grid-wide sums without a serial "last CTA adds everything" phase: every CTA adds its partial into
+// two 64-bit INTEGER accumulators per sum (v * 2^30 rounded to an integer, and the rounding remainder * 2^32), so the
+// total does not depend on the order of the atomics (integer addition is associative) and is exact to 2^-62.
+// Range: |sum| < 2^33 (the host routes larger problems to the first-generation kernels).
+constexpr double kFixHi = 1073741824.0;            // 2^30
+constexpr double kFixLo = 4294967296.0;            // 2^32
+__device__ __forceinline__ void fix_add(unsigned long long* slot2, double v) {
+    const double sc = v * kFixHi;
+    const long long hi = __double2ll_rn(sc);
+    const long long lo = __double2ll_rn((sc - (double)hi) * kFixLo);
+    atomicAdd(slot2, (unsigned long long)hi);
+    atomicAdd(slot2 + 1, (unsigned long long)lo);
+}
+// the accumulators are replicated kFixRep times (CTA b adds into replica b % kFixRep) to spread the L2 atomics
+constexpr int kFixRep = 8;
+__device__ __forceinline__ double fix_get(const unsigned long long* slot2, int rep_stride) {
+    unsigned long long hi = 0ull, lo = 0ull;
+#pragma unroll
+    for (int r = 0; r < kFixRep; ++r) {
+        hi += __ldcg(slot2 + (size_t)r * rep_stride);
+        lo += __ldcg(slot2 + (size_t)r * rep_stride + 1);
+    }
+    return ((double)(long long)hi + (double)(long long)lo * (1.0 / kFixLo)) * (1.0 / kFixHi);
+}
+
+// workspace words of the v2 kernels (all zero between launches)
+struct V2Ws {
+    unsigned int arrive1, arrive2, ready, _pad;
+    unsigned long long fix1[kFixRep][2 * kNAcc];   // pass-1 sums
+    unsigned long long fix2[kFixRep][4];           // pass-2 sums (softplus remainder, focal)
+};
+
+// CTA-level tail of pass 1 (all CONSUMER threads): rare slow pass, then this CTA's 100 partial sums go into the
+// integer accumulators and the CTA arrives.  Returns true in the last CTA to arrive.
+__device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange& tr, StatsSmem& sm, V2Ws* ws) {
+    csync();
+    if (sm.flag) {
+        // some label is not exactly 0 or 1: exact transcendental corrections for this CTA's tiles (rare)
+        const float* gb = reinterpret_cast<const float*>(a.g);
+        for (int t = tr.t_lo; t < tr.t_hi; ++t) {
+            const int n = t / tr.tpp, kk = t - n * tr.tpp;
+            const int64_t p0 = (int64_t)kk * kTP;
+            for (int e = threadIdx.x; e < kTP && p0 + e < a.HW; e += kCThreads) {
+                const float* gp = gb + n * a.g_sn + p0 + e;
+                const float g0 = gp[0], g1 = gp[a.g_sc], g2 = gp[2 * a.g_sc];
+                if ((g0 != 0.f && g0 != 1.f) || (g1 != 0.f && g1 != 1.f) || (g2 != 0.f && g2 != 1.f)) {
+                    label_corrections_role(g0, g1, 0, sm.corr);
+                    label_corrections_role(g0, g2, 1, sm.corr);
+                    label_corrections_role(g1, g2, 2, sm.corr);
+                }
+            }
+        }
+        csync();
+    }
+    if (threadIdx.x < 64) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kCWarps; ++w) v += sm.warp_slots[w][threadIdx.x];
+        sm.sums[threadIdx.x] = v;
+    }
+    csync();
+    int64_t npix = 0;
+    {
+        const int64_t last = a.HW - (int64_t)(tr.tpp - 1) * kTP;   // pixels of the (possibly short) last tile of a plane
+        const int ntiles = tr.t_hi - tr.t_lo;
+        const int n_last = ntiles > 0 ? (tr.t_hi / tr.tpp - tr.t_lo / tr.tpp) : 0;   // tiles with k == tpp - 1
+        npix = (int64_t)(ntiles - n_last) * kTP + (int64_t)n_last * last;
+    }
+    ECO_TL(7);
+    if (threadIdx.x < kNAcc) {
+        fix_add(ws->fix1[blockIdx.x % kFixRep] + 2 * threadIdx.x, flat_to_layout(sm.sums, sm.corr, threadIdx.x, (double)npix));
+        __threadfence();
+    }
+    csync();
+    ECO_TL(8);
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&ws->arrive1, 1u);
+        sm.flag = (prev == gridDim.x - 1);
+    }
+    csync();
+    ECO_TL(9);
+    return sm.flag;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2
+// ---------------------------------------------------------------------------------------------
+// per-leaf scalars in shared memory.  U-type leaves (a = label, b real): 0..2 = channel leaves, 3 + 3p + k = U_{k+1}
+// of pair p.  I-type leaves (a = product, b = label): 3p + k = I_{k+1} of pair p.
+struct Coef2 {
+    float4 ua[12];  // {c_Sb + c_SP/2, c_Sab, 2 c_Sbb, c_SP}
+    float4 uw[12];  // {leaf scale (softplus-remainder sum), leaf scale (focal sum), c_FL, -}
+    float2 ia[9];   // {c_Sa, c_Sab}
+};
+
+__device__ __forceinline__ void fill_coef2(Coef2& c2, const LeafCoef* cf, const double* scale_dev, int t) {
+    if (t >= ECO_C3_NLEAF) return;
+    const LeafCoef c = cf[t];
+    int ul = -1, il = -1;
+    if (t < 3) ul = t;
+    else {
+        const int p = (t - 3) / 6, k = (t - 3) % 6;
+        if (k & 1) ul = 3 + 3 * p + (k >> 1);
+        else il = 3 * p + (k >> 1);
+    }
+    if (ul >= 0) {
+        c2.ua[ul] = make_float4(c.sb + 0.5f * c.sp, c.sab, c.sbb2, c.sp);
+        const float s = scale_dev ? (float)scale_dev[t] : 0.f;
+        c2.uw[ul] = make_float4(s, s, c.fl, 0.f);
+    } else {
+        c2.ia[il] = make_float2(c.sa, c.sab);
+    }
+}
+
+__device__ __forceinline__ float xor_sign(float a, float s) {
+    return __uint_as_float(__float_as_uint(a) ^ (__float_as_uint(s) & 0x80000000u));
+}
+__device__ __forceinline__ f2 apply_sign(f2 v, f2 s) { return make_float2(xor_sign(v.x, s.x), xor_sign(v.y, s.y)); }
+__device__ __forceinline__ f2 neg2(f2 v) { return make_float2(-v.x, -v.y); }
+
+// dT/db of a U-type leaf at b (a = label); SIG: the BCE term carries gradient; FL: the focal term carries gradient;
+// TR: also accumulate the leaf's weighted softplus-remainder and focal sums
+template <bool SIG, bool FL, bool TR>
+__device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, f2 a, f2 b, f2& sp_acc, f2& fl_acc) {
+    f2 t;
+    if (SIG || TR) t = mul2(b, b);
+    const f2 k = fma2(a, splat(ca.y), splat(ca.x));   // c_Sab a + c0'
+    f2 r;
+    if (SIG) {
+        f2 s = fma2(t, splat(kSgS3), splat(kSgS2));
+        s = fma2(s, t, splat(kSgS1));
+        s = fma2(s, t, splat(kSgS0));
+        const f2 w = fma2(s, splat(ca.w), splat(ca.z));
+        r = fma2(b, w, k);
+    } else {
+        r = fma2(b, splat(ca.z), k);
+    }
+    if (TR) {
+        f2 q = fma2(t, splat(kSpR2), splat(kSpR1));
+        q = fma2(q, t, splat(kSpR0));
+        const f2 v = mul2(mul2(t, t), q);
+        sp_acc = fma2(v, splat(cw.x), sp_acc);
+    }
+    if (TR || FL) {
+        const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
+        const f2 sq = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
+        const f2 be = add2(b, splat(kEps));
+        const f2 lg = make_float2(lg2_approx(be.x), lg2_approx(be.y));
+        const f2 w15 = mul2(om, sq);
+        if (TR) fl_acc = fma2(mul2(w15, lg), splat(cw.y), fl_acc);
+        if (FL) {  // + c_FL d/db[-(1-b)^1.5 log(b+eps)] = c_FL (1.5 ln2 sqrt(1-b) lg2(b+eps) - (1-b)^1.5 / (b+eps))
+            const f2 rc = make_float2(rcp_approx(be.x), rcp_approx(be.y));
+            const f2 v = fma2(mul2(sq, splat(1.5f * kLn2)), lg, neg2(mul2(w15, rc)));
+            r = fma2(v, splat(cw.z), r);
+        }
+    }
+    return r;
+}
+
+// the whole gradient of one pixel pair: x = probabilities, g = labels, diffs[p] = x_i - x_j
+template <bool SIG, bool FL, bool TR>
+__device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)[3], const f2 (&diffs)[3],
+                                                 const Coef2& c2, f2 (&gx)[3], f2& sp_acc, f2& fl_acc) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gx[c] = leaf_g<SIG, FL, TR>(c2.ua[c], c2.uw[c], g[c], x[c], sp_acc, fl_acc);
+    f2 hh[2];
+    hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
+    hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int i = pair_i(p), j = pair_j(p);
+        const f2 xi = x[i], xj = x[j], gi = g[i], gj = g[j], h = hh[i];
+        const f2 diff = diffs[p];
+        const f2 d = abs2(diff);
+        const f2 gd = abs2(add2(gi, neg2(gj)));
+        const f2 q = mul2(xi, d);                 // a2 = x_i d   (a1 = x_i x_j and a3 = x_i q are not needed themselves)
+        const f2 u1 = fma2(xj, h, xi);
+        const f2 u2 = fma2(d, h, xi);
+        const f2 u3 = fma2(q, h, xi);
+        const f2 G1 = leaf_g<SIG, FL, TR>(c2.ua[3 + 3 * p + 0], c2.uw[3 + 3 * p + 0], gi, u1, sp_acc, fl_acc);
+        const f2 G2 = leaf_g<SIG, FL, TR>(c2.ua[3 + 3 * p + 1], c2.uw[3 + 3 * p + 1], gi, u2, sp_acc, fl_acc);
+        const f2 G3 = leaf_g<SIG, FL, TR>(c2.ua[3 + 3 * p + 2], c2.uw[3 + 3 * p + 2], gi, u3, sp_acc, fl_acc);
+        const float2 k1 = c2.ia[3 * p + 0], k2 = c2.ia[3 * p + 1], k3 = c2.ia[3 * p + 2];
+        const f2 A1 = fma2(gj, splat(k1.y), splat(k1.x));
+        const f2 A2 = fma2(gd, splat(k2.y), splat(k2.x));
+        const f2 A3 = fma2(gd, splat(k3.y), splat(k3.x));
+        // totals w.r.t. the intermediates: Q = dT/dq, D = dT/dd
+        f2 Q = fma2(A3, xi, A2);
+        Q = fma2(G3, h, Q);
+        f2 D = mul2(Q, xi);
+        D = fma2(G2, h, D);
+        const f2 Ds = apply_sign(D, diff);        // dT/d(x_i - x_j) through the |.| kink
+        // x_i: direct terms of u_k (1 - p_k/2), a1 (x_j), q (d), a3 (q), plus the kink
+        f2 E = mul2(G1, xj);
+        E = fma2(G2, d, E);
+        E = fma2(G3, q, E);
+        f2 gi_acc = add2(add2(G1, G2), add2(G3, gx[i]));
+        gi_acc = fma2(E, splat(-0.5f), gi_acc);
+        gi_acc = fma2(A1, xj, gi_acc);
+        gi_acc = fma2(Q, d, gi_acc);
+        gi_acc = fma2(A3, q, gi_acc);
+        gx[i] = add2(gi_acc, Ds);
+        f2 gj_acc = fma2(A1, xi, gx[j]);
+        gj_acc = fma2(G1, h, gj_acc);
+        gx[j] = add2(gj_acc, neg2(Ds));
+    }
+}
+
+// rare: a pixel whose probabilities tie to within kTieEps -- the sign of the |x_i - x_j| kink (and sign(0) = 0)
+// must come from ATen's exact sigmoid bits.  Scalar path of the first-generation kernel.
+__device__ __noinline__ void tie_pixel_grad(float z0, float z1, float z2, float g0, float g1, float g2,
+                                            const LeafCoef* cf, bool need_sig, bool need_fl, float* o0, float* o1, float* o2) {
+    const float x[3] = {sigmoid_exact(z0), sigmoid_exact(z1), sigmoid_exact(z2)};
+    const float g[3] = {g0, g1, g2};
+    float gx[3];
+    pixel_grad(x, g, cf, need_sig, need_fl, gx);
+    *o0 = gx[0] * ((1.0f - x[0]) * x[0]);
+    *o1 = gx[1] * ((1.0f - x[1]) * x[1]);
+    *o2 = gx[2] * ((1.0f - x[2]) * x[2]);
+}
+
+// consumer side of pass 2.  tr_out (when TR): this thread's weighted softplus-remainder / focal(log2 units) sums.
+template <bool SIG, bool FL, bool TR>
+__device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileRange& tr, bool reverse, uint32_t stage_base,
+                                             PipeSmem& ps, int k0, const Coef2& c2, const LeafCoef* cf, double (&tr_out)[2]) {
+    const CompArgs& a = ga.a;
+    float* __restrict__ ob = reinterpret_cast<float*>(ga.gx);
+    const int lane = threadIdx.x & 31;
+    const int ntiles = tr.t_hi - tr.t_lo;
+    if (ntiles <= 0) return;
+    int t = reverse ? tr.t_hi - 1 : tr.t_lo;
+    int n = t / tr.tpp, kk = t - n * tr.tpp;
+    f2 sp_acc = splat(0.f), fl_acc = splat(0.f);
+    int since_flush = 0;
+    const uint32_t my = stage_base + threadIdx.x * 8;
+    const int pix = 2 * (int)threadIdx.x;
+    for (int k = 0; k < ntiles; ++k) {
+        f2 z[3], g[3];
+        consume_tile(my, ps, k0 + k, lane, z, g);
+        const int64_t p0 = (int64_t)kk * kTP;
+        if (p0 + pix < a.HW) {
+            f2 x[3], gx[3], diffs[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(z[c]);
+#pragma unroll
+            for (int p = 0; p < 3; ++p) diffs[p] = add2(x[pair_i(p)], neg2(x[pair_j(p)]));
+            pixel_pair_grad2<SIG, FL, TR>(x, g, diffs, c2, gx, sp_acc, fl_acc);
+            f2 o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) o[c] = mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
+            const float dx = fminf(fminf(fabsf(diffs[0].x), fabsf(diffs[1].x)), fabsf(diffs[2].x));
+            const float dy = fminf(fminf(fabsf(diffs[0].y), fabsf(diffs[1].y)), fabsf(diffs[2].y));
+            if (fminf(dx, dy) < kTieEps) {
+                if (dx < kTieEps) tie_pixel_grad(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, cf, SIG, FL, &o[0].x, &o[1].x, &o[2].x);
+                if (dy < kTieEps) tie_pixel_grad(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, cf, SIG, FL, &o[0].y, &o[1].y, &o[2].y);
+            }
+            float* op = ob + n * ga.gx_sn + p0 + pix;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) stg_stream_f2(op + c * ga.gx_sc, o[c]);
+        }
+        if (reverse) { if (--kk < 0) { kk = tr.tpp - 1; --n; } }
+        else { if (++kk == tr.tpp) { kk = 0; ++n; } }
+        if (TR && ++since_flush == kFlushTiles) {
+            tr_out[0] += (double)(sp_acc.x + sp_acc.y);
+            tr_out[1] += (double)(fl_acc.x + fl_acc.y);
+            sp_acc = splat(0.f); fl_acc = splat(0.f);
+            since_flush = 0;
+        }
+    }
+    if (TR) {
+        tr_out[0] += (double)(sp_acc.x + sp_acc.y);
+        tr_out[1] += (double)(fl_acc.x + fl_acc.y);
+    }
+}
+
+template <bool TR>
+__device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, const CompGradArgs& ga, const TileRange& tr,
+                                                      bool reverse, uint32_t stage_base, PipeSmem& ps, int k0, const Coef2& c2,
+                                                      const LeafCoef* cf, double (&tr_out)[2]) {
+    // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
+    if (need_fl) {
+        if (need_sig) grad_consume<true, true, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+        else grad_consume<false, true, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+    } else {
+        if (need_sig) grad_consume<true, false, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+        else grad_consume<false, false, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+    }
+}
+
+// stand-alone pass 2 on the tile pipeline: same contract as composite3_grad_packed_kernel (fp32, from logits)
+__global__ void __launch_bounds__(kThreads, 1)
+composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    extern __shared__ __align__(128) char stage_smem[];
+    __shared__ LeafCoef cf[ECO_C3_NLEAF];
+    __shared__ Coef2 c2;
+    __shared__ PipeSmem ps;
+    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
+    pipe_init(ps);
+    fill_coef2(c2, cf, nullptr, threadIdx.x);
+    __syncthreads();
+    const TileRange tr = tile_range(ga.a);
+    const uint32_t sbase = smem_u32(stage_smem);
+    if (threadIdx.x >= kCThreads) {
+        if (threadIdx.x == kCThreads) produce_tiles(ga.a, tr, false, sbase, ps, 0);
+    } else {
+        double t2[2] = {0.0, 0.0};
+        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, ga, tr, false, sbase, ps, 0, c2, cf, t2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused step: pass 1 -> grid-wide hand-over of the 100 sums -> closed forms (redundantly per CTA) -> pass 2 (+ the
+// linear BCE / focal sums) -> last CTA adds those sums to the loss totals.  ONE cooperative launch (all CTAs
+// co-resident); the grid-wide wait is a release/acquire flag set by the CTA that formed the totals.
+// ---------------------------------------------------------------------------------------------
+struct FusedSmem {
+    StatsSmem st;
+    LeafCoef cf[ECO_C3_NLEAF];
+    Coef2 c2;
+    double sl[ECO_C3_NLEAF][ECO_NLOSS];
+    double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
+    double tr_warp[kCWarps][2];
+    double scale[ECO_C3_NLEAF];
+    double acc[kNAcc];
+    float up[ECO_NLOSS + 1];
+    PipeSmem ps;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
+                           V2Ws* __restrict__ ws, double* __restrict__ acc_glob, float* __restrict__ losses_out, XchArgs xch) {
+    extern __shared__ __align__(128) char stage_smem[];
+    __shared__ FusedSmem fs;
+    ECO_TL(0);
+    stats_smem_init(fs.st);
+    if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
+    if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
+    pipe_init(fs.ps);
+    const TileRange tr = tile_range(ga.a);
+    const int ntiles = tr.t_hi - tr.t_lo;
+    const uint32_t sbase = smem_u32(stage_smem);
+    if (threadIdx.x >= kCThreads) {
+        // producer warp: pass 1 forwards, then straight on to pass 2 backwards -- its first tiles land while the
+        // consumers are still exchanging sums
+        if (threadIdx.x == kCThreads) {
+            produce_tiles(ga.a, tr, false, sbase, fs.ps, 0);
+            produce_tiles(ga.a, tr, true, sbase, fs.ps, ntiles);
+        }
+        return;
+    }
+    stats_consume(ga.a, tr, sbase, fs.ps, 0, fs.st);
+    ECO_TL(1);
+    const bool last1 = stats_finish(ga.a, tr, fs.st, ws);
+    ECO_TL(2);
+    // grid-wide hand-over of the 100 totals (all CTAs are co-resident: cooperative launch)
+    if (xch.world <= 1) {
+        // every CTA waits until all have arrived and reads the integer accumulators itself
+        if (threadIdx.x == 0) while (ld_acquire_gpu(&ws->arrive1) < gridDim.x) __nanosleep(32);
+        csync();
+        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
+    } else {
+        // sharded: the last CTA to arrive exchanges the totals with the peer ranks, then releases everybody
+        if (last1) {
+            __threadfence();
+            double total = 0.0;
+            if (threadIdx.x < kNAcc) total = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
+            if (threadIdx.x == 0) fs.st.corr[0] = 0.0;
+            csync();
+            total = peer_allreduce_c(xch, total, 0, kNAcc, 0, fs.st.corr);
+            if (threadIdx.x < kNAcc) { acc_glob[threadIdx.x] = total + fs.st.corr[0]; __threadfence(); }
+            csync();
+            if (threadIdx.x == 0) st_release_gpu(&ws->ready, 1u);
+        }
+        if (threadIdx.x == 0) while (ld_acquire_gpu(&ws->ready) == 0u) __nanosleep(32);
+        csync();
+        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = __ldcg(acc_glob + threadIdx.x);
+    }
+    csync();
+    ECO_TL(3);
+    // closed forms, redundantly per CTA: one thread per (leaf, loss) row, one WARP per loss so that the switch over
+    // the loss kind does not diverge
+    if (threadIdx.x < ECO_NLOSS * 32 && (threadIdx.x & 31) < ECO_C3_NLEAF) {
+        const int leaf = threadIdx.x & 31, k = threadIdx.x >> 5;
+        double s[ECO_NSTAT];
+        composite_leaf_sums(fs.acc, leaf, s);
+        leaf_closed_form_row(s, 0.0, fs.scale[leaf], k, fs.sl[leaf][k], fs.jac_s[leaf][k]);
+    }
+    csync();
+    ECO_TL(12);
+    if (threadIdx.x < ECO_C3_NLEAF) fs.cf[threadIdx.x] = make_coef(&fs.jac_s[threadIdx.x][0][0], fs.up);
+    csync();
+    fill_coef2(fs.c2, fs.cf, fs.scale, threadIdx.x);
+    csync();
+    ECO_TL(4);
+    double trs[2] = {0.0, 0.0};
+    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, fs.c2, fs.cf, trs);
+    trs[0] = warp_sum(trs[0]);
+    trs[1] = warp_sum(trs[1]);
+    if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
+    csync();
+    ECO_TL(5);
+    // second, tiny reduction: the two weighted sums of pass 2
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kCWarps; ++w) v += fs.tr_warp[w][threadIdx.x];
+        fix_add(ws->fix2[blockIdx.x % kFixRep] + 2 * threadIdx.x, v);
+        __threadfence();
+    }
+    csync();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&ws->arrive2, 1u);
+        fs.st.flag = (prev == gridDim.x - 1);
+    }
+    csync();
+    if (fs.st.flag) {
+        // last CTA of the step: every CTA has read the pass-1 totals and added its pass-2 sums
+        __threadfence();
+        if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = fix_get(ws->fix2[0] + 2 * threadIdx.x, 4);
+        csync();
+        if (xch.world > 1) {
+            if (threadIdx.x == 0) fs.st.corr[0] = 0.0;
+            csync();
+            const double mine = threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0;
+            const double all = peer_allreduce_c(xch, mine, 100, 2, 64, fs.st.corr);
+            csync();
+            if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = all + fs.st.corr[0];
+            csync();
+        }
+        if (threadIdx.x < ECO_NLOSS) {
+            double v = 0.0;
+            for (int l = 0; l < ECO_C3_NLEAF; ++l) v += fs.sl[l][threadIdx.x];
+            const double n = fs.acc[A_N];
+            if (threadIdx.x == 1) v += fs.st.sums[0] / n;               // BCE: sum_l scale_l * softplus remainder
+            if (threadIdx.x == 2) v += -kLn2d * fs.st.sums[1] / n;      // focal: sums were taken in log2 units
+            losses_out[threadIdx.x] = (float)v;
+        }
+        // re-arm the workspace for the next step
+        for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kCThreads) (&ws->fix1[0][0])[i] = 0ull;
+        if (threadIdx.x < kFixRep * 4) (&ws->fix2[0][0])[threadIdx.x] = 0ull;
+        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->arrive2 = 0u; ws->ready = 0u; }
+    }
+    ECO_TL(6);
+}
+
+}  // namespace v2
+}  // namespace eco
