@@ -852,7 +852,7 @@ extern "C" int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, 
 // ---- peer exchange buffers (CUDA IPC).  The one place the library allocates: IPC needs a cudaMalloc base pointer. ----
 extern "C" int64_t eco_xch_bytes(int32_t world) {
     if (world < 1 || world > 64) return -1;
-    return (int64_t)xch_flags_offset_doubles(world) * 8 + 512;  // two flag arrays of 64 u32
+    return (int64_t)v2::xch_ll_offset_bytes(world) + (int64_t)2 * world * 128 * 16;  // first-generation slots + flags, then the LL rows
 }
 
 extern "C" int eco_xch_alloc(int32_t world, void** ptr_out, unsigned char* handle_out /*[64]*/, int device) {

@@ -342,37 +342,49 @@ __device__ __forceinline__ void stats_consume(const CompArgs& a, const TileRange
 }
 
 constexpr int kMaxGrid = 192;   // CTAs of one cooperative launch (one per SM)
-// peer all-reduce of `count` doubles starting at slot `slot0` of this rank's row, flags at u32 offset `flag0`
-// (see peer_allreduce() in eco_composite_packed.cuh for the protocol); called by all CONSUMER threads of ONE CTA
-__device__ inline double peer_allreduce_c(const XchArgs& x, double mine, int slot0, int count, int flag0, double* bcast) {
+
+// All-reduce of `count` (<= 128 - slot0) doubles across the ranks of a sharded step over NVLink peer memory, in the
+// style of NCCL's LL protocol: every value travels as ONE 16-byte store {lo32, epoch, hi32, epoch} straight into
+// every peer's exchange buffer, and the receiver spins on its own buffer until both tags carry this step's epoch.
+// No fences and no separate flags: the data validates itself, so the latency is one NVLink write.  Rows are double
+// buffered by epoch parity (a rank can be at most one exchange ahead of a peer that has not read yet); the region
+// starts `xch_ll_offset_bytes(world)` into the buffer, after the first-generation slots.  Every rank adds the `world`
+// contributions in rank order, so all ranks hold bit-identical totals.  Called by all CONSUMER threads of ONE CTA.
+__host__ __device__ inline size_t xch_ll_offset_bytes(int world) { return xch_flags_offset_doubles(world) * 8 + 512; }
+__device__ inline double ll_allreduce(const XchArgs& x, double mine, int slot0, int count, double* bcast /* smem [>= 1] */) {
     const int par = x.epoch & 1u;
-    if ((int)threadIdx.x < count) {
+    const bool active = (int)threadIdx.x < count;
+    const size_t row_bytes = 128 * 16;
+    if (active) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+        const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
         for (int r = 0; r < x.world; ++r) {
-            double* slot = x.peers[r] + ((size_t)(par * x.world + x.rank)) * 128 + slot0;
-            slot[threadIdx.x] = mine;
+            if (r == x.rank) continue;
+            char* dst = reinterpret_cast<char*>(x.peers[r]) + xch_ll_offset_bytes(x.world) +
+                        ((size_t)(par * x.world + x.rank)) * row_bytes + (size_t)(slot0 + threadIdx.x) * 16;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(lo), "r"(x.epoch), "r"(hi), "r"(x.epoch) : "memory");
         }
     }
-    __threadfence_system();
-    csync();
-    if ((int)threadIdx.x < x.world) {
-        unsigned int* flag = reinterpret_cast<unsigned int*>(x.peers[threadIdx.x] + xch_flags_offset_doubles(x.world)) + flag0 + x.rank;
-        st_release_sys(flag, x.epoch);
-        const unsigned int* own = reinterpret_cast<const unsigned int*>(x.peers[x.rank] + xch_flags_offset_doubles(x.world)) + flag0 + threadIdx.x;
-        unsigned int spins = 0;
-        while ((int)(ld_acquire_sys(own) - x.epoch) < 0) {
-            __nanosleep(40);
-            if (++spins > (1u << 26)) {  // seconds: a peer is gone; poison instead of hanging the GPU
-                *x.status = 1u;
-                bcast[0] = __longlong_as_double(0x7ff8000000000000ll);
-                break;
-            }
-        }
-    }
-    csync();
     double tot = 0.0;
-    if ((int)threadIdx.x < count) {
-        const double* own = x.peers[x.rank] + (size_t)(par * x.world) * 128 + slot0;
-        for (int r = 0; r < x.world; ++r) tot += ld_volatile_f64(own + (size_t)r * 128 + threadIdx.x);
+    if (active) {
+        const char* own = reinterpret_cast<const char*>(x.peers[x.rank]) + xch_ll_offset_bytes(x.world) +
+                          ((size_t)(par * x.world)) * row_bytes + (size_t)(slot0 + threadIdx.x) * 16;
+        for (int r = 0; r < x.world; ++r) {
+            if (r == x.rank) { tot += mine; continue; }
+            unsigned int lo, f0, hi, f1, spins = 0;
+            while (true) {
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(own + (size_t)r * row_bytes) : "memory");
+                if (f0 == x.epoch && f1 == x.epoch) break;
+                if (++spins > (1u << 24)) {  // seconds: a peer is gone; poison instead of hanging the GPU
+                    *x.status = 1u;
+                    bcast[0] = __longlong_as_double(0x7ff8000000000000ll);
+                    lo = hi = 0u;
+                    break;
+                }
+                __nanosleep(20);
+            }
+            tot += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+        }
     }
     return tot;
 }
@@ -745,7 +757,8 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
             if (threadIdx.x < kNAcc) total = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
             if (threadIdx.x == 0) fs.st.corr[0] = 0.0;
             csync();
-            total = peer_allreduce_c(xch, total, 0, kNAcc, 0, fs.st.corr);
+            total = ll_allreduce(xch, total, 0, kNAcc, fs.st.corr);
+            csync();
             if (threadIdx.x < kNAcc) { acc_glob[threadIdx.x] = total + fs.st.corr[0]; __threadfence(); }
             csync();
             if (threadIdx.x == 0) st_release_gpu(&ws->ready, 1u);
@@ -801,7 +814,7 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
             if (threadIdx.x == 0) fs.st.corr[0] = 0.0;
             csync();
             const double mine = threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0;
-            const double all = peer_allreduce_c(xch, mine, 100, 2, 64, fs.st.corr);
+            const double all = ll_allreduce(xch, mine, 100, 2, fs.st.corr);
             csync();
             if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = all + fs.st.corr[0];
             csync();
