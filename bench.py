@@ -345,7 +345,7 @@ def main():
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
-                    "kernel": "composite3_fused_packed_kernel" if (world == 1 or args.exchange == "p2p") else "composite3_stats+allreduce+finalize+grad",
+                    "kernel": "composite3_fused_v2_kernel" if (world == 1 or args.exchange == "p2p") else "composite3_stats_packed+allreduce+finalize+composite3_grad_v2",
                     "algorithmic_bytes_per_launch": alg_bytes}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:

@@ -151,10 +151,10 @@ __device__ __forceinline__ void produce_tiles(const CompArgs& a, const TileRange
         const int64_t p0 = (int64_t)kk * kTP;
         const int valid = (int)((a.HW - p0 < kTP) ? (a.HW - p0) : kTP);
         const uint32_t bytes = (uint32_t)valid * 4u;
-        mbar_expect_tx(full, 6u * bytes);
         const uint32_t dst = stage_base + (uint32_t)s * kStageBytes;
         const float* xs = xb + n * a.x_sn + p0;
         const float* gs = gb + n * a.g_sn + p0;
+        mbar_expect_tx(full, 6u * bytes);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             bulk_g2s(dst + (uint32_t)c * (kTP * 4), xs + c * a.x_sc, bytes, full);
