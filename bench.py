@@ -224,6 +224,21 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    # Everything but the one JSON line goes to stderr: libraries (NCCL's version banner, for one) write to fd 1.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run(args):
 
     import torch
     import torch.distributed as dist
@@ -368,11 +383,13 @@ def main():
             "losses": [float(v) for v in losses.cpu()],
             "aux": aux,
         }
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         if hasattr(step, "close"):
             step.close()
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

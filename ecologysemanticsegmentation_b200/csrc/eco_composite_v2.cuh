@@ -351,34 +351,35 @@ constexpr int kMaxGrid = 192;   // CTAs of one cooperative launch (one per SM)
 // starts `xch_ll_offset_bytes(world)` into the buffer, after the first-generation slots.  Every rank adds the `world`
 // contributions in rank order, so all ranks hold bit-identical totals.  Called by all CONSUMER threads of ONE CTA.
 __host__ __device__ inline size_t xch_ll_offset_bytes(int world) { return xch_flags_offset_doubles(world) * 8 + 512; }
-__device__ inline double ll_allreduce(const XchArgs& x, double mine, int slot0, int count, double* bcast /* smem [>= 1] */) {
+// sender half: thread i < count stores `mine` into slot slot0 + i of this rank's row in EVERY rank's buffer (own too)
+__device__ inline void ll_send(const XchArgs& x, double mine, int slot0, int count) {
     const int par = x.epoch & 1u;
-    const bool active = (int)threadIdx.x < count;
-    const size_t row_bytes = 128 * 16;
-    if (active) {
+    if ((int)threadIdx.x < count) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
         const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
         for (int r = 0; r < x.world; ++r) {
-            if (r == x.rank) continue;
             char* dst = reinterpret_cast<char*>(x.peers[r]) + xch_ll_offset_bytes(x.world) +
-                        ((size_t)(par * x.world + x.rank)) * row_bytes + (size_t)(slot0 + threadIdx.x) * 16;
+                        ((size_t)(par * x.world + x.rank)) * (128 * 16) + (size_t)(slot0 + threadIdx.x) * 16;
             asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(lo), "r"(x.epoch), "r"(hi), "r"(x.epoch) : "memory");
         }
     }
+}
+// receiver half: thread i < count waits for slot slot0 + i of every rank's row in the OWN buffer and returns the sum in
+// rank order; any number of CTAs of a rank may receive the same rows.  A dead peer poisons the result (NaN) after seconds.
+__device__ inline double ll_recv_sum(const XchArgs& x, int slot0, int count) {
+    const int par = x.epoch & 1u;
     double tot = 0.0;
-    if (active) {
+    if ((int)threadIdx.x < count) {
         const char* own = reinterpret_cast<const char*>(x.peers[x.rank]) + xch_ll_offset_bytes(x.world) +
-                          ((size_t)(par * x.world)) * row_bytes + (size_t)(slot0 + threadIdx.x) * 16;
+                          ((size_t)(par * x.world)) * (128 * 16) + (size_t)(slot0 + threadIdx.x) * 16;
         for (int r = 0; r < x.world; ++r) {
-            if (r == x.rank) { tot += mine; continue; }
             unsigned int lo, f0, hi, f1, spins = 0;
             while (true) {
-                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(own + (size_t)r * row_bytes) : "memory");
+                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(own + (size_t)r * (128 * 16)) : "memory");
                 if (f0 == x.epoch && f1 == x.epoch) break;
-                if (++spins > (1u << 24)) {  // seconds: a peer is gone; poison instead of hanging the GPU
+                if (++spins > (1u << 24)) {
                     *x.status = 1u;
-                    bcast[0] = __longlong_as_double(0x7ff8000000000000ll);
-                    lo = hi = 0u;
+                    lo = 0u; hi = 0x7ff80000u;   // NaN
                     break;
                 }
                 __nanosleep(20);
@@ -750,22 +751,16 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         csync();
         if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
     } else {
-        // sharded: the last CTA to arrive exchanges the totals with the peer ranks, then releases everybody
+        // sharded: the last CTA to arrive sends this rank's totals to every rank (its own included); EVERY CTA then
+        // receives the `world` rows itself -- one NVLink hop, no second hand-over inside the GPU
         if (last1) {
             __threadfence();
             double total = 0.0;
             if (threadIdx.x < kNAcc) total = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
-            if (threadIdx.x == 0) fs.st.corr[0] = 0.0;
-            csync();
-            total = ll_allreduce(xch, total, 0, kNAcc, fs.st.corr);
-            csync();
-            if (threadIdx.x < kNAcc) { acc_glob[threadIdx.x] = total + fs.st.corr[0]; __threadfence(); }
-            csync();
-            if (threadIdx.x == 0) st_release_gpu(&ws->ready, 1u);
+            ll_send(xch, total, 0, kNAcc);
         }
-        if (threadIdx.x == 0) while (ld_acquire_gpu(&ws->ready) == 0u) __nanosleep(32);
-        csync();
-        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = __ldcg(acc_glob + threadIdx.x);
+        const double all = ll_recv_sum(xch, 0, kNAcc);
+        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = all;
     }
     csync();
     ECO_TL(3);
@@ -811,12 +806,10 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = fix_get(ws->fix2[0] + 2 * threadIdx.x, 4);
         csync();
         if (xch.world > 1) {
-            if (threadIdx.x == 0) fs.st.corr[0] = 0.0;
+            ll_send(xch, threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0, 100, 2);
+            const double all = ll_recv_sum(xch, 100, 2);
             csync();
-            const double mine = threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0;
-            const double all = ll_allreduce(xch, mine, 100, 2, fs.st.corr);
-            csync();
-            if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = all + fs.st.corr[0];
+            if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = all;
             csync();
         }
         if (threadIdx.x < ECO_NLOSS) {
