@@ -158,6 +158,12 @@ int main(int argc, char** argv) {
             printf("  timeline %-22s min %7.2f  avg %7.2f  max %7.2f us  (%d CTAs)\n", nm2[sl], mn, av / (cnt ? cnt : 1), mxv, cnt);
         }
     }
+    {
+        void* dws; const int64_t dwb = eco_dice_ws_bytes(3, 0); CK(cudaMalloc(&dws, dwb)); CK(cudaMemset(dws, 0, dwb));
+        int64_t* cnt; double* soft; CK(cudaMalloc(&cnt, 64 * 8)); CK(cudaMalloc(&soft, 64 * 8));
+        float t_d = time_us([&](int i) { eco_dice_counts(&vz[i % NSETS], &vg[i % NSETS], N, 3, HW, nullptr, 0, 0, dws, dwb, cnt, soft, 0, nullptr); }, iters);
+        printf("dice_counts (LDG streaming of the same 8 B/element): %.2f us = %.0f GB/s\n", t_d, 8.0 * E / t_d * 1e-3);
+    }
     printf("shipped: stats %.2f us  grad %.2f us  fused %.2f us\n", t_st, t_old, t_fu);
     printf("v2     : grad (no sums) %.2f us  fused %.2f us  -> %.1f GB/s (12 B/elem)\n", t_g2, t_f2, 12.0 * E / t_f2 * 1e-3);
     return 0;
