@@ -119,8 +119,6 @@ __device__ __forceinline__ TileRange tile_range(const CompArgs& a) {
 struct PipeSmem {
     unsigned long long full[kStages];
     unsigned long long empty[kStages];
-    int tile_n[kStages];   // pass 2: image of the tile in the stage (-1 = no more tiles) ...
-    int tile_k[kStages];   // ... and its index inside the plane
 };
 
 __device__ __forceinline__ void pipe_init(PipeSmem& ps) {
@@ -167,80 +165,11 @@ __device__ __forceinline__ void produce_tiles(const CompArgs& a, const TileRange
     }
 }
 
-// issue the six plane copies of tile (n, kk) into ring slot kg (waits for the slot to be free)
-__device__ __forceinline__ void issue_tile(const CompArgs& a, int n, int kk, uint32_t stage_base, PipeSmem& ps, int kg) {
-    const float* xb = reinterpret_cast<const float*>(a.x);
-    const float* gb = reinterpret_cast<const float*>(a.g);
-    const int s = kg % kStages;
-    const uint32_t full = smem_u32(&ps.full[s]), empty = smem_u32(&ps.empty[s]);
-    if (kg >= kStages) mbar_wait(empty, ((kg / kStages) - 1) & 1);
-    ps.tile_n[s] = n;
-    ps.tile_k[s] = kk;
-    if (n < 0) {          // sentinel: nothing to copy, complete the phase by hand
-        mbar_arrive(full);
-        return;
-    }
-    const int64_t p0 = (int64_t)kk * kTP;
-    const int valid = (int)((a.HW - p0 < kTP) ? (a.HW - p0) : kTP);
-    const uint32_t bytes = (uint32_t)valid * 4u;
-    mbar_expect_tx(full, 6u * bytes);
-    const uint32_t dst = stage_base + (uint32_t)s * kStageBytes;
-    const float* xs = xb + n * a.x_sn + p0;
-    const float* gs = gb + n * a.g_sn + p0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        bulk_g2s(dst + (uint32_t)c * (kTP * 4), xs + c * a.x_sc, bytes, full);
-        bulk_g2s(dst + (uint32_t)(3 + c) * (kTP * 4), gs + c * a.g_sc, bytes, full);
-    }
-}
-
-// Pass 2 work distribution.  Every CTA walks its own range BACKWARDS (it starts on the lines its pass 1 left in L2)
-// except for the first `pool` tiles of the range, which go into a pool shared by all CTAs and are claimed one at a
-// time with an atomic counter: CTAs that finish early (SMs differ by a few percent in delivered bandwidth) take over
-// tiles of the slow ones.  The gradient of a pixel does not depend on who computes it, and the two sums of pass 2
-// are accumulated as integers, so the result is still bit-reproducible.  pool = 0: purely static (stand-alone pass 2).
-constexpr int kPoolTiles = 4;
-constexpr int kPoolAhead = 2;
-__device__ __forceinline__ int pool_tiles(const CompArgs& a, const TileRange& tr) {
-    const int64_t total = (int64_t)a.N * tr.tpp;
-    return (total / gridDim.x >= 2 * kPoolTiles) ? kPoolTiles : 0;
-}
-__device__ __forceinline__ void produce_pass2(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem& ps, int k0,
-                                              int pool, unsigned int* pool_ctr) {
-    int kg = k0;
-    for (int t = tr.t_hi - 1; t >= tr.t_lo + pool; --t, ++kg) issue_tile(a, t / tr.tpp, t % tr.tpp, stage_base, ps, kg);
-    if (pool > 0) {
-        const int64_t total = (int64_t)a.N * tr.tpp;
-        const unsigned int pool_size = gridDim.x * (unsigned int)pool;
-        while (true) {
-            // claim late: at most kPoolAhead tiles of this CTA may be outstanding (being processed or in flight) when it
-            // takes another one, otherwise the CTAs hoard a ring full of tiles each and the pool balances nothing
-            if (kg - kPoolAhead >= k0 && kg - kPoolAhead >= 0) {
-                const int kw = kg - kPoolAhead;
-                mbar_wait(smem_u32(&ps.empty[kw % kStages]), (kw / kStages) & 1);
-            }
-            const unsigned int p = atomicAdd(pool_ctr, 1u);
-            if (p >= pool_size) break;
-            // pool order: round j of CTA c -> tile t_lo(c) + pool - 1 - j  (CTA-major inside a round)
-            const unsigned int j = p / gridDim.x, c = p - j * gridDim.x;
-            const int t = (int)(total * c / gridDim.x) + pool - 1 - (int)j;
-            issue_tile(a, t / tr.tpp, t % tr.tpp, stage_base, ps, kg++);
-        }
-    }
-    issue_tile(a, -1, 0, stage_base, ps, kg);
-}
-
 // consumer side of one tile: wait, copy this thread's pixel pair of all six planes to registers, release the stage
-template <bool WITH_ID>
-__device__ __forceinline__ void consume_tile(uint32_t my_base, PipeSmem& ps, int kg, int lane, f2 (&z)[3], f2 (&g)[3], int& n,
-                                             int& kk) {
+__device__ __forceinline__ void consume_tile(uint32_t my_base, PipeSmem& ps, int kg, int lane, f2 (&z)[3], f2 (&g)[3]) {
     const int s = kg % kStages;
     mbar_wait(smem_u32(&ps.full[s]), (kg / kStages) & 1);
     const uint32_t sb = my_base + (uint32_t)s * kStageBytes;
-    if (WITH_ID) {   // read before the stage is handed back: the producer rewrites them for the slot's next tile
-        n = *reinterpret_cast<volatile int*>(&ps.tile_n[s]);
-        kk = *reinterpret_cast<volatile int*>(&ps.tile_k[s]);
-    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         z[c] = lds_f2(sb + (uint32_t)c * (kTP * 4));
@@ -393,8 +322,7 @@ __device__ __forceinline__ void stats_consume(const CompArgs& a, const TileRange
     const uint32_t my = stage_base + threadIdx.x * 8;
     for (int k = 0; k < ntiles; ++k) {
         f2 z[3], g[3];
-        int unused_n, unused_k;
-        consume_tile<false>(my, ps, k0 + k, lane, z, g, unused_n, unused_k);
+        consume_tile(my, ps, k0 + k, lane, z, g);
         if ((int64_t)kk * kTP + 2 * (int)threadIdx.x < a.HW) {
 #ifdef ECO_V2_EXP_NOCOMPUTE
             acc[0] += z[0].x + z[1].x + z[2].x + g[0].x + g[1].x + g[2].x + z[0].y + z[1].y + z[2].y + g[0].y + g[1].y + g[2].y;
@@ -489,9 +417,9 @@ __device__ __forceinline__ double fix_get(const unsigned long long* slot2, int r
 
 // workspace words of the v2 kernels (all zero between launches)
 struct V2Ws {
-    unsigned int arrive1, arrive2, pool_ctr, _pad;
+    unsigned int arrive1, arrive2, ready, _pad;
     unsigned long long fix1[kFixRep][2 * kNAcc];   // pass-1 sums
-    unsigned long long fix2[kFixRep][2];           // pass-2 sums (softplus remainder, focal) * 2^24
+    unsigned long long fix2[kFixRep][4];           // pass-2 sums (softplus remainder, focal)
 };
 
 // CTA-level tail of pass 1 (all CONSUMER threads): rare slow pass, then this CTA's 100 partial sums go into the
@@ -683,27 +611,27 @@ __device__ __noinline__ void tie_pixel_grad(float z0, float z1, float z2, float 
     *o2 = gx[2] * ((1.0f - x[2]) * x[2]);
 }
 
-// consumer side of pass 2: tiles arrive with their (image, index) in the ring until the sentinel.  tr_out (when TR):
-// this thread's weighted softplus-remainder / focal (log2 units) sums as integers (value * 2^24, rounded per tile: the
-// total then does not depend on which CTA processed which tile).
-constexpr float kTrFix = 16777216.0f;   // 2^24
+// consumer side of pass 2.  tr_out (when TR): this thread's weighted softplus-remainder / focal(log2 units) sums.
 template <bool SIG, bool FL, bool TR>
-__device__ __forceinline__ void grad_consume(const CompGradArgs& ga, uint32_t stage_base, PipeSmem& ps, int k0, const Coef2& c2,
-                                             const LeafCoef* cf, long long (&tr_out)[2]) {
+__device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileRange& tr, bool reverse, uint32_t stage_base,
+                                             PipeSmem& ps, int k0, const Coef2& c2, const LeafCoef* cf, double (&tr_out)[2]) {
     const CompArgs& a = ga.a;
     float* __restrict__ ob = reinterpret_cast<float*>(ga.gx);
     const int lane = threadIdx.x & 31;
+    const int ntiles = tr.t_hi - tr.t_lo;
+    if (ntiles <= 0) return;
+    int t = reverse ? tr.t_hi - 1 : tr.t_lo;
+    int n = t / tr.tpp, kk = t - n * tr.tpp;
+    f2 sp_acc = splat(0.f), fl_acc = splat(0.f);
+    int since_flush = 0;
     const uint32_t my = stage_base + threadIdx.x * 8;
     const int pix = 2 * (int)threadIdx.x;
-    for (int kg = k0;; ++kg) {
+    for (int k = 0; k < ntiles; ++k) {
         f2 z[3], g[3];
-        int n, kk;   // written by the producer before the stage's barrier completed
-        consume_tile<true>(my, ps, kg, lane, z, g, n, kk);
-        if (n < 0) break;
+        consume_tile(my, ps, k0 + k, lane, z, g);
         const int64_t p0 = (int64_t)kk * kTP;
         if (p0 + pix < a.HW) {
             f2 x[3], gx[3], diffs[3];
-            f2 sp_acc = splat(0.f), fl_acc = splat(0.f);
 #pragma unroll
             for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(z[c]);
 #pragma unroll
@@ -721,25 +649,33 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, uint32_t st
             float* op = ob + n * ga.gx_sn + p0 + pix;
 #pragma unroll
             for (int c = 0; c < 3; ++c) stg_stream_f2(op + c * ga.gx_sc, o[c]);
-            if (TR) {
-                tr_out[0] += __float2ll_rn((sp_acc.x + sp_acc.y) * kTrFix);
-                tr_out[1] += __float2ll_rn((fl_acc.x + fl_acc.y) * kTrFix);
-            }
         }
+        if (reverse) { if (--kk < 0) { kk = tr.tpp - 1; --n; } }
+        else { if (++kk == tr.tpp) { kk = 0; ++n; } }
+        if (TR && ++since_flush == kFlushTiles) {
+            tr_out[0] += (double)(sp_acc.x + sp_acc.y);
+            tr_out[1] += (double)(fl_acc.x + fl_acc.y);
+            sp_acc = splat(0.f); fl_acc = splat(0.f);
+            since_flush = 0;
+        }
+    }
+    if (TR) {
+        tr_out[0] += (double)(sp_acc.x + sp_acc.y);
+        tr_out[1] += (double)(fl_acc.x + fl_acc.y);
     }
 }
 
 template <bool TR>
-__device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, const CompGradArgs& ga, uint32_t stage_base,
-                                                      PipeSmem& ps, int k0, const Coef2& c2, const LeafCoef* cf,
-                                                      long long (&tr_out)[2]) {
+__device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, const CompGradArgs& ga, const TileRange& tr,
+                                                      bool reverse, uint32_t stage_base, PipeSmem& ps, int k0, const Coef2& c2,
+                                                      const LeafCoef* cf, double (&tr_out)[2]) {
     // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
     if (need_fl) {
-        if (need_sig) grad_consume<true, true, TR>(ga, stage_base, ps, k0, c2, cf, tr_out);
-        else grad_consume<false, true, TR>(ga, stage_base, ps, k0, c2, cf, tr_out);
+        if (need_sig) grad_consume<true, true, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+        else grad_consume<false, true, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
     } else {
-        if (need_sig) grad_consume<true, false, TR>(ga, stage_base, ps, k0, c2, cf, tr_out);
-        else grad_consume<false, false, TR>(ga, stage_base, ps, k0, c2, cf, tr_out);
+        if (need_sig) grad_consume<true, false, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+        else grad_consume<false, false, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
     }
 }
 
@@ -757,10 +693,10 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
     const TileRange tr = tile_range(ga.a);
     const uint32_t sbase = smem_u32(stage_smem);
     if (threadIdx.x >= kCThreads) {
-        if (threadIdx.x == kCThreads) produce_pass2(ga.a, tr, sbase, ps, 0, 0, nullptr);
+        if (threadIdx.x == kCThreads) produce_tiles(ga.a, tr, false, sbase, ps, 0);
     } else {
-        long long t2[2] = {0, 0};
-        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, ga, sbase, ps, 0, c2, cf, t2);
+        double t2[2] = {0.0, 0.0};
+        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, ga, tr, false, sbase, ps, 0, c2, cf, t2);
     }
 }
 
@@ -775,7 +711,7 @@ struct FusedSmem {
     Coef2 c2;
     double sl[ECO_C3_NLEAF][ECO_NLOSS];
     double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
-    long long tr_warp[kCWarps][2];
+    double tr_warp[kCWarps][2];
     double scale[ECO_C3_NLEAF];
     double acc[kNAcc];
     float up[ECO_NLOSS + 1];
@@ -800,7 +736,7 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         // consumers are still exchanging sums
         if (threadIdx.x == kCThreads) {
             produce_tiles(ga.a, tr, false, sbase, fs.ps, 0);
-            produce_pass2(ga.a, tr, sbase, fs.ps, ntiles, pool_tiles(ga.a, tr), &ws->pool_ctr);
+            produce_tiles(ga.a, tr, true, sbase, fs.ps, ntiles);
         }
         return;
     }
@@ -843,22 +779,19 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     fill_coef2(fs.c2, fs.cf, fs.scale, threadIdx.x);
     csync();
     ECO_TL(4);
-    long long trs[2] = {0, 0};
-    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, sbase, fs.ps, ntiles, fs.c2, fs.cf, trs);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        trs[0] += __shfl_xor_sync(0xffffffffu, trs[0], o);
-        trs[1] += __shfl_xor_sync(0xffffffffu, trs[1], o);
-    }
+    double trs[2] = {0.0, 0.0};
+    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, fs.c2, fs.cf, trs);
+    trs[0] = warp_sum(trs[0]);
+    trs[1] = warp_sum(trs[1]);
     if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
     csync();
     ECO_TL(5);
-    // second, tiny reduction: the two weighted sums of pass 2, integers all the way
+    // second, tiny reduction: the two weighted sums of pass 2
     if (threadIdx.x < 2) {
-        long long v = 0;
+        double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kCWarps; ++w) v += fs.tr_warp[w][threadIdx.x];
-        atomicAdd(&ws->fix2[blockIdx.x % kFixRep][threadIdx.x], (unsigned long long)v);
+        fix_add(ws->fix2[blockIdx.x % kFixRep] + 2 * threadIdx.x, v);
         __threadfence();
     }
     csync();
@@ -870,12 +803,7 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     if (fs.st.flag) {
         // last CTA of the step: every CTA has read the pass-1 totals and added its pass-2 sums
         __threadfence();
-        if (threadIdx.x < 2) {
-            unsigned long long t = 0ull;
-#pragma unroll
-            for (int r = 0; r < kFixRep; ++r) t += __ldcg(&ws->fix2[r][threadIdx.x]);
-            fs.st.sums[threadIdx.x] = (double)(long long)t * (1.0 / (double)kTrFix);
-        }
+        if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = fix_get(ws->fix2[0] + 2 * threadIdx.x, 4);
         csync();
         if (xch.world > 1) {
             ll_send(xch, threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0, 100, 2);
@@ -894,8 +822,8 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         }
         // re-arm the workspace for the next step
         for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kCThreads) (&ws->fix1[0][0])[i] = 0ull;
-        if (threadIdx.x < kFixRep * 2) (&ws->fix2[0][0])[threadIdx.x] = 0ull;
-        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->arrive2 = 0u; ws->pool_ctr = 0u; }
+        if (threadIdx.x < kFixRep * 4) (&ws->fix2[0][0])[threadIdx.x] = 0ull;
+        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->arrive2 = 0u; ws->ready = 0u; }
     }
     ECO_TL(6);
 }
