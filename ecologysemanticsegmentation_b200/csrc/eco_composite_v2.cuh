@@ -416,15 +416,20 @@ __device__ __forceinline__ double fix_get(const unsigned long long* slot2, int r
 }
 
 // workspace words of the v2 kernels (all zero between launches)
+// fix1 is double buffered by step parity: step k adds into buffer k & 1 while CTA 0 clears buffer (k + 1) & 1 for the
+// next step, so nobody waits for the clearing.  tr2: the two sums of pass 2, each ONE word that carries the sum
+// (value * 2^16, shifted left by 8) and, in its low 8 bits, the number of CTAs that have added to it -- the atomicAdd
+// that delivers a CTA's share also tells it whether it was the last one, without a fence / arrival counter / re-read.
 struct V2Ws {
-    unsigned int arrive1, arrive2, ready, _pad;
-    unsigned long long fix1[kFixRep][2 * kNAcc];   // pass-1 sums
-    unsigned long long fix2[kFixRep][4];           // pass-2 sums (softplus remainder, focal)
+    unsigned int arrive1, step, _pad0, _pad1;
+    unsigned long long tr2[2];
+    unsigned long long fix1[2][kFixRep][2 * kNAcc];   // pass-1 sums
 };
+constexpr double kTr2Scale = 65536.0;   // 2^16
 
 // CTA-level tail of pass 1 (all CONSUMER threads): rare slow pass, then this CTA's 100 partial sums go into the
 // integer accumulators and the CTA arrives.  Returns true in the last CTA to arrive.
-__device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange& tr, StatsSmem& sm, V2Ws* ws) {
+__device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange& tr, StatsSmem& sm, V2Ws* ws, int par) {
     csync();
     if (sm.flag) {
         // some label is not exactly 0 or 1: exact transcendental corrections for this CTA's tiles (rare)
@@ -460,7 +465,7 @@ __device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange&
     }
     ECO_TL(7);
     if (threadIdx.x < kNAcc) {
-        fix_add(ws->fix1[blockIdx.x % kFixRep] + 2 * threadIdx.x, flat_to_layout(sm.sums, sm.corr, threadIdx.x, (double)npix));
+        fix_add(ws->fix1[par][blockIdx.x % kFixRep] + 2 * threadIdx.x, flat_to_layout(sm.sums, sm.corr, threadIdx.x, (double)npix));
         __threadfence();
     }
     csync();
@@ -712,6 +717,7 @@ struct FusedSmem {
     double sl[ECO_C3_NLEAF][ECO_NLOSS];
     double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
     double tr_warp[kCWarps][2];
+    unsigned long long tr_tot[2];
     double scale[ECO_C3_NLEAF];
     double acc[kNAcc];
     float up[ECO_NLOSS + 1];
@@ -725,6 +731,9 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     __shared__ FusedSmem fs;
     ECO_TL(0);
     stats_smem_init(fs.st);
+    const int par = (int)(__ldcg(&ws->step) & 1u);   // written only by the last CTA of the previous step
+    if (blockIdx.x == 0)   // clear the other buffer for the next step (nobody touches it during this one)
+        for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kThreads) (&ws->fix1[par ^ 1][0][0])[i] = 0ull;
     if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
     if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
     pipe_init(fs.ps);
@@ -742,21 +751,21 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     }
     stats_consume(ga.a, tr, sbase, fs.ps, 0, fs.st);
     ECO_TL(1);
-    const bool last1 = stats_finish(ga.a, tr, fs.st, ws);
+    const bool last1 = stats_finish(ga.a, tr, fs.st, ws, par);
     ECO_TL(2);
     // grid-wide hand-over of the 100 totals (all CTAs are co-resident: cooperative launch)
     if (xch.world <= 1) {
         // every CTA waits until all have arrived and reads the integer accumulators itself
         if (threadIdx.x == 0) while (ld_acquire_gpu(&ws->arrive1) < gridDim.x) __nanosleep(32);
         csync();
-        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
+        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = fix_get(ws->fix1[par][0] + 2 * threadIdx.x, 2 * kNAcc);
     } else {
         // sharded: the last CTA to arrive sends this rank's totals to every rank (its own included); EVERY CTA then
         // receives the `world` rows itself -- one NVLink hop, no second hand-over inside the GPU
         if (last1) {
             __threadfence();
             double total = 0.0;
-            if (threadIdx.x < kNAcc) total = fix_get(ws->fix1[0] + 2 * threadIdx.x, 2 * kNAcc);
+            if (threadIdx.x < kNAcc) total = fix_get(ws->fix1[par][0] + 2 * threadIdx.x, 2 * kNAcc);
             ll_send(xch, total, 0, kNAcc);
         }
         const double all = ll_recv_sum(xch, 0, kNAcc);
@@ -774,7 +783,15 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     }
     csync();
     ECO_TL(12);
-    if (threadIdx.x < ECO_C3_NLEAF) fs.cf[threadIdx.x] = make_coef(&fs.jac_s[threadIdx.x][0][0], fs.up);
+    if (threadIdx.x < ECO_C3_NLEAF * ECO_NJAC) {
+        // coefficient j of leaf l = sum_k upstream[k] * d loss_k / d stat_j: one thread each (make_coef, in parallel)
+        const int leaf = threadIdx.x / ECO_NJAC, j = threadIdx.x % ECO_NJAC;
+        double c = 0.0;
+#pragma unroll
+        for (int k = 1; k < ECO_NLOSS; ++k)
+            if (fs.up[k] != 0.f) c += (double)fs.up[k] * fs.jac_s[leaf][k][j];   // (an unused loss may have a non-finite Jacobian)
+        reinterpret_cast<float*>(&fs.cf[leaf])[j] = (float)(j == 3 ? 2.0 * c : c);
+    }
     csync();
     fill_coef2(fs.c2, fs.cf, fs.scale, threadIdx.x);
     csync();
@@ -786,24 +803,32 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
     csync();
     ECO_TL(5);
-    // second, tiny reduction: the two weighted sums of pass 2
+    // second, tiny reduction: the two weighted sums of pass 2.  One atomicAdd per sum delivers this CTA's share and
+    // returns how many CTAs came before it (low 8 bits): the CTA that completes sum 0 finishes the step.
     if (threadIdx.x < 2) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < kCWarps; ++w) v += fs.tr_warp[w][threadIdx.x];
-        fix_add(ws->fix2[blockIdx.x % kFixRep] + 2 * threadIdx.x, v);
-        __threadfence();
-    }
-    csync();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(&ws->arrive2, 1u);
-        fs.st.flag = (prev == gridDim.x - 1);
+        const unsigned long long mine = ((unsigned long long)__double2ll_rn(v * kTr2Scale) << 8) + 1ull;
+        const unsigned long long old = atomicAdd(&ws->tr2[threadIdx.x], mine);
+        if (threadIdx.x == 0) {
+            fs.st.flag = ((old & 255ull) == (unsigned long long)(gridDim.x - 1));
+            fs.tr_tot[0] = old + mine;
+        }
     }
     csync();
     if (fs.st.flag) {
-        // last CTA of the step: every CTA has read the pass-1 totals and added its pass-2 sums
-        __threadfence();
-        if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = fix_get(ws->fix2[0] + 2 * threadIdx.x, 4);
+        // last CTA of the step on sum 0: wait (briefly) until sum 1 is complete as well
+        if (threadIdx.x == 1) {
+            unsigned long long t;
+            while (((t = __ldcg(&ws->tr2[1])) & 255ull) != (unsigned long long)gridDim.x) __nanosleep(20);
+            fs.tr_tot[1] = t;
+        }
+        csync();
+        if (threadIdx.x < 2) {
+            const unsigned long long t = fs.tr_tot[threadIdx.x];
+            fs.st.sums[threadIdx.x] = (double)((long long)(t - (t & 255ull)) >> 8) * (1.0 / kTr2Scale);
+        }
         csync();
         if (xch.world > 1) {
             ll_send(xch, threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0, 100, 2);
@@ -820,10 +845,8 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
             if (threadIdx.x == 2) v += -kLn2d * fs.st.sums[1] / n;      // focal: sums were taken in log2 units
             losses_out[threadIdx.x] = (float)v;
         }
-        // re-arm the workspace for the next step
-        for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kCThreads) (&ws->fix1[0][0])[i] = 0ull;
-        if (threadIdx.x < kFixRep * 4) (&ws->fix2[0][0])[threadIdx.x] = 0ull;
-        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->arrive2 = 0u; ws->ready = 0u; }
+        // re-arm the workspace for the next step (every CTA has long passed the hand-over of pass 1)
+        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->step = (unsigned int)par + 1u; ws->tr2[0] = 0ull; ws->tr2[1] = 0ull; }
     }
     ECO_TL(6);
 }
