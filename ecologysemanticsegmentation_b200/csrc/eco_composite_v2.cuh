@@ -191,7 +191,11 @@ enum : int {
     F_PAIR = 14, // + 15 p + {0 GD, 1 GDD, 2 DS, 3 M1, 4 M1G, 5 M2, 6 M2G, 7 M3, 8 M3G, 9 UU1, 10 GU1, 11 UU2, 12 GU2, 13 UU3, 14 GU3}
     F_NACC = 59
 };
-constexpr int kFlushTiles = 16;   // 32 pixels per fp32 accumulator between folds into fp64
+constexpr int kFlushTiles = 16;
+#ifndef ECO_V2_PREPASS
+#define ECO_V2_PREPASS 2
+#endif
+constexpr int kPrepassTiles = ECO_V2_PREPASS;   // < kStages: tiles whose linear sums are taken while waiting for the grid sums   // 32 pixels per fp32 accumulator between folds into fp64
 
 struct StatsSmem {
     double warp_slots[kCWarps][64];
@@ -490,6 +494,15 @@ struct Coef2 {
     float2 ia[9];   // {c_Sa, c_Sab}
 };
 
+// leaf scales of the real-b leaves (needed by the pre-pass, before the coefficients exist)
+__device__ __forceinline__ void fill_weights(Coef2& c2, const double* scale, int t) {
+    if (t >= ECO_C3_NLEAF) return;
+    int ul = -1;
+    if (t < 3) ul = t;
+    else if ((t - 3) % 6 & 1) ul = 3 + 3 * ((t - 3) / 6) + (((t - 3) % 6) >> 1);
+    if (ul >= 0) { const float s = (float)scale[t]; c2.uw[ul] = make_float4(s, s, 0.f, 0.f); }
+}
+
 __device__ __forceinline__ void fill_coef2(Coef2& c2, const LeafCoef* cf, const double* scale_dev, int t) {
     if (t >= ECO_C3_NLEAF) return;
     const LeafCoef c = cf[t];
@@ -515,6 +528,23 @@ __device__ __forceinline__ float xor_sign(float a, float s) {
 __device__ __forceinline__ f2 apply_sign(f2 v, f2 s) { return make_float2(xor_sign(v.x, s.x), xor_sign(v.y, s.y)); }
 __device__ __forceinline__ f2 neg2(f2 v) { return make_float2(-v.x, -v.y); }
 
+// the linear sums of a real-b leaf: weighted softplus remainder t^2 r(t) (t = b^2) and weighted focal term in log2
+// units.  One definition for pass 2 and for the pre-pass below: the same operations in the same order, bit for bit.
+__device__ __forceinline__ void leaf_tr_sp(const float4 cw, f2 t, f2& sp_acc) {
+    f2 q = fma2(t, splat(kSpR2), splat(kSpR1));
+    q = fma2(q, t, splat(kSpR0));
+    const f2 v = mul2(mul2(t, t), q);
+    sp_acc = fma2(v, splat(cw.x), sp_acc);
+}
+__device__ __forceinline__ void leaf_tr(const float4 cw, f2 b, f2 t, f2& sp_acc, f2& fl_acc) {
+    leaf_tr_sp(cw, t, sp_acc);
+    const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
+    const f2 sq = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
+    const f2 be = add2(b, splat(kEps));
+    const f2 lg = make_float2(lg2_approx(be.x), lg2_approx(be.y));
+    fl_acc = fma2(mul2(mul2(om, sq), lg), splat(cw.y), fl_acc);
+}
+
 // dT/db of a U-type leaf at b (a = label); SIG: the BCE term carries gradient; FL: the focal term carries gradient;
 // TR: also accumulate the leaf's weighted softplus-remainder and focal sums
 template <bool SIG, bool FL, bool TR>
@@ -532,24 +562,21 @@ __device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, f2 a, f2 
     } else {
         r = fma2(b, splat(ca.z), k);
     }
-    if (TR) {
-        f2 q = fma2(t, splat(kSpR2), splat(kSpR1));
-        q = fma2(q, t, splat(kSpR0));
-        const f2 v = mul2(mul2(t, t), q);
-        sp_acc = fma2(v, splat(cw.x), sp_acc);
-    }
-    if (TR || FL) {
+    if (TR && !FL) leaf_tr(cw, b, t, sp_acc, fl_acc);
+    if (FL) {
         const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
         const f2 sq = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
         const f2 be = add2(b, splat(kEps));
         const f2 lg = make_float2(lg2_approx(be.x), lg2_approx(be.y));
         const f2 w15 = mul2(om, sq);
-        if (TR) fl_acc = fma2(mul2(w15, lg), splat(cw.y), fl_acc);
-        if (FL) {  // + c_FL d/db[-(1-b)^1.5 log(b+eps)] = c_FL (1.5 ln2 sqrt(1-b) lg2(b+eps) - (1-b)^1.5 / (b+eps))
-            const f2 rc = make_float2(rcp_approx(be.x), rcp_approx(be.y));
-            const f2 v = fma2(mul2(sq, splat(1.5f * kLn2)), lg, neg2(mul2(w15, rc)));
-            r = fma2(v, splat(cw.z), r);
+        if (TR) {
+            leaf_tr_sp(cw, t, sp_acc);
+            fl_acc = fma2(mul2(w15, lg), splat(cw.y), fl_acc);
         }
+        // + c_FL d/db[-(1-b)^1.5 log(b+eps)] = c_FL (1.5 ln2 sqrt(1-b) lg2(b+eps) - (1-b)^1.5 / (b+eps))
+        const f2 rc = make_float2(rcp_approx(be.x), rcp_approx(be.y));
+        const f2 v = fma2(mul2(sq, splat(1.5f * kLn2)), lg, neg2(mul2(w15, rc)));
+        r = fma2(v, splat(cw.z), r);
     }
     return r;
 }
@@ -616,22 +643,79 @@ __device__ __noinline__ void tie_pixel_grad(float z0, float z1, float z2, float 
     *o2 = gx[2] * ((1.0f - x[2]) * x[2]);
 }
 
-// consumer side of pass 2.  tr_out (when TR): this thread's weighted softplus-remainder / focal(log2 units) sums.
+// per-thread state of the two linear sums: fp32 partials folded into float64 every kFlushTiles accumulated tiles
+struct TrState {
+    f2 sp_acc, fl_acc;
+    int since_flush;
+    double tot[2];
+    __device__ __forceinline__ void init() { sp_acc = splat(0.f); fl_acc = splat(0.f); since_flush = 0; tot[0] = tot[1] = 0.0; }
+    __device__ __forceinline__ void fold() {
+        tot[0] += (double)(sp_acc.x + sp_acc.y);
+        tot[1] += (double)(fl_acc.x + fl_acc.y);
+        sp_acc = splat(0.f); fl_acc = splat(0.f);
+        since_flush = 0;
+    }
+    __device__ __forceinline__ void tile_done() { if (++since_flush == kFlushTiles) fold(); }
+};
+
+// only the linear sums of one pixel pair, in the leaf order of pixel_pair_grad2
+__device__ __forceinline__ void pixel_pair_tr(const f2 (&x)[3], const Coef2& c2, f2& sp_acc, f2& fl_acc) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) leaf_tr(c2.uw[c], x[c], mul2(x[c], x[c]), sp_acc, fl_acc);
+    f2 hh[2];
+    hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
+    hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int i = pair_i(p), j = pair_j(p);
+        const f2 xi = x[i], xj = x[j], h = hh[i];
+        const f2 d = abs2(add2(xi, neg2(xj)));
+        const f2 q = mul2(xi, d);
+        const f2 us[3] = {fma2(xj, h, xi), fma2(d, h, xi), fma2(q, h, xi)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) leaf_tr(c2.uw[3 + 3 * p + k], us[k], mul2(us[k], us[k]), sp_acc, fl_acc);
+    }
+}
+
+// Pre-pass: while a CTA waits for the grid-wide sums it already takes the linear sums of the first `count` tiles of
+// its pass 2 -- they sit in the ring (the producer runs ahead) and do not depend on the coefficients.  The stages are
+// NOT handed back; pass 2 proper consumes them again without the sums.  Same values, same order as in pass 2.
+__device__ __forceinline__ void tr_prepass(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem& ps, int k0,
+                                           int count, const Coef2& c2, TrState& st) {
+    int t = tr.t_hi - 1;
+    int kk = t % tr.tpp;
+    const uint32_t my = stage_base + threadIdx.x * 8;
+    const int pix = 2 * (int)threadIdx.x;
+    for (int k = 0; k < count; ++k) {
+        const int kg = k0 + k, s = kg % kStages;
+        mbar_wait(smem_u32(&ps.full[s]), (kg / kStages) & 1);
+        if ((int64_t)kk * kTP + pix < a.HW) {
+            const uint32_t sb = my + (uint32_t)s * kStageBytes;
+            f2 x[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(lds_f2(sb + (uint32_t)c * (kTP * 4)));
+            pixel_pair_tr(x, c2, st.sp_acc, st.fl_acc);
+        }
+        if (--kk < 0) kk = tr.tpp - 1;
+        st.tile_done();
+    }
+}
+
+// consumer side of pass 2 over this CTA's tiles [k_first, k_first + k_count) (in walking order).  With TR the linear
+// sums are accumulated into `st`.
 template <bool SIG, bool FL, bool TR>
 __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileRange& tr, bool reverse, uint32_t stage_base,
-                                             PipeSmem& ps, int k0, const Coef2& c2, const LeafCoef* cf, double (&tr_out)[2]) {
+                                             PipeSmem& ps, int k0, int k_first, int k_count, const Coef2& c2,
+                                             const LeafCoef* cf, TrState& st) {
     const CompArgs& a = ga.a;
     float* __restrict__ ob = reinterpret_cast<float*>(ga.gx);
     const int lane = threadIdx.x & 31;
-    const int ntiles = tr.t_hi - tr.t_lo;
-    if (ntiles <= 0) return;
-    int t = reverse ? tr.t_hi - 1 : tr.t_lo;
+    if (k_count <= 0) return;
+    int t = reverse ? tr.t_hi - 1 - k_first : tr.t_lo + k_first;
     int n = t / tr.tpp, kk = t - n * tr.tpp;
-    f2 sp_acc = splat(0.f), fl_acc = splat(0.f);
-    int since_flush = 0;
     const uint32_t my = stage_base + threadIdx.x * 8;
     const int pix = 2 * (int)threadIdx.x;
-    for (int k = 0; k < ntiles; ++k) {
+    for (int k = k_first; k < k_first + k_count; ++k) {
         f2 z[3], g[3];
         consume_tile(my, ps, k0 + k, lane, z, g);
         const int64_t p0 = (int64_t)kk * kTP;
@@ -641,7 +725,7 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
             for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(z[c]);
 #pragma unroll
             for (int p = 0; p < 3; ++p) diffs[p] = add2(x[pair_i(p)], neg2(x[pair_j(p)]));
-            pixel_pair_grad2<SIG, FL, TR>(x, g, diffs, c2, gx, sp_acc, fl_acc);
+            pixel_pair_grad2<SIG, FL, TR>(x, g, diffs, c2, gx, st.sp_acc, st.fl_acc);
             f2 o[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) o[c] = mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
@@ -657,30 +741,21 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
         }
         if (reverse) { if (--kk < 0) { kk = tr.tpp - 1; --n; } }
         else { if (++kk == tr.tpp) { kk = 0; ++n; } }
-        if (TR && ++since_flush == kFlushTiles) {
-            tr_out[0] += (double)(sp_acc.x + sp_acc.y);
-            tr_out[1] += (double)(fl_acc.x + fl_acc.y);
-            sp_acc = splat(0.f); fl_acc = splat(0.f);
-            since_flush = 0;
-        }
-    }
-    if (TR) {
-        tr_out[0] += (double)(sp_acc.x + sp_acc.y);
-        tr_out[1] += (double)(fl_acc.x + fl_acc.y);
+        if (TR) st.tile_done();
     }
 }
 
 template <bool TR>
 __device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, const CompGradArgs& ga, const TileRange& tr,
-                                                      bool reverse, uint32_t stage_base, PipeSmem& ps, int k0, const Coef2& c2,
-                                                      const LeafCoef* cf, double (&tr_out)[2]) {
+                                                      bool reverse, uint32_t stage_base, PipeSmem& ps, int k0, int k_first,
+                                                      int k_count, const Coef2& c2, const LeafCoef* cf, TrState& st) {
     // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
     if (need_fl) {
-        if (need_sig) grad_consume<true, true, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
-        else grad_consume<false, true, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+        if (need_sig) grad_consume<true, true, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        else grad_consume<false, true, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
     } else {
-        if (need_sig) grad_consume<true, false, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
-        else grad_consume<false, false, TR>(ga, tr, reverse, stage_base, ps, k0, c2, cf, tr_out);
+        if (need_sig) grad_consume<true, false, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        else grad_consume<false, false, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
     }
 }
 
@@ -700,8 +775,9 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
     if (threadIdx.x >= kCThreads) {
         if (threadIdx.x == kCThreads) produce_tiles(ga.a, tr, false, sbase, ps, 0);
     } else {
-        double t2[2] = {0.0, 0.0};
-        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, ga, tr, false, sbase, ps, 0, c2, cf, t2);
+        TrState st;
+        st.init();
+        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, ga, tr, false, sbase, ps, 0, 0, tr.t_hi - tr.t_lo, c2, cf, st);
     }
 }
 
@@ -737,6 +813,7 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
     if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
     pipe_init(fs.ps);
+    fill_weights(fs.c2, fs.scale, threadIdx.x);   // visible to the consumers after the barriers of stats_finish
     const TileRange tr = tile_range(ga.a);
     const int ntiles = tr.t_hi - tr.t_lo;
     const uint32_t sbase = smem_u32(stage_smem);
@@ -753,6 +830,11 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     ECO_TL(1);
     const bool last1 = stats_finish(ga.a, tr, fs.st, ws, par);
     ECO_TL(2);
+    // every CTA but the one everybody is waiting for uses the wait: linear sums of its first pass-2 tiles
+    TrState st;
+    st.init();
+    const int n_pre = last1 ? 0 : min(ntiles, kPrepassTiles);
+    tr_prepass(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
     // grid-wide hand-over of the 100 totals (all CTAs are co-resident: cooperative launch)
     if (xch.world <= 1) {
         // every CTA waits until all have arrived and reads the integer accumulators itself
@@ -796,10 +878,10 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     fill_coef2(fs.c2, fs.cf, fs.scale, threadIdx.x);
     csync();
     ECO_TL(4);
-    double trs[2] = {0.0, 0.0};
-    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, fs.c2, fs.cf, trs);
-    trs[0] = warp_sum(trs[0]);
-    trs[1] = warp_sum(trs[1]);
+    grad_consume_dispatch<false>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, 0, n_pre, fs.c2, fs.cf, st);
+    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, n_pre, ntiles - n_pre, fs.c2, fs.cf, st);
+    st.fold();
+    double trs[2] = {warp_sum(st.tot[0]), warp_sum(st.tot[1])};
     if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
     csync();
     ECO_TL(5);
