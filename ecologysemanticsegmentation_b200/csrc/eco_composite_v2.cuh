@@ -490,20 +490,28 @@ __device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange&
 // of pair p.  I-type leaves (a = product, b = label): 3p + k = I_{k+1} of pair p.
 struct Coef2 {
     float4 ua[12];  // {c_Sb + c_SP/2, c_Sab, 2 c_Sbb, c_SP}
-    float4 uw[12];  // {leaf scale (softplus-remainder sum), leaf scale (focal sum), c_FL, -}
+    float4 uw[12];  // {R0 w, R1 w, R2 w, w or |w|^(2/3)}: softplus-remainder polynomial times the leaf scale w; focal weight
+    float ufl[12];  // c_FL
     float2 ia[9];   // {c_Sa, c_Sab}
 };
 
-// leaf scales of the real-b leaves (needed by the pre-pass, before the coefficients exist)
-__device__ __forceinline__ void fill_weights(Coef2& c2, const double* scale, int t) {
+// weights of the linear sums of the real-b leaves (needed by the pre-pass, before the coefficients exist).
+// pos = every such leaf has a scale >= 0 (always true for the reference's weights): the focal weight is then stored as
+// w^(2/3), which rides for free on 1 - b:  (w^(2/3) (1-b))^1.5 = w (1-b)^1.5.
+__device__ __forceinline__ int u_leaf_of(int t) {
+    if (t < 3) return t;
+    return ((t - 3) % 6 & 1) ? 3 + 3 * ((t - 3) / 6) + (((t - 3) % 6) >> 1) : -1;
+}
+__device__ __forceinline__ void fill_weights(Coef2& c2, const double* scale, int t, bool pos) {
     if (t >= ECO_C3_NLEAF) return;
-    int ul = -1;
-    if (t < 3) ul = t;
-    else if ((t - 3) % 6 & 1) ul = 3 + 3 * ((t - 3) / 6) + (((t - 3) % 6) >> 1);
-    if (ul >= 0) { const float s = (float)scale[t]; c2.uw[ul] = make_float4(s, s, 0.f, 0.f); }
+    const int ul = u_leaf_of(t);
+    if (ul < 0) return;
+    const double w = scale[t];
+    c2.uw[ul] = make_float4((float)(w * (double)kSpR0), (float)(w * (double)kSpR1), (float)(w * (double)kSpR2),
+                            pos ? (float)cbrt(w * w) : (float)w);
 }
 
-__device__ __forceinline__ void fill_coef2(Coef2& c2, const LeafCoef* cf, const double* scale_dev, int t) {
+__device__ __forceinline__ void fill_coef2(Coef2& c2, const LeafCoef* cf, int t) {
     if (t >= ECO_C3_NLEAF) return;
     const LeafCoef c = cf[t];
     int ul = -1, il = -1;
@@ -515,8 +523,7 @@ __device__ __forceinline__ void fill_coef2(Coef2& c2, const LeafCoef* cf, const 
     }
     if (ul >= 0) {
         c2.ua[ul] = make_float4(c.sb + 0.5f * c.sp, c.sab, c.sbb2, c.sp);
-        const float s = scale_dev ? (float)scale_dev[t] : 0.f;
-        c2.uw[ul] = make_float4(s, s, c.fl, 0.f);
+        c2.ufl[ul] = c.fl;
     } else {
         c2.ia[il] = make_float2(c.sa, c.sab);
     }
@@ -531,24 +538,30 @@ __device__ __forceinline__ f2 neg2(f2 v) { return make_float2(-v.x, -v.y); }
 // the linear sums of a real-b leaf: weighted softplus remainder t^2 r(t) (t = b^2) and weighted focal term in log2
 // units.  One definition for pass 2 and for the pre-pass below: the same operations in the same order, bit for bit.
 __device__ __forceinline__ void leaf_tr_sp(const float4 cw, f2 t, f2& sp_acc) {
-    f2 q = fma2(t, splat(kSpR2), splat(kSpR1));
-    q = fma2(q, t, splat(kSpR0));
-    const f2 v = mul2(mul2(t, t), q);
-    sp_acc = fma2(v, splat(cw.x), sp_acc);
+    f2 q = fma2(t, splat(cw.z), splat(cw.y));   // w r(t), the leaf scale folded into the coefficients
+    q = fma2(q, t, splat(cw.x));
+    sp_acc = fma2(mul2(t, t), q, sp_acc);
 }
+// focal term given om = 1 - b (POSW: times w^(2/3)), sq = sqrt(om), lg = lg2(b + eps)
+template <bool POSW>
+__device__ __forceinline__ void leaf_tr_fl(const float4 cw, f2 om, f2 sq, f2 lg, f2& fl_acc) {
+    if (POSW) fl_acc = fma2(mul2(om, sq), lg, fl_acc);
+    else fl_acc = fma2(mul2(mul2(om, sq), lg), splat(cw.w), fl_acc);
+}
+template <bool POSW>
 __device__ __forceinline__ void leaf_tr(const float4 cw, f2 b, f2 t, f2& sp_acc, f2& fl_acc) {
     leaf_tr_sp(cw, t, sp_acc);
-    const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
+    const f2 om = POSW ? fma2(b, splat(-cw.w), splat(cw.w)) : fma2(b, splat(-1.0f), splat(1.0f));
     const f2 sq = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
     const f2 be = add2(b, splat(kEps));
     const f2 lg = make_float2(lg2_approx(be.x), lg2_approx(be.y));
-    fl_acc = fma2(mul2(mul2(om, sq), lg), splat(cw.y), fl_acc);
+    leaf_tr_fl<POSW>(cw, om, sq, lg, fl_acc);
 }
 
 // dT/db of a U-type leaf at b (a = label); SIG: the BCE term carries gradient; FL: the focal term carries gradient;
 // TR: also accumulate the leaf's weighted softplus-remainder and focal sums
-template <bool SIG, bool FL, bool TR>
-__device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, f2 a, f2 b, f2& sp_acc, f2& fl_acc) {
+template <bool SIG, bool FL, bool TR, bool POSW>
+__device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, const float cfl, f2 a, f2 b, f2& sp_acc, f2& fl_acc) {
     f2 t;
     if (SIG || TR) t = mul2(b, b);
     const f2 k = fma2(a, splat(ca.y), splat(ca.x));   // c_Sab a + c0'
@@ -562,31 +575,31 @@ __device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, f2 a, f2 
     } else {
         r = fma2(b, splat(ca.z), k);
     }
-    if (TR && !FL) leaf_tr(cw, b, t, sp_acc, fl_acc);
+    if (TR && !FL) leaf_tr<POSW>(cw, b, t, sp_acc, fl_acc);
     if (FL) {
         const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
         const f2 sq = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
         const f2 be = add2(b, splat(kEps));
         const f2 lg = make_float2(lg2_approx(be.x), lg2_approx(be.y));
         const f2 w15 = mul2(om, sq);
-        if (TR) {
+        if (TR) {   // (the focal-gradient variants always run with POSW = false: cw.w is the plain leaf scale)
             leaf_tr_sp(cw, t, sp_acc);
-            fl_acc = fma2(mul2(w15, lg), splat(cw.y), fl_acc);
+            leaf_tr_fl<false>(cw, om, sq, lg, fl_acc);
         }
         // + c_FL d/db[-(1-b)^1.5 log(b+eps)] = c_FL (1.5 ln2 sqrt(1-b) lg2(b+eps) - (1-b)^1.5 / (b+eps))
         const f2 rc = make_float2(rcp_approx(be.x), rcp_approx(be.y));
         const f2 v = fma2(mul2(sq, splat(1.5f * kLn2)), lg, neg2(mul2(w15, rc)));
-        r = fma2(v, splat(cw.z), r);
+        r = fma2(v, splat(cfl), r);
     }
     return r;
 }
 
 // the whole gradient of one pixel pair: x = probabilities, g = labels, diffs[p] = x_i - x_j
-template <bool SIG, bool FL, bool TR>
+template <bool SIG, bool FL, bool TR, bool POSW>
 __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)[3], const f2 (&diffs)[3],
                                                  const Coef2& c2, f2 (&gx)[3], f2& sp_acc, f2& fl_acc) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gx[c] = leaf_g<SIG, FL, TR>(c2.ua[c], c2.uw[c], g[c], x[c], sp_acc, fl_acc);
+    for (int c = 0; c < 3; ++c) gx[c] = leaf_g<SIG, FL, TR, POSW>(c2.ua[c], c2.uw[c], c2.ufl[c], g[c], x[c], sp_acc, fl_acc);
     f2 hh[2];
     hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
     hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
@@ -601,9 +614,9 @@ __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)
         const f2 u1 = fma2(xj, h, xi);
         const f2 u2 = fma2(d, h, xi);
         const f2 u3 = fma2(q, h, xi);
-        const f2 G1 = leaf_g<SIG, FL, TR>(c2.ua[3 + 3 * p + 0], c2.uw[3 + 3 * p + 0], gi, u1, sp_acc, fl_acc);
-        const f2 G2 = leaf_g<SIG, FL, TR>(c2.ua[3 + 3 * p + 1], c2.uw[3 + 3 * p + 1], gi, u2, sp_acc, fl_acc);
-        const f2 G3 = leaf_g<SIG, FL, TR>(c2.ua[3 + 3 * p + 2], c2.uw[3 + 3 * p + 2], gi, u3, sp_acc, fl_acc);
+        const f2 G1 = leaf_g<SIG, FL, TR, POSW>(c2.ua[3 + 3 * p + 0], c2.uw[3 + 3 * p + 0], c2.ufl[3 + 3 * p + 0], gi, u1, sp_acc, fl_acc);
+        const f2 G2 = leaf_g<SIG, FL, TR, POSW>(c2.ua[3 + 3 * p + 1], c2.uw[3 + 3 * p + 1], c2.ufl[3 + 3 * p + 1], gi, u2, sp_acc, fl_acc);
+        const f2 G3 = leaf_g<SIG, FL, TR, POSW>(c2.ua[3 + 3 * p + 2], c2.uw[3 + 3 * p + 2], c2.ufl[3 + 3 * p + 2], gi, u3, sp_acc, fl_acc);
         const float2 k1 = c2.ia[3 * p + 0], k2 = c2.ia[3 * p + 1], k3 = c2.ia[3 * p + 2];
         const f2 A1 = fma2(gj, splat(k1.y), splat(k1.x));
         const f2 A2 = fma2(gd, splat(k2.y), splat(k2.x));
@@ -614,7 +627,8 @@ __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)
         f2 D = mul2(Q, xi);
         D = fma2(G2, h, D);
         const f2 Ds = apply_sign(D, diff);        // dT/d(x_i - x_j) through the |.| kink
-        // x_i: direct terms of u_k (1 - p_k/2), a1 (x_j), q (d), a3 (q), plus the kink
+        // x_i: direct terms of u_k (1 - p_k/2), a1 (x_j), q (d), a3 (q), plus the kink.  (Grouping by multiplier,
+        // x_j (A1 - G1/2) + d (Q - G2/2) + q (A3 - G3/2), is 4 issue cycles shorter on paper and 2 us slower measured.)
         f2 E = mul2(G1, xj);
         E = fma2(G2, d, E);
         E = fma2(G3, q, E);
@@ -659,9 +673,10 @@ struct TrState {
 };
 
 // only the linear sums of one pixel pair, in the leaf order of pixel_pair_grad2
+template <bool POSW>
 __device__ __forceinline__ void pixel_pair_tr(const f2 (&x)[3], const Coef2& c2, f2& sp_acc, f2& fl_acc) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) leaf_tr(c2.uw[c], x[c], mul2(x[c], x[c]), sp_acc, fl_acc);
+    for (int c = 0; c < 3; ++c) leaf_tr<POSW>(c2.uw[c], x[c], mul2(x[c], x[c]), sp_acc, fl_acc);
     f2 hh[2];
     hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
     hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
@@ -673,13 +688,14 @@ __device__ __forceinline__ void pixel_pair_tr(const f2 (&x)[3], const Coef2& c2,
         const f2 q = mul2(xi, d);
         const f2 us[3] = {fma2(xj, h, xi), fma2(d, h, xi), fma2(q, h, xi)};
 #pragma unroll
-        for (int k = 0; k < 3; ++k) leaf_tr(c2.uw[3 + 3 * p + k], us[k], mul2(us[k], us[k]), sp_acc, fl_acc);
+        for (int k = 0; k < 3; ++k) leaf_tr<POSW>(c2.uw[3 + 3 * p + k], us[k], mul2(us[k], us[k]), sp_acc, fl_acc);
     }
 }
 
 // Pre-pass: while a CTA waits for the grid-wide sums it already takes the linear sums of the first `count` tiles of
 // its pass 2 -- they sit in the ring (the producer runs ahead) and do not depend on the coefficients.  The stages are
 // NOT handed back; pass 2 proper consumes them again without the sums.  Same values, same order as in pass 2.
+template <bool POSW>
 __device__ __forceinline__ void tr_prepass(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem& ps, int k0,
                                            int count, const Coef2& c2, TrState& st) {
     int t = tr.t_hi - 1;
@@ -694,7 +710,7 @@ __device__ __forceinline__ void tr_prepass(const CompArgs& a, const TileRange& t
             f2 x[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(lds_f2(sb + (uint32_t)c * (kTP * 4)));
-            pixel_pair_tr(x, c2, st.sp_acc, st.fl_acc);
+            pixel_pair_tr<POSW>(x, c2, st.sp_acc, st.fl_acc);
         }
         if (--kk < 0) kk = tr.tpp - 1;
         st.tile_done();
@@ -703,7 +719,7 @@ __device__ __forceinline__ void tr_prepass(const CompArgs& a, const TileRange& t
 
 // consumer side of pass 2 over this CTA's tiles [k_first, k_first + k_count) (in walking order).  With TR the linear
 // sums are accumulated into `st`.
-template <bool SIG, bool FL, bool TR>
+template <bool SIG, bool FL, bool TR, bool POSW>
 __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileRange& tr, bool reverse, uint32_t stage_base,
                                              PipeSmem& ps, int k0, int k_first, int k_count, const Coef2& c2,
                                              const LeafCoef* cf, TrState& st) {
@@ -725,7 +741,7 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
             for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(z[c]);
 #pragma unroll
             for (int p = 0; p < 3; ++p) diffs[p] = add2(x[pair_i(p)], neg2(x[pair_j(p)]));
-            pixel_pair_grad2<SIG, FL, TR>(x, g, diffs, c2, gx, st.sp_acc, st.fl_acc);
+            pixel_pair_grad2<SIG, FL, TR, POSW>(x, g, diffs, c2, gx, st.sp_acc, st.fl_acc);
             f2 o[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) o[c] = mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
@@ -745,17 +761,21 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
     }
 }
 
+// block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1) and on
+// whether the focal weights ride on 1 - b (posw; only the variants that form the linear sums without the focal gradient)
 template <bool TR>
-__device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, const CompGradArgs& ga, const TileRange& tr,
-                                                      bool reverse, uint32_t stage_base, PipeSmem& ps, int k0, int k_first,
-                                                      int k_count, const Coef2& c2, const LeafCoef* cf, TrState& st) {
-    // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1)
+__device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, bool posw, const CompGradArgs& ga,
+                                                      const TileRange& tr, bool reverse, uint32_t stage_base, PipeSmem& ps, int k0,
+                                                      int k_first, int k_count, const Coef2& c2, const LeafCoef* cf, TrState& st) {
     if (need_fl) {
-        if (need_sig) grad_consume<true, true, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-        else grad_consume<false, true, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        if (need_sig) grad_consume<true, true, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        else grad_consume<false, true, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+    } else if (TR && posw) {
+        if (need_sig) grad_consume<true, false, TR, true>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        else grad_consume<false, false, TR, true>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
     } else {
-        if (need_sig) grad_consume<true, false, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-        else grad_consume<false, false, TR>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        if (need_sig) grad_consume<true, false, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        else grad_consume<false, false, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
     }
 }
 
@@ -768,7 +788,7 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
     __shared__ PipeSmem ps;
     if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(jac + threadIdx.x * ECO_NLOSS * ECO_NJAC, upstream);
     pipe_init(ps);
-    fill_coef2(c2, cf, nullptr, threadIdx.x);
+    fill_coef2(c2, cf, threadIdx.x);
     __syncthreads();
     const TileRange tr = tile_range(ga.a);
     const uint32_t sbase = smem_u32(stage_smem);
@@ -777,7 +797,7 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
     } else {
         TrState st;
         st.init();
-        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, ga, tr, false, sbase, ps, 0, 0, tr.t_hi - tr.t_lo, c2, cf, st);
+        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, false, ga, tr, false, sbase, ps, 0, 0, tr.t_hi - tr.t_lo, c2, cf, st);
     }
 }
 
@@ -813,7 +833,10 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
     if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
     pipe_init(fs.ps);
-    fill_weights(fs.c2, fs.scale, threadIdx.x);   // visible to the consumers after the barriers of stats_finish
+    // focal weights ride on 1 - b when every real-b leaf has a non-negative scale and the focal term carries no gradient
+    bool posw = fs.up[2] == 0.f;
+    for (int t = 0; t < ECO_C3_NLEAF; ++t) posw = posw && (u_leaf_of(t) < 0 || fs.scale[t] >= 0.0);
+    fill_weights(fs.c2, fs.scale, threadIdx.x, posw);   // visible to the consumers after the barriers of stats_finish
     const TileRange tr = tile_range(ga.a);
     const int ntiles = tr.t_hi - tr.t_lo;
     const uint32_t sbase = smem_u32(stage_smem);
@@ -834,7 +857,8 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     TrState st;
     st.init();
     const int n_pre = last1 ? 0 : min(ntiles, kPrepassTiles);
-    tr_prepass(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
+    if (posw) tr_prepass<true>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
+    else tr_prepass<false>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
     // grid-wide hand-over of the 100 totals (all CTAs are co-resident: cooperative launch)
     if (xch.world <= 1) {
         // every CTA waits until all have arrived and reads the integer accumulators itself
@@ -875,11 +899,11 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         reinterpret_cast<float*>(&fs.cf[leaf])[j] = (float)(j == 3 ? 2.0 * c : c);
     }
     csync();
-    fill_coef2(fs.c2, fs.cf, fs.scale, threadIdx.x);
+    fill_coef2(fs.c2, fs.cf, threadIdx.x);
     csync();
     ECO_TL(4);
-    grad_consume_dispatch<false>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, 0, n_pre, fs.c2, fs.cf, st);
-    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, ga, tr, true, sbase, fs.ps, ntiles, n_pre, ntiles - n_pre, fs.c2, fs.cf, st);
+    grad_consume_dispatch<false>(fs.up[1] != 0.f, fs.up[2] != 0.f, posw, ga, tr, true, sbase, fs.ps, ntiles, 0, n_pre, fs.c2, fs.cf, st);
+    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, posw, ga, tr, true, sbase, fs.ps, ntiles, n_pre, ntiles - n_pre, fs.c2, fs.cf, st);
     st.fold();
     double trs[2] = {warp_sum(st.tot[0]), warp_sum(st.tot[1])};
     if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
