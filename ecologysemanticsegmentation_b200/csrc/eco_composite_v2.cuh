@@ -81,7 +81,10 @@ __device__ __forceinline__ void stg_stream_f2(float* p, float2 v) {
 // Tile pipeline.  A tile = kTP consecutive pixels of one image x 6 planes (x0 x1 x2 g0 g1 g2); it never straddles
 // two images and the last tile of a plane may be short.  One consumer thread owns one pixel PAIR of a tile.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCWarps = 16;                       // consumer warps (4 per SM sub-partition)
+#ifndef ECO_V2_CWARPS
+#define ECO_V2_CWARPS 16
+#endif
+constexpr int kCWarps = ECO_V2_CWARPS;                       // consumer warps (4 per SM sub-partition)
 constexpr int kCThreads = kCWarps * 32;           // 512
 constexpr int kThreads = kCThreads + 32;          // + the producer warp
 constexpr int kTP = kCThreads * 2;                // pixels per tile
@@ -646,23 +649,27 @@ __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)
 
 // rare: a pixel whose probabilities tie to within kTieEps -- the sign of the |x_i - x_j| kink (and sign(0) = 0)
 // must come from ATen's exact sigmoid bits.  Scalar path of the first-generation kernel.
-__device__ __noinline__ void tie_pixel_grad(float z0, float z1, float z2, float g0, float g1, float g2,
-                                            const LeafCoef* cf, bool need_sig, bool need_fl, float* o0, float* o1, float* o2) {
+__device__ __noinline__ float3 tie_pixel_grad(float z0, float z1, float z2, float g0, float g1, float g2,
+                                              const LeafCoef* cf, bool need_sig, bool need_fl) {
     const float x[3] = {sigmoid_exact(z0), sigmoid_exact(z1), sigmoid_exact(z2)};
     const float g[3] = {g0, g1, g2};
     float gx[3];
     pixel_grad(x, g, cf, need_sig, need_fl, gx);
-    *o0 = gx[0] * ((1.0f - x[0]) * x[0]);
-    *o1 = gx[1] * ((1.0f - x[1]) * x[1]);
-    *o2 = gx[2] * ((1.0f - x[2]) * x[2]);
+    // returned BY VALUE: taking the address of the caller's outputs would push them through local memory on every tile
+    return make_float3(gx[0] * ((1.0f - x[0]) * x[0]), gx[1] * ((1.0f - x[1]) * x[1]), gx[2] * ((1.0f - x[2]) * x[2]));
 }
 
 // per-thread state of the two linear sums: fp32 partials folded into float64 every kFlushTiles accumulated tiles
 struct TrState {
     f2 sp_acc, fl_acc;
     int since_flush;
-    double tot[2];
-    __device__ __forceinline__ void init() { sp_acc = splat(0.f); fl_acc = splat(0.f); since_flush = 0; tot[0] = tot[1] = 0.0; }
+    double* tot;   // this thread's two float64 totals: in SHARED memory (touched once per kFlushTiles tiles; pass 2 has no
+                   // register to spare under the 96-register cap of 17 warps)
+    __device__ __forceinline__ void init(double* tot_smem) {
+        sp_acc = splat(0.f); fl_acc = splat(0.f); since_flush = 0;
+        tot = tot_smem;
+        if (tot) tot[0] = tot[1] = 0.0;
+    }
     __device__ __forceinline__ void fold() {
         tot[0] += (double)(sp_acc.x + sp_acc.y);
         tot[1] += (double)(fl_acc.x + fl_acc.y);
@@ -748,8 +755,14 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
             const float dx = fminf(fminf(fabsf(diffs[0].x), fabsf(diffs[1].x)), fabsf(diffs[2].x));
             const float dy = fminf(fminf(fabsf(diffs[0].y), fabsf(diffs[1].y)), fabsf(diffs[2].y));
             if (fminf(dx, dy) < kTieEps) {
-                if (dx < kTieEps) tie_pixel_grad(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, cf, SIG, FL, &o[0].x, &o[1].x, &o[2].x);
-                if (dy < kTieEps) tie_pixel_grad(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, cf, SIG, FL, &o[0].y, &o[1].y, &o[2].y);
+                if (dx < kTieEps) {
+                    const float3 r = tie_pixel_grad(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, cf, SIG, FL);
+                    o[0].x = r.x; o[1].x = r.y; o[2].x = r.z;
+                }
+                if (dy < kTieEps) {
+                    const float3 r = tie_pixel_grad(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, cf, SIG, FL);
+                    o[0].y = r.x; o[1].y = r.y; o[2].y = r.z;
+                }
             }
             float* op = ob + n * ga.gx_sn + p0 + pix;
 #pragma unroll
@@ -796,7 +809,7 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
         if (threadIdx.x == kCThreads) produce_tiles(ga.a, tr, false, sbase, ps, 0);
     } else {
         TrState st;
-        st.init();
+        st.init(nullptr);
         grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, false, ga, tr, false, sbase, ps, 0, 0, tr.t_hi - tr.t_lo, c2, cf, st);
     }
 }
@@ -813,6 +826,7 @@ struct FusedSmem {
     double sl[ECO_C3_NLEAF][ECO_NLOSS];
     double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
     double tr_warp[kCWarps][2];
+    double tr_thread[kCThreads][2];
     unsigned long long tr_tot[2];
     double scale[ECO_C3_NLEAF];
     double acc[kNAcc];
@@ -826,17 +840,9 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     extern __shared__ __align__(128) char stage_smem[];
     __shared__ FusedSmem fs;
     ECO_TL(0);
+    // the producer must get going first: nothing that waits on global memory sits in front of the first TMA issue
     stats_smem_init(fs.st);
-    const int par = (int)(__ldcg(&ws->step) & 1u);   // written only by the last CTA of the previous step
-    if (blockIdx.x == 0)   // clear the other buffer for the next step (nobody touches it during this one)
-        for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kThreads) (&ws->fix1[par ^ 1][0][0])[i] = 0ull;
-    if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
-    if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
     pipe_init(fs.ps);
-    // focal weights ride on 1 - b when every real-b leaf has a non-negative scale and the focal term carries no gradient
-    bool posw = fs.up[2] == 0.f;
-    for (int t = 0; t < ECO_C3_NLEAF; ++t) posw = posw && (u_leaf_of(t) < 0 || fs.scale[t] >= 0.0);
-    fill_weights(fs.c2, fs.scale, threadIdx.x, posw);   // visible to the consumers after the barriers of stats_finish
     const TileRange tr = tile_range(ga.a);
     const int ntiles = tr.t_hi - tr.t_lo;
     const uint32_t sbase = smem_u32(stage_smem);
@@ -849,13 +855,23 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         }
         return;
     }
+    const int par = (int)(__ldcg(&ws->step) & 1u);   // written only by the last CTA of the previous step
+    if (blockIdx.x == 0)   // clear the other buffer for the next step (nobody touches it during this one)
+        for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kCThreads) (&ws->fix1[par ^ 1][0][0])[i] = 0ull;
+    if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
+    if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
+    csync();
+    // focal weights ride on 1 - b when every real-b leaf has a non-negative scale and the focal term carries no gradient
+    bool posw = fs.up[2] == 0.f;
+    for (int t = 0; t < ECO_C3_NLEAF; ++t) posw = posw && (u_leaf_of(t) < 0 || fs.scale[t] >= 0.0);
+    fill_weights(fs.c2, fs.scale, threadIdx.x, posw);   // visible to the consumers after the barriers of stats_finish
     stats_consume(ga.a, tr, sbase, fs.ps, 0, fs.st);
     ECO_TL(1);
     const bool last1 = stats_finish(ga.a, tr, fs.st, ws, par);
     ECO_TL(2);
     // every CTA but the one everybody is waiting for uses the wait: linear sums of its first pass-2 tiles
     TrState st;
-    st.init();
+    st.init(&fs.tr_thread[threadIdx.x][0]);
     const int n_pre = last1 ? 0 : min(ntiles, kPrepassTiles);
     if (posw) tr_prepass<true>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
     else tr_prepass<false>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
@@ -905,7 +921,7 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     grad_consume_dispatch<false>(fs.up[1] != 0.f, fs.up[2] != 0.f, posw, ga, tr, true, sbase, fs.ps, ntiles, 0, n_pre, fs.c2, fs.cf, st);
     grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, posw, ga, tr, true, sbase, fs.ps, ntiles, n_pre, ntiles - n_pre, fs.c2, fs.cf, st);
     st.fold();
-    double trs[2] = {warp_sum(st.tot[0]), warp_sum(st.tot[1])};
+    double trs[2] = {warp_sum(st.tot[0]), warp_sum(st.tot[1])};   // (own slots: no barrier needed)
     if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
     csync();
     ECO_TL(5);
