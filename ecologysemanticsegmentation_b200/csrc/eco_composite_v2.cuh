@@ -872,7 +872,8 @@ composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     // every CTA but the one everybody is waiting for uses the wait: linear sums of its first pass-2 tiles
     TrState st;
     st.init(&fs.tr_thread[threadIdx.x][0]);
-    const int n_pre = last1 ? 0 : min(ntiles, kPrepassTiles);
+    // (sharded: the wait also spans an NVLink exchange, so up to a ring's worth of tiles fits)
+    const int n_pre = last1 ? 0 : min(ntiles, xch.world > 1 ? kStages - 1 : kPrepassTiles);
     if (posw) tr_prepass<true>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
     else tr_prepass<false>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
     // grid-wide hand-over of the 100 totals (all CTAs are co-resident: cooperative launch)
