@@ -9,7 +9,7 @@
 //     those cycles, and the loops below are written to minimise it rather than to "balance pipes":
 //     universal polynomial constants are immediates, per-leaf coefficients are scalars, the chain rule is factored
 //     through the intermediates d = |x_i - x_j| and q = x_i d (17 instead of 32 FMA-class instructions per pair).
-//   * Pass 1 is SCALAR and not role-split: one thread owns all 59 sums of its pixels, so each sigmoid is computed
+//   * Pass 1 is SCALAR and not role-split: one thread owns all 55 sums of its pixels, so each sigmoid is computed
 //     once (the role-split packed kernel computes it twice) and the float2 packing, which buys no issue cycles,
 //     is dropped where it would cost 2x the accumulator registers.
 //   * BCE and focal are LINEAR in their per-pixel sums, so those sums do not feed the gradient coefficients: they
@@ -183,16 +183,16 @@ __device__ __forceinline__ void consume_tile(uint32_t my_base, PipeSmem& ps, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 1: scalar, all 59 sums of a pixel in one thread
+// pass 1: scalar, all 55 sums of a pixel in one thread
 // ---------------------------------------------------------------------------------------------
 enum : int {
     F_G = 0,     // + c           sum g_c
-    F_GG = 3,    // + c - 1       sum g_c^2, c = 1, 2 (labels that appear as the b of an intersection leaf)
-    F_X = 5,     // + c
-    F_XX = 8,    // + c
-    F_GX = 11,   // + c
-    F_PAIR = 14, // + 15 p + {0 GD, 1 GDD, 2 DS, 3 M1, 4 M1G, 5 M2, 6 M2G, 7 M3, 8 M3G, 9 UU1, 10 GU1, 11 UU2, 12 GU2, 13 UU3, 14 GU3}
-    F_NACC = 59
+    F_NB = 3,    //               sum_c (g_c^2 - g_c)^2: non-zero iff some label is not exactly 0 or 1 (-> slow pass)
+    F_X = 4,     // + c
+    F_XX = 7,    // + c
+    F_GX = 10,   // + c
+    F_PAIR = 13, // + 14 p + {0 GD, 1 DS, 2 M1, 3 M1G, 4 M2, 5 M2G, 6 M3, 7 M3G, 8 UU1, 9 GU1, 10 UU2, 11 GU2, 12 UU3, 13 GU3}
+    F_NACC = 55
 };
 constexpr int kFlushTiles = 16;
 #ifndef ECO_V2_PREPASS
@@ -217,13 +217,16 @@ __device__ __forceinline__ void stats_pixel(float z0, float z1, float z2, float 
         acc[F_XX + c] = fmaf(x[c], x[c], acc[F_XX + c]);
         acc[F_GX + c] = fmaf(g[c], x[c], acc[F_GX + c]);
     }
-    acc[F_GG + 0] = fmaf(g1, g1, acc[F_GG + 0]);
-    acc[F_GG + 1] = fmaf(g2, g2, acc[F_GG + 1]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float e = fmaf(g[c], g[c], -g[c]);
+        acc[F_NB] = fmaf(e, e, acc[F_NB]);
+    }
     const float hh[2] = {fmaf(x[0], -0.5f, 0.5f), fmaf(x[1], -0.5f, 0.5f)};
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         const int i = pair_i(p), j = pair_j(p);
-        float* pa = &acc[F_PAIR + 15 * p];
+        float* pa = &acc[F_PAIR + 14 * p];
         const float xi = x[i], xj = x[j], gi = g[i], gj = g[j], h = hh[i];
         const float d = fabsf(xi - xj);
         const float gd = fabsf(gi - gj);
@@ -234,27 +237,24 @@ __device__ __forceinline__ void stats_pixel(float z0, float z1, float z2, float 
         const float u2 = fmaf(d, h, xi);
         const float u3 = fmaf(q, h, xi);
         pa[0] += gd;
-        pa[1] = fmaf(gd, gd, pa[1]);
-        pa[2] += d;
-        pa[3] += m1;
-        pa[4] = fmaf(m1, gj, pa[4]);
-        pa[5] += q;
-        pa[6] = fmaf(q, gd, pa[6]);
-        pa[7] += m3;
-        pa[8] = fmaf(m3, gd, pa[8]);
-        pa[9] = fmaf(u1, u1, pa[9]);
-        pa[10] = fmaf(gi, u1, pa[10]);
-        pa[11] = fmaf(u2, u2, pa[11]);
-        pa[12] = fmaf(gi, u2, pa[12]);
-        pa[13] = fmaf(u3, u3, pa[13]);
-        pa[14] = fmaf(gi, u3, pa[14]);
+        pa[1] += d;
+        pa[2] += m1;
+        pa[3] = fmaf(m1, gj, pa[3]);
+        pa[4] += q;
+        pa[5] = fmaf(q, gd, pa[5]);
+        pa[6] += m3;
+        pa[7] = fmaf(m3, gd, pa[7]);
+        pa[8] = fmaf(u1, u1, pa[8]);
+        pa[9] = fmaf(gi, u1, pa[9]);
+        pa[10] = fmaf(u2, u2, pa[10]);
+        pa[11] = fmaf(gi, u2, pa[11]);
+        pa[12] = fmaf(u3, u3, pa[12]);
+        pa[13] = fmaf(gi, u3, pa[13]);
     }
 }
 
 __device__ __forceinline__ bool flush_flat_acc(float (&acc)[F_NACC], double* warp_slot /* smem [64] */, int lane) {
-    bool nonbinary = acc[F_GG + 0] != acc[F_G + 1] || acc[F_GG + 1] != acc[F_G + 2];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) nonbinary |= acc[F_PAIR + 15 * p + 1] != acc[F_PAIR + 15 * p + 0];
+    const bool nonbinary = acc[F_NB] != 0.f;
 #pragma unroll
     for (int grp = 0; grp < 2; ++grp) {
         float v[32];
@@ -275,7 +275,7 @@ __device__ inline double flat_to_layout(const double* S, const double* corr, int
     auto sp_of = [&](double sb, double sbb) { return n_blk * kLn2d + 0.5 * sb + 0.125 * sbb; };
     if (idx == A_N) return n_blk;
     if (idx < A_GD) return S[F_G + idx - A_G];
-    if (idx < A_CH) return S[F_PAIR + 15 * (idx - A_GD) + 0];
+    if (idx < A_CH) return S[F_PAIR + 14 * (idx - A_GD) + 0];
     if (idx < A_PAIR) {
         const int c = (idx - A_CH) / 5, k = (idx - A_CH) % 5;
         switch (k) {
@@ -288,26 +288,39 @@ __device__ inline double flat_to_layout(const double* S, const double* corr, int
     }
     if (idx < A_CORR) {
         const int p = (idx - A_PAIR) / 21, k = (idx - A_PAIR) % 21;
-        const double* r = S + F_PAIR + 15 * p;
+        const double* r = S + F_PAIR + 14 * p;
         const int i = pair_i(p), j = pair_j(p);
         const int grp = k / 7, kk = k % 7;
-        const double m = r[3 + 2 * grp], mg = r[4 + 2 * grp];
-        const double psum = grp == 0 ? S[F_X + j] : (grp == 1 ? r[2] : r[5]);
+        const double m = r[2 + 2 * grp], mg = r[3 + 2 * grp];
+        const double psum = grp == 0 ? S[F_X + j] : (grp == 1 ? r[1] : r[4]);
         const double usum = S[F_X + i] + 0.5 * (psum - m);
         switch (kk) {
             case 0: return m;
             case 1: return mg;
             case 2: return usum;
-            case 3: return r[9 + 2 * grp];
-            case 4: return r[10 + 2 * grp];
-            case 5: return sp_of(usum, r[9 + 2 * grp]);
+            case 3: return r[8 + 2 * grp];
+            case 4: return r[9 + 2 * grp];
+            case 5: return sp_of(usum, r[8 + 2 * grp]);
             default: return 0.0;
         }
     }
-    const int L = (idx - A_CORR) / 3, k = (idx - A_CORR) % 3;
-    if (k != 0) return corr[idx - A_CORR];
-    if (L < 2) return S[F_GG + L] - S[F_G + 1 + L];                                   // g1, g2
-    return S[F_PAIR + 15 * (L - 2) + 1] - S[F_PAIR + 15 * (L - 2) + 0];               // gd of pair L-2
+    return corr[idx - A_CORR];   // label-b corrections (non-binary labels only), all from the slow pass
+}
+
+// rare path: exact corrections of the label-b sums of one pixel whose labels are not all 0/1 (double math, shared
+// atomics).  Slots 3L + {0 sum(b^2 - b), 1 softplus, 2 focal} for L = g1, g2, gd01, gd02, gd12 (eco_composite.cu).
+__device__ __noinline__ void label_corrections_v2(float g0, float g1, float g2, double* corr) {
+    const float lb[5] = {g1, g2, fabsf(g0 - g1), fabsf(g0 - g2), fabsf(g1 - g2)};
+    for (int L = 0; L < 5; ++L) {
+        const double b = (double)lb[L];
+        if (b == 0.0 || b == 1.0) continue;
+        const double be = (double)(lb[L] + kEps);  // fp32 add like the reference
+        const double sp = fmax(b, 0.0) + log1p(exp(-fabs(b)));
+        const double fl = -pow(1.0 - b, 1.5) * log(be);
+        atomicAdd(&corr[3 * L + 0], b * b - b);
+        atomicAdd(&corr[3 * L + 1], sp - ((1.0 - b) * kSP0 + b * kSP1));
+        atomicAdd(&corr[3 * L + 2], fl - (1.0 - b) * kFL0);
+    }
 }
 
 __device__ __forceinline__ void stats_smem_init(StatsSmem& sm) {
@@ -447,11 +460,8 @@ __device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange&
             for (int e = threadIdx.x; e < kTP && p0 + e < a.HW; e += kCThreads) {
                 const float* gp = gb + n * a.g_sn + p0 + e;
                 const float g0 = gp[0], g1 = gp[a.g_sc], g2 = gp[2 * a.g_sc];
-                if ((g0 != 0.f && g0 != 1.f) || (g1 != 0.f && g1 != 1.f) || (g2 != 0.f && g2 != 1.f)) {
-                    label_corrections_role(g0, g1, 0, sm.corr);
-                    label_corrections_role(g0, g2, 1, sm.corr);
-                    label_corrections_role(g1, g2, 2, sm.corr);
-                }
+                if ((g0 != 0.f && g0 != 1.f) || (g1 != 0.f && g1 != 1.f) || (g2 != 0.f && g2 != 1.f))
+                    label_corrections_v2(g0, g1, g2, sm.corr);
             }
         }
         csync();
