@@ -1,7 +1,8 @@
 // Second-generation 3-organ composite kernels (fp32, from-logits, 16-byte aligned planes).
-// Included by eco_composite.cu after eco_composite_packed.cuh.
+// Included by eco_composite.cu after eco_composite_packed.cuh; other inputs (bf16, probabilities, ragged planes) keep
+// the first-generation kernels.
 //
-// Design notes (all numbers measured on B200; profiles/microbench/regbw2.cu, profiles/README.md):
+// Design notes (all numbers measured on B200; profiles/microbench/regbw2.cu, profiles/README.md, DESIGN.md section 4):
 //   * An SM sub-partition issues one warp instruction per clock and an instruction holds the issue path for
 //     max(1, its register-file read cycles): FFMA2/FMUL2/FADD2 take 2 cycles with <= 2 distinct vector-register
 //     operands (immediates, ".F32" scalar pairs and reuse-cache hits are free) and 3 cycles with 3; MUFU, ALU, LDS
@@ -14,12 +15,17 @@
 //     is dropped where it would cost 2x the accumulator registers.
 //   * BCE and focal are LINEAR in their per-pixel sums, so those sums do not feed the gradient coefficients: they
 //     are accumulated in pass 2, where the union operands u_k and their squares are formed anyway, as two scalars
-//     already weighted by the leaf scales.  Pass 1 is left with 6 MUFU and ~100 FMA-class instructions per pixel
-//     and runs close to the HBM roofline of its 8 B/element.
+//     already weighted by the leaf scales (folded into the polynomial coefficients and into the focal base).  CTAs
+//     that wait for the grid-wide sums already take these sums of their first pass-2 tiles (pre-pass).
 //   * Both passes read their input through a ring of shared-memory stages filled by 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp; 16 consumer warps (4 per
-//     sub-partition, 120 registers) do nothing but math.  Pass 2 walks the CTA's tiles backwards so that it starts
-//     on the lines pass 1 left in L2.
+//     (cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp that runs ahead from pass 1 into
+//     pass 2; 16 consumer warps (4 per sub-partition, 96 registers) do nothing but math.  Pass 2 walks the CTA's tiles
+//     backwards so that it starts on the lines pass 1 left in L2.
+//   * Grid-wide sums are 64-bit INTEGER atomics (exact to 2^-62, order-independent => deterministic, no serial
+//     "last CTA adds everything"); every CTA polls the arrival counter itself (cooperative launch: co-resident) and
+//     derives the closed forms; the two sums of pass 2 travel as one word each that carries value and arrival count.
+//   * Sharded (one process per GPU): the rank totals cross NVLink as self-validating 16-byte stores (NCCL LL style),
+//     sent by the CTA that completes the rank's sums and received by every CTA of every rank.
 //   * Tied pixels (|x_i - x_j| < 4e-6, ~2e-5 of all pixels) are recomputed in pass 2 by a scalar slow path with
 //     ATen's exact sigmoid bits and sign(0) = 0; the sign of the |.| kink is otherwise one LOP3 per lane.
 #pragma once
@@ -81,17 +87,11 @@ __device__ __forceinline__ void stg_stream_f2(float* p, float2 v) {
 // Tile pipeline.  A tile = kTP consecutive pixels of one image x 6 planes (x0 x1 x2 g0 g1 g2); it never straddles
 // two images and the last tile of a plane may be short.  One consumer thread owns one pixel PAIR of a tile.
 // ---------------------------------------------------------------------------------------------
-#ifndef ECO_V2_CWARPS
-#define ECO_V2_CWARPS 16
-#endif
-constexpr int kCWarps = ECO_V2_CWARPS;                       // consumer warps (4 per SM sub-partition)
+constexpr int kCWarps = 16;                       // consumer warps (4 per SM sub-partition)
 constexpr int kCThreads = kCWarps * 32;           // 512
 constexpr int kThreads = kCThreads + 32;          // + the producer warp
 constexpr int kTP = kCThreads * 2;                // pixels per tile
-#ifndef ECO_V2_STAGES
-#define ECO_V2_STAGES 5
-#endif
-constexpr int kStages = ECO_V2_STAGES;
+constexpr int kStages = 5;
 constexpr int kStageBytes = 6 * kTP * 4;          // 24 KB
 constexpr int kSmemBytes = kStages * kStageBytes; // 120 KB of dynamic shared memory
 
@@ -194,11 +194,9 @@ enum : int {
     F_PAIR = 13, // + 14 p + {0 GD, 1 DS, 2 M1, 3 M1G, 4 M2, 5 M2G, 6 M3, 7 M3G, 8 UU1, 9 GU1, 10 UU2, 11 GU2, 12 UU3, 13 GU3}
     F_NACC = 55
 };
-constexpr int kFlushTiles = 16;
-#ifndef ECO_V2_PREPASS
-#define ECO_V2_PREPASS 2
-#endif
-constexpr int kPrepassTiles = ECO_V2_PREPASS;   // < kStages: tiles whose linear sums are taken while waiting for the grid sums   // 32 pixels per fp32 accumulator between folds into fp64
+constexpr int kFlushTiles = 16;    // 32 pixels per fp32 accumulator between folds into fp64
+constexpr int kPrepassTiles = 2;   // < kStages: tiles whose linear sums are taken while waiting for the grid sums (0/2/3/4
+                                   // measured: 81.3 / 80.2 / 80.4 / 80.7 us on one box)
 
 struct StatsSmem {
     double warp_slots[kCWarps][64];
@@ -344,12 +342,8 @@ __device__ __forceinline__ void stats_consume(const CompArgs& a, const TileRange
         f2 z[3], g[3];
         consume_tile(my, ps, k0 + k, lane, z, g);
         if ((int64_t)kk * kTP + 2 * (int)threadIdx.x < a.HW) {
-#ifdef ECO_V2_EXP_NOCOMPUTE
-            acc[0] += z[0].x + z[1].x + z[2].x + g[0].x + g[1].x + g[2].x + z[0].y + z[1].y + z[2].y + g[0].y + g[1].y + g[2].y;
-#else
             stats_pixel(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, acc);
             stats_pixel(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
-#endif
         }
         if (++kk == tr.tpp) kk = 0;
         if (++since_flush == kFlushTiles) {

@@ -1,4 +1,6 @@
-// Experiment harness (not part of the library): times / checks new composite kernels against the shipped ones.
+// Experiment harness (not part of the library): launches the second-generation composite kernels directly, prints the
+// in-kernel %globaltimer timeline of the fused step (ECO_V2_TIMELINE), and times them next to the C ABI entry points
+// (which, for fp32 logits, route to the same kernels -- the "shipped" columns are a launch-path check, not a baseline).
 // Build: nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a exp/harness.cu \
 //        ecologysemanticsegmentation_b200/csrc/build/eco_api.o -o exp/harness
 #define ECO_V2_TIMELINE 1
