@@ -216,6 +216,24 @@ def measure_aux(dev):
         out["dice_eval_cfg3_" + label] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
                                           "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 8}
     del z, g
+    # the plain 3-organ multi-class loss step (the loss train_multiclass.py trains with), cfg2's shape, one launch
+    from ecologysemanticsegmentation_b200 import fused
+    n, c, s = 54, 3, 256
+    sets = [tuple(t.to(dev) for t in make_inputs(n, c, s, 102 + 7 * k)) for k in range(4)]
+    outs = [torch.empty_like(zz) for zz, _ in sets]
+    mstep = fused.MulticlassLossStep(fused.loss_weights(bce=1.0, generalized_dice=1.0, twersky=1.0, focal_dice=1.0), device=dev)
+    state = {"i": 0}
+
+    def run_mc():
+        k = state["i"] % 4
+        state["i"] += 1
+        mstep(sets[k][0], sets[k][1], out=outs[k])
+
+    t = timed(run_mc, 100)
+    gbs = 12.0 * n * c * s * s / t / 1e9
+    out["multiclass_plain_cfg2_shape"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
+                                          "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 12,
+                                          "what": "train_multiclass.losses_fn (3 plain leaves) fwd+bwd from logits, one launch"}
     return out
 
 

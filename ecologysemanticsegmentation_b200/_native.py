@@ -52,6 +52,7 @@ SIGNATURES = {
     "eco_composite3_finalize": (C.c_int, [_vp, C.POINTER(_f64), _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "eco_composite3_grad": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _OUT, C.c_int, _vp]),
     "eco_composite3_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
+    "eco_multiclass3_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i64, C.c_double, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
     "eco_composite3_fused_sharded": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, _vp, _i32, _i32,
                                                _u32, C.c_int, _vp]),
     "eco_xch_bytes": (_i64, [_i32]),

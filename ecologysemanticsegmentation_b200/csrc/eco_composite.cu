@@ -531,6 +531,7 @@ __device__ __noinline__ void label_corrections_role(float gi, float gj, int role
 
 #include "eco_composite_packed.cuh"
 #include "eco_composite_v2.cuh"
+#include "eco_multiclass_v2.cuh"
 
 namespace eco {
 
@@ -651,6 +652,7 @@ static int ensure_packed_smem() {
     ECO_SMEM_ALL(__nv_bfloat16)
 #undef ECO_SMEM_ALL
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, fused v2)");
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
     if (!rc) done_for_device[dev] = 1;
     return rc;
@@ -847,6 +849,36 @@ extern "C" int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, 
     xch.world = world;
     xch.epoch = epoch;
     return launch_fused(x, g, N, HW, from_logits, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+}
+
+extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
+                                     const float* upstream, void* ws, int64_t ws_bytes, float* losses_out,
+                                     const EcoOut* gx, int device, void* stream) {
+    int rc = check_comp(x, g, N, HW);
+    if (rc) return rc;
+    if (!upstream || !losses_out || !gx || !gx->ptr) { set_error("null upstream/output"); return -5; }
+    if (!ws || ws_bytes < eco_composite3_ws_bytes()) { set_error("workspace too small"); return -5; }
+    if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW) &&
+                     c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
+    if (!v2_eligible(x, 1, vec, N, HW)) {
+        set_error("eco_multiclass3_fused serves fp32 logits with 16-byte aligned planes (H*W %% 4 == 0); use eco_pair_* otherwise");
+        return -8;
+    }
+    CompGradArgs ga{};
+    fill_comp(ga.a, x, g, N, HW, vec);
+    ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
+    rc = ensure_packed_smem();
+    if (rc) return rc;
+    const int grid = v2_grid(device, N, HW);
+    if (grid < 0) return -10;
+    v2::V2Ws* ws2 = reinterpret_cast<v2::V2Ws*>(reinterpret_cast<char*>(ws) + kWsV2Offset);
+    void* args[] = {&ga, &leaf_scale, (void*)&upstream, &ws2, &losses_out};
+    return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::multiclass3_fused_v2_kernel, dim3(grid), dim3(v2::kThreads), args,
+                                                  v2::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)),
+                      "multiclass3_fused_v2_kernel launch");
 }
 
 // ---- peer exchange buffers (CUDA IPC).  The one place the library allocates: IPC needs a cudaMalloc base pointer. ----

@@ -52,6 +52,24 @@ class CompositeLossStep:
         return LossList(losses.unbind(0))
 
 
+class MulticlassLossStep:
+    """The loss ``train()`` actually trains with, as ONE launch: ``train_multiclass.losses_fn(outputs, labels, ...)``
+    for 3 organs is the plain sum over channels of the 7-loss leaf (train_multiclass.py:253-274; the composite branch is
+    dead there), applied to ``F.sigmoid(net(x))`` (:134) and followed by ``loss.backward()`` (:147).
+
+    step(logits, labels) -> (the 7 loss values, d(sum_k w_k loss_k)/d logits).  ``doubling`` = 1.0 for the
+    train_multiclass flavour, 2.0 for loss_composite.losses_fn(composite_set_theory=False) (loss_composite.py:40).
+    fp32 logits [N,3,H,W] with H*W % 4 == 0."""
+
+    def __init__(self, weights, doubling=1.0, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.doubling = float(doubling)
+        self.upstream = torch.tensor([float(w) for w in weights], dtype=torch.float32, device=self.device)
+
+    def __call__(self, logits, labels, out=None):
+        return ops.multiclass3_fused(logits, labels, self.doubling, self.upstream, out=out)
+
+
 class ShardedCompositeLossStep(CompositeLossStep):
     """Batch sharded over a process group (one process per GPU): statistics kernel -> ONE all-reduce of the
     100 float64 sums (800 B) over NCCL/NVLink -> closed forms -> gradient kernel for this rank's shard.

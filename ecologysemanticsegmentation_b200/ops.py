@@ -300,6 +300,33 @@ def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None):
     return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group)
 
 
+def multiclass3_fused(x, g, leaf_scale, upstream, out=None):
+    """ONE cooperative launch for the plain 3-organ multi-class loss (train_multiclass.py:253-274, C == 3): losses of
+    the three (g_c, sigmoid(x_c)) leaves summed over channels, each times ``leaf_scale``, and the gradient of
+    sum_k upstream[k] * loss_k w.r.t. the LOGITS x.  Returns (losses f32 [7], grad)."""
+    nat.require_cuda(x, g, upstream)
+    if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"multiclass3 expects two [N,3,H,W] tensors, got {tuple(x.shape)} and {tuple(g.shape)}")
+    if upstream.dtype != torch.float32 or upstream.numel() != nat.NLOSS:
+        raise ValueError("upstream must be float32 [7]")
+    if g.dtype != torch.float32:
+        g = g.float()
+    x, x_sn, x_sc = nat.planes(x)
+    g, g_sn, g_sc = nat.planes(g)
+    n, c, h, w = x.shape
+    L = nat.lib()
+    ws = nat.workspace("mc3", L.eco_composite3_ws_bytes(), x.device)
+    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
+    gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+    vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
+    og = nat.out_of(gx, c * h * w, h * w)
+    rc = L.eco_multiclass3_fused(C.byref(vx), C.byref(vg), n, h * w, float(leaf_scale), upstream.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og), _dev(x),
+                                 nat.current_stream_ptr(x.device))
+    nat.check(rc, "eco_multiclass3_fused")
+    return losses, gx
+
+
 def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None):
     """ONE cooperative launch: statistics -> grid barrier -> closed forms -> gradient of
     sum_k upstream[k] * loss_k.  leaf_scales: float64 CUDA [21]; upstream: float32 CUDA [7].

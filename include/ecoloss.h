@@ -138,6 +138,16 @@ int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t 
                          const double* leaf_scale_dev, const float* upstream, void* ws,
                          int64_t ws_bytes, float* losses_out, const EcoOut* gx, int device, void* stream);
 
+/* The plain 3-organ multi-class loss step in ONE cooperative launch: ess/train_multiclass.py:253-274
+ * `losses_fn(outputs, labels, composite_set_theory=False, ...)` for C == 3 (= the sum over channels of the 7-loss leaf
+ * (a = g_c, b = x_c), :260-262; ess/loss_composite.py:28-40 is the same with leaf_scale = 2), with `F.sigmoid` (:134)
+ * and `loss.backward()` (:147) fused: x are fp32 LOGITS with 16-byte aligned planes (H*W % 4 == 0; -8 otherwise, use
+ * eco_pair_*), gx = d(sum_k upstream[k] * loss_k)/d logits, losses_out = float32[7] totals over the channels.
+ * ws: eco_composite3_ws_bytes() bytes, zeroed once, not shared with a concurrent eco_composite3_* call. */
+int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
+                          const float* upstream, void* ws, int64_t ws_bytes, float* losses_out, const EcoOut* gx,
+                          int device, void* stream);
+
 /* Sharded flavour of eco_composite3_fused: one process per GPU, each with its batch shard; the 100 sums are
  * all-reduced INSIDE the kernel over NVLink peer memory (P2P stores + release/acquire flags), so the whole
  * data-parallel step -- ess/train_multiclass.py:133-147 on a sharded batch -- stays one launch per rank.

@@ -158,3 +158,46 @@ def test_grad_v2_all_upstream_variants_match_first_generation():
         ours = ops.composite3_grad(z, g, True, jac, up)
         ref = ops.composite3_grad(zc, gc, True, jac, up)
         assert_grad_close(ours[:, :, :39, :51].cpu(), ref.cpu(), tol=2e-6, what=f"grad v2 vs scalar, up={up_list}")
+
+
+# ---- the plain multi-class loss step (train_multiclass.losses_fn for C == 3) in one launch ---------------------------
+@pytest.mark.parametrize("doubling", [1.0, 2.0])
+@pytest.mark.parametrize("up", [UP, UP_ALL, UP_DICE, UP_FOCAL])
+@pytest.mark.parametrize("shape", [(2, 3, 36, 28), (3, 3, 100, 100), (54, 3, 64, 64), (5, 3, 128, 136)])
+def test_multiclass_step_vs_oracle(shape, up, doubling):
+    """fused.MulticlassLossStep against the reference's ops on the same GPU: train_multiclass.losses_fn (doubling 1,
+    train_multiclass.py:253-274) and loss_composite.losses_fn(composite_set_theory=False) (doubling 2, :28-40)."""
+    from ecologysemanticsegmentation_b200.fused import MulticlassLossStep
+    from oracle import torch_port as tp
+    gen = torch.Generator().manual_seed(shape[0] * 31 + shape[3])
+    z_cpu = torch.randn(shape, generator=gen) * 1.5
+    g_cpu = _nested_masks(shape, gen)
+    z = z_cpu.cuda().requires_grad_(True)
+    fn = tp.losses_train_multiclass if doubling == 1.0 else tp.losses_composite
+    ref = fn(torch.sigmoid(z), g_cpu.cuda(), False)
+    _combine(ref, up).backward()
+    losses, dz = MulticlassLossStep(up, doubling=doubling)(z_cpu.cuda(), g_cpu.cuda())
+    assert_losses_close(losses.cpu(), [float(v) for v in ref], what=f"multiclass step {shape}")
+    assert_grad_close(dz.cpu(), z.grad.cpu(), what=f"multiclass step {shape}")
+
+
+def test_multiclass_step_matches_drop_in_and_is_deterministic():
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200 import train_multiclass as tm
+    from ecologysemanticsegmentation_b200.fused import MulticlassLossStep
+    gen = torch.Generator().manual_seed(4)
+    shape = (54, 3, 128, 128)
+    z = torch.randn(shape, generator=gen).cuda()
+    g = (torch.rand(shape, generator=gen) > 0.6).float().cuda()
+    step = MulticlassLossStep(UP_ALL)
+    l0, d0 = step(z, g)
+    l0, d0 = l0.clone(), d0.clone()
+    for _ in range(3):
+        l, d = step(z, g)
+        assert torch.equal(l, l0) and torch.equal(d, d0)
+    z2 = z.clone().requires_grad_(True)
+    ref = tm.losses_fn(z2, g, from_logits=True)     # the drop-in callable: statistics -> finalize -> gradient kernels
+    _combine(ref, UP_ALL).backward()
+    assert_losses_close(l0.cpu(), [float(v) for v in ref], tol=2e-6, what="multiclass step vs drop-in")
+    assert_grad_close(d0.cpu(), z2.grad.cpu(), tol=2e-6, what="multiclass step vs drop-in")
+    assert eco is not None
