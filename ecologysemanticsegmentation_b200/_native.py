@@ -28,6 +28,15 @@ class EcoOut(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sn", C.c_int64), ("sc", C.c_int64), ("dtype", C.c_int32), ("_pad", C.c_int32)]
 
 
+class EcoLeafShape(C.Structure):
+    """Keyword parameters of the stand-alone primitives (loss_functions.py:46,82,96); defaults = the reference's."""
+    _fields_ = [("focal_gamma", C.c_double), ("tversky_alpha", C.c_double), ("tversky_beta", C.c_double),
+                ("focal_dice_gamma", C.c_double)]
+
+
+DEFAULT_SHAPE = (1.5, 0.5, 0.3, 1.8)
+
+
 class EcoLossError(RuntimeError):
     pass
 
@@ -36,7 +45,7 @@ _lib = None
 _lock = threading.Lock()
 
 _vp, _i32, _i64, _u32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_double
-_VIEW, _OUT = C.POINTER(EcoView), C.POINTER(EcoOut)
+_VIEW, _OUT, _SHAPE = C.POINTER(EcoView), C.POINTER(EcoOut), C.POINTER(EcoLeafShape)
 
 # name -> (restype, argtypes); must list every symbol of include/ecoloss.h (tests check this)
 SIGNATURES = {
@@ -47,6 +56,10 @@ SIGNATURES = {
     "eco_pair_stats": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _u32, _vp, _i64, _vp, C.c_int, _vp]),
     "eco_pair_finalize": (C.c_int, [_vp, _i32, _f64, C.POINTER(_f64), _vp, _vp, _vp, C.c_int, _vp]),
     "eco_pair_grad": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _u32, _vp, _vp, _OUT, _OUT, _i32, C.c_int, _vp]),
+    "eco_pair_stats_shaped": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _u32, _SHAPE, _vp, _i64, _vp, C.c_int, _vp]),
+    "eco_pair_finalize_shaped": (C.c_int, [_vp, _i32, _f64, C.POINTER(_f64), _SHAPE, _vp, _vp, _vp, C.c_int, _vp]),
+    "eco_pair_grad_shaped": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _u32, _SHAPE, _vp, _vp, _OUT, _OUT, _i32, C.c_int,
+                                       _vp]),
     "eco_composite3_ws_bytes": (_i64, []),
     "eco_composite3_stats": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _i64, _vp, C.c_int, _vp]),
     "eco_composite3_finalize": (C.c_int, [_vp, C.POINTER(_f64), _vp, _vp, _vp, _vp, C.c_int, _vp]),

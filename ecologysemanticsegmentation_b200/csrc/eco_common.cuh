@@ -172,6 +172,20 @@ __device__ __forceinline__ float dfocal_bg(float b) {
     return -1.5f * s * (lg2_approx(te) * kLn2) + (b * s) * rcp_approx(te);
 }
 
+// Non-default focal exponent (focal_loss(gamma=...), loss_functions.py:46-48): the same terms through powf, which
+// is what torch.pow lowers to on this device (so negative bases / integer exponents behave as in the reference).
+// Off the hot path: no caller in the reference passes gamma, the kernels take this branch only when asked.
+__device__ __forceinline__ float focal_fg_log2_gen(float b, float gamma) { return powf(1.0f - b, gamma) * lg2_approx(b + kEps); }
+__device__ __forceinline__ float focal_bg_log2_gen(float b, float gamma) { return powf(b, gamma) * lg2_approx((1.0f - b) + kEps); }
+__device__ __forceinline__ float dfocal_fg_gen(float b, float gamma) {
+    const float t = 1.0f - b, be = b + kEps;
+    return gamma * powf(t, gamma - 1.0f) * (lg2_approx(be) * kLn2) - powf(t, gamma) * rcp_approx(be);
+}
+__device__ __forceinline__ float dfocal_bg_gen(float b, float gamma) {
+    const float te = (1.0f - b) + kEps;
+    return -gamma * powf(b, gamma - 1.0f) * (lg2_approx(te) * kLn2) + powf(b, gamma) * rcp_approx(te);
+}
+
 // ---------------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------------
@@ -206,6 +220,19 @@ __device__ __forceinline__ void phi_fd(double omt, double te, double& phi, doubl
     phi = -p18 * (double)l;
     dphi = 1.8 * (double)p08 * (double)l - p18 / te;
 }
+// same with a caller-chosen exponent (focal_dice_coefficient(gamma=...)); float64 throughout, off the hot path
+__device__ inline void phi_fd_gen(double omt, double te, double gamma, double& phi, double& dphi) {
+    const double l = log(te);
+    const double pg = pow(omt, gamma);
+    phi = -pg * l;
+    dphi = gamma * pow(omt, gamma - 1.0) * l - pg / te;
+}
+
+// Shape parameters of the Tversky and focal-Dice closed forms (loss_functions.py:82,96); the fused kernels use the
+// reference's defaults at compile time, the stand-alone primitives may pass their own.
+struct LeafShape {
+    double alpha = 0.5, beta = 0.3, fd_gamma = 1.8;
+};
 
 struct LeafMoments {
     double n, I, D, Ib, Db, FN, FP;
@@ -224,9 +251,11 @@ __device__ __forceinline__ LeafMoments leaf_moments(const double* s) {
 
 // One of the 7 losses of a leaf (k = 0..6) and its row of the Jacobian, both times `scale`.
 // Rows are independent, so the fused kernel spreads them over threads.
+template <bool kDefaultShape = true>
 __device__ inline void leaf_closed_form_row(const double* s, double bw, double scale, int k, double& loss,
-                                            double (&jrow)[ECO_NJAC]) {
-    const double eps = 1e-7, m = 10 * 0.33, alpha = 0.5, beta = 0.3;
+                                            double (&jrow)[ECO_NJAC], const LeafShape& shape = LeafShape()) {
+    const double eps = 1e-7, m = 10 * 0.33;
+    const double alpha = kDefaultShape ? 0.5 : shape.alpha, beta = kDefaultShape ? 0.3 : shape.beta;
     const LeafMoments M = leaf_moments(s);
     const double n = M.n, I = M.I, D = M.D, Ib = M.Ib, Db = M.Db, FN = M.FN, FP = M.FP;
 #pragma unroll
@@ -277,7 +306,8 @@ __device__ inline void leaf_closed_form_row(const double* s, double bw, double s
             const double r = 1.0 / (D + eps);
             const double dc = (2 * I + eps) * r;
             double phi, dphi;
-            phi_fd((D - 2 * I) * r, dc + eps, phi, dphi);  // 1 - dc = (D - 2I)/(D + eps)
+            if constexpr (kDefaultShape) phi_fd((D - 2 * I) * r, dc + eps, phi, dphi);  // 1 - dc = (D - 2I)/(D + eps)
+            else phi_fd_gen((D - 2 * I) * r, dc + eps, shape.fd_gamma, phi, dphi);
             loss = m * phi;
             dI = m * dphi * 2 * r;
             dD = -m * dphi * dc * r;
@@ -285,7 +315,8 @@ __device__ inline void leaf_closed_form_row(const double* s, double bw, double s
                 const double rb = 1.0 / (Db + eps);
                 const double dcb = (2 * Ib + eps) * rb;
                 double phib, dphib;
-                phi_fd((Db - 2 * Ib) * rb, dcb + eps, phib, dphib);
+                if constexpr (kDefaultShape) phi_fd((Db - 2 * Ib) * rb, dcb + eps, phib, dphib);
+                else phi_fd_gen((Db - 2 * Ib) * rb, dcb + eps, shape.fd_gamma, phib, dphib);
                 loss += m * bw * phib;
                 dIb = m * bw * dphib * 2 * rb;
                 dDb = -m * bw * dphib * dcb * rb;
@@ -309,6 +340,9 @@ __device__ inline void leaf_closed_form_row(const double* s, double bw, double s
 
 __device__ inline void leaf_closed_form(const double* s, double bw, double scale, LeafOut& o) {
     for (int k = 0; k < ECO_NLOSS; ++k) leaf_closed_form_row(s, bw, scale, k, o.loss[k], o.jac[k]);
+}
+__device__ inline void leaf_closed_form(const double* s, double bw, double scale, const LeafShape& shape, LeafOut& o) {
+    for (int k = 0; k < ECO_NLOSS; ++k) leaf_closed_form_row<false>(s, bw, scale, k, o.loss[k], o.jac[k], shape);
 }
 
 // coefficient vector c[j] = sum_k upstream[k] * jac[k][j]  (7 values), as floats for the per-pixel pass.

@@ -26,6 +26,7 @@ struct PairArgs {
     int32_t tiles_per_plane;
     int64_t tiles_per_channel;
     int32_t tiles_per_cta;
+    float focal_gamma;  // read by the GEN instantiations only
 };
 
 // ws layout: [0, 64*C) bytes: one uint32 arrival counter per channel (padded);
@@ -34,7 +35,8 @@ constexpr int kMaxCtasPerChannel = 148 * kCtasPerSm * 2;
 
 __host__ __device__ inline int64_t pair_ws_partials_offset(int C) { return ((int64_t)C * 4 + 255) / 256 * 256; }
 
-template <typename TA, typename TB, int VEC>
+// GEN: caller-chosen focal exponent (powf path); the default instantiation keeps the sqrt closed form.
+template <typename TA, typename TB, int VEC, bool GEN>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __restrict__ partials,
                   double* __restrict__ sums_out) {
@@ -92,8 +94,13 @@ pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __res
                     acc[2] = fmaf(a, b, acc[2]);
                     acc[3] = fmaf(b, b, acc[3]);
                     acc[4] += fmaf(softplus_neg_abs_log2(b), kLn2, fmaxf(b, 0.f));
-                    acc[5] -= focal_fg_log2(b);
-                    if (need_bg) acc[6] -= focal_bg_log2(b);
+                    if constexpr (GEN) {
+                        acc[5] -= focal_fg_log2_gen(b, p.focal_gamma);
+                        if (need_bg) acc[6] -= focal_bg_log2_gen(b, p.focal_gamma);
+                    } else {
+                        acc[5] -= focal_fg_log2(b);
+                        if (need_bg) acc[6] -= focal_bg_log2(b);
+                    }
                 }
             }
         }
@@ -154,6 +161,8 @@ pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __res
 struct FinalizeArgs {
     double bw;
     double scale[64];
+    LeafShape shape;
+    int32_t shaped;
 };
 
 __global__ void pair_finalize_kernel(const double* __restrict__ sums, int C, FinalizeArgs fa,
@@ -163,7 +172,8 @@ __global__ void pair_finalize_kernel(const double* __restrict__ sums, int C, Fin
     const int c = threadIdx.x;
     if (c < C) {
         LeafOut o;
-        leaf_closed_form(sums + c * ECO_NSTAT, fa.bw, fa.scale[c], o);
+        if (fa.shaped) leaf_closed_form(sums + c * ECO_NSTAT, fa.bw, fa.scale[c], fa.shape, o);
+        else leaf_closed_form(sums + c * ECO_NSTAT, fa.bw, fa.scale[c], o);
         for (int k = 0; k < ECO_NLOSS; ++k) {
             sl[c][k] = o.loss[k];
             if (losses_out) losses_out[c * ECO_NLOSS + k] = (float)o.loss[k];
@@ -190,7 +200,7 @@ struct GradArgs {
     int32_t accumulate;
 };
 
-template <typename TA, typename TB, int VEC>
+template <typename TA, typename TB, int VEC, bool GEN>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __restrict__ upstream) {
     constexpr int kTile = kThreads * VEC * kUnroll;
@@ -249,8 +259,13 @@ pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __rest
                 float da = fmaf(cf.sab, b, cf.sa);
                 float db = fmaf(cf.sab, a, fmaf(cf.sbb2, b, cf.sb));
                 if (need_sig) db = fmaf(cf.sp, sigmoid_fast(b), db);
-                if (need_fl) db = fmaf(cf.fl, dfocal_fg(b), db);
-                if (need_flb) db = fmaf(cf.flb, dfocal_bg(b), db);
+                if constexpr (GEN) {
+                    if (need_fl) db = fmaf(cf.fl, dfocal_fg_gen(b, p.focal_gamma), db);
+                    if (need_flb) db = fmaf(cf.flb, dfocal_bg_gen(b, p.focal_gamma), db);
+                } else {
+                    if (need_fl) db = fmaf(cf.fl, dfocal_fg(b), db);
+                    if (need_flb) db = fmaf(cf.flb, dfocal_bg(b), db);
+                }
                 if (a_logit) da *= (1.0f - a) * a;
                 if (b_logit) db *= (1.0f - b) * b;
                 oa[v] = da;
@@ -334,20 +349,33 @@ static int fill_args(PairArgs& p, const EcoView* a, const EcoView* b, int32_t N,
     return 0;
 }
 
-#define ECO_DISPATCH_PAIR(KERNEL, adt, bdt, vec, ...)                                              \
-    do {                                                                                            \
-        if (vec == 4) {                                                                             \
-            if (adt == ECO_F32 && bdt == ECO_F32) KERNEL<float, float, 4> __VA_ARGS__;              \
-            else if (adt == ECO_BF16 && bdt == ECO_F32) KERNEL<__nv_bfloat16, float, 4> __VA_ARGS__; \
-            else if (adt == ECO_F32 && bdt == ECO_BF16) KERNEL<float, __nv_bfloat16, 4> __VA_ARGS__; \
-            else KERNEL<__nv_bfloat16, __nv_bfloat16, 4> __VA_ARGS__;                                \
-        } else {                                                                                    \
-            if (adt == ECO_F32 && bdt == ECO_F32) KERNEL<float, float, 1> __VA_ARGS__;              \
-            else if (adt == ECO_BF16 && bdt == ECO_F32) KERNEL<__nv_bfloat16, float, 1> __VA_ARGS__; \
-            else if (adt == ECO_F32 && bdt == ECO_BF16) KERNEL<float, __nv_bfloat16, 1> __VA_ARGS__; \
-            else KERNEL<__nv_bfloat16, __nv_bfloat16, 1> __VA_ARGS__;                                \
-        }                                                                                           \
+#define ECO_DISPATCH_PAIR_G(KERNEL, adt, bdt, vec, GEN, ...)                                             \
+    do {                                                                                                 \
+        if (vec == 4) {                                                                                  \
+            if (adt == ECO_F32 && bdt == ECO_F32) KERNEL<float, float, 4, GEN> __VA_ARGS__;              \
+            else if (adt == ECO_BF16 && bdt == ECO_F32) KERNEL<__nv_bfloat16, float, 4, GEN> __VA_ARGS__; \
+            else if (adt == ECO_F32 && bdt == ECO_BF16) KERNEL<float, __nv_bfloat16, 4, GEN> __VA_ARGS__; \
+            else KERNEL<__nv_bfloat16, __nv_bfloat16, 4, GEN> __VA_ARGS__;                                \
+        } else {                                                                                         \
+            if (adt == ECO_F32 && bdt == ECO_F32) KERNEL<float, float, 1, GEN> __VA_ARGS__;              \
+            else if (adt == ECO_BF16 && bdt == ECO_F32) KERNEL<__nv_bfloat16, float, 1, GEN> __VA_ARGS__; \
+            else if (adt == ECO_F32 && bdt == ECO_BF16) KERNEL<float, __nv_bfloat16, 1, GEN> __VA_ARGS__; \
+            else KERNEL<__nv_bfloat16, __nv_bfloat16, 1, GEN> __VA_ARGS__;                                \
+        }                                                                                                \
     } while (0)
+#define ECO_DISPATCH_PAIR(KERNEL, adt, bdt, vec, gen, ...)                       \
+    do {                                                                         \
+        if (gen) ECO_DISPATCH_PAIR_G(KERNEL, adt, bdt, vec, true, __VA_ARGS__);  \
+        else ECO_DISPATCH_PAIR_G(KERNEL, adt, bdt, vec, false, __VA_ARGS__);     \
+    } while (0)
+
+// shape == NULL or the reference's default exponent -> the sqrt closed form; anything else -> powf instantiation
+static bool general_focal(const EcoLeafShape* shape, float& gamma_out) {
+    gamma_out = 1.5f;
+    if (!shape) return false;
+    gamma_out = (float)shape->focal_gamma;
+    return shape->focal_gamma != 1.5;
+}
 
 }  // namespace eco
 
@@ -360,7 +388,15 @@ extern "C" int64_t eco_pair_ws_bytes(int32_t C) {
 
 extern "C" int eco_pair_stats(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
                               void* ws, int64_t ws_bytes, double* sums_out, int device, void* stream) {
+    return eco_pair_stats_shaped(a, b, N, C, HW, flags, nullptr, ws, ws_bytes, sums_out, device, stream);
+}
+
+extern "C" int eco_pair_stats_shaped(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW,
+                                     uint32_t flags, const EcoLeafShape* shape_host, void* ws, int64_t ws_bytes,
+                                     double* sums_out, int device, void* stream) {
     PairArgs p{};
+    const bool gen = general_focal(shape_host, p.focal_gamma);
+    const float gamma = p.focal_gamma;
     int rc = fill_args(p, a, b, N, C, HW, flags);
     if (rc) return rc;
     if (!ws || ws_bytes < eco_pair_ws_bytes(C) || !sums_out) { set_error("workspace too small or null output"); return -5; }
@@ -371,21 +407,36 @@ extern "C" int eco_pair_stats(const EcoView* a, const EcoView* b, int32_t N, int
     dim3 grid;
     rc = plan(p, vec, device, grid);
     if (rc) return rc;
+    p.focal_gamma = gamma;
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + pair_ws_partials_offset(C));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    ECO_DISPATCH_PAIR(pair_stats_kernel, a->dtype, b->dtype, vec, <<<grid, kThreads, 0, st>>>(p, counters, partials, sums_out));
+    ECO_DISPATCH_PAIR(pair_stats_kernel, a->dtype, b->dtype, vec, gen, <<<grid, kThreads, 0, st>>>(p, counters, partials, sums_out));
     return check_cuda(cudaGetLastError(), "pair_stats_kernel launch");
 }
 
 extern "C" int eco_pair_finalize(const double* sums, int32_t C, double background_weight, const double* scale_host,
                                  float* losses_out, float* total_out, double* jac_out, int device, void* stream) {
+    return eco_pair_finalize_shaped(sums, C, background_weight, scale_host, nullptr, losses_out, total_out, jac_out,
+                                    device, stream);
+}
+
+extern "C" int eco_pair_finalize_shaped(const double* sums, int32_t C, double background_weight,
+                                        const double* scale_host, const EcoLeafShape* shape_host, float* losses_out,
+                                        float* total_out, double* jac_out, int device, void* stream) {
     if (!sums || C <= 0 || C > 64) { set_error("eco_pair_finalize: C must be in [1,64] (got %d)", C); return -1; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     FinalizeArgs fa{};
     fa.bw = background_weight;
     for (int c = 0; c < C; ++c) fa.scale[c] = scale_host ? scale_host[c] : 1.0;
+    if (shape_host && (shape_host->tversky_alpha != 0.5 || shape_host->tversky_beta != 0.3 ||
+                       shape_host->focal_dice_gamma != 1.8)) {
+        fa.shaped = 1;
+        fa.shape.alpha = shape_host->tversky_alpha;
+        fa.shape.beta = shape_host->tversky_beta;
+        fa.shape.fd_gamma = shape_host->focal_dice_gamma;
+    }
     pair_finalize_kernel<<<1, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sums, C, fa, losses_out, total_out, jac_out);
     return check_cuda(cudaGetLastError(), "pair_finalize_kernel launch");
 }
@@ -393,7 +444,16 @@ extern "C" int eco_pair_finalize(const double* sums, int32_t C, double backgroun
 extern "C" int eco_pair_grad(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
                              const double* jac, const float* upstream, const EcoOut* ga, const EcoOut* gb,
                              int32_t accumulate, int device, void* stream) {
+    return eco_pair_grad_shaped(a, b, N, C, HW, flags, nullptr, jac, upstream, ga, gb, accumulate, device, stream);
+}
+
+extern "C" int eco_pair_grad_shaped(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW,
+                                    uint32_t flags, const EcoLeafShape* shape_host, const double* jac,
+                                    const float* upstream, const EcoOut* ga, const EcoOut* gb, int32_t accumulate,
+                                    int device, void* stream) {
     GradArgs g{};
+    float gamma;
+    const bool gen = general_focal(shape_host, gamma);
     int rc = fill_args(g.p, a, b, N, C, HW, flags);
     if (rc) return rc;
     if (!jac || !upstream) { set_error("null jac/upstream"); return -5; }
@@ -411,7 +471,8 @@ extern "C" int eco_pair_grad(const EcoView* a, const EcoView* b, int32_t N, int3
     dim3 grid;
     rc = plan(g.p, vec, device, grid);
     if (rc) return rc;
+    g.p.focal_gamma = gamma;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    ECO_DISPATCH_PAIR(pair_grad_kernel, a->dtype, b->dtype, vec, <<<grid, kThreads, 0, st>>>(g, jac, upstream));
+    ECO_DISPATCH_PAIR(pair_grad_kernel, a->dtype, b->dtype, vec, gen, <<<grid, kThreads, 0, st>>>(g, jac, upstream));
     return check_cuda(cudaGetLastError(), "pair_grad_kernel launch");
 }

@@ -55,7 +55,7 @@ def _per_channel(x, g, doubling, group=None, from_logits=False):
     """C>1 recursion (loss_composite.py:28-30): leaf(a = g_c, b = x_c) summed over channels;
     ``background_weight`` is dropped there."""
     flags = ops.nat.FLAG_B_LOGIT if from_logits else 0
-    return LossList(ops.PairLeaves.apply(g, x, 0.0, float(doubling), flags, group))
+    return LossList(ops.PairLeaves.apply(g, x, 0.0, float(doubling), flags, group, None))
 
 
 def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopped=False,
@@ -70,10 +70,16 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
     ops.nat.require_cuda(x, g)
     C = g.shape[CLASS_INDEX]
 
-    if composite_set_theory and C == 3 and x.dim() == 4:
+    labels_need_grad = g.requires_grad and torch.is_grad_enabled()
+    if composite_set_theory and C == 3 and x.dim() == 4 and not labels_need_grad:
         weights = draw_pair_weights(relative_set_ratios, early_stopped)
         scales = composite3_leaf_scales(weights)
         return LossList(ops.Composite3.apply(x, g, scales, bool(from_logits), group))
+
+    if composite_set_theory and from_logits:
+        # the pair-by-pair composition below works on probabilities (organ counts other than 3, or labels that
+        # require grad): one explicit sigmoid, exactly the reference's F.sigmoid at train_multiclass.py:134
+        x, from_logits = torch.sigmoid(x), False
 
     if C > 1:
         return_losses = _per_channel(x, g, 2.0, group, from_logits)
@@ -83,9 +89,8 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
         return_losses = LossList(ops.leaf7(x, g, background_weight, scale=2.0, flags=flags, group=group))
 
     if composite_set_theory:
-        # generic organ count: the reference's own composition, each leaf one fused kernel pass
-        if from_logits:
-            raise NotImplementedError("from_logits composite is fused for 3 organs only")
+        # generic organ count (and labels that require grad): the reference's own composition, each leaf one
+        # pass of the pair-leaf kernels, gradients w.r.t. BOTH slots
         for (idx, jdx, w_idx, w_jdx, w_diff) in draw_pair_weights(relative_set_ratios, early_stopped):
             xi, xj = x[:, idx:idx + 1, ...], x[:, jdx:jdx + 1, ...]
             gi, gj = g[:, idx:idx + 1, ...], g[:, jdx:jdx + 1, ...]

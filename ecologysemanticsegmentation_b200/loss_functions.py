@@ -15,12 +15,11 @@ from . import ops
 _M = ops.M_DICE
 
 
-def _only_defaults(**kw):
-    for name, (val, default) in kw.items():
-        if float(val) != float(default):
-            raise NotImplementedError(
-                f"{name}={val}: the CUDA kernels implement the reference's default {name}={default} "
-                "(the only value any caller in the reference uses)")
+def _shape(focal_gamma=1.5, alpha=0.5, beta=0.3, focal_dice_gamma=1.8):
+    """Keyword parameters of the primitives -> the kernels' shape tuple (None = the reference's defaults, which keep
+    the sqrt closed forms; any other value takes the powf instantiation of the same kernels)."""
+    t = (float(focal_gamma), float(alpha), float(beta), float(focal_dice_gamma))
+    return None if t == ops.nat.DEFAULT_SHAPE else t
 
 
 def binary_cross_entropy_list(gt, pred):
@@ -55,8 +54,7 @@ def cross_entropy_loss(gt, pred, weight=0.3, bce=False, background_weight=0):
 
 def focal_loss(gt, pred, gamma=1.5, factor=0.1, background_weight=0):
     """loss_functions.py:46-50 (``gt`` is unused there too)."""
-    _only_defaults(gamma=(gamma, 1.5))
-    return ops.leaf7(gt, pred, background_weight, scale=factor)[2]
+    return ops.leaf7(gt, pred, background_weight, scale=factor, shape=_shape(focal_gamma=gamma))[2]
 
 
 def dice_loss(gt, pred, generalized=False, background_weight=1):
@@ -67,14 +65,12 @@ def dice_loss(gt, pred, generalized=False, background_weight=1):
 
 def twersky_loss(gt, pred, alpha=0.5, beta=0.3, background_weight=0):
     """loss_functions.py:82-94."""
-    _only_defaults(alpha=(alpha, 0.5), beta=(beta, 0.3))
-    return ops.leaf7(gt, pred, background_weight, scale=1.0 / _M)[5]
+    return ops.leaf7(gt, pred, background_weight, scale=1.0 / _M, shape=_shape(alpha=alpha, beta=beta))[5]
 
 
 def focal_dice_coefficient(gt, pred, alpha=0.5, beta=0.3, gamma=1.8, background_weight=0):
     """loss_functions.py:96-108 (alpha/beta unused there too)."""
-    _only_defaults(gamma=(gamma, 1.8))
-    return ops.leaf7(gt, pred, background_weight, scale=1.0 / _M)[6]
+    return ops.leaf7(gt, pred, background_weight, scale=1.0 / _M, shape=_shape(focal_dice_gamma=gamma))[6]
 
 
 def classification_dice_loss(gt, pred, factor=1e3, background_weight=1):

@@ -23,7 +23,14 @@ def _dev(t):
     return t.device.index if t.device.index is not None else torch.cuda.current_device()
 
 
-def pair_stats(a, b, flags=0):
+def _shape_ref(shape):
+    """None or (focal_gamma, tversky_alpha, tversky_beta, focal_dice_gamma) -> ctypes argument (NULL = defaults)."""
+    if shape is None or tuple(shape) == nat.DEFAULT_SHAPE:
+        return None
+    return C.byref(nat.EcoLeafShape(*[float(v) for v in shape]))
+
+
+def pair_stats(a, b, flags=0, shape=None):
     """a, b: [N,C,H,W] CUDA tensors -> float64 [C, 8] sums of the C (a_c, b_c) leaves of this shard."""
     nat.require_cuda(a, b)
     if a.shape != b.shape or a.dim() != 4:
@@ -35,13 +42,13 @@ def pair_stats(a, b, flags=0):
     ws = nat.workspace("pair", L.eco_pair_ws_bytes(c), a.device)
     sums = torch.empty((c, nat.NSTAT), dtype=torch.float64, device=a.device)
     va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
-    rc = L.eco_pair_stats(C.byref(va), C.byref(vb), n, c, h * w, flags, ws.data_ptr(), ws.numel(), sums.data_ptr(),
-                          _dev(a), nat.current_stream_ptr(a.device))
+    rc = L.eco_pair_stats_shaped(C.byref(va), C.byref(vb), n, c, h * w, flags, _shape_ref(shape), ws.data_ptr(),
+                                 ws.numel(), sums.data_ptr(), _dev(a), nat.current_stream_ptr(a.device))
     nat.check(rc, "eco_pair_stats")
     return sums
 
 
-def pair_finalize(sums, background_weight, scales):
+def pair_finalize(sums, background_weight, scales, shape=None):
     """sums float64 [C,8] -> (losses f32 [C,7], total f32 [7], jac f64 [C,7,7])."""
     c = sums.shape[0]
     dev = sums.device
@@ -49,13 +56,14 @@ def pair_finalize(sums, background_weight, scales):
     total = torch.empty((nat.NLOSS,), dtype=torch.float32, device=dev)
     jac = torch.empty((c, nat.NLOSS, nat.NJAC), dtype=torch.float64, device=dev)
     sc = (C.c_double * c)(*[float(s) for s in scales])
-    rc = nat.lib().eco_pair_finalize(sums.data_ptr(), c, float(background_weight), sc, losses.data_ptr(), total.data_ptr(),
-                                     jac.data_ptr(), _dev(sums), nat.current_stream_ptr(dev))
+    rc = nat.lib().eco_pair_finalize_shaped(sums.data_ptr(), c, float(background_weight), sc, _shape_ref(shape),
+                                            losses.data_ptr(), total.data_ptr(), jac.data_ptr(), _dev(sums),
+                                            nat.current_stream_ptr(dev))
     nat.check(rc, "eco_pair_finalize")
     return losses, total, jac
 
 
-def pair_grad(a, b, flags, jac, upstream, want_a, want_b):
+def pair_grad(a, b, flags, jac, upstream, want_a, want_b, shape=None):
     a, a_sn, a_sc = nat.planes(a)
     b, b_sn, b_sc = nat.planes(b)
     n, c, h, w = a.shape
@@ -63,8 +71,9 @@ def pair_grad(a, b, flags, jac, upstream, want_a, want_b):
     gb = torch.empty((n, c, h, w), dtype=b.dtype, device=b.device) if want_b else None
     va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
     oa, ob = nat.out_of(ga, c * h * w, h * w), nat.out_of(gb, c * h * w, h * w)
-    rc = nat.lib().eco_pair_grad(C.byref(va), C.byref(vb), n, c, h * w, flags, jac.data_ptr(), upstream.data_ptr(),
-                                 C.byref(oa), C.byref(ob), 0, _dev(a), nat.current_stream_ptr(a.device))
+    rc = nat.lib().eco_pair_grad_shaped(C.byref(va), C.byref(vb), n, c, h * w, flags, _shape_ref(shape), jac.data_ptr(),
+                                        upstream.data_ptr(), C.byref(oa), C.byref(ob), 0, _dev(a),
+                                        nat.current_stream_ptr(a.device))
     nat.check(rc, "eco_pair_grad")
     return ga, gb
 
@@ -214,13 +223,13 @@ class PairLeaves(torch.autograd.Function):
     per-leaf sums are all-reduced before the closed forms."""
 
     @staticmethod
-    def forward(ctx, a, b, background_weight, scale, flags, group):
+    def forward(ctx, a, b, background_weight, scale, flags, group, shape):
         c = a.shape[1]
-        sums = pair_stats(a.detach(), b.detach(), flags | (nat.FLAG_NEED_BG if background_weight != 0 else 0))
+        sums = pair_stats(a.detach(), b.detach(), flags | (nat.FLAG_NEED_BG if background_weight != 0 else 0), shape)
         sums = dist_.allreduce_sums_(sums, group)
-        _, total, jac = pair_finalize(sums, background_weight, [scale] * c)
+        _, total, jac = pair_finalize(sums, background_weight, [scale] * c, shape)
         ctx.save_for_backward(a, b, jac)
-        ctx.flags = flags
+        ctx.flags, ctx.shape = flags, shape
         ctx.set_materialize_grads(False)
         return tuple(total.unbind(0))
 
@@ -229,10 +238,10 @@ class PairLeaves(torch.autograd.Function):
         a, b, jac = ctx.saved_tensors
         want_a, want_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (want_a or want_b) or all(g is None for g in grads):
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         up = _stack_upstream(grads, a)
-        ga, gb = pair_grad(a.detach(), b.detach(), ctx.flags, jac, up, want_a, want_b)
-        return ga, gb, None, None, None, None
+        ga, gb = pair_grad(a.detach(), b.detach(), ctx.flags, jac, up, want_a, want_b, ctx.shape)
+        return ga, gb, None, None, None, None, None
 
 
 class Composite3(torch.autograd.Function):
@@ -252,8 +261,8 @@ class Composite3(torch.autograd.Function):
     def backward(ctx, *grads):
         x, g, jac = ctx.saved_tensors
         if ctx.needs_input_grad[1]:
-            raise NotImplementedError("the fused composite kernel produces gradients for the predictions only; "
-                                      "labels that require grad are not supported on this path")
+            raise RuntimeError("the fused composite kernel produces gradients for the predictions only; "
+                               "loss_composite.losses_fn routes labels that require grad to the pair-leaf kernels")
         if not ctx.needs_input_grad[0] or all(gr is None for gr in grads):
             return None, None, None, None, None
         up = _stack_upstream(grads, x)
@@ -294,10 +303,11 @@ def as_single_leaf(a, b):
     return a.contiguous().view(1, 1, 1, -1), b.contiguous().view(1, 1, 1, -1)
 
 
-def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None):
-    """The 7 losses of ONE leaf over all elements of (a, b), each times ``scale``."""
+def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None, shape=None):
+    """The 7 losses of ONE leaf over all elements of (a, b), each times ``scale``.  ``shape``: optional
+    (focal_gamma, tversky_alpha, tversky_beta, focal_dice_gamma) when a primitive is called with its own keywords."""
     a4, b4 = as_single_leaf(a, b)
-    return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group)
+    return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group, shape)
 
 
 def multiclass3_fused(x, g, leaf_scale, upstream, out=None):

@@ -30,7 +30,7 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
         ops.nat.require_cuda(x, g)
     if not isinstance(g, list) and g.shape[CLASS_INDEX] > 1:
         flags = ops.nat.FLAG_B_LOGIT if from_logits else 0
-        return list(ops.PairLeaves.apply(g, x, 0.0, 1.0, flags, group))
+        return list(ops.PairLeaves.apply(g, x, 0.0, 1.0, flags, group, None))
 
     if isinstance(x, list):
         # deep-supervision branch (:264-267): binary_cross_entropy_list works, the next helper raises

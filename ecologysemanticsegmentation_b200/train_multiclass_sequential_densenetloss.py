@@ -12,7 +12,7 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
     CLASS_INDEX = 1
     ops.nat.require_cuda(x, g)
     if g.shape[CLASS_INDEX] > 1:
-        per_channel = ops.PairLeaves.apply(g, x, 0.0, 1.0, 0, group)
+        per_channel = ops.PairLeaves.apply(g, x, 0.0, 1.0, 0, group, None)
         # direct optimisation of the target objective: superset 1 minus subset 2 (:283-285)
         extra = ops.leaf7(g[:, 1:2, :, :] - g[:, 2:3, :, :], torch.abs(x[:, 1:2, :, :] - x[:, 2:3, :, :]), 0.0, 1.0,
                           group=group)

@@ -105,6 +105,28 @@ int eco_pair_grad(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int6
                   const double* jac, const float* upstream, const EcoOut* ga, const EcoOut* gb, int32_t accumulate,
                   int device, void* stream);
 
+/* The same three calls with the shape parameters the reference's primitives accept as keyword arguments:
+ * focal_loss(gamma=1.5) (ess/loss_functions.py:46), twersky_loss(alpha=0.5, beta=0.3) (:82),
+ * focal_dice_coefficient(gamma=1.8) (:96).  shape_host == NULL = those defaults (= the calls above).  A non-default
+ * focal_gamma changes stat [6]/[7] to sum -(1-b)^gamma log(b+1e-7) / sum -b^gamma log(1-b+1e-7), so the SAME shape
+ * must be passed to stats, finalize and grad of one evaluation. */
+typedef struct EcoLeafShape {
+    double focal_gamma;
+    double tversky_alpha;
+    double tversky_beta;
+    double focal_dice_gamma;
+} EcoLeafShape;
+
+int eco_pair_stats_shaped(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                          const EcoLeafShape* shape_host, void* ws, int64_t ws_bytes, double* sums_out, int device,
+                          void* stream);
+int eco_pair_finalize_shaped(const double* sums, int32_t C, double background_weight, const double* scale_host,
+                             const EcoLeafShape* shape_host, float* losses_out, float* total_out, double* jac_out,
+                             int device, void* stream);
+int eco_pair_grad_shaped(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                         const EcoLeafShape* shape_host, const double* jac, const float* upstream, const EcoOut* ga,
+                         const EcoOut* gb, int32_t accumulate, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 3-organ composite loss: ess/loss_composite.py:21-94 `losses_fn(x, g, composite_set_theory=True)`
  * with C == 3 (whole_body, ventral+dorsal, dorsal): the 3 per-channel leaves (:28) plus, per organ

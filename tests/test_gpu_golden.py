@@ -106,6 +106,50 @@ def test_primitives_vs_reference_outputs(name):
     assert_grad_close(b.grad.cpu(), ref_b, what=name + " d/db")
 
 
+GS = np.load(os.path.join(HERE, "golden", "golden_shaped.npz"))
+SHAPED = {
+    "focal_g2": lambda lf, a, b: lf.focal_loss(a, b, gamma=2.0),
+    "focal_g07_bw": lambda lf, a, b: lf.focal_loss(a, b, gamma=0.7, factor=1, background_weight=0.4),
+    "focal_g3_bw": lambda lf, a, b: lf.focal_loss(a, b, gamma=3, factor=0.5, background_weight=1),
+    "twersky_a7b3": lambda lf, a, b: lf.twersky_loss(a, b, alpha=0.7, beta=0.3),
+    "twersky_a2b8_bw": lambda lf, a, b: lf.twersky_loss(a, b, alpha=0.2, beta=0.8, background_weight=0.25),
+    "focal_dice_g1": lambda lf, a, b: lf.focal_dice_coefficient(a, b, gamma=1.0),
+    "focal_dice_g25_bw": lambda lf, a, b: lf.focal_dice_coefficient(a, b, gamma=2.5, background_weight=0.25),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPED))
+def test_primitives_with_nondefault_keywords_vs_reference_outputs(name):
+    """focal_loss(gamma=), twersky_loss(alpha=, beta=), focal_dice_coefficient(gamma=): golden_shaped.npz holds
+    the unmodified reference's values and gradients (tests/golden/make_golden_shaped.py)."""
+    from ecologysemanticsegmentation_b200 import loss_functions as lf
+    a = _c("prim_a").requires_grad_(True)
+    b = _c("prim_b").requires_grad_(True)
+    out = SHAPED[name](lf, a, b)
+    out.backward()
+    assert_losses_close([float(out)], GS[f"{name}_val"], what=name)
+    ref_a, ref_b = GS[f"{name}_ga"], GS[f"{name}_gb"]
+    if np.abs(ref_a).max() > 0:
+        assert_grad_close(a.grad.cpu(), ref_a, what=name + " d/da")
+    else:
+        assert a.grad is None or float(a.grad.abs().max()) == 0.0
+    assert_grad_close(b.grad.cpu(), ref_b, what=name + " d/db")
+
+
+def test_nondefault_focal_gamma_edge_values_match_torch_pow():
+    """b exactly 0 and 1 (labels in the pred slot) and an integer exponent: powf semantics = torch.pow's."""
+    from ecologysemanticsegmentation_b200 import loss_functions as lf
+    from oracle import torch_port as tp
+    torch.manual_seed(9)
+    b = (torch.rand(2, 1, 16, 16) > 0.5).float()
+    b[0, 0, 0, :8] = torch.rand(8)
+    a = torch.rand(2, 1, 16, 16)
+    for gamma, bw in ((2.0, 0.0), (2.0, 0.5), (1.0, 0.3)):
+        ref = tp.pair_focal(a, b, gamma=gamma, factor=1, background_weight=bw)
+        ours = lf.focal_loss(a.cuda(), b.cuda(), gamma=gamma, factor=1, background_weight=bw)
+        assert_losses_close([float(ours)], [float(ref)], what=f"focal gamma={gamma} bw={bw}")
+
+
 def test_binary_cross_entropy_list_sums_through_cpu_buffer():
     from ecologysemanticsegmentation_b200 import loss_functions as lf
     a, b = _c("prim_a"), _c("prim_b")

@@ -106,6 +106,45 @@ def test_labels_that_require_grad_on_leaf_path():
     assert_grad_close(g.grad.cpu(), gr.grad, what="d/dg")
 
 
+def test_labels_that_require_grad_on_composite_path():
+    """composite_set_theory=True with C == 3 and labels that require grad: the fused kernel only differentiates the
+    predictions, so losses_fn composes the 21 leaves from pair-leaf passes (gradients w.r.t. both arguments)."""
+    import ecologysemanticsegmentation_b200 as eco
+    from oracle import torch_port as tp
+    torch.manual_seed(18)
+    x0, g0 = torch.rand(2, 3, 8, 8) * 0.9 + 0.05, torch.rand(2, 3, 8, 8) * 0.9 + 0.05
+    xr, gr = x0.clone().requires_grad_(True), g0.clone().requires_grad_(True)
+    np.random.seed(3)
+    ref = tp.losses_composite(xr, gr, True)
+    _combine(ref, UP_ALL).backward()
+    x, g = x0.cuda().requires_grad_(True), g0.cuda().requires_grad_(True)
+    np.random.seed(3)
+    ours = eco.losses_fn(x, g, True)
+    _combine(ours, UP_ALL).backward()
+    assert_losses_close(ours, ref, what="composite, labels with grad")
+    assert_grad_close(x.grad.cpu(), xr.grad, what="d/dx")
+    assert_grad_close(g.grad.cpu(), gr.grad, what="d/dg")
+
+
+def test_from_logits_composite_with_generic_organ_count():
+    import ecologysemanticsegmentation_b200 as eco
+    torch.manual_seed(14)
+    ratios = [1.0, 0.6, 0.3, 0.1]
+    z0 = torch.randn(2, 4, 8, 8)
+    g = (torch.rand(2, 4, 8, 8) > 0.5).float()
+    zr = z0.clone().requires_grad_(True)
+    np.random.seed(1)
+    from oracle import torch_port as tp
+    ref = tp.losses_composite(torch.sigmoid(zr), g, True, 0, False, ratios)
+    _combine(ref, UP_ALL).backward()
+    z = z0.cuda().requires_grad_(True)
+    np.random.seed(1)
+    ours = eco.losses_fn(z, g.cuda(), True, relative_set_ratios=ratios, from_logits=True)
+    _combine(ours, UP_ALL).backward()
+    assert_losses_close(ours, ref, what="C=4 from logits")
+    assert_grad_close(z.grad.cpu(), zr.grad, what="C=4 from logits")
+
+
 def test_bf16_inputs_within_1e2():
     import ecologysemanticsegmentation_b200 as eco
     from ecologysemanticsegmentation_b200.synthetic import make_inputs

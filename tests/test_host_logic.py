@@ -106,8 +106,12 @@ def test_reference_quirks_kept_on_the_host_side():
     for fn in (lf.focal_list, lf.classification_dice_list):  # unexpected keyword 'bce'
         with pytest.raises(TypeError):
             fn([x], [g])
-    with pytest.raises(NotImplementedError):
-        lf.focal_loss(x, g, gamma=2.0)
+    # non-default keywords are accepted (powf instantiation of the kernels) and still need CUDA tensors
+    from ecologysemanticsegmentation_b200 import _native
+    for call in (lambda: lf.focal_loss(x, g, gamma=2.0), lambda: lf.twersky_loss(x, g, alpha=0.7),
+                 lambda: lf.focal_dice_coefficient(x, g, gamma=1.0)):
+        with pytest.raises(_native.EcoLossError, match="no CPU fallback"):
+            call()
 
 
 def test_shard_bounds_cover_the_batch():

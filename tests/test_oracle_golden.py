@@ -147,3 +147,27 @@ def test_adjacent_steps_against_golden():
     np.testing.assert_allclose(gr, G["seq_grad"], rtol=1e-4, atol=1e-9)
     l, gr = _run(tp.losses_sequential_densenet, _t("p")[:, :1], _t("g_iid")[:, :1], UP_ALL, False, 0.5)
     np.testing.assert_allclose(l, G["seq_c1_losses"], rtol=RT)
+
+
+def test_torch_port_primitives_with_nondefault_keywords():
+    """The oracle's parametric primitives against the reference's outputs for non-default gamma / alpha / beta
+    (tests/golden/make_golden_shaped.py)."""
+    from oracle import torch_port as tp
+    GS = np.load(os.path.join(HERE, "golden", "golden_shaped.npz"))
+    cases = {
+        "focal_g2": lambda a, b: tp.pair_focal(a, b, gamma=2.0),
+        "focal_g07_bw": lambda a, b: tp.pair_focal(a, b, gamma=0.7, factor=1, background_weight=0.4),
+        "focal_g3_bw": lambda a, b: tp.pair_focal(a, b, gamma=3, factor=0.5, background_weight=1),
+        "twersky_a7b3": lambda a, b: tp.pair_tversky(a, b, alpha=0.7, beta=0.3),
+        "twersky_a2b8_bw": lambda a, b: tp.pair_tversky(a, b, alpha=0.2, beta=0.8, background_weight=0.25),
+        "focal_dice_g1": lambda a, b: tp.pair_focal_dice(a, b, gamma=1.0),
+        "focal_dice_g25_bw": lambda a, b: tp.pair_focal_dice(a, b, gamma=2.5, background_weight=0.25),
+    }
+    for name, fn in cases.items():
+        a, b = _t("prim_a").requires_grad_(True), _t("prim_b").requires_grad_(True)
+        v = fn(a, b)
+        v.backward()
+        np.testing.assert_allclose(float(v.detach()), GS[f"{name}_val"][0], rtol=RT, err_msg=name)
+        np.testing.assert_allclose(b.grad.numpy(), GS[f"{name}_gb"], rtol=1e-4, atol=1e-9, err_msg=name)
+        if a.grad is not None:
+            np.testing.assert_allclose(a.grad.numpy(), GS[f"{name}_ga"], rtol=1e-4, atol=1e-9, err_msg=name)
