@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["eco_api.cu", "eco_leaf.cu", "eco_composite.cu", "eco_eval.cu", "eco_softce.cu", "eco_union.cu"]
+SOURCES = ["eco_api.cu", "eco_leaf.cu", "eco_composite.cu", "eco_eval.cu", "eco_masks.cu", "eco_softce.cu", "eco_union.cu"]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + [os.path.join(ROOT, "include", "ecoloss.h")]
 LIB = os.path.join(HERE, "libecoloss.so")
 OBJ_DIR = os.path.join(HERE, "build")

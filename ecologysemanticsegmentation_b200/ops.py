@@ -169,6 +169,23 @@ def dice_finalize(counts, soft, nthr):
     return dice, sdice
 
 
+def masks_u8(x, threshold=None, inputs_are_probs=False):
+    """[N,C,H,W] logits (or probabilities / labels) -> uint8 [N,C,H,W] = trunc(q * 255), q = sigmoid(x) (or x),
+    thresholded first when ``threshold`` is given (test_multiclass.py:58,68-69,90-92): one 5 B/element pass."""
+    nat.require_cuda(x)
+    if x.dim() != 4:
+        raise ValueError(f"masks_u8 expects a [N,C,H,W] tensor, got {tuple(x.shape)}")
+    x, sn, sc = nat.planes(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.uint8, device=x.device)
+    v = nat.view_of(x, sn, sc)
+    rc = nat.lib().eco_masks_u8(C.byref(v), n, c, h * w, float(threshold) if threshold is not None else 0.0,
+                                int(threshold is not None), int(inputs_are_probs), out.data_ptr(), _dev(x),
+                                nat.current_stream_ptr(x.device))
+    nat.check(rc, "eco_masks_u8")
+    return out
+
+
 def softce_stats(a, b, need_bg):
     nat.require_cuda(a, b)
     a, a_sn, a_sc = nat.planes(a)

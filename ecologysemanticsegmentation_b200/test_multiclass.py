@@ -56,6 +56,14 @@ def score_batch(logits, labels, threshold=None, *, group=None, inputs_are_probs=
     return out
 
 
+def to_uint8_masks(x, threshold=None, *, inputs_are_probs=False):
+    """The byte tensors the reference dumps after scoring -- ``(t.numpy() * 255).astype(np.uint8)`` for the outputs
+    ``t = sigmoid(net(x))`` (optionally thresholded, :68-69), the labels and the images (test_multiclass.py:90-92;
+    test_video.py:129-130) -- produced on the device in one pass, so only 1 B/element crosses to the host.
+    ``x``: logits, or probabilities / labels / images with ``inputs_are_probs=True``.  Returns uint8 CUDA [N,C,H,W]."""
+    return ops.masks_u8(x, threshold, inputs_are_probs)
+
+
 class DiceAccumulator:
     """Running ``test_dice = [[sum of per-batch Dice per class], number of batches]`` of test_multiclass.py:32,82,104,
     kept on the device."""

@@ -207,6 +207,14 @@ int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int
 int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
                       float* soft_dice_out, int device, void* stream);
 
+/* Byte masks for the result dumps that follow the scoring: ess/test_multiclass.py:58 (sigmoid), :68-69 (optional
+ * threshold rule), :90-92 `(t.numpy() * 255).astype(np.uint8)` for images / labels / outputs, ess/test_video.py:129-130.
+ * out[n][c][i] = uint8(trunc(fp32(q * 255))) with q = x (x_is_prob) or sigmoid(x), then, if use_threshold,
+ * q = 1 where q > threshold (or q == 1), else 0.  x: f32 / bf16 view; out: contiguous uint8 [N][C][HW].
+ * One pass, 5 B/element; bit-identical to the reference ops on the same device for q in [0, 1]. */
+int eco_masks_u8(const EcoView* x, int32_t N, int32_t C, int64_t HW, float threshold, int32_t use_threshold,
+                 int32_t x_is_prob, uint8_t* out, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Soft-label cross entropy over the channel dim: ess/loss_functions.py:29-30
  * `F.cross_entropy(pred, gt) + bw * F.cross_entropy(1-pred, 1-gt)` with float targets.

@@ -42,3 +42,9 @@ def batch_soft_sums(logits: torch.Tensor, labels: torch.Tensor):
     C = labels.shape[1]
     return np.array([[float((out[:, c] * lab[:, c]).sum()), float(out[:, c].sum()), float((lab[:, c] ** 2).sum())]
                      for c in range(C)])
+
+
+def masks_u8(t: torch.Tensor) -> np.ndarray:
+    """ess/test_multiclass.py:90-92 (and ess/test_video.py:129-130): ``(t.numpy() * 255).astype(np.uint8)`` on the
+    host copy of a float32 tensor (outputs after the sigmoid / threshold rule, labels, images)."""
+    return (t.detach().cpu().numpy() * 255).astype(np.uint8)

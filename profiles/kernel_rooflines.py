@@ -58,6 +58,12 @@ def main():
         thr = None if nthr == 0 else torch.linspace(0.8, 0.98, nthr, device="cuda")
         t = timeit(lambda i: ops.dice_counts(zc, gc, thr), 20, 1)
         report(f"dice_counts cfg3 n_thr={nthr}", t, 8 * elems)
+    # --- byte masks for the result dumps (sigmoid -> threshold -> *255 -> uint8), cfg3 shape: 4 B in + 1 B out ---
+    for label, thr in (("sigmoid", None), ("threshold 0.8", 0.8)):
+        t = timeit(lambda i: ops.masks_u8(zc, thr), 20, 1)
+        report(f"masks_u8 cfg3 {label}", t, 5 * elems)
+    t = timeit(lambda i: ops.masks_u8(gc, None, True), 20, 1)
+    report("masks_u8 cfg3 labels", t, 5 * elems)
 
 
 if __name__ == "__main__":

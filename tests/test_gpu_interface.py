@@ -305,3 +305,30 @@ def test_cfg5_frame_stream_scoring():
         ours = tmc.score_stream(batches, thr)
         ref = tp.eval_stream_dice(batches, thr)
         assert_losses_close(ours.cpu().numpy(), ref.numpy(), what=f"cfg5 stream thr={thr}")
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 2, 5, 7), (54, 3, 256, 256)])
+def test_uint8_masks_bit_exact(shape):
+    """test_multiclass.py:58,68-69,90-92: sigmoid -> optional threshold rule -> (t.numpy() * 255).astype(uint8).
+    Bit-exact against the reference ops with the sigmoid evaluated on the same device."""
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    from oracle import counts as oc
+    from oracle import torch_port as tp
+    torch.manual_seed(31)
+    z = (torch.randn(shape) * 3).cuda()
+    lab = (torch.rand(shape) > 0.5).float().cuda()
+    assert (tmc.to_uint8_masks(z).cpu().numpy() == oc.masks_u8(torch.sigmoid(z))).all()
+    for thr in (0.8, 0.5, 0.93):
+        ref = oc.masks_u8(tp.threshold_inplace(torch.sigmoid(z), thr))
+        ours = tmc.to_uint8_masks(z, thr)
+        assert ours.dtype == torch.uint8 and tuple(ours.shape) == shape
+        assert (ours.cpu().numpy() == ref).all()
+        assert set(np.unique(ref).tolist()) <= {0, 255}
+    assert (tmc.to_uint8_masks(lab, inputs_are_probs=True).cpu().numpy() == oc.masks_u8(lab)).all()
+    p = torch.rand(shape).cuda()
+    assert (tmc.to_uint8_masks(p, inputs_are_probs=True).cpu().numpy() == oc.masks_u8(p)).all()
+    # a channel slice (strided view) and bf16 probabilities
+    if shape[1] > 1:
+        assert (tmc.to_uint8_masks(z[:, 1:2], 0.8).cpu().numpy() == oc.masks_u8(tp.threshold_inplace(torch.sigmoid(z[:, 1:2]), 0.8))).all()
+    pb = p.bfloat16()
+    assert (tmc.to_uint8_masks(pb, inputs_are_probs=True).cpu().numpy() == oc.masks_u8(pb.float())).all()
