@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+                    help="cfg2 (default, the headline) / cfg4: fused composite loss fwd+bwd; cfg5: frame-stream Dice "
+                         "scoring (sigmoid -> threshold 0.8 -> exact counts -> per-batch Dice), 64x3x512x512 per GPU")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: all-reduce of the sums inside the fused kernel over peer memory, or NCCL between kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -56,8 +58,43 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+
+    def _start_nvml(self):
+        """The timed region of a default run is ~15 ms, shorter than one nvidia-smi period: read the same counters
+        (SM clock, max SM clock, clocks-event reasons) through NVML from a thread every 2 ms instead."""
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        state = {"sm": [], "reasons": set(), "stop": False, "max": mx}
+
+        def pump():
+            while not state["stop"]:
+                try:
+                    state["sm"].append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for nm, bit in bits.items():
+                        if r & bit:
+                            state["reasons"].add(nm)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        state["thread"] = threading.Thread(target=pump, daemon=True)
+        state["thread"].start()
+        self.nvml = state
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
@@ -72,6 +109,14 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.nvml["stop"] = True
+            self.nvml["thread"].join(timeout=1)
+            sm = sorted(self.nvml["sm"])
+            if sm:
+                return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.nvml["max"], "reasons": sorted(self.nvml["reasons"]),
+                        "samples": len(sm), "source": "nvml polled from a thread, warm-up + timed region"}
+            return None
         if self.proc is None:
             return None
         time.sleep(0.12)
@@ -111,12 +156,19 @@ def workload_shape(name):
     return seed, n, c, s
 
 
-def cpu_reference_step(z, g, weights):
+STREAM_THRESHOLD = 0.8   # cfg5: the first threshold of the reference's beam (test_multiclass.py:64)
+
+
+def cpu_reference_step(z, g, weights, scoring=False):
     """The reference path on the CPU (oracle port = op-for-op restatement of the reference's eager ops):
-    sigmoid -> losses_fn(composite) -> weighted sum -> backward."""
+    sigmoid -> losses_fn(composite) -> weighted sum -> backward; ``scoring``: one batch of test()'s scoring
+    (sigmoid -> threshold rule -> per-class dice_loss, test_multiclass.py:58,68-69,80-82)."""
     import numpy as np
     import torch
     from oracle import torch_port as tp
+    if scoring:
+        with torch.no_grad():
+            return [float(v) for v in tp.eval_batch_dice(z, g, STREAM_THRESHOLD)], None
     zz = z.clone().requires_grad_(True)
     np.random.seed(0)
     comp = z.shape[1] == 3
@@ -138,13 +190,14 @@ def time_cpu_baseline(name, budget_s=20.0, n_images=None, steps=None, warmup=1):
     if n_images is None:
         n_images = n
     z, g = make_inputs(n_images, c, s, seed)
+    scoring = name == "cfg5"
     for _ in range(warmup):
-        cpu_reference_step(z, g, weights)
+        cpu_reference_step(z, g, weights, scoring)
     times = []
     t_start = time.perf_counter()
     while True:
         t0 = time.perf_counter()
-        cpu_reference_step(z, g, weights)
+        cpu_reference_step(z, g, weights, scoring)
         times.append(time.perf_counter() - t0)
         if steps is not None:
             if len(times) >= steps:
@@ -171,11 +224,13 @@ def run_reference_arm(args):
     t = sum(res["times"]) / len(res["times"])
     value = res["pixels"] / t / 1e9
     sample = f"{n_images} of {n} images of {args.workload} ({n_images}x{c}x{s}x{s}) per step, {args.steps} steps"
+    scoring = args.workload == "cfg5"
     line = {
-        "impl": "reference", "metric": "Gpixel/s fused loss fwd+bwd", "value": value, "unit": "Gpixel/s",
+        "impl": "reference", "metric": "Gpixel/s Dice eval" if scoring else "Gpixel/s fused loss fwd+bwd", "value": value, "unit": "Gpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: composite 3-organ loss fwd+bwd from logits, {n}x{c}x{s}x{s} f32",
+        "config": {"workload": (f"{args.workload}: frame-stream Dice scoring (sigmoid, threshold {STREAM_THRESHOLD}, per-class Dice), {n}x{c}x{s}x{s} f32 per batch"
+                                if scoring else f"{args.workload}: composite 3-organ loss fwd+bwd from logits, {n}x{c}x{s}x{s} f32"),
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -256,7 +311,133 @@ def main():
         print(json.dumps(line), flush=True)
 
 
+def _run_stream(args):
+    """--workload cfg5 (BASELINE.json configs[4]): the frame stream of test_video / the batch loop of test_multiclass.
+    One step = one batch of 64x3x512x512 logits + masks per GPU scored by ONE launch of the scoring kernel (sigmoid ->
+    strict '>' 0.8 -> exact int64 counts + soft sums) into its slot of the stream buffer; the global batch is sharded
+    over the ranks, and because the per-batch Dice is only needed at the end (mean over batches, test_multiclass.py:104)
+    the whole [steps, C, 3] buffer is all-reduced ONCE, inside the timed region, followed by the closed forms."""
+    import torch
+    import torch.distributed as dist
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    seed, n, c, s = workload_shape("cfg5")
+    nsets = 2   # 2 x 403 MB per GPU: every batch is 3x larger than L2, nothing is L2-resident between steps
+    host_sets = [make_inputs(n, c, s, seed + 1000 * rank + 17 * k, pin=True) for k in range(nsets)]
+    dev_sets = [(z.to(dev), g.to(dev)) for z, g in host_sets]
+    group = "world" if world > 1 else None
+    warm = max(args.warmup, 3)
+    scorer = tmc.StreamScorer(c, max(args.steps, warm), STREAM_THRESHOLD, device=dev, group=group)
+    pixels_per_step = n * s * s * world
+    elems_per_gpu = n * c * s * s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # from the warm-up on, through the timed region
+    if sampler:
+        sampler.start()
+    for i in range(warm):
+        scorer.add(*dev_sets[i % nsets])
+    scorer.result()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scorer.reset()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        scorer.add(*dev_sets[i % nsets])
+    dice = scorer.result()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = pixels_per_step / (ms_per_step * 1e-3) / 1e9
+
+    e2e = None
+    if not args.no_e2e:
+        e_steps = max(3, min(args.steps, 20))
+        zd, gd = torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])
+
+        def stream_e2e(k):
+            scorer.reset()
+            for i in range(k):
+                zh, gh = host_sets[i % nsets]
+                zd.copy_(zh, non_blocking=True)
+                gd.copy_(gh, non_blocking=True)
+                scorer.add(zd, gd)
+            return scorer.result().cpu()   # device -> host read of the stream's result (synchronises)
+
+        stream_e2e(2)
+        barrier()
+        ev0.record()
+        stream_e2e(e_steps)
+        ev1.record()
+        barrier()
+        te = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te.item()) / e_steps
+        e2e = {"value": pixels_per_step / (e_ms * 1e-3) / 1e9, "unit": "Gpixel/s",
+               "h2d_bytes_per_step": 2 * elems_per_gpu * 4 * world, "d2h_bytes_per_step": c * 4 * world / e_steps,
+               "ms_per_step": e_ms, "steps": e_steps}
+
+    line = None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = 8.0 * elems_per_gpu   # read logits 4 + read masks 4 per element; outputs are O(C)
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            res = time_cpu_baseline("cfg5", budget_s=15.0, n_images=16)
+            tb = min(res["times"])
+            cpu_baseline = {"value": res["pixels"] / tb / 1e9, "unit": "Gpixel/s", "cores": res["cores"], "kind": "port",
+                            "sample": f"{len(res['times'])} batches of 16 of the 64 images of a cfg5 batch (16x{c}x{s}x{s}), best of; "
+                                      "oracle/torch_port.py eval_batch_dice (the reference's eager scoring ops)",
+                            "ms_per_step": tb * 1e3}
+        line = {
+            "metric": "Gpixel/s Dice eval", "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg5: frame-stream Dice scoring (sigmoid -> threshold {STREAM_THRESHOLD} -> exact counts -> "
+                                   f"per-batch per-class Dice, mean over batches), {n}x{c}x{s}x{s} f32 logits + f32 masks per GPU and step",
+                       "global_batch": n * world,
+                       "parallelism": (f"dp{world} (each batch sharded over the ranks; the [steps,{c},3] int64 counts are all-reduced by NCCL "
+                                       "ONCE at the end of the stream, inside the timed region)") if world > 1 else "single GPU, one launch per batch",
+                       "l2": f"rotating {nsets} batches of {2 * elems_per_gpu * 4 / 1e6:.0f} MB (> 126 MB L2 each)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "dice_counts_kernel<float,float,4,1>", "algorithmic_bytes_per_launch": alg_bytes},
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": (args.steps + 1) * world,
+            "dice": [float(v) for v in dice.cpu()],
+        }
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
 def _run(args):
+    if args.workload == "cfg5":
+        return _run_stream(args)
 
     import torch
     import torch.distributed as dist
@@ -303,13 +484,15 @@ def _run(args):
         z, g = dev_sets[i % N_BUFFER_SETS]
         return step(z, g, out=grads[i % N_BUFFER_SETS])
 
+    # clocks are sampled from the warm-up on (same kernel, same load) through the timed region: a default timed
+    # region lasts ~15 ms, about one sampling period
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for i in range(max(args.warmup, 3)):
         one(i)
     barrier()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

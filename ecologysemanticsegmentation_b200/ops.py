@@ -128,9 +128,10 @@ def composite3_grad(x, g, from_logits, jac, upstream, out=None):
     return gx
 
 
-def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False):
+def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False, out_counts=None, out_soft=None):
     """One pass over logits+labels -> (counts int64 [T,C,3] = (I, |out|, |lab|) per threshold,
-    soft float64 [C,3] = (sum p*lab, sum p, sum lab^2)).  thresholds: float32 CUDA tensor [T] or None."""
+    soft float64 [C,3] = (sum p*lab, sum p, sum lab^2)).  thresholds: float32 CUDA tensor [T] or None.
+    ``out_counts`` / ``out_soft``: optional contiguous destinations of those shapes (e.g. one slot of a stream buffer)."""
     nat.require_cuda(logits, labels)
     if logits.shape != labels.shape or logits.dim() != 4:
         raise ValueError("dice_counts expects two [N,C,H,W] tensors of equal shape")
@@ -148,8 +149,18 @@ def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False):
         thresholds = thresholds.contiguous()
     L = nat.lib()
     ws = nat.workspace("dice%d" % nthr, L.eco_dice_ws_bytes(c, nthr), logits.device)
-    counts = torch.zeros((max(nthr, 1), c, 3), dtype=torch.int64, device=logits.device)
-    soft = torch.empty((c, 3), dtype=torch.float64, device=logits.device)
+    if out_counts is None:
+        counts = torch.zeros((max(nthr, 1), c, 3), dtype=torch.int64, device=logits.device)
+    else:
+        counts = out_counts
+        if counts.dtype != torch.int64 or counts.numel() != max(nthr, 1) * c * 3 or not counts.is_contiguous():
+            raise ValueError("out_counts must be a contiguous int64 tensor of max(T,1)*C*3 elements")
+    if out_soft is None:
+        soft = torch.empty((c, 3), dtype=torch.float64, device=logits.device)
+    else:
+        soft = out_soft
+        if soft.dtype != torch.float64 or soft.numel() != c * 3 or not soft.is_contiguous():
+            raise ValueError("out_soft must be a contiguous float64 tensor of C*3 elements")
     vz, vl = nat.view_of(logits, z_sn, z_sc), nat.view_of(labels, l_sn, l_sc, allow_u8=True)
     rc = L.eco_dice_counts(C.byref(vz), C.byref(vl), n, c, h * w, thresholds.data_ptr() if nthr else None, nthr,
                            int(inputs_are_probs), ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),

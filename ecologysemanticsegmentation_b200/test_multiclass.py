@@ -80,6 +80,52 @@ class DiceAccumulator:
         return self.total / float(self.count)
 
 
+class StreamScorer:
+    """Scores a stream of batches (the frame stream of test_video.py / the batch loop of test_multiclass.py:50-104)
+    with ONE kernel launch per batch and nothing else: each batch's exact counts and soft sums land in their own
+    slot of a device buffer, and -- because the per-batch Dice is only needed at the end (:104 takes the mean) --
+    a sharded stream all-reduces the whole ``[batches, C, 3]`` buffer ONCE at the end instead of once per batch.
+    ``result()`` = mean over batches of the per-batch per-class Dice, float32 [C] on the device, identical to
+    ``score_stream`` (same counts, same float64 closed form)."""
+
+    def __init__(self, n_classes, capacity, threshold=None, *, device=None, group=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.c, self.capacity, self.group = int(n_classes), int(capacity), group
+        self.thr = None if threshold is None else torch.tensor([float(threshold)], dtype=torch.float32, device=device)
+        self.counts = torch.zeros((self.capacity, self.c, 3), dtype=torch.int64, device=device)
+        self.soft = torch.zeros((self.capacity, self.c, 3), dtype=torch.float64, device=device)
+        self.n = 0
+
+    def reset(self):
+        self.n = 0
+
+    def add(self, logits, labels, *, inputs_are_probs=False):
+        if self.n >= self.capacity:
+            raise IndexError(f"StreamScorer holds {self.capacity} batches")
+        if logits.shape[1] != self.c:
+            raise ValueError(f"expected {self.c} classes, got {logits.shape[1]}")
+        ops.dice_counts(logits, labels, self.thr, inputs_are_probs=inputs_are_probs,
+                        out_counts=self.counts[self.n], out_soft=self.soft[self.n])
+        self.n += 1
+
+    def per_batch(self):
+        """float32 [batches, C]: the Dice of every batch scored so far (all-reduced over ``group`` first)."""
+        if self.n == 0:
+            raise ValueError("no batch scored yet")
+        counts, soft = self.counts[:self.n], self.soft[:self.n]
+        if dist_.world_size(self.group) > 1:
+            counts = dist_.allreduce_sums_(counts.clone(), self.group)
+            soft = dist_.allreduce_sums_(soft.clone(), self.group)
+        if self.thr is not None:
+            dice, _ = ops.dice_finalize(counts, soft[0], self.n)       # batches ride on the threshold axis: [n, C]
+            return dice
+        _, sdice = ops.dice_finalize(counts, soft.reshape(self.n * self.c, 3), 0)   # ... or on the class axis
+        return sdice.reshape(self.n, self.c)
+
+    def result(self):
+        return self.per_batch().sum(0) / float(self.n)
+
+
 def score_stream(batches, threshold=None, *, group=None):
     """Mean over batches of the per-batch per-class Dice (test_multiclass.py:104).  ``batches`` yields
     (logits, labels) CUDA tensor pairs."""

@@ -65,7 +65,13 @@ def _worker(rank, world, port, q):
         e_plain = max(abs(float(a) - float(b)) / max(abs(float(b)), 1e-30) for a, b in zip(o2[1:], r2[1:]))
         d_full, c_full, _ = tmc.score_batch(zf, gf, 0.8, return_counts=True)
         d_sh, c_sh, _ = tmc.score_batch(zs.detach(), gs, 0.8, group=D.WORLD, return_counts=True)
-        q.put((rank, e_loss, e_grad, e_step, e_plain, bool(torch.equal(c_full, c_sh)), bool(torch.equal(d_full, d_sh))))
+        # frame stream (cfg5): sharded batches, ONE all-reduce of the whole counts buffer at the end
+        sc, full = tmc.StreamScorer(3, 4, 0.8, group=D.WORLD), tmc.StreamScorer(3, 4, 0.8)
+        for f in (1.0, 0.5, 2.0):
+            sc.add(zs.detach() * f, gs)
+            full.add(zf * f, gf)
+        stream_eq = bool(torch.equal(sc.per_batch(), full.per_batch())) and bool(torch.equal(sc.result(), full.result()))
+        q.put((rank, e_loss, e_grad, e_step, e_plain, bool(torch.equal(c_full, c_sh)), bool(torch.equal(d_full, d_sh)) and stream_eq))
     finally:
         dist.destroy_process_group()
 

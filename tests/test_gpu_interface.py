@@ -332,3 +332,29 @@ def test_uint8_masks_bit_exact(shape):
         assert (tmc.to_uint8_masks(z[:, 1:2], 0.8).cpu().numpy() == oc.masks_u8(tp.threshold_inplace(torch.sigmoid(z[:, 1:2]), 0.8))).all()
     pb = p.bfloat16()
     assert (tmc.to_uint8_masks(pb, inputs_are_probs=True).cpu().numpy() == oc.masks_u8(pb.float())).all()
+
+
+def test_stream_scorer_equals_per_batch_scoring():
+    """StreamScorer (one launch per batch into a slot, closed forms for all batches at the end) gives exactly the
+    per-batch Dice of score_batch and the mean of score_stream -- thresholded and soft."""
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    from oracle import torch_port as tp
+    torch.manual_seed(77)
+    batches = [((torch.randn(4, 3, 32, 32) * 2).cuda(), (torch.rand(4, 3, 32, 32) > 0.6).float().cuda()) for _ in range(5)]
+    for thr in (None, 0.8):
+        sc = tmc.StreamScorer(3, 8, thr)
+        for z, lab in batches:
+            sc.add(z, lab)
+        per = sc.per_batch()
+        assert tuple(per.shape) == (5, 3)
+        for k, (z, lab) in enumerate(batches):
+            assert torch.equal(per[k], tmc.score_batch(z, lab, thr))
+        ref = tp.eval_stream_dice([(z.cpu(), lab.cpu()) for z, lab in batches], thr)
+        assert_losses_close(sc.result().cpu().numpy(), ref.numpy(), what=f"stream thr={thr}")
+        sc.reset()
+        sc.add(*batches[2])
+        assert torch.equal(sc.result(), tmc.score_batch(*batches[2], thr))
+    with pytest.raises(IndexError):
+        sc = tmc.StreamScorer(3, 1, 0.8)
+        sc.add(*batches[0])
+        sc.add(*batches[1])
