@@ -262,6 +262,35 @@ def measure_aux(dev):
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / iters * 1e-3
 
+    def timed_graph(fn, per_replay, replays):
+        """Short kernels (tens of us) are launch-path bound from Python: capture `per_replay` calls of `fn` (one per
+        rotating buffer set) in a CUDA graph and time its replays.  Returns (seconds per call, "graph" | "eager")."""
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(per_replay):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(per_replay):
+                    fn()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(replays):
+                graph.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) / (replays * per_replay) * 1e-3, "graph"
+        except Exception as exc:  # capture not possible on this driver: plain launches
+            print("graph capture failed, timing plain launches:", repr(exc), file=sys.stderr)
+            torch.cuda.synchronize()
+            return timed(fn, replays * per_replay), "eager"
+
     n, c, s = 54, 3, 1024
     z, g = make_inputs(n, c, s, 103)
     z, g = z.to(dev), g.to(dev)
@@ -284,11 +313,28 @@ def measure_aux(dev):
         state["i"] += 1
         mstep(sets[k][0], sets[k][1], out=outs[k])
 
-    t = timed(run_mc, 100)
+    t, how = timed_graph(run_mc, 4, 25)
     gbs = 12.0 * n * c * s * s / t / 1e9
     out["multiclass_plain_cfg2_shape"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
-                                          "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 12,
+                                          "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 12, "launch": how,
                                           "what": "train_multiclass.losses_fn (3 plain leaves) fwd+bwd from logits, one launch"}
+    # cfg1 (BASELINE.json configs[0]): ORGANS=whole_body single-class loss fwd+bwd from logits, one launch (eco_pair_fused)
+    n, c, s = 54, 1, 256
+    sets1 = [tuple(t.to(dev) for t in make_inputs(n, c, s, 101 + 7 * k)) for k in range(12)]   # 12 x 28 MB > L2
+    outs1 = [torch.empty_like(zz) for zz, _ in sets1]
+    lstep = fused.LeafLossStep(fused.loss_weights(bce=1.0, generalized_dice=1.0, twersky=1.0), doubling=1.0, device=dev)
+    state1 = {"i": 0}
+
+    def run_leaf():
+        k = state1["i"] % 12
+        state1["i"] += 1
+        lstep(sets1[k][0], sets1[k][1], out=outs1[k])
+
+    t, how = timed_graph(run_leaf, 12, 20)
+    gbs = 12.0 * n * c * s * s / t / 1e9
+    out["leaf_cfg1"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak,
+                        "bytes_per_element": 12, "launch": how,
+                        "what": "cfg1: single-class losses_fn (bce + gdice + twersky) fwd+bwd from logits, 54x1x256x256, one launch"}
     return out
 
 

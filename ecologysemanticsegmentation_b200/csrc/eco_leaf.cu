@@ -36,10 +36,12 @@ constexpr int kMaxCtasPerChannel = 148 * kCtasPerSm * 2;
 __host__ __device__ inline int64_t pair_ws_partials_offset(int C) { return ((int64_t)C * 4 + 255) / 256 * 256; }
 
 // GEN: caller-chosen focal exponent (powf path); the default instantiation keeps the sqrt closed form.
+// Pass 1 of one CTA: streams its tiles, reduces over the CTA, parks the 7 partial sums, arrives; the last CTA of the
+// channel adds the partials of all CTAs in a fixed order and writes the channel's sums.  Returns true in that CTA
+// (uniformly over its threads).  `rearm`: reset the arrival counter for the next launch on this workspace.
 template <typename TA, typename TB, int VEC, bool GEN>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
-pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __restrict__ partials,
-                  double* __restrict__ sums_out) {
+__device__ __forceinline__ bool pair_stats_cta(const PairArgs& p, unsigned int* __restrict__ counters,
+                                               double* __restrict__ partials, double* __restrict__ sums_out) {
     constexpr int kTile = kThreads * VEC * kUnroll;
     const int c = blockIdx.y;
     const bool a_logit = p.flags & ECO_A_LOGIT, b_logit = p.flags & ECO_B_LOGIT;
@@ -139,7 +141,7 @@ pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __res
         is_last = (prev == gridDim.x - 1);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) return false;
     __threadfence();
     // deterministic final reduction by the last CTA of this channel: warp k sums stat k
     if (warp < 7) {
@@ -153,6 +155,14 @@ pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __res
         sums_out[c * ECO_NSTAT + S_N] = (double)p.N * (double)p.HW;
         counters[c] = 0;  // re-arm for the next launch on this workspace
     }
+    return true;
+}
+
+template <typename TA, typename TB, int VEC, bool GEN>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+pair_stats_kernel(PairArgs p, unsigned int* __restrict__ counters, double* __restrict__ partials,
+                  double* __restrict__ sums_out) {
+    pair_stats_cta<TA, TB, VEC, GEN>(p, counters, partials, sums_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,9 +210,9 @@ struct GradArgs {
     int32_t accumulate;
 };
 
+// Pass 2 of one CTA over its tiles with the channel's coefficients.
 template <typename TA, typename TB, int VEC, bool GEN>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
-pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __restrict__ upstream) {
+__device__ __forceinline__ void pair_grad_cta(const GradArgs& g, const LeafCoef cf) {
     constexpr int kTile = kThreads * VEC * kUnroll;
     const PairArgs& p = g.p;
     const int c = blockIdx.y;
@@ -211,11 +221,6 @@ pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __rest
     const TB* __restrict__ bbase = reinterpret_cast<const TB*>(p.b) + (int64_t)c * p.b_sc;
     TA* gabase = g.ga ? reinterpret_cast<TA*>(g.ga) + (int64_t)c * g.ga_sc : nullptr;
     TB* gbbase = g.gb ? reinterpret_cast<TB*>(g.gb) + (int64_t)c * g.gb_sc : nullptr;
-
-    __shared__ LeafCoef coef_s;
-    if (threadIdx.x == 0) coef_s = make_coef(jac + (int64_t)c * ECO_NLOSS * ECO_NJAC, upstream);
-    __syncthreads();
-    const LeafCoef cf = coef_s;
     const bool need_sig = cf.sp != 0.f, need_fl = cf.fl != 0.f, need_flb = cf.flb != 0.f;
 
     int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
@@ -305,6 +310,117 @@ pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __rest
             ++n;
         }
     }
+}
+
+template <typename TA, typename TB, int VEC, bool GEN>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+pair_grad_kernel(GradArgs g, const double* __restrict__ jac, const float* __restrict__ upstream) {
+    __shared__ LeafCoef coef_s;
+    if (threadIdx.x == 0) coef_s = make_coef(jac + (int64_t)blockIdx.y * ECO_NLOSS * ECO_NJAC, upstream);
+    __syncthreads();
+    pair_grad_cta<TA, TB, VEC, GEN>(g, coef_s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One cooperative launch for a whole step of C leaves: pass 1 -> per-channel hand-over (the last CTA of a channel
+// forms the sums, the closed forms and the gradient coefficients and releases the channel's other CTAs) -> pass 2
+// over the same tiles (mostly L2 hits).  All CTAs are co-resident (grid = one resident wave, cooperative launch).
+// Workspace words after the stats layout: per channel {done generation u32}, the coefficients, the losses; one
+// grid-wide counter of finished channels so that the last one adds up the 7 totals in channel order.
+// ---------------------------------------------------------------------------------------------
+struct FusedWs {
+    unsigned int done[64];       // generation of the last completed hand-over per channel
+    unsigned int chan_count;     // channels finalized in this launch
+    unsigned int _pad[63];
+    LeafCoef coef[64];
+    double loss[64][ECO_NLOSS];
+};
+
+struct FusedArgs {
+    GradArgs g;
+    double bw, scale;
+    LeafShape shape;
+    int32_t shaped;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// hand-over by the channel's last CTA (all its threads call this): warp k forms loss k and its Jacobian row -- one
+// warp per loss kind, because the seven float64 closed forms are seven different code paths and would serialise inside
+// one warp -- then seven threads contract the rows with the upstream weights into the gradient coefficients.  Kept
+// out of line: the float64 code must not weigh on the register allocation of the two streaming loops.
+__device__ __noinline__ void fused_handover(const FusedArgs& fa, const float* __restrict__ upstream, FusedWs* __restrict__ fw,
+                                            const double* __restrict__ sums_out, float* __restrict__ losses_out, int c,
+                                            unsigned int gen) {
+    __shared__ double sl[ECO_NLOSS];
+    __shared__ double sj[ECO_NLOSS][ECO_NJAC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* s = sums_out + c * ECO_NSTAT;
+    for (int k = warp; k < ECO_NLOSS; k += kThreads / 32) {
+        if (lane == 0) {
+            if (fa.shaped) leaf_closed_form_row<false>(s, fa.bw, fa.scale, k, sl[k], sj[k], fa.shape);
+            else leaf_closed_form_row(s, fa.bw, fa.scale, k, sl[k], sj[k]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < ECO_NJAC) {
+        const int j = threadIdx.x;
+        double v = 0.0;
+        for (int k = 1; k < ECO_NLOSS; ++k) {
+            const double w = (double)upstream[k];
+            if (w != 0.0) v += w * sj[k][j];
+        }
+        reinterpret_cast<float*>(&fw->coef[c])[j] = (float)(j == 3 ? 2.0 * v : v);   // LeafCoef order; [3] = 2 c_Sbb
+        fw->loss[c][j] = sl[j];
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    st_release_u32(&fw->done[c], gen + 1u);
+    // the last channel to get here adds the totals in channel order (deterministic)
+    const unsigned int prev = atomicAdd(&fw->chan_count, 1u);
+    if (prev == gridDim.y - 1) {
+        __threadfence();
+        for (int k = 0; k < ECO_NLOSS; ++k) {
+            double v = 0.0;
+            for (int cc = 0; cc < (int)gridDim.y; ++cc) v += __ldcg(&fw->loss[cc][k]);
+            losses_out[k] = (float)v;
+        }
+        fw->chan_count = 0u;
+    }
+}
+
+template <typename TA, typename TB, int VEC, bool GEN>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+pair_fused_kernel(FusedArgs fa, const float* __restrict__ upstream, unsigned int* __restrict__ counters,
+                  double* __restrict__ partials, FusedWs* __restrict__ fw, double* __restrict__ sums_out,
+                  float* __restrict__ losses_out) {
+    const int c = blockIdx.y;
+    __shared__ unsigned int gen_s;
+    __shared__ LeafCoef coef_s;
+    // the generation is read BEFORE this CTA arrives: the hand-over of this launch cannot have happened yet
+    if (threadIdx.x == 0) gen_s = ld_acquire_u32(&fw->done[c]);
+    __syncthreads();
+    const unsigned int gen = gen_s;
+    const bool last = pair_stats_cta<TA, TB, VEC, GEN>(fa.g.p, counters, partials, sums_out);
+    if (last) {
+        __syncthreads();   // the channel's sums are in sums_out (written by this CTA)
+        fused_handover(fa, upstream, fw, sums_out, losses_out, c, gen);
+    }
+    if (threadIdx.x == 0) {
+        while (ld_acquire_u32(&fw->done[c]) == gen) __nanosleep(64);
+        for (int j = 0; j < 7; ++j)
+            reinterpret_cast<float*>(&coef_s)[j] = __ldcg(reinterpret_cast<const float*>(&fw->coef[c]) + j);
+    }
+    __syncthreads();
+    pair_grad_cta<TA, TB, VEC, GEN>(fa.g, coef_s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,4 +591,74 @@ extern "C" int eco_pair_grad_shaped(const EcoView* a, const EcoView* b, int32_t 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     ECO_DISPATCH_PAIR(pair_grad_kernel, a->dtype, b->dtype, vec, gen, <<<grid, kThreads, 0, st>>>(g, jac, upstream));
     return check_cuda(cudaGetLastError(), "pair_grad_kernel launch");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused step
+// ------------------------------------------------------------------------------------------------------------------
+static int64_t fused_ws_offset(int32_t C) { return (eco_pair_ws_bytes(C) + 255) / 256 * 256; }
+
+extern "C" int64_t eco_pair_fused_ws_bytes(int32_t C) {
+    if (C <= 0 || C > 64) return -1;
+    return fused_ws_offset(C) + (int64_t)sizeof(FusedWs);
+}
+
+extern "C" int eco_pair_fused(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                              double background_weight, double scale, const EcoLeafShape* shape_host,
+                              const float* upstream, void* ws, int64_t ws_bytes, double* sums_out, float* losses_out,
+                              const EcoOut* ga, const EcoOut* gb, int device, void* stream) {
+    FusedArgs fa{};
+    GradArgs& g = fa.g;
+    int rc = fill_args(g.p, a, b, N, C, HW, flags | (background_weight != 0.0 ? ECO_NEED_BG : 0u));
+    if (rc) return rc;
+    if (C > 64) { set_error("eco_pair_fused: C must be <= 64 (got %d); use eco_pair_stats/finalize/grad", C); return -3; }
+    if (!upstream || !sums_out || !losses_out) { set_error("null upstream / sums_out / losses_out"); return -5; }
+    if (!ws || ws_bytes < eco_pair_fused_ws_bytes(C)) { set_error("workspace too small"); return -5; }
+    const bool want_a = ga && ga->ptr, want_b = gb && gb->ptr;
+    if (want_a && ga->dtype != a->dtype) { set_error("ga dtype must match slot a"); return -7; }
+    if (want_b && gb->dtype != b->dtype) { set_error("gb dtype must match slot b"); return -7; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    bool v4 = aligned_for_vec4(a->ptr, a->sn, a->sc, a->dtype, HW) && aligned_for_vec4(b->ptr, b->sn, b->sc, b->dtype, HW);
+    if (want_a) { g.ga = ga->ptr; g.ga_sn = ga->sn; g.ga_sc = ga->sc; v4 = v4 && aligned_for_vec4(ga->ptr, ga->sn, ga->sc, ga->dtype, HW); }
+    if (want_b) { g.gb = gb->ptr; g.gb_sn = gb->sn; g.gb_sc = gb->sc; v4 = v4 && aligned_for_vec4(gb->ptr, gb->sn, gb->sc, gb->dtype, HW); }
+    const int vec = v4 ? 4 : 1;
+    float gamma;
+    const bool gen = general_focal(shape_host, gamma);
+    dim3 grid;
+    rc = plan(g.p, vec, device, grid);
+    if (rc) return rc;
+    g.p.focal_gamma = gamma;
+    const int sms = sm_count_cached(device);
+    if ((int64_t)grid.x * grid.y > (int64_t)sms * kCtasPerSm) {
+        set_error("eco_pair_fused: %d leaves do not fit one resident wave; use eco_pair_stats/finalize/grad", C);
+        return -8;
+    }
+    fa.bw = background_weight;
+    fa.scale = scale;
+    if (shape_host && (shape_host->tversky_alpha != 0.5 || shape_host->tversky_beta != 0.3 || shape_host->focal_dice_gamma != 1.8)) {
+        fa.shaped = 1;
+        fa.shape.alpha = shape_host->tversky_alpha;
+        fa.shape.beta = shape_host->tversky_beta;
+        fa.shape.fd_gamma = shape_host->focal_dice_gamma;
+    }
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + pair_ws_partials_offset(C));
+    FusedWs* fw = reinterpret_cast<FusedWs*>(reinterpret_cast<char*>(ws) + fused_ws_offset(C));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    void* args[] = {&fa, (void*)&upstream, &counters, &partials, &fw, &sums_out, &losses_out};
+    const void* fn = nullptr;
+#define ECO_PICK(TA, TB, V, G) fn = (const void*)pair_fused_kernel<TA, TB, V, G>
+#define ECO_PICK_T(V, G)                                                                       \
+    do {                                                                                       \
+        if (a->dtype == ECO_F32 && b->dtype == ECO_F32) ECO_PICK(float, float, V, G);          \
+        else if (a->dtype == ECO_BF16 && b->dtype == ECO_F32) ECO_PICK(__nv_bfloat16, float, V, G); \
+        else if (a->dtype == ECO_F32 && b->dtype == ECO_BF16) ECO_PICK(float, __nv_bfloat16, V, G); \
+        else ECO_PICK(__nv_bfloat16, __nv_bfloat16, V, G);                                     \
+    } while (0)
+    if (vec == 4) { if (gen) ECO_PICK_T(4, true); else ECO_PICK_T(4, false); }
+    else { if (gen) ECO_PICK_T(1, true); else ECO_PICK_T(1, false); }
+#undef ECO_PICK_T
+#undef ECO_PICK
+    return check_cuda(cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads), args, 0, st), "pair_fused_kernel launch");
 }

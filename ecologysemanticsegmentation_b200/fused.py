@@ -70,6 +70,34 @@ class MulticlassLossStep:
         return ops.multiclass3_fused(logits, labels, self.doubling, self.upstream, out=out)
 
 
+class LeafLossStep:
+    """The plain (non-composite) ``losses_fn`` on LOGITS as ONE launch, for any organ count up to 64 and fp32 / bf16
+    inputs -- in particular the single-organ configuration ORGANS=whole_body (BASELINE.json configs[0]):
+
+    * C == 1 (loss_composite.py:32-40 / train_multiclass.py:264-274): the leaf with the PREDICTION in the gt slot,
+      ``a = sigmoid(z)``, ``b = labels``, ``background_weight`` honoured;
+    * C > 1 (loss_composite.py:28 / train_multiclass.py:260-262): sum over channels of the leaf
+      ``a = labels_c, b = sigmoid(z_c)``; ``background_weight`` is dropped there, and here.
+
+    step(logits, labels) -> (the 7 loss values, d(sum_k w_k loss_k)/d logits).  ``doubling`` = 2.0 for
+    loss_composite.losses_fn (:40), 1.0 for the train_multiclass flavour."""
+
+    def __init__(self, weights, doubling=2.0, background_weight=0.0, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.doubling = float(doubling)
+        self.background_weight = float(background_weight)
+        self.upstream = torch.tensor([float(w) for w in weights], dtype=torch.float32, device=self.device)
+
+    def __call__(self, logits, labels, out=None):
+        if logits.shape[1] == 1:
+            losses, ga, _, _ = ops.pair_fused(logits, labels, ops.nat.FLAG_A_LOGIT, self.background_weight, self.doubling,
+                                              self.upstream, want_a=True, want_b=False, out_a=out)
+            return losses, ga
+        losses, _, gb, _ = ops.pair_fused(labels, logits, ops.nat.FLAG_B_LOGIT, 0.0, self.doubling, self.upstream,
+                                          want_a=False, want_b=True, out_b=out)
+        return losses, gb
+
+
 class ShardedCompositeLossStep(CompositeLossStep):
     """Batch sharded over a process group (one process per GPU): statistics kernel -> ONE all-reduce of the
     100 float64 sums (800 B) over NCCL/NVLink -> closed forms -> gradient kernel for this rank's shard.

@@ -78,6 +78,37 @@ def pair_grad(a, b, flags, jac, upstream, want_a, want_b, shape=None):
     return ga, gb
 
 
+def pair_fused(a, b, flags, background_weight, scale, upstream, want_a=False, want_b=True, out_a=None, out_b=None,
+               shape=None):
+    """ONE cooperative launch for a step of C independent leaves (eco_pair_fused): sums -> closed forms -> gradient of
+    sum_k upstream[k] * loss_k w.r.t. slot a and/or slot b (w.r.t. the logits where a slot is flagged as logits).
+    Returns (losses f32 [7] summed over the channels, ga, gb, sums f64 [C, 8])."""
+    nat.require_cuda(a, b, upstream)
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError(f"pair_fused expects two [N,C,H,W] tensors of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+    if upstream.dtype != torch.float32 or upstream.numel() != nat.NLOSS:
+        raise ValueError("upstream must be float32 [7]")
+    a, a_sn, a_sc = nat.planes(a)
+    b, b_sn, b_sc = nat.planes(b)
+    n, c, h, w = a.shape
+    L = nat.lib()
+    nbytes = L.eco_pair_fused_ws_bytes(c)
+    if nbytes < 0:
+        raise ValueError(f"pair_fused serves at most 64 leaves per launch (got {c})")
+    ws = nat.workspace("pairfused", nbytes, a.device)
+    sums = torch.empty((c, nat.NSTAT), dtype=torch.float64, device=a.device)
+    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=a.device)
+    ga = (out_a if out_a is not None else torch.empty((n, c, h, w), dtype=a.dtype, device=a.device)) if want_a else None
+    gb = (out_b if out_b is not None else torch.empty((n, c, h, w), dtype=b.dtype, device=b.device)) if want_b else None
+    va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
+    oa, ob = nat.out_of(ga, c * h * w, h * w), nat.out_of(gb, c * h * w, h * w)
+    rc = L.eco_pair_fused(C.byref(va), C.byref(vb), n, c, h * w, int(flags), float(background_weight), float(scale),
+                          _shape_ref(shape), upstream.data_ptr(), ws.data_ptr(), ws.numel(), sums.data_ptr(),
+                          losses.data_ptr(), C.byref(oa), C.byref(ob), _dev(a), nat.current_stream_ptr(a.device))
+    nat.check(rc, "eco_pair_fused")
+    return losses, ga, gb, sums
+
+
 def composite3_stats(x, g, from_logits):
     nat.require_cuda(x, g)
     if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:

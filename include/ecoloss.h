@@ -127,6 +127,20 @@ int eco_pair_grad_shaped(const EcoView* a, const EcoView* b, int32_t N, int32_t 
                          const EcoLeafShape* shape_host, const double* jac, const float* upstream, const EcoOut* ga,
                          const EcoOut* gb, int32_t accumulate, int device, void* stream);
 
+/* One step of C independent leaves in ONE cooperative launch (C <= 64, grid = one resident wave): pass 1 ->
+ * per-channel hand-over of the sums (closed forms and gradient coefficients by the channel's last CTA) -> pass 2 over
+ * the same tiles.  This is `loss.backward()` of ess/train_multiclass.py:139-147 for the single-organ configuration
+ * (ORGANS=whole_body: C == 1, a = prediction, b = label, background_weight honoured, ess/loss_composite.py:32-40) and
+ * for any plain multi-channel losses_fn (a = labels, b = predictions, :28), with upstream = dT/dloss_k known up front.
+ * scale multiplies every leaf's 7 losses (2.0 for ess/loss_composite.py:40).  sums_out: float64[C][ECO_NSTAT];
+ * losses_out: float32[7] totals over the channels; ga / gb as in eco_pair_grad (overwritten, not accumulated).
+ * ws: eco_pair_fused_ws_bytes(C) bytes, zeroed once.  Returns -8 when C leaves do not fit one resident wave. */
+int64_t eco_pair_fused_ws_bytes(int32_t C);
+int eco_pair_fused(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                   double background_weight, double scale, const EcoLeafShape* shape_host, const float* upstream,
+                   void* ws, int64_t ws_bytes, double* sums_out, float* losses_out, const EcoOut* ga, const EcoOut* gb,
+                   int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 3-organ composite loss: ess/loss_composite.py:21-94 `losses_fn(x, g, composite_set_theory=True)`
  * with C == 3 (whole_body, ventral+dorsal, dorsal): the 3 per-channel leaves (:28) plus, per organ

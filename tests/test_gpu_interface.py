@@ -358,3 +358,41 @@ def test_stream_scorer_equals_per_batch_scoring():
         sc = tmc.StreamScorer(3, 1, 0.8)
         sc.add(*batches[0])
         sc.add(*batches[1])
+
+
+@pytest.mark.parametrize("case", [(54, 1, 256, 256, 0.0), (54, 1, 256, 256, 0.5), (3, 1, 17, 19, 0.5), (4, 2, 32, 32, 0.0),
+                                  (54, 3, 256, 256, 0.0), (2, 5, 8, 24, 0.0)])
+def test_leaf_loss_step_one_launch(case):
+    """fused.LeafLossStep (eco_pair_fused: stats -> hand-over -> gradient in one cooperative launch) against the
+    oracle on the same logits: cfg1 (C == 1, prediction in the gt slot, background_weight honoured) and plain C > 1."""
+    from ecologysemanticsegmentation_b200 import fused
+    from oracle import torch_port as tp
+    n, c, h, w, bw = case
+    torch.manual_seed(1000 + c + h)
+    z0 = torch.randn(n, c, h, w)
+    g = (torch.rand(n, c, h, w) > 0.5).float()
+    for doubling, fn in ((2.0, tp.losses_composite), (1.0, tp.losses_train_multiclass)):
+        zr = z0.clone().requires_grad_(True)
+        ref = fn(torch.sigmoid(zr), g, False, bw)
+        _combine(ref, UP_ALL).backward()
+        step = fused.LeafLossStep(UP_ALL, doubling=doubling, background_weight=bw)
+        for _ in range(3):   # several launches on the same workspace: generations / re-armed counters
+            losses, grad = step(z0.cuda(), g.cuda())
+        assert_losses_close(losses.cpu().numpy(), ref, what=f"leaf step {case} x{doubling}")
+        assert_grad_close(grad.cpu(), zr.grad, what=f"leaf step {case} x{doubling}")
+
+
+def test_leaf_loss_step_bf16_and_out_buffer():
+    from ecologysemanticsegmentation_b200 import fused
+    from oracle import torch_port as tp
+    torch.manual_seed(5)
+    z0 = torch.randn(6, 1, 64, 64)
+    g = (torch.rand(6, 1, 64, 64) > 0.5).float()
+    zr = z0.bfloat16().float().requires_grad_(True)
+    ref = tp.losses_composite(torch.sigmoid(zr), g, False, 0.0)
+    _combine(ref, UP_ALL).backward()
+    out = torch.empty(6, 1, 64, 64, dtype=torch.bfloat16, device="cuda")
+    losses, grad = fused.LeafLossStep(UP_ALL)(z0.bfloat16().cuda(), g.cuda(), out=out)
+    assert grad.data_ptr() == out.data_ptr()
+    assert_losses_close(losses.cpu().numpy(), ref, tol=TOL_BF16, what="leaf step bf16")
+    assert_grad_close(grad.float().cpu(), zr.grad, tol=TOL_BF16, what="leaf step bf16")
