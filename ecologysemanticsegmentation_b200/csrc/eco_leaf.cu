@@ -39,9 +39,16 @@ __host__ __device__ inline int64_t pair_ws_partials_offset(int C) { return ((int
 // Pass 1 of one CTA: streams its tiles, reduces over the CTA, parks the 7 partial sums, arrives; the last CTA of the
 // channel adds the partials of all CTAs in a fixed order and writes the channel's sums.  Returns true in that CTA
 // (uniformly over its threads).  `rearm`: reset the arrival counter for the next launch on this workspace.
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 template <typename TA, typename TB, int VEC, bool GEN>
 __device__ __forceinline__ bool pair_stats_cta(const PairArgs& p, unsigned int* __restrict__ counters,
-                                               double* __restrict__ partials, double* __restrict__ sums_out) {
+                                               double* __restrict__ partials, double* __restrict__ sums_out,
+                                               double* sums_sm = nullptr /* shared-memory copy, [ECO_NSTAT] */) {
     constexpr int kTile = kThreads * VEC * kUnroll;
     const int c = blockIdx.y;
     const bool a_logit = p.flags & ECO_A_LOGIT, b_logit = p.flags & ECO_B_LOGIT;
@@ -134,25 +141,30 @@ __device__ __forceinline__ bool pair_stats_cta(const PairArgs& p, unsigned int* 
         for (int w = 0; w < kThreads / 32; ++w) v += sm[w][threadIdx.x];
         my_partials[threadIdx.x] = v;
     }
-    __threadfence();
+    // Arrival without stand-alone fences (a sequentially-consistent MEMBAR costs ~1 us here, twice): the partial
+    // stores of threads 0..6 precede thread 0's RELEASE through the CTA barrier (release is cumulative), and the last
+    // CTA's reads below follow thread 0's ACQUIRE through the next barrier; they go to L2 (__ldcg), not to a stale L1.
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int prev = atomicAdd(&counters[c], 1u);
+        unsigned int prev = atom_add_acq_rel_gpu(&counters[c], 1u);
         is_last = (prev == gridDim.x - 1);
     }
     __syncthreads();
     if (!is_last) return false;
-    __threadfence();
     // deterministic final reduction by the last CTA of this channel: warp k sums stat k
     if (warp < 7) {
         const double* base = partials + (int64_t)c * kMaxCtasPerChannel * 8;
         double v = 0.0;
         for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(base + (int64_t)i * 8 + warp);
         v = warp_sum(v);
-        if (lane == 0) sums_out[c * ECO_NSTAT + 1 + warp] = v;
+        if (lane == 0) {
+            sums_out[c * ECO_NSTAT + 1 + warp] = v;
+            if (sums_sm) sums_sm[1 + warp] = v;
+        }
     }
     if (threadIdx.x == 0) {
         sums_out[c * ECO_NSTAT + S_N] = (double)p.N * (double)p.HW;
+        if (sums_sm) sums_sm[S_N] = (double)p.N * (double)p.HW;
         counters[c] = 0;  // re-arm for the next launch on this workspace
     }
     return true;
@@ -357,12 +369,11 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
 // one warp -- then seven threads contract the rows with the upstream weights into the gradient coefficients.  Kept
 // out of line: the float64 code must not weigh on the register allocation of the two streaming loops.
 __device__ __noinline__ void fused_handover(const FusedArgs& fa, const float* __restrict__ upstream, FusedWs* __restrict__ fw,
-                                            const double* __restrict__ sums_out, float* __restrict__ losses_out, int c,
-                                            unsigned int gen) {
+                                            const double* s /* shared: the channel's sums */, float* __restrict__ losses_out,
+                                            int c, unsigned int gen) {
     __shared__ double sl[ECO_NLOSS];
     __shared__ double sj[ECO_NLOSS][ECO_NJAC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double* s = sums_out + c * ECO_NSTAT;
     for (int k = warp; k < ECO_NLOSS; k += kThreads / 32) {
         if (lane == 0) {
             if (fa.shaped) leaf_closed_form_row<false>(s, fa.bw, fa.scale, k, sl[k], sj[k], fa.shape);
@@ -379,15 +390,13 @@ __device__ __noinline__ void fused_handover(const FusedArgs& fa, const float* __
         }
         reinterpret_cast<float*>(&fw->coef[c])[j] = (float)(j == 3 ? 2.0 * v : v);   // LeafCoef order; [3] = 2 c_Sbb
         fw->loss[c][j] = sl[j];
-        __threadfence();
     }
-    __syncthreads();
+    __syncthreads();   // those stores precede thread 0's release below (cumulative through the barrier)
     if (threadIdx.x != 0) return;
     st_release_u32(&fw->done[c], gen + 1u);
     // the last channel to get here adds the totals in channel order (deterministic)
-    const unsigned int prev = atomicAdd(&fw->chan_count, 1u);
+    const unsigned int prev = atom_add_acq_rel_gpu(&fw->chan_count, 1u);
     if (prev == gridDim.y - 1) {
-        __threadfence();
         for (int k = 0; k < ECO_NLOSS; ++k) {
             double v = 0.0;
             for (int cc = 0; cc < (int)gridDim.y; ++cc) v += __ldcg(&fw->loss[cc][k]);
@@ -409,13 +418,14 @@ pair_fused_kernel(FusedArgs fa, const float* __restrict__ upstream, unsigned int
     if (threadIdx.x == 0) gen_s = ld_acquire_u32(&fw->done[c]);
     __syncthreads();
     const unsigned int gen = gen_s;
-    const bool last = pair_stats_cta<TA, TB, VEC, GEN>(fa.g.p, counters, partials, sums_out);
+    __shared__ double sums_s[ECO_NSTAT];
+    const bool last = pair_stats_cta<TA, TB, VEC, GEN>(fa.g.p, counters, partials, sums_out, sums_s);
     if (last) {
-        __syncthreads();   // the channel's sums are in sums_out (written by this CTA)
-        fused_handover(fa, upstream, fw, sums_out, losses_out, c, gen);
+        __syncthreads();   // the channel's sums are in sums_s (and in sums_out for the caller)
+        fused_handover(fa, upstream, fw, sums_s, losses_out, c, gen);
     }
     if (threadIdx.x == 0) {
-        while (ld_acquire_u32(&fw->done[c]) == gen) __nanosleep(64);
+        while (ld_acquire_u32(&fw->done[c]) == gen) __nanosleep(20);
         for (int j = 0; j < 7; ++j)
             reinterpret_cast<float*>(&coef_s)[j] = __ldcg(reinterpret_cast<const float*>(&fw->coef[c]) + j);
     }
