@@ -12,6 +12,14 @@
 
 namespace eco {
 
+#ifdef ECO_LEAF_TIMELINE   // exp/leaf_timeline.py: %globaltimer stamps per CTA (not compiled into the library)
+__device__ unsigned long long g_leaf_tl[4096 * 8];
+__device__ __forceinline__ unsigned long long leaf_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ECO_LTL(slot) do { if (threadIdx.x == 0) g_leaf_tl[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = leaf_gtime(); } while (0)
+#else
+#define ECO_LTL(slot) do { } while (0)
+#endif
+
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 constexpr int kCtasPerSm = 4;
@@ -120,6 +128,7 @@ __device__ __forceinline__ bool pair_stats_cta(const PairArgs& p, unsigned int* 
             ++n;
         }
     }
+    ECO_LTL(1);
     // focal terms were accumulated in log2 units
     dacc[5] *= kLn2d;
     dacc[6] *= kLn2d;
@@ -368,7 +377,7 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
 // warp per loss kind, because the seven float64 closed forms are seven different code paths and would serialise inside
 // one warp -- then seven threads contract the rows with the upstream weights into the gradient coefficients.  Kept
 // out of line: the float64 code must not weigh on the register allocation of the two streaming loops.
-__device__ __noinline__ void fused_handover(const FusedArgs& fa, const float* __restrict__ upstream, FusedWs* __restrict__ fw,
+__device__ __noinline__ void fused_handover(const FusedArgs& fa, const float* upstream /* shared [7] */, FusedWs* __restrict__ fw,
                                             const double* s /* shared: the channel's sums */, float* __restrict__ losses_out,
                                             int c, unsigned int gen) {
     __shared__ double sl[ECO_NLOSS];
@@ -381,20 +390,26 @@ __device__ __noinline__ void fused_handover(const FusedArgs& fa, const float* __
         }
     }
     __syncthreads();
+    ECO_LTL(7);
     if (threadIdx.x < ECO_NJAC) {
         const int j = threadIdx.x;
         double v = 0.0;
+#pragma unroll
         for (int k = 1; k < ECO_NLOSS; ++k) {
             const double w = (double)upstream[k];
-            if (w != 0.0) v += w * sj[k][j];
+            if (w != 0.0) v += w * sj[k][j];   // rows without upstream weight stay out (their Jacobian may be non-finite)
         }
         reinterpret_cast<float*>(&fw->coef[c])[j] = (float)(j == 3 ? 2.0 * v : v);   // LeafCoef order; [3] = 2 c_Sbb
         fw->loss[c][j] = sl[j];
+        if (gridDim.y == 1) losses_out[j] = (float)sl[j];   // a single leaf: its losses are the totals
     }
     __syncthreads();   // those stores precede thread 0's release below (cumulative through the barrier)
-    if (threadIdx.x != 0) return;
-    st_release_u32(&fw->done[c], gen + 1u);
-    // the last channel to get here adds the totals in channel order (deterministic)
+    if (threadIdx.x == 0) st_release_u32(&fw->done[c], gen + 1u);
+}
+
+// Second half of the hand-over, off the critical path: ONE thread of the channel's last CTA, after its pass 2.  The
+// last channel to get here adds the 7 totals in channel order (deterministic).
+__device__ __forceinline__ void fused_totals(FusedWs* __restrict__ fw, float* __restrict__ losses_out) {
     const unsigned int prev = atom_add_acq_rel_gpu(&fw->chan_count, 1u);
     if (prev == gridDim.y - 1) {
         for (int k = 0; k < ECO_NLOSS; ++k) {
@@ -414,15 +429,22 @@ pair_fused_kernel(FusedArgs fa, const float* __restrict__ upstream, unsigned int
     const int c = blockIdx.y;
     __shared__ unsigned int gen_s;
     __shared__ LeafCoef coef_s;
+    __shared__ float up_s[ECO_NLOSS + 1];
+    // fetched now, under pass 1: nothing on the hand-over path between the two passes waits for a global load
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + ECO_NLOSS) up_s[threadIdx.x - 32] = upstream[threadIdx.x - 32];
     // the generation is read BEFORE this CTA arrives: the hand-over of this launch cannot have happened yet
     if (threadIdx.x == 0) gen_s = ld_acquire_u32(&fw->done[c]);
     __syncthreads();
     const unsigned int gen = gen_s;
+    ECO_LTL(0);
     __shared__ double sums_s[ECO_NSTAT];
     const bool last = pair_stats_cta<TA, TB, VEC, GEN>(fa.g.p, counters, partials, sums_out, sums_s);
+    ECO_LTL(2);
     if (last) {
         __syncthreads();   // the channel's sums are in sums_s (and in sums_out for the caller)
-        fused_handover(fa, upstream, fw, sums_s, losses_out, c, gen);
+        ECO_LTL(5);
+        fused_handover(fa, up_s, fw, sums_s, losses_out, c, gen);
+        ECO_LTL(6);
     }
     if (threadIdx.x == 0) {
         while (ld_acquire_u32(&fw->done[c]) == gen) __nanosleep(20);
@@ -430,7 +452,10 @@ pair_fused_kernel(FusedArgs fa, const float* __restrict__ upstream, unsigned int
             reinterpret_cast<float*>(&coef_s)[j] = __ldcg(reinterpret_cast<const float*>(&fw->coef[c]) + j);
     }
     __syncthreads();
+    ECO_LTL(3);
     pair_grad_cta<TA, TB, VEC, GEN>(fa.g, coef_s);
+    if (last && threadIdx.x == 0 && gridDim.y > 1) fused_totals(fw, losses_out);
+    ECO_LTL(4);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -672,3 +697,9 @@ extern "C" int eco_pair_fused(const EcoView* a, const EcoView* b, int32_t N, int
 #undef ECO_PICK
     return check_cuda(cudaLaunchCooperativeKernel(fn, grid, dim3(kThreads), args, 0, st), "pair_fused_kernel launch");
 }
+
+#ifdef ECO_LEAF_TIMELINE
+extern "C" int eco_debug_leaf_timeline(unsigned long long* host_out, int n_words) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_leaf_tl, (size_t)n_words * 8);
+}
+#endif
