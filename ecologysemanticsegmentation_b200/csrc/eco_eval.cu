@@ -212,6 +212,248 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
     if (threadIdx.x == 0) counters[c] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Threshold beam (5..20 thresholds, ess/test_multiclass.py:64-77) by BINNING instead of one compare per threshold:
+// the thresholds are sorted once per CTA; an element's bin = number of thresholds below its probability (a
+// 5-step branch-free search: two levels in registers, three in shared memory) and it bumps ONE packed counter
+// {low 16 bits: elements, high 16 bits: elements with label 1} of its thread-private shared-memory histogram
+// (a plain read-modify-write: shared-memory atomics, even uncontended, run at a fraction of the LDS/STS rate).  counts(T_r) = sum of the bins above r.  The sigmoid is the 4-instruction MUFU form; ATen's exact
+// bits are recomputed only for elements within kThrEps of one of the thresholds (the two neighbours of the bin come
+// from one 8-byte load), after the branch-free phase over the thread's 16 elements.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBeamMax = 20;
+constexpr int kBeamBins = kBeamMax + 1;
+constexpr int kBeamThreads = 256;
+#ifndef ECO_BEAM_CTAS
+#define ECO_BEAM_CTAS 4
+#endif
+constexpr int kBeamCtasPerSm = ECO_BEAM_CTAS;   // 64 registers; the 21 KB histogram of 4 CTAs fits the SM's shared memory
+
+struct BeamSmem {
+    float sorted[32];            // [0..30] ascending thresholds padded with +inf (31 entries are searched)
+    float2 nbr[32];              // per bin b: {largest threshold below, smallest threshold at or above}
+    int rank_of[kBeamMax];       // original index k -> position in the sorted order
+    unsigned int hist[kBeamBins][kBeamThreads];
+    long long cnt[2 * kBeamMax + 1];
+    double soft[kBeamThreads / 32][3];
+    bool is_last;
+};
+
+__device__ __forceinline__ int beam_bin(float p, const BeamSmem& sm, float t15, float t7, float t23) {
+    int b = p > t15 ? 16 : 0;
+    b += (p > (b ? t23 : t7)) ? 8 : 0;
+    b += (p > sm.sorted[b + 3]) ? 4 : 0;
+    b += (p > sm.sorted[b + 1]) ? 2 : 0;
+    b += (p > sm.sorted[b]) ? 1 : 0;
+    return b;   // number of thresholds T with p > T (strict, fp32), 0..n_thr
+}
+
+template <typename TZ, typename TL, int VEC>
+__global__ void __launch_bounds__(kBeamThreads, kBeamCtasPerSm)
+dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
+                 long long* __restrict__ partials, long long* __restrict__ counts_out, double* __restrict__ soft_out) {
+    constexpr int kTile = kBeamThreads * VEC * kEvUnroll;
+    constexpr int NTA = kBeamMax;
+    __shared__ BeamSmem sm;
+    const int c = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TZ* __restrict__ zbase = reinterpret_cast<const TZ*>(p.z) + (int64_t)c * p.z_sc;
+    const TL* __restrict__ lbase = reinterpret_cast<const TL*>(p.l) + (int64_t)c * p.l_sc;
+
+    // ---- sort the thresholds (rank = number of smaller ones; ties by index), neighbours per bin ------------------------
+    if (tid < 32) sm.sorted[tid] = __int_as_float(0x7f800000);
+    if (tid < 2 * NTA + 1) sm.cnt[tid] = 0;
+#pragma unroll
+    for (int b = 0; b < kBeamBins; ++b) sm.hist[b][tid] = 0u;
+    __syncthreads();
+    if (tid < p.n_thr) {
+        float t = thresholds[tid];
+        if (t != t) t = __int_as_float(0x7f800000);   // p > NaN is never true: same as +inf
+        int r = 0;
+        for (int j = 0; j < p.n_thr; ++j) {
+            float u = thresholds[j];
+            if (u != u) u = __int_as_float(0x7f800000);
+            r += (u < t || (u == t && j < tid)) ? 1 : 0;
+        }
+        sm.sorted[r] = t;
+        sm.rank_of[tid] = r;
+    }
+    __syncthreads();
+    if (tid < 32) sm.nbr[tid] = make_float2(tid > 0 ? sm.sorted[tid - 1] : -__int_as_float(0x7f800000), sm.sorted[tid < 31 ? tid : 31]);
+    __syncthreads();
+    const float t15 = sm.sorted[15], t7 = sm.sorted[7], t23 = sm.sorted[23];
+
+    int cnt_l = 0, since_fold = 0;
+    double dsoft[3] = {0.0, 0.0, 0.0};
+    int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+    int64_t tile_end = tile + p.tiles_per_cta;
+    if (tile_end > p.tiles_per_channel) tile_end = p.tiles_per_channel;
+    int64_t n = tile / p.tiles_per_plane;
+    int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
+
+    for (; tile < tile_end; ++tile) {
+        const TZ* zp = zbase + n * p.z_sn;
+        const TL* lp = lbase + n * p.l_sn;
+        const int64_t e0 = (int64_t)t * kTile + (int64_t)tid * VEC;
+        float zv[kEvUnroll][VEC], lv[kEvUnroll][VEC];
+        bool ok[kEvUnroll];
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u) {
+            const int64_t e = e0 + (int64_t)u * kBeamThreads * VEC;
+            ok[u] = e < p.HW;
+            if (ok[u]) {
+                if constexpr (VEC == 4) {
+                    Vec4<TZ>::load(zp + e, reinterpret_cast<float(&)[4]>(zv[u]));
+                    Vec4<TL>::load(lp + e, reinterpret_cast<float(&)[4]>(lv[u]));
+                } else {
+                    zv[u][0] = Vec4<TZ>::load1(zp + e);
+                    lv[u][0] = Vec4<TL>::load1(lp + e);
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { zv[u][v] = 0.f; lv[u][v] = 0.f; }
+            }
+        }
+        // branch-free phase: probability, bin, doubtful flag of all elements (their MUFU / LDS latencies overlap)
+        int bins[kEvUnroll][VEC];
+        unsigned int redo = 0u;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float pr = p.probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
+                const int b = beam_bin(pr, sm, t15, t7, t23);
+                bins[u][v] = b;
+                const float2 nb = sm.nbr[b];
+                const bool near = !p.probs && ((pr - nb.x) < kThrEps || (nb.y - pr) < kThrEps);
+                redo |= near ? (1u << (u * VEC + v)) : 0u;
+                const float lab = lv[u][v];
+                const float w = ok[u] ? 1.f : 0.f;
+                s0 = fmaf(pr * w, lab, s0);
+                s1 = fmaf(pr, w, s1);
+                s2 = fmaf(lab, lab, s2);
+            }
+        }
+        if (redo) {   // rare: the strict '>' must see ATen's bits
+#pragma unroll
+            for (int u = 0; u < kEvUnroll; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (redo & (1u << (u * VEC + v))) bins[u][v] = beam_bin(sigmoid_exact(zv[u][v]), sm, t15, t7, t23);
+        }
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u) {
+            if (!ok[u]) continue;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int li = fabsf(lv[u][v]) >= 1.0f ? 1 : 0;
+                cnt_l += li;
+                sm.hist[bins[u][v]][tid] += 1u + ((unsigned int)li << 16);   // thread-private slot: plain LDS / IADD / STS
+            }
+        }
+        dsoft[0] += (double)s0;
+        dsoft[1] += (double)s1;
+        dsoft[2] += (double)s2;
+        if ((since_fold += kEvUnroll * VEC) >= kPackFlushElems) {   // before a 16-bit half can overflow
+#pragma unroll 1
+            for (int b = 1; b < kBeamBins; ++b) {
+                const unsigned int h = sm.hist[b][tid];
+                sm.hist[b][tid] = 0u;
+                // bin b counts towards the sorted thresholds r < b
+                for (int r = 0; r < b && r < p.n_thr; ++r) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r]), (unsigned long long)(h & 0xffffu));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r + 1]), (unsigned long long)(h >> 16));
+                }
+            }
+            sm.hist[0][tid] = 0u;
+            since_fold = 0;
+        }
+        if (++t == p.tiles_per_plane) {
+            t = 0;
+            ++n;
+        }
+    }
+
+    // ---- CTA reduction: per bin over the threads, then suffix sums -> per sorted threshold ----------------------------
+    __syncthreads();
+    for (int b = 1 + warp; b < kBeamBins; b += kBeamThreads / 32) {
+        int o = 0, i = 0;
+        for (int k = lane; k < kBeamThreads; k += 32) {
+            const unsigned int h = sm.hist[b][k];
+            o += (int)(h & 0xffffu);
+            i += (int)(h >> 16);
+        }
+        o = __reduce_add_sync(0xffffffffu, o);
+        i = __reduce_add_sync(0xffffffffu, i);
+        if (lane == 0) {
+            for (int r = 0; r < b && r < p.n_thr; ++r) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r]), (unsigned long long)o);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r + 1]), (unsigned long long)i);
+            }
+        }
+    }
+    {
+        int l = __reduce_add_sync(0xffffffffu, cnt_l);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * NTA]), (unsigned long long)l);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double v = warp_sum(dsoft[k]);
+        if (lane == 0) sm.soft[warp][k] = v;
+    }
+    __syncthreads();
+    // partial record in the layout of dice_counts_kernel<.., 20>: word 2k = |out| and 2k+1 = intersection of the
+    // caller's k-th threshold (= sorted position rank_of[k]), word 40 = label count, then the three soft sums
+    const int64_t rec = eval_rec_words(NTA);
+    long long* mine = partials + ((int64_t)c * kEvMaxCtas + blockIdx.x) * rec;
+    if (tid < 2 * NTA) {
+        const int k = tid >> 1;
+        mine[tid] = k < p.n_thr ? sm.cnt[2 * sm.rank_of[k] + (tid & 1)] : 0;
+    }
+    if (tid == 2 * NTA) mine[tid] = sm.cnt[2 * NTA];
+    if (tid < 3) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBeamThreads / 32; ++w) v += sm.soft[w][tid];
+        reinterpret_cast<double*>(mine)[2 * NTA + 1 + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(&counters[c], 1u);
+        sm.is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!sm.is_last) return;
+    __threadfence();
+    const long long* base = partials + (int64_t)c * kEvMaxCtas * rec;
+    for (int w = warp; w < 2 * NTA + 1 + 3; w += kBeamThreads / 32) {
+        if (w < 2 * NTA + 1) {
+            long long v = 0;
+            for (int i = lane; i < (int)gridDim.x; i += 32) v += __ldcg(base + (int64_t)i * rec + w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) {
+                if (w == 2 * NTA) {
+                    for (int k = 0; k < p.n_thr; ++k) counts_out[((int64_t)k * p.C + c) * 3 + 2] = v;
+                } else {
+                    const int k = w >> 1;
+                    if (k < p.n_thr) counts_out[((int64_t)k * p.C + c) * 3 + ((w & 1) ? 0 : 1)] = v;
+                }
+            }
+        } else {
+            const int sidx = w - (2 * NTA + 1);
+            double v = 0.0;
+            for (int i = lane; i < (int)gridDim.x; i += 32)
+                v += __ldcg(reinterpret_cast<const double*>(base + (int64_t)i * rec) + 2 * NTA + 1 + sidx);
+            v = warp_sum(v);
+            if (lane == 0) soft_out[c * 3 + sidx] = v;
+        }
+    }
+    if (tid == 0) counters[c] = 0;
+}
+
 struct DiceFinArgs {
     int C, n_thr;
 };
@@ -255,6 +497,26 @@ static void launch_nt(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cud
 #undef ECO_EV
 }
 
+static void launch_beam(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cudaStream_t st, const float* thr,
+                        unsigned int* counters, long long* partials, long long* counts_out, double* soft_out) {
+#define ECO_BM(TZ, TL, V) dice_beam_kernel<TZ, TL, V><<<grid, kBeamThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out)
+    if (ld == ECO_U8) {
+        if (vec == 4) { if (zd == ECO_F32) ECO_BM(float, uint8_t, 4); else ECO_BM(__nv_bfloat16, uint8_t, 4); }
+        else { if (zd == ECO_F32) ECO_BM(float, uint8_t, 1); else ECO_BM(__nv_bfloat16, uint8_t, 1); }
+    } else if (vec == 4) {
+        if (zd == ECO_F32 && ld == ECO_F32) ECO_BM(float, float, 4);
+        else if (zd == ECO_BF16 && ld == ECO_F32) ECO_BM(__nv_bfloat16, float, 4);
+        else if (zd == ECO_F32 && ld == ECO_BF16) ECO_BM(float, __nv_bfloat16, 4);
+        else ECO_BM(__nv_bfloat16, __nv_bfloat16, 4);
+    } else {
+        if (zd == ECO_F32 && ld == ECO_F32) ECO_BM(float, float, 1);
+        else if (zd == ECO_BF16 && ld == ECO_F32) ECO_BM(__nv_bfloat16, float, 1);
+        else if (zd == ECO_F32 && ld == ECO_BF16) ECO_BM(float, __nv_bfloat16, 1);
+        else ECO_BM(__nv_bfloat16, __nv_bfloat16, 1);
+    }
+#undef ECO_BM
+}
+
 static int nt_bucket(int n_thr) { return n_thr == 0 ? 0 : n_thr == 1 ? 1 : n_thr <= 4 ? 4 : 20; }
 
 }  // namespace eco
@@ -293,7 +555,8 @@ extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int
     p.tiles_per_channel = (int64_t)p.tiles_per_plane * N;
     const int sms = sm_count_cached(device);
     if (sms <= 0) return -10;
-    int64_t max_ctas = (int64_t)sms * kEvCtasPerSm / C;
+    const int ctas_per_sm = nt_bucket(n_thr) == 20 ? kBeamCtasPerSm : kEvCtasPerSm;
+    int64_t max_ctas = (int64_t)sms * ctas_per_sm / C;
     if (max_ctas < 1) max_ctas = 1;
     if (max_ctas > kEvMaxCtas) max_ctas = kEvMaxCtas;
     int64_t per = (p.tiles_per_channel + max_ctas - 1) / max_ctas;
@@ -308,7 +571,7 @@ extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int
         case 0: launch_nt<0>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
         case 1: launch_nt<1>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
         case 4: launch_nt<4>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
-        default: launch_nt<20>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
+        default: launch_beam(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
     }
     return check_cuda(cudaGetLastError(), "dice_counts_kernel launch");
 }

@@ -396,3 +396,41 @@ def test_leaf_loss_step_bf16_and_out_buffer():
     assert grad.data_ptr() == out.data_ptr()
     assert_losses_close(losses.cpu().numpy(), ref, tol=TOL_BF16, what="leaf step bf16")
     assert_grad_close(grad.float().cpu(), zr.grad, tol=TOL_BF16, what="leaf step bf16")
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 7, 9), (4, 3, 64, 64), (8, 3, 256, 256)])
+def test_threshold_beam_binning_kernel_edge_cases(shape):
+    """5..20 thresholds go through the binning kernel: unsorted and duplicated thresholds, thresholds that hit
+    probabilities exactly, byte masks, probabilities as input, odd plane sizes -- each row must equal the
+    single-threshold call bit for bit (counts) and value for value (Dice)."""
+    from ecologysemanticsegmentation_b200 import ops, test_multiclass as tmc
+    torch.manual_seed(99)
+    z = (torch.randn(shape) * 3).cuda()
+    lab = (torch.rand(shape) > 0.5).float().cuda()
+    prob = torch.sigmoid(z)
+    exact_hits = [float(prob.flatten()[i]) for i in (0, 5, 17)]        # '>' is strict: these pixels must NOT count
+    cases = [
+        [0.9, 0.1, 0.5, 0.5, 0.97, 0.8],
+        list(np.arange(0.8, 0.99, step=0.01)) + [0.5],                 # 20 thresholds
+        exact_hits + [0.3, 0.6, 0.999999],
+        [0.0, 1.0, -1.0, 2.0, 0.5],
+    ]
+    for thrs in cases:
+        for labels in (lab, lab.to(torch.uint8)):
+            many, counts, soft = tmc.score_batch(z, labels, thrs, return_counts=True)
+            assert tuple(many.shape) == (len(thrs), shape[1])
+            for k, t in enumerate(thrs):
+                one, c1, s1 = tmc.score_batch(z, labels, float(t), return_counts=True)
+                assert torch.equal(c1[0], counts[k]), (thrs, k)
+                assert torch.equal(one, many[k])
+            assert torch.allclose(soft, s1, rtol=1e-6)
+        # probabilities as input: no sigmoid, plain strict compare
+        many_p, counts_p, _ = tmc.score_batch(prob, lab, thrs, inputs_are_probs=True, return_counts=True)
+        for k, t in enumerate(thrs):
+            ref_out = (prob > torch.tensor(float(t), dtype=torch.float32)).long()
+            for c in range(shape[1]):
+                assert int(counts_p[k, c, 1]) == int(ref_out[:, c].sum())
+                assert int(counts_p[k, c, 0]) == int((ref_out[:, c] * lab[:, c].long()).sum())
+    thr_nan = torch.tensor([0.5, float("nan"), 0.7, 0.2, 0.9], device="cuda")
+    c_nan, _ = ops.dice_counts(z, lab, thr_nan)
+    assert int(c_nan[1, :, :2].abs().sum()) == 0                       # p > NaN is never true
