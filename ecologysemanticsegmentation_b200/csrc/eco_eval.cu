@@ -224,10 +224,11 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
 constexpr int kBeamMax = 20;
 constexpr int kBeamBins = kBeamMax + 1;
 constexpr int kBeamThreads = 256;
+constexpr int kBeamCells = 256;   // power of two
 #ifndef ECO_BEAM_CTAS
-#define ECO_BEAM_CTAS 4
+#define ECO_BEAM_CTAS 3
 #endif
-constexpr int kBeamCtasPerSm = ECO_BEAM_CTAS;   // 64 registers; the 21 KB histogram of 4 CTAs fits the SM's shared memory
+constexpr int kBeamCtasPerSm = ECO_BEAM_CTAS;   // 80 registers (64 spill in the streaming loop); measured 2 / 3 / 4 CTAs per SM within 3 %
 
 struct BeamSmem {
     float sorted[32];            // [0..30] ascending thresholds padded with +inf (31 entries are searched)
@@ -237,7 +238,22 @@ struct BeamSmem {
     long long cnt[2 * kBeamMax + 1];
     double soft[kBeamThreads / 32][3];
     bool is_last;
+    // direct lookup (thresholds at least two cells apart, e.g. the reference's np.arange(0.8, 0.99, 0.01)): cell j of a
+    // uniform grid over [T_min, T_max] -> {thresholds in the cells below (as int bits), the cell's own threshold or +inf,
+    // nearest threshold below the cell or -inf, nearest above or +inf}
+    float4 lut[kBeamCells];
+    float lut_scale, lut_bias;
+    int lut_ok;
+    int cell_owner[kBeamCells];
 };
+
+// cell of a value: ONE monotone function for thresholds and probabilities alike, so every threshold in a lower cell is
+// below the value and every threshold in a higher cell above it -- the bin is exact whatever the rounding of the FMA.
+// No F2I: the round-down add of 2^23 leaves floor(x) in the low mantissa bits.
+__device__ __forceinline__ int beam_cell(float v, float scale, float bias) {
+    const float x = fminf(fmaxf(fmaf(v, scale, bias), 0.0f), (float)(kBeamCells - 1));
+    return (int)(__float_as_uint(__fadd_rd(x, 8388608.0f)) & (unsigned)(kBeamCells - 1));
+}
 
 __device__ __forceinline__ int beam_bin(float p, const BeamSmem& sm, float t15, float t7, float t23) {
     int b = p > t15 ? 16 : 0;
@@ -280,10 +296,44 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
     }
     __syncthreads();
     if (tid < 32) sm.nbr[tid] = make_float2(tid > 0 ? sm.sorted[tid - 1] : -__int_as_float(0x7f800000), sm.sorted[tid < 31 ? tid : 31]);
+    // ---- direct-lookup table, when the thresholds allow it ----------------------------------------------------------------
+    if (tid == 0) {
+        const int nt = p.n_thr;
+        const float lo = sm.sorted[0], hi = sm.sorted[nt - 1];
+        float dmin = __int_as_float(0x7f800000);
+        for (int r = 0; r + 1 < nt; ++r) dmin = fminf(dmin, sm.sorted[r + 1] - sm.sorted[r]);
+        const float w = (hi - lo) / (float)(kBeamCells - 2);
+        // finite, distinct, and at least two cells apart (cell 0 = everything below T_min, T_min sits in cell 1)
+        const bool ok = nt >= 2 && fabsf(lo) < 1e30f && fabsf(hi) < 1e30f && hi > lo && dmin >= 2.0f * w && w > 0.0f;
+        sm.lut_ok = ok ? 1 : 0;
+        sm.lut_scale = ok ? 1.0f / w : 0.0f;
+        sm.lut_bias = ok ? 1.0f - lo * (1.0f / w) : 0.0f;
+    }
+    sm.cell_owner[tid] = -1;
     __syncthreads();
+    if (sm.lut_ok) {
+        if (tid < p.n_thr) {   // tid = position in the sorted order
+            const int cell = beam_cell(sm.sorted[tid], sm.lut_scale, sm.lut_bias);
+            if (cell == 0 || atomicCAS(&sm.cell_owner[cell], -1, tid) != -1) sm.lut_ok = 0;   // never with the spacing above
+        }
+        __syncthreads();
+        if (sm.lut_ok) {
+            // thresholds below cell `tid` = those whose cell is lower; the cell function is monotone, so they are a prefix
+            int below = 0;
+            for (int r = 0; r < p.n_thr; ++r) below += beam_cell(sm.sorted[r], sm.lut_scale, sm.lut_bias) < tid ? 1 : 0;
+            const int own = sm.cell_owner[tid];
+            const int nx = below + (own >= 0 ? 1 : 0);
+            const float inf = __int_as_float(0x7f800000);
+            sm.lut[tid] = make_float4(__int_as_float(below), own >= 0 ? sm.sorted[own] : inf,
+                                      below > 0 ? sm.sorted[below - 1] : -inf, nx < p.n_thr ? sm.sorted[nx] : inf);
+        }
+    }
+    __syncthreads();
+    const bool use_lut = sm.lut_ok != 0;
+    const float lut_scale = sm.lut_scale, lut_bias = sm.lut_bias;
     const float t15 = sm.sorted[15], t7 = sm.sorted[7], t23 = sm.sorted[23];
 
-    int cnt_l = 0, since_fold = 0;
+    int since_fold = 0;
     double dsoft[3] = {0.0, 0.0, 0.0};
     int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
     int64_t tile_end = tile + p.tiles_per_cta;
@@ -310,63 +360,92 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
                     lv[u][0] = Vec4<TL>::load1(lp + e);
                 }
             } else {
+                // outside the plane: probability 0 and label 0 add nothing to the soft sums; the bins are not counted
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) { zv[u][v] = 0.f; lv[u][v] = 0.f; }
+                for (int v = 0; v < VEC; ++v) { zv[u][v] = p.probs ? 0.f : -__int_as_float(0x7f800000); lv[u][v] = 0.f; }
             }
         }
         // branch-free phase: probability, bin, doubtful flag of all elements (their MUFU / LDS latencies overlap)
         int bins[kEvUnroll][VEC];
         unsigned int redo = 0u;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        if (use_lut) {
 #pragma unroll
-        for (int u = 0; u < kEvUnroll; ++u) {
+            for (int u = 0; u < kEvUnroll; ++u) {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const float pr = p.probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
-                const int b = beam_bin(pr, sm, t15, t7, t23);
-                bins[u][v] = b;
-                const float2 nb = sm.nbr[b];
-                const bool near = !p.probs && ((pr - nb.x) < kThrEps || (nb.y - pr) < kThrEps);
-                redo |= near ? (1u << (u * VEC + v)) : 0u;
-                const float lab = lv[u][v];
-                const float w = ok[u] ? 1.f : 0.f;
-                s0 = fmaf(pr * w, lab, s0);
-                s1 = fmaf(pr, w, s1);
-                s2 = fmaf(lab, lab, s2);
+                for (int v = 0; v < VEC; ++v) {
+                    const float pr = p.probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
+                    const float4 e = sm.lut[beam_cell(pr, lut_scale, lut_bias)];
+                    bins[u][v] = __float_as_int(e.x) + (pr > e.y ? 1 : 0);
+                    const bool near = !p.probs && fminf(fminf(fabsf(pr - e.y), pr - e.z), e.w - pr) < kThrEps;
+                    redo |= near ? (1u << (u * VEC + v)) : 0u;
+                    const float lab = lv[u][v];
+                    s0 = fmaf(pr, lab, s0);
+                    s1 += pr;
+                    s2 = fmaf(lab, lab, s2);
+                }
             }
-        }
-        if (redo) {   // rare: the strict '>' must see ATen's bits
+            if (redo) {   // rare: the strict '>' must see ATen's bits
 #pragma unroll
-            for (int u = 0; u < kEvUnroll; ++u)
+                for (int u = 0; u < kEvUnroll; ++u)
 #pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                    if (redo & (1u << (u * VEC + v))) bins[u][v] = beam_bin(sigmoid_exact(zv[u][v]), sm, t15, t7, t23);
+                    for (int v = 0; v < VEC; ++v)
+                        if (redo & (1u << (u * VEC + v))) {
+                            const float pe = sigmoid_exact(zv[u][v]);
+                            const float4 e = sm.lut[beam_cell(pe, lut_scale, lut_bias)];
+                            bins[u][v] = __float_as_int(e.x) + (pe > e.y ? 1 : 0);
+                        }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kEvUnroll; ++u) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const float pr = p.probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
+                    const int b = beam_bin(pr, sm, t15, t7, t23);
+                    bins[u][v] = b;
+                    const float2 nb = sm.nbr[b];
+                    const bool near = !p.probs && ((pr - nb.x) < kThrEps || (nb.y - pr) < kThrEps);
+                    redo |= near ? (1u << (u * VEC + v)) : 0u;
+                    const float lab = lv[u][v];
+                    s0 = fmaf(pr, lab, s0);
+                    s1 += pr;
+                    s2 = fmaf(lab, lab, s2);
+                }
+            }
+            if (redo) {   // rare: the strict '>' must see ATen's bits
+#pragma unroll
+                for (int u = 0; u < kEvUnroll; ++u)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        if (redo & (1u << (u * VEC + v))) bins[u][v] = beam_bin(sigmoid_exact(zv[u][v]), sm, t15, t7, t23);
+            }
         }
 #pragma unroll
         for (int u = 0; u < kEvUnroll; ++u) {
             if (!ok[u]) continue;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const int li = fabsf(lv[u][v]) >= 1.0f ? 1 : 0;
-                cnt_l += li;
-                sm.hist[bins[u][v]][tid] += 1u + ((unsigned int)li << 16);   // thread-private slot: plain LDS / IADD / STS
+                const unsigned int li = fabsf(lv[u][v]) >= 1.0f ? 0x10000u : 0u;
+                sm.hist[bins[u][v]][tid] += 1u + li;   // thread-private slot: plain LDS / IADD / STS
             }
         }
         dsoft[0] += (double)s0;
         dsoft[1] += (double)s1;
         dsoft[2] += (double)s2;
-        if ((since_fold += kEvUnroll * VEC) >= kPackFlushElems) {   // before a 16-bit half can overflow
+        if ((since_fold += kEvUnroll * VEC) >= kPackFlushElems) {   // before a 16-bit half can overflow (huge inputs only)
 #pragma unroll 1
-            for (int b = 1; b < kBeamBins; ++b) {
+            for (int b = 0; b < kBeamBins; ++b) {
                 const unsigned int h = sm.hist[b][tid];
                 sm.hist[b][tid] = 0u;
-                // bin b counts towards the sorted thresholds r < b
+                if (h == 0u) continue;
+                // bin b counts towards the sorted thresholds r < b; every bin counts towards the label total
                 for (int r = 0; r < b && r < p.n_thr; ++r) {
                     atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r]), (unsigned long long)(h & 0xffffu));
                     atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r + 1]), (unsigned long long)(h >> 16));
                 }
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * NTA]), (unsigned long long)(h >> 16));
             }
-            sm.hist[0][tid] = 0u;
             since_fold = 0;
         }
         if (++t == p.tiles_per_plane) {
@@ -377,7 +456,7 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
 
     // ---- CTA reduction: per bin over the threads, then suffix sums -> per sorted threshold ----------------------------
     __syncthreads();
-    for (int b = 1 + warp; b < kBeamBins; b += kBeamThreads / 32) {
+    for (int b = warp; b < kBeamBins; b += kBeamThreads / 32) {
         int o = 0, i = 0;
         for (int k = lane; k < kBeamThreads; k += 32) {
             const unsigned int h = sm.hist[b][k];
@@ -391,11 +470,8 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
                 atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r]), (unsigned long long)o);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r + 1]), (unsigned long long)i);
             }
+            atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * NTA]), (unsigned long long)i);   // label total: all bins
         }
-    }
-    {
-        int l = __reduce_add_sync(0xffffffffu, cnt_l);
-        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * NTA]), (unsigned long long)l);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
