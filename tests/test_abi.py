@@ -47,3 +47,23 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc < 0 and b"empty" in L.eco_last_error()
     rc = L.eco_dice_counts(ctypes.byref(v), ctypes.byref(v), 1, 1, 16, None, 25, 0, None, 0, None, None, 0, None)
     assert rc < 0 and b"n_thr" in L.eco_last_error()
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    from ecologysemanticsegmentation_b200 import _native
+    L = _native.lib()
+    assert L.eco_pair_fused_ws_bytes(1) > L.eco_pair_ws_bytes(1) and L.eco_pair_fused_ws_bytes(65) < 0
+    v = _native.EcoView(1 << 20, 16, 16, 0, 0)
+    rc = L.eco_pair_fused(ctypes.byref(v), ctypes.byref(v), 1, 65, 16, 0, 0.0, 1.0, None, None, None, 0, None, None, None, None,
+                          0, None)
+    assert rc < 0 and b"C must be <= 64" in L.eco_last_error()
+    rc = L.eco_pair_fused(ctypes.byref(v), ctypes.byref(v), 1, 1, 16, 0, 0.0, 1.0, None, None, None, 0, None, None, None, None,
+                          0, None)
+    assert rc < 0 and b"null" in L.eco_last_error()
+    rc = L.eco_masks_u8(None, 1, 1, 16, 0.0, 0, 0, None, 0, None)
+    assert rc < 0 and b"null" in L.eco_last_error()
+    rc = L.eco_masks_u8(ctypes.byref(v), 0, 1, 16, 0.0, 0, 0, None, 0, None)
+    assert rc < 0 and b"empty" in L.eco_last_error()
+    shape = _native.EcoLeafShape(2.0, 0.7, 0.3, 1.0)
+    rc = L.eco_pair_stats_shaped(None, None, 1, 1, 16, 0, ctypes.byref(shape), None, 0, None, 0, None)
+    assert rc < 0 and b"null" in L.eco_last_error()
