@@ -452,6 +452,13 @@ def _run_stream(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg_bytes = 8.0 * elems_per_gpu   # read logits 4 + read masks 4 per element; outputs are O(C)
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None   # dram__bytes_read + write per launch of the scoring kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("cfg5")
+            except Exception:
+                traffic = None
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             res = time_cpu_baseline("cfg5", budget_s=15.0, n_images=16)
@@ -470,7 +477,7 @@ def _run_stream(args):
                        "parallelism": (f"dp{world} (each batch sharded over the ranks; the [steps,{c},3] int64 counts are all-reduced by NCCL "
                                        "ONCE at the end of the stream, inside the timed region)") if world > 1 else "single GPU, one launch per batch",
                        "l2": f"rotating {nsets} batches of {2 * elems_per_gpu * 4 / 1e6:.0f} MB (> 126 MB L2 each)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "dice_counts_kernel<float,float,4,1>", "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": (args.steps + 1) * world,
