@@ -311,7 +311,9 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
     }
     sm.cell_owner[tid] = -1;
     __syncthreads();
-    if (sm.lut_ok) {
+    const bool lut_candidate = sm.lut_ok != 0;   // CTA-uniform; read by everyone BEFORE any thread may clear the flag below
+    __syncthreads();
+    if (lut_candidate) {
         if (tid < p.n_thr) {   // tid = position in the sorted order
             const int cell = beam_cell(sm.sorted[tid], sm.lut_scale, sm.lut_bias);
             if (cell == 0 || atomicCAS(&sm.cell_owner[cell], -1, tid) != -1) sm.lut_ok = 0;   // never with the spacing above
