@@ -171,3 +171,17 @@ def test_torch_port_primitives_with_nondefault_keywords():
         np.testing.assert_allclose(b.grad.numpy(), GS[f"{name}_gb"], rtol=1e-4, atol=1e-9, err_msg=name)
         if a.grad is not None:
             np.testing.assert_allclose(a.grad.numpy(), GS[f"{name}_ga"], rtol=1e-4, atol=1e-9, err_msg=name)
+
+
+def test_masks_u8_known_answers():
+    """test_multiclass.py:90-92 `(t.numpy() * 255).astype(np.uint8)`: float32 product, truncation toward zero."""
+    from oracle import counts as oc
+    from oracle import torch_port as tp
+    t = torch.tensor([0.0, 1.0, 0.5, 0.999, 0.003921569, 0.0039, 0.99999994], dtype=torch.float32)
+    assert oc.masks_u8(t).tolist() == [0, 255, 127, 254, 1, 0, 254]
+    assert oc.masks_u8(t).dtype == np.uint8
+    z = _t("eval_z")
+    out = tp.threshold_inplace(torch.sigmoid(z), 0.8)
+    m = oc.masks_u8(out)
+    assert set(np.unique(m).tolist()) <= {0, 255}
+    assert int((m == 255).sum()) == int(G["eval_counts_0.8"][:, 1].sum())   # |out| counts of the golden file
