@@ -214,12 +214,15 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
 
 // ---------------------------------------------------------------------------------------------
 // Threshold beam (5..20 thresholds, ess/test_multiclass.py:64-77) by BINNING instead of one compare per threshold:
-// the thresholds are sorted once per CTA; an element's bin = number of thresholds below its probability (a
-// 5-step branch-free search: two levels in registers, three in shared memory) and it bumps ONE packed counter
-// {low 16 bits: elements, high 16 bits: elements with label 1} of its thread-private shared-memory histogram
-// (a plain read-modify-write: shared-memory atomics, even uncontended, run at a fraction of the LDS/STS rate).  counts(T_r) = sum of the bins above r.  The sigmoid is the 4-instruction MUFU form; ATen's exact
-// bits are recomputed only for elements within kThrEps of one of the thresholds (the two neighbours of the bin come
-// from one 8-byte load), after the branch-free phase over the thread's 16 elements.
+// the thresholds are sorted once per CTA; an element's bin = number of thresholds below its probability and it bumps
+// ONE packed counter {low 16 bits: elements, high 16 bits: elements with label 1} of its thread-private
+// shared-memory histogram (a plain read-modify-write; measured equal to an uncontended shared-memory atomic).
+// counts(T_r) = sum of the bins above r.  The bin comes from a 256-cell direct-lookup table when the thresholds are at
+// least two cells apart (the reference's np.arange(0.8, 0.99, 0.01)), else from a 5-step branch-free search (two
+// levels in registers, three in shared memory).  The sigmoid is the 4-instruction MUFU form; ATen's exact bits are
+// recomputed only for elements within kThrEps of a threshold (the neighbouring thresholds come with the table entry /
+// from one 8-byte load), after the branch-free phase over the thread's 16 elements.  Issue-bound: ~50 instructions
+// per element (profiles/r1v5_dice_beam_ncu_full.json).
 // ---------------------------------------------------------------------------------------------
 constexpr int kBeamMax = 20;
 constexpr int kBeamBins = kBeamMax + 1;
