@@ -159,23 +159,66 @@ def workload_shape(name):
 STREAM_THRESHOLD = 0.8   # cfg5: the first threshold of the reference's beam (test_multiclass.py:64)
 
 
+def reference_impl():
+    """("reference", lf, lc) = the UNMODIFIED reference modules staged under oracle/_ref/ by oracle/make_ref.py (they
+    travel to the GPU box; /root/reference does not), else ("port", None, None) = the op-for-op restatement
+    oracle/torch_port.py (bit-identical to the reference on CPU, tests/test_oracle_vs_reference.py)."""
+    try:
+        from oracle import make_ref
+        if make_ref.staged():
+            lf, lc = make_ref.load()
+            return "reference", lf, lc
+    except Exception as exc:   # fall back to the port, loudly
+        print("oracle/_ref not usable, timing the port:", repr(exc), file=sys.stderr)
+    return "port", None, None
+
+
+def reference_kind_text(kind):
+    return ("the reference's own loss_composite.losses_fn / loss_functions.dice_loss, unmodified (staged under oracle/_ref/)"
+            if kind == "reference" else "oracle/torch_port.py (op-for-op restatement of the reference's eager path)")
+
+
 def cpu_reference_step(z, g, weights, scoring=False):
-    """The reference path on the CPU (oracle port = op-for-op restatement of the reference's eager ops):
-    sigmoid -> losses_fn(composite) -> weighted sum -> backward; ``scoring``: one batch of test()'s scoring
+    """The reference path on the tensors' device (the CPU for the baseline legs): sigmoid (train_multiclass.py:134) ->
+    losses_fn(composite) -> weighted sum (:145) -> backward (:147); ``scoring``: one batch of test()'s scoring
     (sigmoid -> threshold rule -> per-class dice_loss, test_multiclass.py:58,68-69,80-82)."""
     import numpy as np
     import torch
     from oracle import torch_port as tp
+    kind, lf, lc = reference_impl()
     if scoring:
         with torch.no_grad():
+            if kind == "reference":
+                out = tp.threshold_inplace(torch.sigmoid(z), STREAM_THRESHOLD)   # test_multiclass.py:58,68-69 (two statements)
+                return [float(-lf.dice_loss(out[:, c:c + 1], g[:, c:c + 1], background_weight=0)) for c in range(g.shape[1])], None
             return [float(v) for v in tp.eval_batch_dice(z, g, STREAM_THRESHOLD)], None
     zz = z.clone().requires_grad_(True)
     np.random.seed(0)
     comp = z.shape[1] == 3
-    losses = tp.losses_composite(torch.sigmoid(zz), g, comp)
+    if kind == "reference":
+        losses = lc.losses_fn(torch.sigmoid(zz), g, comp)
+    else:
+        losses = tp.losses_composite(torch.sigmoid(zz), g, comp)
     total = sum(w * l for w, l in zip(weights, losses) if w != 0.0)
     total.backward()
     return [float(l) for l in losses], zz.grad
+
+
+def config_dict(workload, world, exchange="p2p"):
+    """The `config` object of the JSON line: ONE definition for both arms (ours / --impl reference), a function of
+    the workload and the GPU count only."""
+    seed, n, c, s = workload_shape(workload)
+    if workload == "cfg5":
+        return {"workload": f"cfg5: frame-stream Dice scoring (sigmoid -> threshold {STREAM_THRESHOLD} -> exact counts -> "
+                            f"per-batch per-class Dice, mean over batches), {n}x{c}x{s}x{s} f32 logits + f32 masks per GPU and step",
+                "global_batch": n * world,
+                "parallelism": f"dp{world}: batches sharded over the ranks, counts all-reduced once per stream" if world > 1 else "single GPU",
+                "l2": "GPU arm: rotating 2 batches of 403 MB (> 126 MB L2 each)"}
+    return {"workload": f"{workload}: ORGANS=whole_body,ventral_side,dorsal_side composite multiclass loss "
+                        f"fwd+bwd from logits, {n}x{c}x{s}x{s} f32 per GPU, loss=bce+gdice+twersky+focal_dice",
+            "global_batch": n * world,
+            "parallelism": f"dp{world}: batch sharded, per-class partial sums all-reduced" if world > 1 else "single GPU",
+            "l2": f"GPU arm: rotating {N_BUFFER_SETS} buffer sets ({N_BUFFER_SETS * 3 * n * c * s * s * 4 / 1e6:.0f} MB) > 126 MB L2 between timed iterations"}
 
 
 def time_cpu_baseline(name, budget_s=20.0, n_images=None, steps=None, warmup=1):
@@ -223,16 +266,16 @@ def run_reference_arm(args):
     res = time_cpu_baseline(args.workload, n_images=n_images, steps=args.steps, warmup=args.warmup)
     t = sum(res["times"]) / len(res["times"])
     value = res["pixels"] / t / 1e9
-    sample = f"{n_images} of {n} images of {args.workload} ({n_images}x{c}x{s}x{s}) per step, {args.steps} steps"
+    kind = reference_impl()[0]
+    sample = (f"{n_images} of {n} images of {args.workload} ({n_images}x{c}x{s}x{s}) per step, {args.steps} steps, "
+              f"{res['cores']} host threads; {reference_kind_text(kind)}")
     scoring = args.workload == "cfg5"
     line = {
         "impl": "reference", "metric": "Gpixel/s Dice eval" if scoring else "Gpixel/s fused loss fwd+bwd", "value": value, "unit": "Gpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"{args.workload}: frame-stream Dice scoring (sigmoid, threshold {STREAM_THRESHOLD}, per-class Dice), {n}x{c}x{s}x{s} f32 per batch"
-                                if scoring else f"{args.workload}: composite 3-organ loss fwd+bwd from logits, {n}x{c}x{s}x{s} f32"),
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": res["cores"], "kind": "port", "sample": sample},
+        "config": config_dict(args.workload, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Gpixel/s", "cores": res["cores"], "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -338,6 +381,93 @@ def measure_aux(dev):
     return out
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# parity checks printed with the line (outside the timed region); a failure exits non-zero
+# ----------------------------------------------------------------------------------------------------
+def _gather_batch(t, world):
+    """All ranks' tensors concatenated along the batch, in rank order, on every rank."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return t
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts, 0)
+
+
+def _max_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def composite_parity(step, z, g, weights, dev, world, rank):
+    """the sharded step must equal the single-device step on the concatenated batch.  Every rank
+    gathers the global batch, runs the single-GPU fused step on it and compares the 7 losses (relative) and its own
+    gradient shard (max-norm, relative to the global max) with what the sharded step returned for the same inputs.
+    At N=1 the same check runs against the ORACLE on this device (reference semantics, autograd) at the full size."""
+    import numpy as np
+    import torch
+    from ecologysemanticsegmentation_b200 import fused
+    out = {}
+    losses, grad = step(z, g)
+    torch.cuda.synchronize()
+    if world > 1:
+        zf, gf = _gather_batch(z, world), _gather_batch(g, world)
+        np.random.seed(0)
+        single = fused.CompositeLossStep(weights, device=dev)
+        lf, gradf = single(zf, gf)
+        torch.cuda.synchronize()
+        n = z.shape[0]
+        mine = gradf[rank * n:(rank + 1) * n]
+        e_loss = float(((losses[1:] - lf[1:]).abs() / lf[1:].abs()).max())
+        e_grad = float((grad - mine).abs().max() / gradf.abs().max())
+        nan = float(not (bool(torch.isfinite(losses).all()) and bool(torch.isfinite(grad).all())))
+        e_loss, e_grad, nan = _max_over_ranks([e_loss, e_grad, nan], dev, world)
+        out = {"vs": f"single-GPU fused step on the gathered global batch ({zf.shape[0]}x{zf.shape[1]}x{zf.shape[2]}x{zf.shape[3]}), max over ranks",
+               "loss_rel": e_loss, "grad_maxnorm": e_grad, "tol": 1e-6, "ok": bool(e_loss <= 1e-6 and e_grad <= 1e-6 and nan == 0.0)}
+        del zf, gf, gradf
+    else:
+        from oracle import torch_port as tp
+        zr = z.clone().requires_grad_(True)
+        np.random.seed(0)
+        ref = tp.losses_composite(torch.sigmoid(zr), g, True)
+        sum(w * l for w, l in zip(weights, ref) if w != 0.0).backward()
+        rl = torch.stack([v.detach() for v in ref]).double()
+        e_loss = float(((losses.double()[1:] - rl[1:]).abs() / rl[1:].abs()).max())
+        d = (grad - zr.grad).double()
+        e_max = float(d.abs().max() / zr.grad.abs().max())
+        e_l2 = float(d.norm() / zr.grad.double().norm())
+        out = {"vs": "oracle/torch_port.py (reference semantics, eager autograd) on the same device, same inputs, full size",
+               "loss_rel": e_loss, "grad_maxnorm": e_max, "grad_rel_l2": e_l2, "tol": 1e-5,
+               "ok": bool(e_loss <= 1e-5 and e_max <= 1e-5 and e_l2 <= 1e-5 and float(losses[0]) == 0.0)}
+        del zr, ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def stream_parity(z, g, dev, world, group):
+    """cfg5: the sharded scorer's counts for one batch must equal (integer-exactly) the counts of the gathered global
+    batch scored on one GPU; at N=1 the counts are compared with the oracle's exact-integer counter on this device."""
+    import torch
+    from ecologysemanticsegmentation_b200 import test_multiclass as tmc
+    d_sh, c_sh, _ = tmc.score_batch(z, g, STREAM_THRESHOLD, group=group, return_counts=True)
+    if world > 1:
+        zf, gf = _gather_batch(z, world), _gather_batch(g, world)
+        d_f, c_f, _ = tmc.score_batch(zf, gf, STREAM_THRESHOLD, return_counts=True)
+        bad = float(not (torch.equal(c_sh, c_f) and torch.equal(d_sh, d_f)))
+        bad = _max_over_ranks([bad], dev, world)[0]
+        return {"vs": f"single-GPU scoring of the gathered global batch ({zf.shape[0]} images)", "counts_equal": bad == 0.0, "ok": bad == 0.0}
+    from oracle import counts as oc
+    ref = oc.batch_counts(z, g, STREAM_THRESHOLD)
+    ok = bool((c_sh[0].cpu().numpy() == ref).all())
+    return {"vs": "oracle/counts.py (reference threshold rule + int64 sums) on the same device", "counts_equal": ok, "ok": ok}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -355,6 +485,10 @@ def main():
         os.close(_real_stdout)
     if line is not None:
         print(json.dumps(line), flush=True)
+        par = line.get("parity")
+        if isinstance(par, dict) and par.get("ok") is False:
+            print("PARITY FAILED:", json.dumps(par), file=sys.stderr)
+            sys.exit(3)
 
 
 def _run_stream(args):
@@ -443,6 +577,8 @@ def _run_stream(args):
                "h2d_bytes_per_step": 2 * elems_per_gpu * 4 * world, "d2h_bytes_per_step": c * 4 * world / e_steps,
                "ms_per_step": e_ms, "steps": e_steps}
 
+    parity = stream_parity(dev_sets[0][0], dev_sets[0][1], dev, world, group)
+
     line = None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -463,25 +599,22 @@ def _run_stream(args):
         if not args.no_cpu_baseline and world == 1:
             res = time_cpu_baseline("cfg5", budget_s=15.0, n_images=16)
             tb = min(res["times"])
-            cpu_baseline = {"value": res["pixels"] / tb / 1e9, "unit": "Gpixel/s", "cores": res["cores"], "kind": "port",
+            kind = reference_impl()[0]
+            cpu_baseline = {"value": res["pixels"] / tb / 1e9, "unit": "Gpixel/s", "cores": res["cores"], "kind": kind,
                             "sample": f"{len(res['times'])} batches of 16 of the 64 images of a cfg5 batch (16x{c}x{s}x{s}), best of; "
-                                      "oracle/torch_port.py eval_batch_dice (the reference's eager scoring ops)",
+                                      + reference_kind_text(kind),
                             "ms_per_step": tb * 1e3}
         line = {
             "metric": "Gpixel/s Dice eval", "value": value, "unit": "Gpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg5: frame-stream Dice scoring (sigmoid -> threshold {STREAM_THRESHOLD} -> exact counts -> "
-                                   f"per-batch per-class Dice, mean over batches), {n}x{c}x{s}x{s} f32 logits + f32 masks per GPU and step",
-                       "global_batch": n * world,
-                       "parallelism": (f"dp{world} (each batch sharded over the ranks; the [steps,{c},3] int64 counts are all-reduced by NCCL "
-                                       "ONCE at the end of the stream, inside the timed region)") if world > 1 else "single GPU, one launch per batch",
-                       "l2": f"rotating {nsets} batches of {2 * elems_per_gpu * 4 / 1e6:.0f} MB (> 126 MB L2 each)"},
+            "config": config_dict("cfg5", world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "dice_counts_kernel<float,float,4,1>", "algorithmic_bytes_per_launch": alg_bytes},
             "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": (args.steps + 1) * world,
             "dice": [float(v) for v in dice.cpu()],
+            "parity": parity,
         }
     if world > 1:
         dist.destroy_process_group()
@@ -592,6 +725,9 @@ def _run(args):
                "h2d_bytes_per_step": 2 * elems_per_gpu * 4 * world, "d2h_bytes_per_step": 7 * 4 * world,
                "ms_per_step": e_ms, "steps": e_steps}
 
+    # ---- parity of what was just timed (outside the timed region) ----------------------------------------------
+    parity = composite_parity(step, dev_sets[0][0], dev_sets[0][1], weights, dev, world, rank)
+
     # ---- auxiliary line items (not the headline): the Dice-scoring kernel and the un-fused leaf path ----------
     aux = None
     if world == 1 and not args.no_aux:
@@ -620,21 +756,20 @@ def _run(args):
         if not args.no_cpu_baseline and world == 1:
             res = time_cpu_baseline(args.workload, budget_s=15.0)
             tb = min(res["times"])
+            kind = reference_impl()[0]
             cpu_baseline = {"value": res["pixels"] / tb / 1e9, "unit": "Gpixel/s", "cores": res["cores"],
-                            "kind": "port", "sample": f"{len(res['times'])} full steps of {args.workload} "
-                            f"({res['shape'][0]}x{c}x{s}x{s}), best of; oracle/torch_port.py (op-for-op restatement of the reference's eager path)",
+                            "kind": kind, "sample": f"{len(res['times'])} full steps of {args.workload} "
+                            f"({res['shape'][0]}x{c}x{s}x{s}), best of; " + reference_kind_text(kind),
                             "ms_per_step": tb * 1e3}
         line = {
             "metric": "Gpixel/s fused loss fwd+bwd", "value": value, "unit": "Gpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: ORGANS=whole_body,ventral_side,dorsal_side composite multiclass loss "
-                                   f"fwd+bwd from logits, {n}x{c}x{s}x{s} f32 per GPU, loss=bce+gdice+twersky+focal_dice",
-                       "global_batch": n * world, "parallelism": (f"dp{world} (batch sharded, 800 B of sums all-reduced " + ("in-kernel over NVLink peer memory, one launch per rank)" if args.exchange == "p2p" else "by NCCL between the two kernels)")) if world > 1 else "single GPU, one cooperative launch per step",
-                       "l2": f"rotating {N_BUFFER_SETS} buffer sets ({N_BUFFER_SETS * 3 * elems_per_gpu * 4 / 1e6:.0f} MB) > 126 MB L2 between timed iterations"},
+            "config": config_dict(args.workload, world, args.exchange),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches_per_step * args.steps * world,
             "losses": [float(v) for v in losses.cpu()],
+            "parity": parity,
             "aux": aux,
         }
     else:

@@ -28,6 +28,14 @@ class EcoOut(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("sn", C.c_int64), ("sc", C.c_int64), ("dtype", C.c_int32), ("_pad", C.c_int32)]
 
 
+class EcoPeerExchange(C.Structure):
+    _fields_ = [("peer_xch_dev", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32),
+                ("_pad", C.c_uint32), ("status", C.c_void_p), ("timeout_ms", C.c_double)]
+
+
+C3_UNION_LABELS, C3_PROBS = 1, 2
+
+
 class EcoLeafShape(C.Structure):
     """Keyword parameters of the stand-alone primitives (loss_functions.py:46,82,96); defaults = the reference's."""
     _fields_ = [("focal_gamma", C.c_double), ("tversky_alpha", C.c_double), ("tversky_beta", C.c_double),
@@ -71,6 +79,9 @@ SIGNATURES = {
     "eco_multiclass3_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i64, C.c_double, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
     "eco_composite3_fused_sharded": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, _vp, _i32, _i32,
                                                _u32, C.c_int, _vp]),
+    "eco_composite3_step": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _u32, _vp, _vp, _vp, _i64, _vp, _OUT, C.POINTER(EcoPeerExchange),
+                                      C.c_int, _vp]),
+    "eco_xch_poll_status": (C.c_int, [_vp, _i64, C.POINTER(C.c_uint32), C.c_int, _vp]),
     "eco_xch_bytes": (_i64, [_i32]),
     "eco_xch_alloc": (C.c_int, [_i32, C.POINTER(_vp), C.c_char_p, C.c_int]),
     "eco_xch_open": (C.c_int, [C.c_char_p, C.POINTER(_vp), C.c_int]),

@@ -531,6 +531,7 @@ __device__ __noinline__ void label_corrections_role(float gi, float gj, int role
 
 #include "eco_composite_packed.cuh"
 #include "eco_composite_v2.cuh"
+#include "eco_composite_v3.cuh"
 #include "eco_multiclass_v2.cuh"
 
 namespace eco {
@@ -626,7 +627,11 @@ static int check_comp(const EcoView* x, const EcoView* g, int32_t N, int64_t HW)
     if (N <= 0 || HW <= 0) { set_error("empty input (N=%d HW=%lld)", N, (long long)HW); return -2; }
     if (!x || !g || !x->ptr || !g->ptr) { set_error("null input view"); return -1; }
     if (x->dtype != ECO_F32 && x->dtype != ECO_BF16) { set_error("x dtype must be f32 or bf16"); return -4; }
-    if (g->dtype != ECO_F32) { set_error("composite3: labels must be f32"); return -4; }
+    if (g->dtype != ECO_F32 && g->dtype != ECO_U8) { set_error("composite3: labels must be f32 or u8"); return -4; }
+    return 0;
+}
+static int need_f32_labels(const EcoView* g, const char* what) {
+    if (g->dtype != ECO_F32) { set_error("%s takes f32 labels (byte labels: eco_composite3_step on fp32 logits with 16-byte aligned planes)", what); return -4; }
     return 0;
 }
 
@@ -654,6 +659,8 @@ static int ensure_packed_smem() {
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, fused v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<float>::kSmem), "cudaFuncSetAttribute(smem, fused v3 f32 labels)");
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<uint8_t>::kSmem), "cudaFuncSetAttribute(smem, fused v3 u8 labels)");
     if (!rc) done_for_device[dev] = 1;
     return rc;
 }
@@ -673,6 +680,11 @@ static int comp_grid(int device, int64_t units, int ctas_per_sm, int threads_per
 static bool v2_eligible(const EcoView* x, int32_t from_logits, int vec, int32_t N, int64_t HW) {
     return vec == 4 && from_logits != 0 && x->dtype == ECO_F32 && (int64_t)N * HW <= ((int64_t)1 << 31);
 }
+// third-generation fused step: as v2, plus byte labels whose planes and tiles are 16-byte aligned (TMA bulk copies)
+static bool v3_labels_ok(const EcoView* g, int64_t HW) {
+    if (g->dtype == ECO_F32) return true;   // alignment checked by c_aligned
+    return g->dtype == ECO_U8 && reinterpret_cast<uintptr_t>(g->ptr) % 16 == 0 && g->sn % 16 == 0 && g->sc % 16 == 0 && HW % 16 == 0;
+}
 static int v2_grid(int device, int32_t N, int64_t HW) {
     const int sms = sm_count_cached(device);
     if (sms <= 0) return -1;
@@ -689,7 +701,8 @@ using namespace eco;
 
 // workspace: [0,256) arrival counters / status | 128 doubles of totals | per-CTA partials | v2 integer accumulators
 static constexpr int64_t kWsV2Offset = 256 + 128 * 8 + (int64_t)kMaxCompCtas * kNAcc * (int64_t)sizeof(double);
-extern "C" int64_t eco_composite3_ws_bytes(void) { return kWsV2Offset + (int64_t)sizeof(v2::V2Ws); }
+static constexpr int64_t kWsV3Offset = (kWsV2Offset + (int64_t)sizeof(v2::V2Ws) + 255) / 256 * 256;
+extern "C" int64_t eco_composite3_ws_bytes(void) { return kWsV3Offset + (int64_t)sizeof(v2::V3Ws); }
 
 // scalar kernels serve the unaligned / ragged path (VEC == 1); the aligned path runs the packed kernels
 #define ECO_DISPATCH_SCALAR(KERNEL, xdt, logits, ...)                                            \
@@ -707,6 +720,7 @@ extern "C" int eco_composite3_stats(const EcoView* x, const EcoView* g, int32_t 
                                     void* ws, int64_t ws_bytes, double* acc_out, int device, void* stream) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
+    if ((rc = need_f32_labels(g, "eco_composite3_stats"))) return rc;
     if (!ws || ws_bytes < eco_composite3_ws_bytes() || !acc_out) { set_error("workspace too small or null output"); return -5; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
@@ -746,6 +760,7 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
                                    void* stream) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
+    if ((rc = need_f32_labels(g, "eco_composite3_grad"))) return rc;
     if (!jac || !upstream || !gx || !gx->ptr) { set_error("null jac/upstream/gx"); return -5; }
     if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
     DeviceGuard guard(device);
@@ -775,7 +790,7 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
     return check_cuda(cudaGetLastError(), "composite3_grad kernel launch");
 }
 
-static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
+static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
                         const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
                         float* losses_out, const EcoOut* gx, XchArgs xch, int device, void* stream) {
     int rc = check_comp(x, g, N, HW);
@@ -783,33 +798,42 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
     if (!leaf_scale_dev || !upstream || !losses_out || !gx || !gx->ptr) { set_error("null scale/upstream/output"); return -5; }
     if (!ws || ws_bytes < eco_composite3_ws_bytes()) { set_error("workspace too small"); return -5; }
     if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
+    if (flags & ~(uint32_t)(ECO_C3_UNION_LABELS | ECO_C3_PROBS)) { set_error("unknown flags 0x%x", flags); return -3; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
-    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW) &&
+    const bool lg = (flags & ECO_C3_PROBS) == 0;
+    const bool g_f32 = g->dtype == ECO_F32;
+    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && (!g_f32 || c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW)) &&
                      c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
-    if (xch.world > 1 && vec != 4) { set_error("the peer-exchange fused step needs 16-byte aligned planes with H*W %% 4 == 0"); return -8; }
     CompGradArgs ga{};
     fill_comp(ga.a, x, g, N, HW, vec);
     ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
-    const int grid = comp_grid(device, ga.a.units_total, 1, vec == 4 ? kRoleThreads : kCThreads);  // one CTA per SM: co-resident
-    if (grid < 0) return -10;
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
     double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
     double* partials = acc_glob + 128;
-    xch.status = counter + 32;
+    if (!xch.status) xch.status = counter + 32;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const bool lg = from_logits != 0;
-    if (v2_eligible(x, from_logits, vec, N, HW)) {
+    if (v2_eligible(x, lg ? 1 : 0, vec, N, HW) && v3_labels_ok(g, HW)) {
         rc = ensure_packed_smem();
         if (rc) return rc;
         const int g2 = v2_grid(device, N, HW);
         if (g2 < 0) return -10;
-        v2::V2Ws* ws2 = reinterpret_cast<v2::V2Ws*>(reinterpret_cast<char*>(ws) + kWsV2Offset);
-        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws2, &acc_glob, &losses_out, &xch};
-        return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v2_kernel, dim3(g2), dim3(v2::kThreads), args,
-                                                      v2::kSmemBytes, st),
-                          "composite3_fused_v2_kernel launch");
+        v2::V3Ws* ws3 = reinterpret_cast<v2::V3Ws*>(reinterpret_cast<char*>(ws) + kWsV3Offset);
+        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws3, &losses_out, &flags, &xch};
+        if (g_f32)
+            return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v3_kernel<float>, dim3(g2), dim3(v2::kThreads3), args,
+                                                          v2::Stage3<float>::kSmem, st), "composite3_fused_v3_kernel<f32 labels> launch");
+        return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v3_kernel<uint8_t>, dim3(g2), dim3(v2::kThreads3), args,
+                                                      v2::Stage3<uint8_t>::kSmem, st), "composite3_fused_v3_kernel<u8 labels> launch");
     }
+    // everything below: first-generation kernels (bf16 or probability inputs, ragged / unaligned planes), f32 labels only
+    if (!g_f32 || (flags & ECO_C3_UNION_LABELS)) {
+        set_error("byte labels / the fused label union need fp32 logits with 16-byte aligned planes (H*W %% 16 == 0 for byte labels, %% 4 otherwise)");
+        return -8;
+    }
+    if (xch.world > 1 && vec != 4) { set_error("the peer-exchange fused step needs 16-byte aligned planes with H*W %% 4 == 0"); return -8; }
+    const int grid = comp_grid(device, ga.a.units_total, 1, vec == 4 ? kRoleThreads : kCThreads);  // one CTA per SM: co-resident
+    if (grid < 0) return -10;
     if (vec == 4) {
         rc = ensure_packed_smem();
         if (rc) return rc;
@@ -826,12 +850,43 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
     return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCThreads), args, 0, st), "composite3_fused_kernel launch");
 }
 
+static constexpr double kDefaultXchTimeoutMs = 30000.0;
+
+static int fill_xch(XchArgs& xch, void* const* peer_xch_dev, int32_t rank, int32_t world, uint32_t epoch, uint32_t* status,
+                    double timeout_ms) {
+    if (!peer_xch_dev || world < 1 || world > 64 || rank < 0 || rank >= world || epoch == 0) {
+        set_error("bad exchange arguments (world=%d rank=%d epoch=%u)", world, rank, epoch);
+        return -9;
+    }
+    xch.peers = reinterpret_cast<double* const*>(peer_xch_dev);
+    xch.rank = rank;
+    xch.world = world;
+    xch.epoch = epoch;
+    xch.status = status;
+    if (!(timeout_ms > 0.0)) timeout_ms = kDefaultXchTimeoutMs;
+    xch.timeout_ns = (unsigned long long)(timeout_ms * 1e6);
+    return 0;
+}
+
+extern "C" int eco_composite3_step(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
+                                   const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
+                                   float* losses_out, const EcoOut* gx, const EcoPeerExchange* peers, int device,
+                                   void* stream) {
+    XchArgs xch{};
+    xch.world = 1;
+    if (peers) {
+        int rc = fill_xch(xch, peers->peer_xch_dev, peers->rank, peers->world, peers->epoch, peers->status, peers->timeout_ms);
+        if (rc) return rc;
+    }
+    return launch_fused(x, g, N, HW, flags, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+}
+
 extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
                                     const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
                                     float* losses_out, const EcoOut* gx, int device, void* stream) {
     XchArgs xch{};
     xch.world = 1;
-    return launch_fused(x, g, N, HW, from_logits, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+    return launch_fused(x, g, N, HW, from_logits ? 0u : ECO_C3_PROBS, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
 }
 
 extern "C" int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,
@@ -839,16 +894,24 @@ extern "C" int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, 
                                             int64_t ws_bytes, float* losses_out, const EcoOut* gx,
                                             void* const* peer_xch_dev, int32_t rank, int32_t world, uint32_t epoch,
                                             int device, void* stream) {
-    if (!peer_xch_dev || world < 1 || world > 64 || rank < 0 || rank >= world || epoch == 0) {
-        set_error("bad exchange arguments (world=%d rank=%d epoch=%u)", world, rank, epoch);
-        return -9;
-    }
     XchArgs xch{};
-    xch.peers = reinterpret_cast<double* const*>(peer_xch_dev);
-    xch.rank = rank;
-    xch.world = world;
-    xch.epoch = epoch;
-    return launch_fused(x, g, N, HW, from_logits, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+    int rc = fill_xch(xch, peer_xch_dev, rank, world, epoch, nullptr, 0.0);
+    if (rc) return rc;
+    return launch_fused(x, g, N, HW, from_logits ? 0u : ECO_C3_PROBS, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+}
+
+// Status word of the peer exchange inside `ws` (set by a kernel whose wait on a peer timed out): copies it to the host,
+// clears it when set.  Synchronises `stream`.
+extern "C" int eco_xch_poll_status(void* ws, int64_t ws_bytes, uint32_t* status_out_host, int device, void* stream) {
+    if (!ws || ws_bytes < eco_composite3_ws_bytes() || !status_out_host) { set_error("bad eco_xch_poll_status arguments"); return -1; }
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* word = reinterpret_cast<unsigned int*>(ws) + 32;
+    ECO_CUDA(cudaMemcpyAsync(status_out_host, word, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ECO_CUDA(cudaStreamSynchronize(st));
+    if (*status_out_host) ECO_CUDA(cudaMemsetAsync(word, 0, sizeof(uint32_t), st));
+    return 0;
 }
 
 extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
@@ -856,6 +919,7 @@ extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t
                                      const EcoOut* gx, int device, void* stream) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
+    if ((rc = need_f32_labels(g, "eco_multiclass3_fused"))) return rc;
     if (!upstream || !losses_out || !gx || !gx->ptr) { set_error("null upstream/output"); return -5; }
     if (!ws || ws_bytes < eco_composite3_ws_bytes()) { set_error("workspace too small"); return -5; }
     if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }

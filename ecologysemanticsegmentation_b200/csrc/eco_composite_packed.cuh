@@ -143,7 +143,8 @@ struct XchArgs {
     double* const* peers;  // device array [world] of peer-mapped exchange buffers ([rank] = own)
     int rank, world;
     unsigned int epoch;
-    unsigned int* status;  // device word: set to 1 if the wait timed out
+    unsigned int* status;  // device-visible word (workspace or mapped pinned host memory): set to 1 if a wait timed out
+    unsigned long long timeout_ns;  // v3 kernels: wall-clock limit of one wait on a peer
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {

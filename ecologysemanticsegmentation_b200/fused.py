@@ -24,28 +24,62 @@ def loss_weights(ce=0.0, bce=0.0, focal=0.0, dice=0.0, generalized_dice=0.0, twe
 class CompositeLossStep:
     """Callable that owns the small device-side parameter buffers so a step is launch-only (CUDA-graph friendly).
 
-    step(logits, labels) -> (LossList of the 7 loss values, d(sum_k w_k loss_k)/d logits)
-    """
+    step(logits, labels) -> (the 7 loss values f32 [7], d(sum_k w_k loss_k)/d logits)
+
+    labels: float32, or uint8 / bool masks (1 B/element on the bus and in HBM; fp32 logits with H*W % 16 == 0).
+    union_labels=True: ``labels`` are the raw per-organ masks and the label union train() applies before the loss
+    (train_multiclass.py:110 -> utils/subsets_union.py:8-32, exclude_indices=[0]) is folded into the kernel's load stage.
+
+    Pair weights and the numpy RNG (loss_composite.py:49-52): the reference draws 6 numbers per organ pair on EVERY call,
+    also when ``early_stopped`` is False and the draws do not change the weights.  Here the weights are drawn at
+    construction and, when ``early_stopped`` is True, again on every call (they change).  With ``early_stopped=False``
+    the per-call draws are skipped unless ``advance_rng=True`` asks for the reference's exact consumption of the global
+    numpy stream (18 draws per call, ~0.1 ms of host time)."""
 
     def __init__(self, weights, relative_set_ratios=DEFAULT_RATIOS, early_stopped=False, from_logits=True,
-                 device=None):
+                 device=None, union_labels=False, advance_rng=False):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.ratios = list(relative_set_ratios)
         self.early_stopped = early_stopped
         self.from_logits = from_logits
+        self.union_labels = bool(union_labels)
+        self.advance_rng = bool(advance_rng)
         self.upstream = torch.tensor([float(w) for w in weights], dtype=torch.float32, device=self.device)
         self.scales = torch.empty(ops.nat.C3_NLEAF, dtype=torch.float64, device=self.device)
-        self._host_scales = torch.empty(ops.nat.C3_NLEAF, dtype=torch.float64).pin_memory()
+        # two pinned staging buffers, alternated, each guarded by the event of its last upload: the host never rewrites
+        # a buffer whose asynchronous copy may not have run yet
+        self._host_scales = [torch.empty(ops.nat.C3_NLEAF, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self._host_events = [None, None]
+        self._host_turn = 0
+        self._first = True
         self.redraw()
 
     def redraw(self):
         """Draw the pair weights with the reference's numpy RNG stream (loss_composite.py:49-52) and upload them."""
         sc = composite3_leaf_scales(draw_pair_weights(self.ratios, self.early_stopped))
-        self._host_scales.copy_(torch.tensor(sc, dtype=torch.float64))
-        self.scales.copy_(self._host_scales, non_blocking=True)
+        k = self._host_turn
+        self._host_turn ^= 1
+        if self._host_events[k] is not None:
+            self._host_events[k].synchronize()
+        self._host_scales[k].copy_(torch.tensor(sc, dtype=torch.float64))
+        with torch.cuda.device(self.device):
+            self.scales.copy_(self._host_scales[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._host_events[k] = ev
+
+    def _per_call_draws(self):
+        if self._first:          # the construction-time draw serves the first call
+            self._first = False
+        elif self.early_stopped:
+            self.redraw()
+        elif self.advance_rng:
+            draw_pair_weights(self.ratios, False)   # same 18 draws as the reference; the weights do not change
 
     def __call__(self, logits, labels, out=None):
-        losses, grad = ops.composite3_fused(logits, labels, self.scales, self.upstream, self.from_logits, out=out)
+        self._per_call_draws()
+        losses, grad = ops.composite3_fused(logits, labels, self.scales, self.upstream, self.from_logits, out=out,
+                                            union_labels=self.union_labels)
         return losses, grad
 
     def as_losslist(self, losses):
@@ -109,6 +143,10 @@ class ShardedCompositeLossStep(CompositeLossStep):
 
     def __call__(self, logits, labels, out=None):
         from . import distributed as dist_
+        self._per_call_draws()
+        if self.union_labels:   # the two-kernel path has no fused union: the in-place kernel on a float copy
+            from .subsets_union import return_union_sets_descending_order
+            labels = return_union_sets_descending_order(labels.float().clone())
         acc = ops.composite3_stats(logits, labels, self.from_logits)
         acc = dist_.allreduce_sums_(acc, self.group)
         losses, jac, _ = ops.composite3_finalize(acc, self.scales)
@@ -122,10 +160,12 @@ class PeerShardedCompositeLossStep(CompositeLossStep):
     acquire flags, fixed-order sum) -> closed forms -> gradient of the local shard.  No NCCL call on the step.
 
     torch.distributed is used once, at construction, to swap the 64-byte CUDA IPC handles of the exchange buffers.
-    Every rank must call the step the same number of times (it is a collective).  Needs 16-byte aligned planes
-    with H*W % 4 == 0 (otherwise use ShardedCompositeLossStep)."""
+    Every rank must call the step the same number of times (it is a collective, and like one it waits for the slowest
+    rank: while it waits the cooperative grid holds all SMs of the device).  A peer that does not show up within
+    ``timeout_ms`` poisons the step's outputs with NaN and sets a status word that the NEXT call (or ``check()``) turns
+    into an EcoLossError.  Needs 16-byte aligned planes with H*W % 4 == 0 (otherwise use ShardedCompositeLossStep)."""
 
-    def __init__(self, weights, group="world", **kw):
+    def __init__(self, weights, group="world", timeout_ms=30000.0, **kw):
         import ctypes as C
         import torch.distributed as dist
         from . import distributed as dist_
@@ -153,31 +193,27 @@ class PeerShardedCompositeLossStep(CompositeLossStep):
             self._peers.append(p.value)
             ptrs.append(p.value)
         self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        # time-out word in mapped pinned host memory: the kernel sets it, the host reads it without synchronising
+        self._status = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.timeout_ms = float(timeout_ms)
         dist.barrier(group=self.pg)
 
+    def check(self):
+        """Raise if a wait on a peer timed out in an earlier step (its outputs were poisoned with NaN)."""
+        if int(self._status[0]) != 0:
+            self._status[0] = 0
+            raise ops.nat.EcoLossError(
+                f"rank {self.rank}: a peer did not deliver its partial sums within {self.timeout_ms / 1e3:.1f} s "
+                "(in-kernel NVLink exchange); every rank must call the step the same number of times")
+
     def __call__(self, logits, labels, out=None):
-        import ctypes as C
-        x, g = logits, labels
-        ops.nat.require_cuda(x, g)
-        if g.dtype != torch.float32:
-            g = g.float()
-        x, x_sn, x_sc = ops.nat.planes(x)
-        g, g_sn, g_sc = ops.nat.planes(g)
-        n, c, h, w = x.shape
-        L = ops.nat.lib()
-        ws = ops.nat.workspace("comp3", L.eco_composite3_ws_bytes(), x.device)
-        losses = torch.empty((ops.nat.NLOSS,), dtype=torch.float32, device=x.device)
-        gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
-        vx, vg = ops.nat.view_of(x, x_sn, x_sc), ops.nat.view_of(g, g_sn, g_sc)
-        og = ops.nat.out_of(gx, c * h * w, h * w)
+        self.check()
+        self._per_call_draws()
         self.epoch += 1
-        rc = L.eco_composite3_fused_sharded(C.byref(vx), C.byref(vg), n, h * w, int(self.from_logits),
-                                            self.scales.data_ptr(), self.upstream.data_ptr(), ws.data_ptr(), ws.numel(),
-                                            losses.data_ptr(), C.byref(og), self.peer_ptrs.data_ptr(), self.rank,
-                                            self.world, self.epoch & 0xFFFFFFFF or 1, x.device.index,
-                                            ops.nat.current_stream_ptr(x.device))
-        ops.nat.check(rc, "eco_composite3_fused_sharded")
-        return losses, gx
+        peers = ops.nat.EcoPeerExchange(self.peer_ptrs.data_ptr(), self.rank, self.world, self.epoch & 0xFFFFFFFF or 1, 0,
+                                        self._status.data_ptr(), self.timeout_ms)
+        return ops.composite3_fused(logits, labels, self.scales, self.upstream, self.from_logits, out=out,
+                                    union_labels=self.union_labels, peers=peers)
 
     def close(self):
         """Unmap the peers' buffers and free the own one (collective: all ranks should call it)."""
@@ -185,6 +221,7 @@ class PeerShardedCompositeLossStep(CompositeLossStep):
         if self._own is None:
             return
         torch.cuda.synchronize(self.device)
+        self.check()
         dist.barrier(group=self.pg)
         L = ops.nat.lib()
         for p in self._peers:

@@ -396,9 +396,20 @@ def multiclass3_fused(x, g, leaf_scale, upstream, out=None):
     return losses, gx
 
 
-def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None):
-    """ONE cooperative launch: statistics -> grid barrier -> closed forms -> gradient of
+def _byte_labels_ok(x, g, from_logits):
+    """uint8 / bool masks go to the kernel as bytes when the byte-label kernel serves the case (fp32 logits, planes and
+    tiles 16-byte aligned); otherwise they are widened to float32 here, as the reference does (train_multiclass.py:119-123)."""
+    n, c, h, w = x.shape
+    return (from_logits and x.dtype == torch.float32 and (h * w) % 16 == 0 and g.is_contiguous()
+            and g.data_ptr() % 16 == 0)
+
+
+def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None, union_labels=False, peers=None):
+    """ONE cooperative launch (eco_composite3_step): statistics -> grid hand-over -> closed forms -> gradient of
     sum_k upstream[k] * loss_k.  leaf_scales: float64 CUDA [21]; upstream: float32 CUDA [7].
+    g: float32 labels, or uint8 / bool masks (kept as bytes on the device where the kernel takes them).
+    union_labels: g holds the raw per-organ masks; the label union of utils/subsets_union.py:8-32 (exclude_indices=[0])
+    is applied at load.  peers: an EcoPeerExchange for a batch sharded over processes.
     Returns (losses f32 [7], grad w.r.t. x -- w.r.t. the logits when from_logits)."""
     nat.require_cuda(x, g, leaf_scales, upstream)
     if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
@@ -407,7 +418,12 @@ def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None):
         raise ValueError("leaf_scales must be float64 [21]")
     if upstream.dtype != torch.float32 or upstream.numel() != nat.NLOSS:
         raise ValueError("upstream must be float32 [7]")
-    if g.dtype != torch.float32:
+    if g.dtype == torch.bool:
+        g = g.view(torch.uint8)
+    if g.dtype == torch.uint8:
+        if not _byte_labels_ok(x, g, from_logits):
+            g = g.float()
+    elif g.dtype != torch.float32:
         g = g.float()
     x, x_sn, x_sc = nat.planes(x)
     g, g_sn, g_sc = nat.planes(g)
@@ -416,10 +432,16 @@ def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None):
     ws = nat.workspace("comp3", L.eco_composite3_ws_bytes(), x.device)
     losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
     gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
-    vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
+    vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc, allow_u8=True)
     og = nat.out_of(gx, c * h * w, h * w)
-    rc = L.eco_composite3_fused(C.byref(vx), C.byref(vg), n, h * w, int(from_logits), leaf_scales.data_ptr(),
-                                upstream.data_ptr(), ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og),
-                                _dev(x), nat.current_stream_ptr(x.device))
-    nat.check(rc, "eco_composite3_fused")
+    flags = (0 if from_logits else nat.C3_PROBS) | (nat.C3_UNION_LABELS if union_labels else 0)
+    rc = L.eco_composite3_step(C.byref(vx), C.byref(vg), n, h * w, flags, leaf_scales.data_ptr(), upstream.data_ptr(),
+                               ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og),
+                               C.byref(peers) if peers is not None else None, _dev(x), nat.current_stream_ptr(x.device))
+    if rc == -8 and union_labels:
+        # no fused union for this input (bf16 / probabilities / ragged planes): the in-place union kernel on a float copy
+        from .subsets_union import return_union_sets_descending_order
+        return composite3_fused(x, return_union_sets_descending_order(g.float().clone()), leaf_scales, upstream, from_logits,
+                                out=out, union_labels=False, peers=peers)
+    nat.check(rc, "eco_composite3_step")
     return losses, gx

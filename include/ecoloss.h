@@ -19,7 +19,7 @@
  *     described by its base pointer and two element strides: `sn` between images and `sc`
  *     between channels, so `x[:, c:c+1]` slices of a contiguous tensor need no copy;
  *   - dtype codes: ECO_F32 = 0, ECO_BF16 = 1 (logits / probabilities / labels / gradients), ECO_U8 = 2 (byte
- *     masks, accepted for the labels of eco_dice_counts);
+ *     masks, accepted for the labels of eco_dice_counts and of eco_composite3_step);
  *   - "slots": `a` is the reference's FIRST positional argument ("gt"), `b` the SECOND ("pred").
  *     Which one is really the label depends on the caller.
  *
@@ -40,7 +40,7 @@ extern "C" {
 
 #define ECO_F32 0
 #define ECO_BF16 1
-#define ECO_U8 2 /* labels only, eco_dice_counts: masks stored as bytes */
+#define ECO_U8 2 /* labels only (eco_dice_counts, eco_composite3_step): masks stored as bytes */
 
 #define ECO_NSTAT 8
 #define ECO_NLOSS 7
@@ -194,6 +194,38 @@ int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, int32_t N, 
                                  const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
                                  float* losses_out, const EcoOut* gx, void* const* peer_xch_dev, int32_t rank,
                                  int32_t world, uint32_t epoch, int device, void* stream);
+
+/* The composite step, general form (the two calls above are this one with flags = from_logits ? 0 : ECO_C3_PROBS and no /
+ * one peer exchange): ess/train_multiclass.py:133-147 for 3 organs with the composite loss of ess/loss_composite.py:21-94.
+ *   - g may be ECO_U8: the datasets produce {0,1} masks (ess/dataset/fish/fish_dataset.py:159-171) that the reference
+ *     converts to float before the loss (ess/train_multiclass.py:119-123); as bytes they cost 1 B instead of 4 B per
+ *     element on the bus and in HBM.  Needs fp32 logits, 16-byte aligned planes and H*W % 16 == 0 (-8 otherwise);
+ *   - ECO_C3_UNION_LABELS: g holds the RAW per-organ masks and the label union of ess/utils/subsets_union.py:8-32
+ *     `return_union_sets_descending_order(ann, exclude_indices=[0])` (channel 1 <- channel 1 + channel 2, then everything
+ *     above 1 set to 1; called on the labels at ess/train_multiclass.py:110) is applied in registers at load -- g itself is
+ *     not modified, the separate in-place sweep (eco_union_sets) is not needed;
+ *   - ECO_C3_PROBS: x holds probabilities (gradient w.r.t. them) instead of logits;
+ *   - peers == NULL: one GPU.  Otherwise the batch is sharded over peers->world processes and the per-class partial sums
+ *     are all-reduced inside the kernel over NVLink peer memory (see eco_composite3_fused_sharded for the contract).
+ *     A wait on a peer that exceeds timeout_ms (<= 0: 30 s) poisons the step's outputs with NaN and sets *status to 1:
+ *     `status` is any device-visible word -- e.g. mapped pinned host memory, which the host can read without a
+ *     synchronisation -- or NULL for a word inside `ws` (read and cleared by eco_xch_poll_status). */
+#define ECO_C3_UNION_LABELS 1u
+#define ECO_C3_PROBS 2u
+typedef struct EcoPeerExchange {
+    void* const* peer_xch_dev; /* device array of `world` exchange-buffer pointers, [rank] = own */
+    int32_t rank;
+    int32_t world;
+    uint32_t epoch;            /* 1, 2, 3, ... identical on all ranks */
+    uint32_t _pad;
+    uint32_t* status;          /* device-visible word or NULL */
+    double timeout_ms;         /* <= 0: default */
+} EcoPeerExchange;
+int eco_composite3_step(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
+                        const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
+                        float* losses_out, const EcoOut* gx, const EcoPeerExchange* peers, int device, void* stream);
+/* Reads (and clears, when set) the time-out word inside `ws`; synchronises `stream`. */
+int eco_xch_poll_status(void* ws, int64_t ws_bytes, uint32_t* status_out_host, int device, void* stream);
 
 /* Exchange buffers for the call above (CUDA IPC needs a cudaMalloc base pointer, so this is the one place the
  * library allocates).  alloc: zeroed buffer of eco_xch_bytes(world) + its 64-byte IPC handle to send to the peers;

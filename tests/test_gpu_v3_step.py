@@ -1,0 +1,185 @@
+"""The third-generation fused composite step (eco_composite3_step): byte labels, the label union folded into the load
+stage, the in-kernel peer exchange exercised by two ranks on ONE device, and its time-out reporting.
+Reference lines: ess/loss_composite.py:21-94, ess/train_multiclass.py:110,119-123,133-147, ess/utils/subsets_union.py:8-32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from parity import assert_grad_close, assert_losses_close, TOL
+
+pytestmark = pytest.mark.gpu
+
+UP = [0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 1.0]
+UP_ALL = [0.3, 1.0, 0.7, 0.2, 1.0, 0.5, 1.0]
+
+
+def _oracle(z, g, up):
+    from oracle import torch_port as tp
+    zr = z.clone().requires_grad_(True)
+    np.random.seed(0)
+    ref = tp.losses_composite(torch.sigmoid(zr), g, True)
+    sum(w * l for w, l in zip(up, ref) if w).backward()
+    return [float(v) for v in ref], zr.grad
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 3, 48, 48), (5, 3, 64, 64), (54, 3, 256, 256)])
+@pytest.mark.parametrize("up", [UP, UP_ALL])
+def test_v3_vs_oracle_and_byte_labels_bit_identical(shape, up):
+    """fp32 labels against the same-device oracle; uint8 and bool masks must give bit-identical results (the bytes are
+    widened exactly in registers, the arithmetic is the same)."""
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(shape[0], 3, shape[2], 7, nested=True)
+    z, g = z.cuda(), g.cuda()
+    np.random.seed(0)
+    step = CompositeLossStep(up)
+    l32, d32 = step(z, g)
+    rl, rg = _oracle(z, g, up)
+    assert_losses_close(l32.cpu().numpy(), rl, tol=TOL, what=f"v3 {shape}")
+    assert_grad_close(d32.cpu(), rg.cpu(), tol=TOL, what=f"v3 {shape}")
+    l8, d8 = step(z, g.to(torch.uint8))
+    assert torch.equal(l8, l32) and torch.equal(d8, d32)
+    lb, db = step(z, g.bool())
+    assert torch.equal(lb, l32) and torch.equal(db, d32)
+
+
+def test_v3_is_deterministic_and_rearms_its_workspace():
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(9, 3, 128, 11)
+    z, g = z.cuda(), g.cuda()
+    step = CompositeLossStep(UP)
+    first = step(z, g)
+    for _ in range(5):   # odd and even step parities
+        l, d = step(z, g)
+        assert torch.equal(l, first[0]) and torch.equal(d, first[1])
+
+
+def test_v3_label_union_folded_into_the_load_stage():
+    """raw disjoint masks + ECO_C3_UNION_LABELS == explicit in-place union (utils/subsets_union.py:8-32) + plain step,
+    bit for bit, for float and byte masks; the caller's masks are not modified."""
+    from ecologysemanticsegmentation_b200 import subsets_union as su
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(6, 3, 64, 21)
+    z = z.cuda()
+    raw = torch.stack([g[:, 0], g[:, 1] - g[:, 2], g[:, 2]], 1).contiguous().cuda()   # whole_body, ventral only, dorsal
+    raw[0, 1, :4, :4] = 1.0
+    raw[0, 2, :4, :4] = 1.0            # overlapping pixels: the sum 2 must be clamped to 1
+    raw[1, 0, 0, :8] = 3.0             # and everything above 1 anywhere (:28 of the reference)
+    united = su.return_union_sets_descending_order(raw.clone())
+    ref_l, ref_d = CompositeLossStep(UP)(z, united)
+    keep = raw.clone()
+    l, d = CompositeLossStep(UP, union_labels=True)(z, raw)
+    assert torch.equal(raw, keep)
+    assert torch.equal(l, ref_l) and torch.equal(d, ref_d)
+    raw8 = torch.stack([g[:, 0], g[:, 1] - g[:, 2], g[:, 2]], 1).contiguous().to(torch.uint8).cuda()
+    united8 = su.return_union_sets_descending_order(raw8.float())
+    ref_l, ref_d = CompositeLossStep(UP)(z, united8)
+    l, d = CompositeLossStep(UP, union_labels=True)(z, raw8)
+    assert torch.equal(l, ref_l) and torch.equal(d, ref_d)
+    # inputs the fused union does not serve (bf16 logits) fall back to the explicit union
+    l16, d16 = CompositeLossStep(UP, union_labels=True)(z.bfloat16(), raw)
+    r16, rd16 = CompositeLossStep(UP)(z.bfloat16(), united)
+    assert torch.equal(l16, r16) and torch.equal(d16, rd16)
+
+
+def test_v3_nonbinary_labels_take_the_exact_slow_path():
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    torch.manual_seed(11)
+    z = torch.randn(3, 3, 32, 32).cuda()
+    g = (torch.rand(3, 3, 32, 32) > 0.5).float()
+    g[0, 1, 3, 4] = 0.25
+    g[1, 2, 0, 0] = 0.6
+    g[2, 0, 5, 5] = 0.5
+    g = g.cuda()
+    np.random.seed(0)
+    l, d = CompositeLossStep(UP_ALL)(z, g)
+    rl, rg = _oracle(z, g, UP_ALL)
+    assert_losses_close(l.cpu().numpy(), rl, tol=TOL, what="v3 nonbinary")
+    assert_grad_close(d.cpu(), rg.cpu(), tol=TOL, what="v3 nonbinary")
+
+
+def _raw_step(L, nat, z, g, scales, up, ws, losses, gx, peers, stream):
+    n, c, h, w = z.shape
+    vx, vg = nat.view_of(z, c * h * w, h * w), nat.view_of(g, c * h * w, h * w, allow_u8=True)
+    og = nat.out_of(gx, c * h * w, h * w)
+    rc = L.eco_composite3_step(C.byref(vx), C.byref(vg), n, h * w, 0, scales.data_ptr(), up.data_ptr(), ws.data_ptr(), ws.numel(),
+                               losses.data_ptr(), C.byref(og), C.byref(peers) if peers is not None else None,
+                               z.device.index, stream.cuda_stream)
+    nat.check(rc, "eco_composite3_step")
+
+
+def test_peer_exchange_two_ranks_on_one_device():
+    """The in-kernel all-reduce (LL stores into every rank's exchange buffer, every CTA receives) with TWO ranks as two
+    concurrent cooperative launches on two streams of ONE device -- each rank's grid is small enough for both to be
+    co-resident -- so the protocol is covered on a single-GPU box too.  The sharded result must equal the single-launch
+    step on the concatenated batch: losses to 1e-6, each shard's gradient to 1e-6 of the max."""
+    from ecologysemanticsegmentation_b200 import _native as nat
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    L = nat.lib()
+    dev = torch.device("cuda", 0)
+    z, g = make_inputs(8, 3, 64, 99)      # 2 ranks x 4 images x 4 tiles = 16 CTAs per rank
+    z, g = z.cuda(), g.cuda()
+    np.random.seed(0)
+    single = CompositeLossStep(UP, device=dev)
+    ref_l, ref_d = single(z, g)
+    world = 2
+    bufs = [torch.zeros(int(L.eco_xch_bytes(world)), dtype=torch.uint8, device=dev) for _ in range(world)]
+    peer_ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32).pin_memory()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    wss = [torch.zeros(int(L.eco_composite3_ws_bytes()), dtype=torch.uint8, device=dev) for _ in range(world)]
+    losses = [torch.empty(7, dtype=torch.float32, device=dev) for _ in range(world)]
+    shards = [(z[:4].contiguous(), g[:4].contiguous()), (z[4:].contiguous(), g[4:].to(torch.uint8).contiguous())]  # rank 1: byte labels
+    grads = [torch.empty_like(s[0]) for s in shards]
+    torch.cuda.synchronize()
+    for epoch in range(1, 6):
+        for r in range(world):
+            peers = nat.EcoPeerExchange(peer_ptrs.data_ptr(), r, world, epoch, 0, status.data_ptr(), 3000.0)
+            _raw_step(L, nat, shards[r][0], shards[r][1], single.scales, single.upstream, wss[r], losses[r], grads[r], peers, streams[r])
+        torch.cuda.synchronize()
+        assert int(status[0]) == 0, "a rank timed out waiting for its peer (the two launches did not run concurrently?)"
+        for r in range(world):
+            rel = ((losses[r][1:] - ref_l[1:]).abs() / ref_l[1:].abs()).max()
+            assert float(rel) <= 1e-6, (epoch, r, losses[r], ref_l)
+            err = (grads[r] - ref_d[4 * r:4 * r + 4]).abs().max() / ref_d.abs().max()
+            assert float(err) <= 1e-6, (epoch, r, float(err))
+        assert torch.equal(losses[0], losses[1]), "every rank must hold bit-identical totals"
+
+
+def test_peer_exchange_timeout_is_reported():
+    """A peer that never shows up: the wait gives up after timeout_ms, the outputs are poisoned with NaN (not silently
+    wrong) and the status word is set, where the host sees it without a synchronisation of its own."""
+    from ecologysemanticsegmentation_b200 import _native as nat
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    L = nat.lib()
+    dev = torch.device("cuda", 0)
+    z, g = make_inputs(2, 3, 32, 5)
+    z, g = z.cuda(), g.cuda()
+    single = CompositeLossStep(UP, device=dev)
+    world = 2
+    bufs = [torch.zeros(int(L.eco_xch_bytes(world)), dtype=torch.uint8, device=dev) for _ in range(world)]
+    peer_ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32).pin_memory()
+    ws = torch.zeros(int(L.eco_composite3_ws_bytes()), dtype=torch.uint8, device=dev)
+    losses = torch.zeros(7, dtype=torch.float32, device=dev)
+    gx = torch.zeros_like(z)
+    peers = nat.EcoPeerExchange(peer_ptrs.data_ptr(), 0, world, 1, 0, status.data_ptr(), 50.0)   # rank 1 never runs
+    _raw_step(L, nat, z, g, single.scales, single.upstream, ws, losses, gx, peers, torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert int(status[0]) == 1
+    assert not bool(torch.isfinite(losses[1:]).any()) and not bool(torch.isfinite(gx).all())
+    # same through the workspace word + eco_xch_poll_status (status == NULL)
+    peers = nat.EcoPeerExchange(peer_ptrs.data_ptr(), 0, world, 2, 0, None, 50.0)
+    ws2 = torch.zeros(int(L.eco_composite3_ws_bytes()), dtype=torch.uint8, device=dev)
+    _raw_step(L, nat, z, g, single.scales, single.upstream, ws2, losses, gx, peers, torch.cuda.current_stream())
+    out = C.c_uint32(7)
+    nat.check(L.eco_xch_poll_status(ws2.data_ptr(), ws2.numel(), C.byref(out), 0, torch.cuda.current_stream().cuda_stream), "poll")
+    assert out.value == 1
+    nat.check(L.eco_xch_poll_status(ws2.data_ptr(), ws2.numel(), C.byref(out), 0, torch.cuda.current_stream().cuda_stream), "poll")
+    assert out.value == 0, "the word is cleared once it has been read"
