@@ -53,6 +53,7 @@ constexpr int kStages3 = 5;
 constexpr int kLinStages = 4;                                 // ring of the linear warps: logit planes only
 constexpr int kLinStageBytes = 3 * kTP * 4;                   // 12 KB
 constexpr int kLinFlushTiles = 16;                            // 2 pixel pairs per thread and tile -> 64 values per fp32 partial
+constexpr int kFlushTiles3 = 32;                              // 64 pixels per fp32 accumulator between folds into fp64 (cfg2: one fold per CTA)
 constexpr int kNFlat = 72;                                    // 55 flat sums | 15 label corrections | n | (pad)
 constexpr int F_CORR = 55, F_N = 70;
 
@@ -229,7 +230,6 @@ struct Fused3Smem {
     double scale[ECO_C3_NLEAF];     // linear warps' copy
     double scale_c[ECO_C3_NLEAF];   // statistics warps' copy
     double flat[kNFlat];
-    double acc[kNAcc];
     double lin_part[kLinWarps][2];
     double lin_tot[2];
     float up[ECO_NLOSS + 1];
@@ -338,7 +338,7 @@ __device__ __forceinline__ void stats_consume3(const CompArgs& a, const TileRang
             stats_pixel(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
         }
         if (++kk == tr.tpp) kk = 0;
-        if (++since_flush == kFlushTiles) {
+        if (++since_flush == kFlushTiles3) {
             any_nonbinary |= flush_flat_acc(acc, sm.warp_slots[warp], lane);
             since_flush = 0;
         }
@@ -393,6 +393,7 @@ __device__ __forceinline__ bool stats_finish3(const CompArgs& a, const TileRange
         }
     }
     csync();
+    ECO_TL(15);
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(&ws->arrive1[par][0], 1u);
         sm.flag = (prev == gridDim.x - 1);
@@ -449,8 +450,41 @@ __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const Tile
     }
 }
 
-// raw sums + corrections + n -> the shared 100-slot layout of eco_composite.cu (see flat_to_layout)
-__device__ inline double flat3_to_layout(const double* F, int idx) { return flat_to_layout(F, F + F_CORR, idx, F[F_N]); }
+// raw sums + corrections + n -> the 8 statistics of one of the 21 leaves, directly (composite_leaf_sums of
+// eco_composite.cu applied to flat_to_layout, without materialising the 100-slot layout: one phase and one barrier less on
+// the critical path between the passes).  The SP entries of the real-b leaves hold only the algebraic part
+// n ln2 + sum b / 2 + sum b^2 / 8 and their FL entries are 0: the linear warps supply the rest.
+__device__ inline void flat_leaf_sums(const double* F, int leaf, double* s /*[8]*/) {
+    const double n = F[F_N];
+    s[S_N] = n;
+    s[S_FLB] = 0.0;
+    if (leaf < 3) {
+        s[S_A] = F[F_G + leaf]; s[S_B] = F[F_X + leaf]; s[S_BB] = F[F_XX + leaf]; s[S_AB] = F[F_GX + leaf];
+        s[S_SP] = n * kLn2d + 0.5 * s[S_B] + 0.125 * s[S_BB];
+        s[S_FL] = 0.0;
+        return;
+    }
+    const int p = (leaf - 3) / 6, t = (leaf - 3) % 6, grp = t >> 1;
+    const int i = pair_i(p), j = pair_j(p);
+    const double* r = F + F_PAIR + 14 * p;
+    const double m = r[2 + 2 * grp];
+    if (t & 1) {   // U-leaf: a = g_i, b = u_k = x_i + (p_k - x_i p_k) / 2
+        const double psum = grp == 0 ? F[F_X + j] : (grp == 1 ? r[1] : r[4]);
+        s[S_A] = F[F_G + i];
+        s[S_B] = F[F_X + i] + 0.5 * (psum - m);
+        s[S_BB] = r[8 + 2 * grp];
+        s[S_AB] = r[9 + 2 * grp];
+        s[S_SP] = n * kLn2d + 0.5 * s[S_B] + 0.125 * s[S_BB];
+        s[S_FL] = 0.0;
+    } else {       // I-leaf: a = m_k, b = label (g_j for I1, |g_i - g_j| for I2 / I3)
+        const double sb = (t == 0) ? F[F_G + j] : r[0];
+        const double* co = F + F_CORR + 3 * ((t == 0) ? (j - 1) : (2 + p));
+        s[S_A] = m; s[S_AB] = r[3 + 2 * grp]; s[S_B] = sb;
+        s[S_BB] = sb + co[0];
+        s[S_SP] = (n - sb) * kSP0 + sb * kSP1 + co[1];
+        s[S_FL] = (n - sb) * kFL0 + co[2];
+    }
+}
 
 template <typename TG>
 __global__ void __launch_bounds__(kThreads3, 1)
@@ -548,26 +582,35 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     }
     csync();
     ECO_TL(3);
-    if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = flat3_to_layout(fs.flat, threadIdx.x);
-    csync();
-    // closed forms, redundantly per CTA: one thread per (leaf, loss) row, one WARP per loss kind (no divergent switch)
+    // closed forms, redundantly per CTA: one thread per (leaf, loss) row, one WARP per loss kind (no divergent switch);
+    // each row leaves its Jacobian already weighted by its upstream gradient
     if (threadIdx.x < ECO_NLOSS * 32 && (threadIdx.x & 31) < ECO_C3_NLEAF) {
         const int leaf = threadIdx.x & 31, k = threadIdx.x >> 5;
-        double s[ECO_NSTAT];
-        composite_leaf_sums(fs.acc, leaf, s);
-        leaf_closed_form_row(s, 0.0, fs.scale_c[leaf], k, fs.sl[leaf][k], fs.jac_s[leaf][k]);
-    }
-    csync();
-    if (threadIdx.x < ECO_C3_NLEAF * ECO_NJAC) {
-        const int leaf = threadIdx.x / ECO_NJAC, j = threadIdx.x % ECO_NJAC;
-        double c = 0.0;
+        double s[ECO_NSTAT], jrow[ECO_NJAC];
+        flat_leaf_sums(fs.flat, leaf, s);
+        leaf_closed_form_row(s, 0.0, fs.scale_c[leaf], k, fs.sl[leaf][k], jrow);
+        const float u = k == 0 ? 0.f : fs.up[k];
 #pragma unroll
-        for (int k = 1; k < ECO_NLOSS; ++k)
-            if (fs.up[k] != 0.f) c += (double)fs.up[k] * fs.jac_s[leaf][k][j];   // (an unused loss may have a non-finite Jacobian)
-        reinterpret_cast<float*>(&fs.cf[leaf])[j] = (float)(j == 3 ? 2.0 * c : c);
+        for (int j = 0; j < ECO_NJAC; ++j) fs.jac_s[leaf][k][j] = u != 0.f ? (double)u * jrow[j] : 0.0;   // (an unused loss may have a non-finite Jacobian)
     }
     csync();
-    fill_coef2(fs.c2, fs.cf, threadIdx.x);
+    ECO_TL(12);
+    if (threadIdx.x < ECO_C3_NLEAF) {
+        // coefficient j of leaf l = sum_k upstream[k] * d loss_k / d stat_j, in a fixed order
+        const int leaf = threadIdx.x;
+        float c[ECO_NJAC];
+#pragma unroll
+        for (int j = 0; j < ECO_NJAC; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 1; k < ECO_NLOSS; ++k) v += fs.jac_s[leaf][k][j];
+            c[j] = (float)(j == 3 ? 2.0 * v : v);
+        }
+        LeafCoef lc;
+        lc.sa = c[0]; lc.sb = c[1]; lc.sab = c[2]; lc.sbb2 = c[3]; lc.sp = c[4]; lc.fl = c[5]; lc.flb = c[6];
+        fs.cf[leaf] = lc;
+        fill_coef2(fs.c2, fs.cf, leaf);   // (reads back this thread's own entry)
+    }
     csync();
     ECO_TL(4);
     {
@@ -597,7 +640,7 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     if (threadIdx.x < ECO_NLOSS) {
         double v = 0.0;
         for (int l = 0; l < ECO_C3_NLEAF; ++l) v += fs.sl[l][threadIdx.x];
-        const double n = fs.acc[A_N];
+        const double n = fs.flat[F_N];
         if (threadIdx.x == 1) v += fs.lin_tot[0] / n;               // BCE: sum_l scale_l * softplus remainder
         if (threadIdx.x == 2) v += -kLn2d * fs.lin_tot[1] / n;      // focal: sums were taken in log2 units
         losses_out[threadIdx.x] = (float)v;

@@ -57,7 +57,8 @@ int main(int argc, char** argv) {
         XchArgs xch{}; xch.world = 1; xch.status = status;
         const double* sd = scale_dev; const float* u = up; unsigned int flags = 0;
         void* args[] = {&ga, (void*)&sd, (void*)&u, &ws3, &losses, &flags, &xch};
-        CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float>, dim3(sms), dim3(kThreads3), args, Stage3<float>::kSmem, nullptr));
+        if (argc > 2) composite3_fused_v3_kernel<float><<<sms, kThreads3, Stage3<float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch);
+        else CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float>, dim3(sms), dim3(kThreads3), args, Stage3<float>::kSmem, nullptr));
     };
     for (int i = 0; i < 5; ++i) launch(i % NSETS);
     CK(cudaDeviceSynchronize());
@@ -75,9 +76,9 @@ int main(int argc, char** argv) {
     static unsigned long long tl[1024 * 16];
     CK(cudaMemcpyFromSymbol(tl, g_timeline, sizeof(tl)));
     unsigned long long t0 = ~0ull; for (int b = 0; b < sms; ++b) t0 = tl[b * 16] < t0 ? tl[b * 16] : t0;
-    const int order[10] = {0, 8, 1, 9, 10, 2, 3, 4, 5, 6};
-    const char* nm[16] = {"start", "pass1 loop end", "stats_finish end", "sums received", "coef ready", "pass2 loop end", "cta0 end", "", "lin start", "lin loop end", "lin arrived"};
-    for (int oi = 0; oi < 10; ++oi) {
+    const int order[14] = {0, 8, 1, 14, 15, 2, 3, 13, 12, 4, 5, 9, 10, 6};
+    const char* nm[16] = {"start", "pass1 loop end", "stats_finish end", "sums received", "coef ready", "pass2 loop end", "cta0 end", "", "lin start", "lin loop end", "lin arrived", "", "closed forms done", "layout done", "flush done", "sums in L2"};
+    for (int oi = 0; oi < 14; ++oi) {
         const int sl = order[oi];
         double mn = 1e30, mxv = 0, av = 0; int cnt = 0;
         for (int b = 0; b < sms; ++b) { if (tl[b * 16 + sl] < t0) continue; const double v = (double)(tl[b * 16 + sl] - t0) * 1e-3; mn = fmin(mn, v); mxv = fmax(mxv, v); av += v; ++cnt; }
