@@ -378,7 +378,123 @@ def measure_aux(dev):
     out["leaf_cfg1"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak,
                         "bytes_per_element": 12, "launch": how,
                         "what": "cfg1: single-class losses_fn (bce + gdice + twersky) fwd+bwd from logits, 54x1x256x256, one launch"}
+    del sets1, outs1
+    # ---- the composite step on the other shapes / input forms ------------------------------------------------------
+    import numpy as np
+    import ecologysemanticsegmentation_b200 as eco
+    w = fused.loss_weights(**WEIGHTS)
+    np.random.seed(0)
+    cstep = fused.CompositeLossStep(w, device=dev)
+    # (a) byte masks on the device: 9 instead of 12 B/element
+    n, c, s = 54, 3, 256
+    sets8 = [(zz, gg.to(torch.uint8)) for zz, gg in sets]
+    st8 = {"i": 0}
+
+    def run_u8():
+        k = st8["i"] % 4
+        st8["i"] += 1
+        cstep(sets8[k][0], sets8[k][1], out=outs[k])
+
+    t, how = timed_graph(run_u8, 4, 25)
+    out["composite_cfg2_u8_masks"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": 9.0 * n * c * s * s / t / 1e9,
+                                      "frac_of_hbm_peak": 9.0 * n * c * s * s / t / 1e9 / peak, "bytes_per_element": 9, "launch": how,
+                                      "what": "cfg2 with uint8 masks (ECO_U8), one launch"}
+    # (b) the drop-in path through the reference's own signature: losses_fn(...) -> weighted sum -> backward(), exactly as
+    #     ess/train_multiclass.py:139-147 calls it (from_logits=True fuses the sigmoid of :134); eager launches
+    zs = [zz.clone().requires_grad_(True) for zz, _ in sets]
+
+    def run_dropin():
+        k = st8["i"] % 4
+        st8["i"] += 1
+        zs[k].grad = None
+        ce, bce, fl, dice, gdice, tw, fd = eco.losses_fn(zs[k], sets[k][1], True, from_logits=True)
+        loss = 1.0 * fd + 1.0 * bce + 1.0 * (gdice + tw)      # :145 with all three weights at 1
+        loss.backward()
+
+    t = timed(run_dropin, 40)
+    out["dropin_autograd_cfg2"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "launch": "eager (autograd): host-bound, "
+                                   "~25 python-level torch calls per step",
+                                   "what": "eco.losses_fn(z, g, True, from_logits=True) -> weighted sum -> .backward(), cfg2"}
+    # the same step (forward through the reference signature + autograd backward) captured in a CUDA graph, the way a
+    # training loop that is launch-bound from python would run it: what the GPU needs for the drop-in path
+    try:
+        zg = sets[0][0].clone().requires_grad_(True)
+        gg = sets[0][1]
+
+        def dropin_step():
+            ce, bce, fl, dice, gdice, tw, fd = eco.losses_fn(zg, gg, True, from_logits=True)
+            loss = 1.0 * fd + 1.0 * bce + 1.0 * (gdice + tw)
+            loss.backward()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                zg.grad = None
+                dropin_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        zg.grad = None
+        with torch.cuda.graph(graph, stream=side):
+            dropin_step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        ref_grad = zg.grad.clone()
+        ev0.record()
+        for _ in range(100):
+            graph.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        t = ev0.elapsed_time(ev1) / 100 * 1e-3
+        zz = sets[0][0].clone().requires_grad_(True)
+        l2 = eco.losses_fn(zz, gg, True, from_logits=True)
+        (1.0 * l2[6] + 1.0 * l2[1] + 1.0 * (l2[4] + l2[5])).backward()
+        same = bool(torch.equal(zz.grad, ref_grad))
+        out["dropin_autograd_cfg2_graphed"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "launch": "one CUDA graph per step (forward + autograd backward captured)",
+                                               "grad_equals_eager": same,
+                                               "what": "the same drop-in step replayed as a CUDA graph"}
+        del graph
+    except Exception as exc:
+        out["dropin_autograd_cfg2_graphed"] = {"error": repr(exc)[:300]}
+    # (c) the reference's own eager ops on THIS GPU (the like-for-like 'before'): same step, cfg2, oracle port on cuda
+    try:
+        t = timed(lambda: cpu_reference_step(sets[0][0], sets[0][1], w), 3)
+        out["reference_eager_same_gpu_cfg2"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6,
+                                                "what": "the reference path (sigmoid -> losses_fn composite -> backward) in eager torch ops on this GPU: "
+                                                        + reference_kind_text(reference_impl()[0])}
+    except Exception as exc:
+        out["reference_eager_same_gpu_cfg2"] = {"error": repr(exc)}
+    del sets8, zs, sets, outs
+    torch.cuda.empty_cache()
+    # (d) cfg4's per-GPU shard (BASELINE configs[3]: 432x3x512x512 over 8 GPUs = 54x3x512x512 per GPU), single GPU
+    out["composite_cfg4_shard"] = time_cfg4_shard(dev, cstep, peak)
     return out
+
+
+def time_cfg4_shard(dev, step, peak, nsets=2, iters=40):
+    """us per step of `step` on 54x3x512x512 fp32 (cfg4's per-GPU shard), rotating `nsets` buffer sets (340 MB each, > L2)."""
+    import torch
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    n, c, s = 54, 3, 512
+    sets = [tuple(t.to(dev) for t in make_inputs(n, c, s, 104 + 7 * k)) for k in range(nsets)]
+    outs = [torch.empty_like(zz) for zz, _ in sets]
+    for i in range(3):
+        step(sets[i % nsets][0], sets[i % nsets][1], out=outs[i % nsets])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(iters):
+        step(sets[i % nsets][0], sets[i % nsets][1], out=outs[i % nsets])
+    ev1.record()
+    torch.cuda.synchronize()
+    t = ev0.elapsed_time(ev1) / iters * 1e-3
+    gbs = 12.0 * n * c * s * s / t / 1e9
+    del sets, outs
+    torch.cuda.empty_cache()
+    return {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak,
+            "bytes_per_element": 12, "what": "cfg4 per-GPU shard: composite loss fwd+bwd, 54x3x512x512 f32, one launch"}
 
 
 
@@ -466,6 +582,39 @@ def stream_parity(z, g, dev, world, group):
     ref = oc.batch_counts(z, g, STREAM_THRESHOLD)
     ok = bool((c_sh[0].cpu().numpy() == ref).all())
     return {"vs": "oracle/counts.py (reference threshold rule + int64 sums) on the same device", "counts_equal": ok, "ok": ok}
+
+
+def bind_host_to_gpu_numa_node(device_index):
+    """Pinned host buffers are allocated on the NUMA node of the allocating thread (first touch): run this process on the
+    cores next to its GPU so that every rank's H2D stream leaves from local memory.  Returns a note for the JSON line."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        if hasattr(props, "pci_bus_id"):
+            bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        else:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else device_index
+            bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(phys)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]   # nvml prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "numa node of the GPU unknown"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f"numa node {node}: none of its cores is available to this process"
+        os.sched_setaffinity(0, allowed)
+        return f"process bound to the {len(allowed)} cores of NUMA node {node} (GPU {bus})"
+    except Exception as exc:
+        return "no NUMA binding: " + repr(exc)
 
 
 def main():
@@ -637,6 +786,7 @@ def _run(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_host_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -697,33 +847,80 @@ def _run(args):
     launches_per_step = 1 if (world == 1 or args.exchange == "p2p") else 3
 
     # ---- end to end: pinned host buffers in, 7 losses out, every step --------------------------------
+    # The call a user of the step makes, fed from HOST memory: every step copies its logits (fp32) and its masks from
+    # pinned buffers, runs the fused step and reads the 7 loss values back to the host.  The masks travel as uint8 -- the
+    # datasets produce {0,1} masks (ess/dataset/fish/fish_dataset.py:159-171), the byte form is lossless and the kernel
+    # takes it directly (ECO_U8): 53 instead of 85 MB per step.  Copies run on their own stream into two rotating device
+    # buffer sets, so step i+1's input crosses PCIe while step i computes; the losses of step i are read one step late.
+    # `e2e_f32_masks` is the same loop with fp32 masks and no overlap (copy -> copy -> step -> read), as in round 1.
     e2e = None
+    e2e_variants = {}
     if not args.no_e2e:
         e_steps = max(3, min(args.steps, 50))
-        zd, gd = torch.empty_like(dev_sets[0][0]), torch.empty_like(dev_sets[0][1])
+        host8 = [(z, g.to(torch.uint8).pin_memory()) for z, g in host_sets]
 
-        def one_e2e(i):
-            zh, gh = host_sets[i % N_BUFFER_SETS]
-            zd.copy_(zh, non_blocking=True)
-            gd.copy_(gh, non_blocking=True)
-            l, _ = step(zd, gd, out=grads[0])
-            return l.cpu()  # device -> host read of the step's result (synchronises)
+        def e2e_state(masks_u8, overlap):
+            main = torch.cuda.current_stream()
+            return {"zd": [torch.empty_like(dev_sets[0][0]) for _ in range(2)],
+                    "gd": [torch.empty((n, c, s, s), dtype=torch.uint8 if masks_u8 else torch.float32, device=dev) for _ in range(2)],
+                    "loss_host": [torch.empty(7, dtype=torch.float32).pin_memory() for _ in range(2)],
+                    "main": main, "copy": torch.cuda.Stream() if overlap else main,
+                    "ev": [[torch.cuda.Event() for _ in range(2)] for _ in range(3)]}
 
-        for i in range(3):
-            one_e2e(i)
-        barrier()
-        ev0.record()
-        for i in range(e_steps):
-            one_e2e(i)
-        ev1.record()
-        barrier()
-        te = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_ms = float(te.item()) / e_steps
-        e2e = {"value": pixels_per_step / (e_ms * 1e-3) / 1e9, "unit": "Gpixel/s",
-               "h2d_bytes_per_step": 2 * elems_per_gpu * 4 * world, "d2h_bytes_per_step": 7 * 4 * world,
-               "ms_per_step": e_ms, "steps": e_steps}
+        def run_e2e(k, masks_u8, overlap, st):
+            src = host8 if masks_u8 else host_sets
+            zd, gd, loss_host, main, copy_stream = st["zd"], st["gd"], st["loss_host"], st["main"], st["copy"]
+            ready, free, done = st["ev"]
+            got = []
+            for i in range(k):
+                b = i % 2
+                zh, gh = src[i % N_BUFFER_SETS]
+                with torch.cuda.stream(copy_stream):
+                    if overlap and i >= 2:
+                        copy_stream.wait_event(free[b])      # the step that last used this buffer set has finished
+                    zd[b].copy_(zh, non_blocking=True)
+                    gd[b].copy_(gh, non_blocking=True)
+                    ready[b].record(copy_stream)
+                main.wait_event(ready[b])
+                l, _ = step(zd[b], gd[b], out=grads[b])
+                free[b].record(main)
+                loss_host[b].copy_(l, non_blocking=True)
+                done[b].record(main)
+                if overlap:
+                    if i >= 1:
+                        done[b ^ 1].synchronize()            # host reads the previous step's losses
+                        got.append(float(loss_host[b ^ 1][1]))
+                else:
+                    done[b].synchronize()
+                    got.append(float(loss_host[b][1]))
+            if overlap:
+                done[(k - 1) % 2].synchronize()
+                got.append(float(loss_host[(k - 1) % 2][1]))
+            return got
+
+        def time_e2e(masks_u8, overlap):
+            st = e2e_state(masks_u8, overlap)
+            run_e2e(3, masks_u8, overlap, st)
+            barrier()
+            ev0.record()
+            got = run_e2e(e_steps, masks_u8, overlap, st)
+            ev1.record()
+            barrier()
+            assert len(got) == e_steps and all(v == v for v in got)
+            te = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e_ms = float(te.item()) / e_steps
+            mask_bytes = 1 if masks_u8 else 4
+            return {"value": pixels_per_step / (e_ms * 1e-3) / 1e9, "unit": "Gpixel/s",
+                    "h2d_bytes_per_step": elems_per_gpu * (4 + mask_bytes) * world, "d2h_bytes_per_step": 7 * 4 * world,
+                    "ms_per_step": e_ms, "steps": e_steps,
+                    "how": ("fp32 logits + uint8 masks from pinned host memory, H2D of step i+1 on a copy stream under step i, "
+                            "7 losses read back every step (one step late)") if overlap else
+                           "fp32 logits + fp32 masks from pinned host memory, copy -> copy -> step -> read, no overlap"}
+
+        e2e = time_e2e(True, True)
+        e2e_variants["e2e_f32_masks_serial"] = time_e2e(False, False)
 
     # ---- parity of what was just timed (outside the timed region) ----------------------------------------------
     parity = composite_parity(step, dev_sets[0][0], dev_sets[0][1], weights, dev, world, rank)
@@ -732,6 +929,26 @@ def _run(args):
     aux = None
     if world == 1 and not args.no_aux:
         aux = measure_aux(dev)
+    elif world > 1 and not args.no_aux and args.workload == "cfg2":
+        # BASELINE configs[3] (cfg4): 432x3x512x512 over 8 GPUs = 54x3x512x512 per GPU.  Timed here on every rank with the
+        # sharded step (max over ranks), next to the single-GPU step on the same shard on rank 0's GPU.
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        barrier()
+        sh = time_cfg4_shard(dev, step, peak)
+        tt = torch.tensor([sh["us"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        barrier()
+        np.random.seed(0)
+        single = time_cfg4_shard(dev, fused.CompositeLossStep(weights, device=dev), peak) if rank == 0 else None
+        barrier()
+        if rank == 0:
+            us_n = float(tt.item())
+            aux = {"cfg4": {"what": f"BASELINE configs[3]: composite loss fwd+bwd, 54x3x512x512 f32 per GPU, global batch {54 * world}, "
+                                    "sums all-reduced in-kernel; us per step = max over ranks",
+                            "us_per_step": us_n, "gpixel_per_s": 54 * 512 * 512 * world / (us_n * 1e-6) / 1e9,
+                            "single_gpu_same_shard_us": single["us"], "speedup_vs_1gpu": world * single["us"] / us_n,
+                            "frac_of_hbm_peak_per_gpu": 12.0 * 54 * 3 * 512 * 512 / (us_n * 1e-6) / 1e9 / peak}}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -750,7 +967,7 @@ def _run(args):
                 traffic = None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src,
-                    "kernel": "composite3_fused_v2_kernel" if (world == 1 or args.exchange == "p2p") else "composite3_stats_packed+allreduce+finalize+composite3_grad_v2",
+                    "kernel": "composite3_fused_v3_kernel" if (world == 1 or args.exchange == "p2p") else "composite3_stats_packed+allreduce+finalize+composite3_grad_v2",
                     "algorithmic_bytes_per_launch": alg_bytes}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
@@ -770,6 +987,7 @@ def _run(args):
             "gpu_launches": launches_per_step * args.steps * world,
             "losses": [float(v) for v in losses.cpu()],
             "parity": parity,
+            "e2e_variants": e2e_variants, "host": numa_note,
             "aux": aux,
         }
     else:

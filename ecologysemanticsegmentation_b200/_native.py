@@ -81,6 +81,7 @@ SIGNATURES = {
                                                _u32, C.c_int, _vp]),
     "eco_composite3_step": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _u32, _vp, _vp, _vp, _i64, _vp, _OUT, C.POINTER(EcoPeerExchange),
                                       C.c_int, _vp]),
+    "eco_composite3_step_if_changed": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _u32, _vp, _vp, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
     "eco_xch_poll_status": (C.c_int, [_vp, _i64, C.POINTER(C.c_uint32), C.c_int, _vp]),
     "eco_xch_bytes": (_i64, [_i32]),
     "eco_xch_alloc": (C.c_int, [_i32, C.POINTER(_vp), C.c_char_p, C.c_int]),

@@ -792,7 +792,8 @@ extern "C" int eco_composite3_grad(const EcoView* x, const EcoView* g, int32_t N
 
 static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
                         const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
-                        float* losses_out, const EcoOut* gx, XchArgs xch, int device, void* stream) {
+                        float* losses_out, const EcoOut* gx, XchArgs xch, int device, void* stream,
+                        const float* upstream_prev = nullptr) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
     if (!leaf_scale_dev || !upstream || !losses_out || !gx || !gx->ptr) { set_error("null scale/upstream/output"); return -5; }
@@ -819,13 +820,14 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
         const int g2 = v2_grid(device, N, HW);
         if (g2 < 0) return -10;
         v2::V3Ws* ws3 = reinterpret_cast<v2::V3Ws*>(reinterpret_cast<char*>(ws) + kWsV3Offset);
-        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws3, &losses_out, &flags, &xch};
+        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws3, &losses_out, &flags, &xch, (void*)&upstream_prev};
         if (g_f32)
             return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v3_kernel<float>, dim3(g2), dim3(v2::kThreads3), args,
                                                           v2::Stage3<float>::kSmem, st), "composite3_fused_v3_kernel<f32 labels> launch");
         return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v3_kernel<uint8_t>, dim3(g2), dim3(v2::kThreads3), args,
                                                       v2::Stage3<uint8_t>::kSmem, st), "composite3_fused_v3_kernel<u8 labels> launch");
     }
+    if (upstream_prev) { set_error("eco_composite3_step_if_changed needs fp32 logits with 16-byte aligned planes"); return -8; }
     // everything below: first-generation kernels (bf16 or probability inputs, ragged / unaligned planes), f32 labels only
     if (!g_f32 || (flags & ECO_C3_UNION_LABELS)) {
         set_error("byte labels / the fused label union need fp32 logits with 16-byte aligned planes (H*W %% 16 == 0 for byte labels, %% 4 otherwise)");
@@ -879,6 +881,16 @@ extern "C" int eco_composite3_step(const EcoView* x, const EcoView* g, int32_t N
         if (rc) return rc;
     }
     return launch_fused(x, g, N, HW, flags, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream);
+}
+
+extern "C" int eco_composite3_step_if_changed(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
+                                              const double* leaf_scale_dev, const float* upstream, const float* upstream_prev,
+                                              void* ws, int64_t ws_bytes, float* losses_out, const EcoOut* gx, int device,
+                                              void* stream) {
+    if (!upstream_prev) { set_error("null upstream_prev"); return -5; }
+    XchArgs xch{};
+    xch.world = 1;
+    return launch_fused(x, g, N, HW, flags, leaf_scale_dev, upstream, ws, ws_bytes, losses_out, gx, xch, device, stream, upstream_prev);
 }
 
 extern "C" int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, int32_t from_logits,

@@ -489,10 +489,19 @@ __device__ inline void flat_leaf_sums(const double* F, int leaf, double* s /*[8]
 template <typename TG>
 __global__ void __launch_bounds__(kThreads3, 1)
 composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
-                           V3Ws* __restrict__ ws, float* __restrict__ losses_out, unsigned int flags, XchArgs xch) {
+                           V3Ws* __restrict__ ws, float* __restrict__ losses_out, unsigned int flags, XchArgs xch,
+                           const float* __restrict__ upstream_prev) {
     extern __shared__ __align__(128) char stage_smem[];
     __shared__ Fused3Smem fs;
     const int warp = threadIdx.x >> 5;
+    if (upstream_prev) {
+        // "only if changed": the outputs already hold the step for `upstream_prev`; every thread of every CTA compares the
+        // two weight vectors (same memory, same answer) and the whole grid leaves before it touches anything
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < ECO_NLOSS; ++k) same = same && (__float_as_uint(upstream[k]) == __float_as_uint(upstream_prev[k]));
+        if (same) return;
+    }
     stats_smem_init(fs.st);
     pipe_init3(fs.ps);
     const TileRange tr = tile_range(ga.a);

@@ -29,14 +29,18 @@ def draw_pair_weights(relative_set_ratios, early_stopped):
     """The host-side weight draw of loss_composite.py:46-52, verbatim in its use of the GLOBAL numpy RNG:
     two draws (choice, rand) per weight, three weights per pair in the order w_idx, w_jdx, w_diff, taken even
     when ``early_stopped`` is False.  Returns [(i, j, w_i, w_j, w_d), ...]."""
+    # ``np.random.choice([0, 1])`` is written as ``np.random.randint(0, 2)``: the legacy RandomState implements the former
+    # as exactly that call after converting the list to an array, so value and stream consumption are identical (asserted
+    # in tests/test_host_logic.py) at a third of the host time -- this runs on every losses_fn call.
     out = []
+    coin, rand = np.random.randint, np.random.rand
+    es = int(early_stopped)
     length = len(relative_set_ratios)
     for idx in range(length - 1):
         for jdx in range(idx + 1, length):
-            w_idx = (1 / relative_set_ratios[idx]) * (1 - int(early_stopped) * np.random.choice([0, 1]) * np.random.rand())
-            w_jdx = (1 / relative_set_ratios[jdx]) * (1 - int(early_stopped) * np.random.choice([0, 1]) * np.random.rand())
-            w_diff = (1 / (relative_set_ratios[idx] - relative_set_ratios[jdx])) * \
-                (1 - int(early_stopped) * np.random.choice([0, 1]) * np.random.rand())
+            w_idx = (1 / relative_set_ratios[idx]) * (1 - es * coin(0, 2) * rand())
+            w_jdx = (1 / relative_set_ratios[jdx]) * (1 - es * coin(0, 2) * rand())
+            w_diff = (1 / (relative_set_ratios[idx] - relative_set_ratios[jdx])) * (1 - es * coin(0, 2) * rand())
             out.append((idx, jdx, w_idx, w_jdx, w_diff))
     return out
 

@@ -263,6 +263,8 @@ def softce_grad(a, b, bw, n_pix, upstream, want_a, want_b):
 # ------------------------------------------------------------------------------------------------
 def _stack_upstream(grads, like):
     """7 optional 0-d grads -> one float32 [7] device tensor, without a host sync."""
+    if all(gr is not None and gr.dtype == torch.float32 and gr.dim() == 0 for gr in grads):
+        return torch.stack(grads)
     zero = None
     parts = []
     for gr in grads:
@@ -303,27 +305,88 @@ class PairLeaves(torch.autograd.Function):
         return ga, gb, None, None, None, None, None
 
 
+# Anticipated upstream weights of the drop-in composite path, per device: the float32 [7] vector dT/dloss_k that the LAST
+# backward through Composite3 received.  train() forms T = focal_dice_w*focal_dice + bce_l_w*bce_l + generalized_dice_w*
+# (generalized_dice + twersky_dice) with weights that depend on the epoch only (train_multiclass.py:92-100,145), so the
+# next step's backward will almost always receive the same vector.  Tensors in here are never modified in place.
+_anticipated_upstream = {}
+_scales_cache = {}
+
+
+def _device_scales(leaf_scales, device):
+    """21 python floats -> float64 CUDA tensor, re-uploaded only when the values change (they do not unless
+    early_stopped draws random weights, loss_composite.py:49-52)."""
+    key = (device.index, tuple(float(v) for v in leaf_scales))
+    hit = _scales_cache.get(device.index)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    t = torch.tensor(key[1], dtype=torch.float64, device=device)
+    _scales_cache[device.index] = (key, t)
+    return t
+
+
+def _fused_dropin_ok(x, g, from_logits, group):
+    """Inputs the third-generation fused kernel serves (so that the backward's "only if changed" launch is valid too)."""
+    if group is not None or not from_logits or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+        return False
+    hw = x.shape[2] * x.shape[3]
+    if hw % 4 or not x.is_contiguous() or x.data_ptr() % 16 or not g.is_contiguous() or g.data_ptr() % 16:
+        return False
+    if g.dtype == torch.float32:
+        return True
+    return g.dtype in (torch.uint8, torch.bool) and hw % 16 == 0
+
+
 class Composite3(torch.autograd.Function):
-    """Fused 21-leaf composite loss for C == 3 (loss_composite.py:21-94, composite_set_theory=True)."""
+    """Fused 21-leaf composite loss for C == 3 (loss_composite.py:21-94, composite_set_theory=True).
+
+    Fast path (fp32 logits, one GPU): the forward is ONE launch of the fused step with the upstream weights anticipated
+    from the previous backward; it already leaves d(sum_k w_k loss_k)/d logits in a buffer.  The backward launches the
+    "only if changed" form of the same kernel with the weights autograd really delivered: the kernel compares the two
+    vectors on the device and returns at once when they agree (no host synchronisation), otherwise it redoes the step.
+    Everything else: statistics kernel -> (all-reduce) -> closed forms in the forward, gradient kernel in the backward."""
 
     @staticmethod
     def forward(ctx, x, g, leaf_scales, from_logits, group):
+        ctx.from_logits = from_logits
+        ctx.set_materialize_grads(False)
+        ctx.fast = ctx.needs_input_grad[0] and not ctx.needs_input_grad[1] and _fused_dropin_ok(x, g, from_logits, group)
+        if ctx.fast:
+            dev = x.device
+            used = _anticipated_upstream.get(dev.index)
+            if used is None:
+                used = torch.zeros(nat.NLOSS, dtype=torch.float32, device=dev)
+            scales = _device_scales(leaf_scales, dev)
+            losses, gx = _dropin_prepared(x, g, scales, used).run(upstream=used, scales=scales)
+            ctx.save_for_backward(x, g, scales, losses, gx)
+            ctx.holds = used          # the weights `gx` currently holds the gradient for
+            ctx.returned = False
+            return tuple(losses.clone().unbind(0))   # (the saved `losses` buffer is rewritten by the backward's launch)
         acc = composite3_stats(x.detach(), g.detach(), from_logits)
         acc = dist_.allreduce_sums_(acc, group)
         losses, jac, _ = composite3_finalize(acc, leaf_scales)
         ctx.save_for_backward(x, g, jac)
-        ctx.from_logits = from_logits
-        ctx.set_materialize_grads(False)
         return tuple(losses.unbind(0))
 
     @staticmethod
     def backward(ctx, *grads):
-        x, g, jac = ctx.saved_tensors
         if ctx.needs_input_grad[1]:
             raise RuntimeError("the fused composite kernel produces gradients for the predictions only; "
                                "loss_composite.losses_fn routes labels that require grad to the pair-leaf kernels")
         if not ctx.needs_input_grad[0] or all(gr is None for gr in grads):
             return None, None, None, None, None
+        if ctx.fast:
+            x, g, scales, losses, gx = ctx.saved_tensors
+            up = _stack_upstream(grads, x)
+            _anticipated_upstream[x.device.index] = up
+            ent = _dropin_prepared(x, g, scales, up)
+            if ctx.returned:   # a second backward through the same graph: autograd may own the first buffer by now
+                _, gx = ent.run(upstream=up, scales=scales)
+                return gx, None, None, None, None
+            ent.run(out=gx, upstream=up, scales=scales, upstream_prev=ctx.holds, losses=losses)
+            ctx.holds, ctx.returned = up, True
+            return gx, None, None, None, None
+        x, g, jac = ctx.saved_tensors
         up = _stack_upstream(grads, x)
         gx = composite3_grad(x.detach(), g.detach(), ctx.from_logits, jac, up)
         return gx, None, None, None, None
@@ -404,12 +467,15 @@ def _byte_labels_ok(x, g, from_logits):
             and g.data_ptr() % 16 == 0)
 
 
-def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None, union_labels=False, peers=None):
+def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None, union_labels=False, peers=None,
+                     upstream_prev=None, losses_out=None):
     """ONE cooperative launch (eco_composite3_step): statistics -> grid hand-over -> closed forms -> gradient of
     sum_k upstream[k] * loss_k.  leaf_scales: float64 CUDA [21]; upstream: float32 CUDA [7].
     g: float32 labels, or uint8 / bool masks (kept as bytes on the device where the kernel takes them).
     union_labels: g holds the raw per-organ masks; the label union of utils/subsets_union.py:8-32 (exclude_indices=[0])
     is applied at load.  peers: an EcoPeerExchange for a batch sharded over processes.
+    upstream_prev: `out` / `losses_out` already hold the step for these weights -- the launch returns at once unless
+    `upstream` differs from them (compared on the device; eco_composite3_step_if_changed).
     Returns (losses f32 [7], grad w.r.t. x -- w.r.t. the logits when from_logits)."""
     nat.require_cuda(x, g, leaf_scales, upstream)
     if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
@@ -430,11 +496,17 @@ def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None, un
     n, c, h, w = x.shape
     L = nat.lib()
     ws = nat.workspace("comp3", L.eco_composite3_ws_bytes(), x.device)
-    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
+    losses = losses_out if losses_out is not None else torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
     gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
     vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc, allow_u8=True)
     og = nat.out_of(gx, c * h * w, h * w)
     flags = (0 if from_logits else nat.C3_PROBS) | (nat.C3_UNION_LABELS if union_labels else 0)
+    if upstream_prev is not None:
+        rc = L.eco_composite3_step_if_changed(C.byref(vx), C.byref(vg), n, h * w, flags, leaf_scales.data_ptr(),
+                                              upstream.data_ptr(), upstream_prev.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              losses.data_ptr(), C.byref(og), _dev(x), nat.current_stream_ptr(x.device))
+        nat.check(rc, "eco_composite3_step_if_changed")
+        return losses, gx
     rc = L.eco_composite3_step(C.byref(vx), C.byref(vg), n, h * w, flags, leaf_scales.data_ptr(), upstream.data_ptr(),
                                ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og),
                                C.byref(peers) if peers is not None else None, _dev(x), nat.current_stream_ptr(x.device))
@@ -445,3 +517,77 @@ def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None, un
                                 out=out, union_labels=False, peers=peers)
     nat.check(rc, "eco_composite3_step")
     return losses, gx
+
+
+class PreparedComposite3:
+    """The argument block of one eco_composite3_step launch, built once for a (logits, labels) pair of buffers and reused:
+    a training loop presents the same device buffers step after step, and re-deriving views, strides, workspace and
+    ctypes structures costs more host time (~70 us) than the kernel takes.  ``run`` is a dictionary-free ctypes call."""
+
+    __slots__ = ("sig", "vx", "vg", "og", "n", "hw", "flags", "scales", "upstream", "ws", "peers", "keep", "dev", "shape",
+                 "dtype", "fn", "L")
+
+    @staticmethod
+    def signature(x, g):
+        return (x.data_ptr(), g.data_ptr(), x.shape, g.shape, x.dtype, g.dtype, x.stride(), g.stride())
+
+    def __init__(self, x, g, leaf_scales, upstream, from_logits=True, union_labels=False, peers=None):
+        nat.require_cuda(x, g, leaf_scales, upstream)
+        if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"composite3 expects two [N,3,H,W] tensors, got {tuple(x.shape)} and {tuple(g.shape)}")
+        self.sig = self.signature(x, g)
+        gg = g.view(torch.uint8) if g.dtype == torch.bool else g
+        if gg.dtype == torch.uint8 and not _byte_labels_ok(x, gg, from_logits):
+            raise ValueError("byte labels not servable here")    # caller falls back to composite3_fused (which widens them)
+        if gg.dtype not in (torch.uint8, torch.float32):
+            raise ValueError("labels must be float32 / uint8 / bool")
+        xx, x_sn, x_sc = nat.planes(x)
+        g2, g_sn, g_sc = nat.planes(gg)
+        if xx is not x or g2 is not gg:
+            raise ValueError("strided planes")                    # a copy would not be reusable
+        n, c, h, w = x.shape
+        self.L = nat.lib()
+        self.fn = self.L.eco_composite3_step
+        self.n, self.hw, self.shape, self.dtype, self.dev = n, h * w, (n, c, h, w), x.dtype, x.device
+        self.vx, self.vg = nat.view_of(x, x_sn, x_sc), nat.view_of(gg, g_sn, g_sc, allow_u8=True)
+        self.og = nat.EcoOut(None, c * h * w, h * w, nat.dtype_code(x), 0)
+        self.flags = (0 if from_logits else nat.C3_PROBS) | (nat.C3_UNION_LABELS if union_labels else 0)
+        self.scales, self.upstream, self.peers = leaf_scales, upstream, peers
+        self.ws = nat.workspace("comp3", self.L.eco_composite3_ws_bytes(), x.device)
+        self.keep = (x, g, gg)
+
+    def run(self, out=None, upstream=None, scales=None, upstream_prev=None, losses=None):
+        """Launch.  ``upstream`` / ``scales`` override the tensors given at construction; with ``upstream_prev`` the launch is
+        the "only if changed" form (``out`` and ``losses`` then hold the step for ``upstream_prev``)."""
+        dev = self.dev
+        if losses is None:
+            losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=dev)
+        gx = out if out is not None else torch.empty(self.shape, dtype=self.dtype, device=dev)
+        self.og.ptr = gx.data_ptr()
+        up = (self.upstream if upstream is None else upstream).data_ptr()
+        sc = (self.scales if scales is None else scales).data_ptr()
+        stream = torch._C._cuda_getCurrentRawStream(dev.index)
+        if upstream_prev is None:
+            rc = self.fn(self.vx, self.vg, self.n, self.hw, self.flags, sc, up, self.ws.data_ptr(), self.ws.numel(),
+                         losses.data_ptr(), self.og, self.peers, dev.index, stream)
+        else:
+            rc = self.L.eco_composite3_step_if_changed(self.vx, self.vg, self.n, self.hw, self.flags, sc, up,
+                                                       upstream_prev.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                                       losses.data_ptr(), self.og, dev.index, stream)
+        if rc:
+            nat.check(rc, "eco_composite3_step")
+        return losses, gx
+
+
+_dropin_launches = {}
+
+
+def _dropin_prepared(x, g, scales, upstream):
+    """Launch block of the drop-in fast path for this pair of buffers (see PreparedComposite3)."""
+    key = (x.data_ptr(), g.data_ptr(), torch._C._cuda_getCurrentRawStream(x.device.index))
+    ent = _dropin_launches.get(key)
+    if ent is None or ent.sig != PreparedComposite3.signature(x, g):
+        if len(_dropin_launches) >= 64:
+            _dropin_launches.clear()
+        ent = _dropin_launches[key] = PreparedComposite3(x, g, scales, upstream, True)
+    return ent

@@ -56,8 +56,9 @@ int main(int argc, char** argv) {
         ga.gx = o; ga.gx_sn = C * HW; ga.gx_sc = HW;
         XchArgs xch{}; xch.world = 1; xch.status = status;
         const double* sd = scale_dev; const float* u = up; unsigned int flags = 0;
-        void* args[] = {&ga, (void*)&sd, (void*)&u, &ws3, &losses, &flags, &xch};
-        if (argc > 2) composite3_fused_v3_kernel<float><<<sms, kThreads3, Stage3<float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch);
+        const float* prev = nullptr;
+        void* args[] = {&ga, (void*)&sd, (void*)&u, &ws3, &losses, &flags, &xch, (void*)&prev};
+        if (argc > 2) composite3_fused_v3_kernel<float><<<sms, kThreads3, Stage3<float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch, nullptr);
         else CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float>, dim3(sms), dim3(kThreads3), args, Stage3<float>::kSmem, nullptr));
     };
     for (int i = 0; i < 5; ++i) launch(i % NSETS);

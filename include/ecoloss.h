@@ -224,6 +224,16 @@ typedef struct EcoPeerExchange {
 int eco_composite3_step(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
                         const double* leaf_scale_dev, const float* upstream, void* ws, int64_t ws_bytes,
                         float* losses_out, const EcoOut* gx, const EcoPeerExchange* peers, int device, void* stream);
+/* The same step, run only if the weights changed: `losses_out` / `gx` already hold the step for `upstream_prev` (an
+ * earlier eco_composite3_step on the same inputs); the kernel compares the two float32[7] vectors ON THE DEVICE and returns at
+ * once when they are equal, otherwise it recomputes the step for `upstream`.  This is how the drop-in `losses_fn(...)` ->
+ * `loss.backward()` of ess/train_multiclass.py:139-147 becomes one launch in the forward (with the weights of :145 anticipated
+ * from the previous step -- they depend on the epoch only, :92-100) and one empty launch in the backward, without a host
+ * synchronisation to look at the weights.  Single GPU; fp32 logits with 16-byte aligned planes (-8 otherwise). */
+int eco_composite3_step_if_changed(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, uint32_t flags,
+                                   const double* leaf_scale_dev, const float* upstream, const float* upstream_prev,
+                                   void* ws, int64_t ws_bytes, float* losses_out, const EcoOut* gx, int device,
+                                   void* stream);
 /* Reads (and clears, when set) the time-out word inside `ws`; synchronises `stream`. */
 int eco_xch_poll_status(void* ws, int64_t ws_bytes, uint32_t* status_out_host, int device, void* stream);
 

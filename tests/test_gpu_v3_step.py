@@ -183,3 +183,50 @@ def test_peer_exchange_timeout_is_reported():
     assert out.value == 1
     nat.check(L.eco_xch_poll_status(ws2.data_ptr(), ws2.numel(), C.byref(out), 0, torch.cuda.current_stream().cuda_stream), "poll")
     assert out.value == 0, "the word is cleared once it has been read"
+
+
+def test_dropin_autograd_fast_path_anticipates_the_weights():
+    """eco.losses_fn(z, g, True, from_logits=True) -> weighted sum -> backward(), as ess/train_multiclass.py:139-147 calls
+    it: the forward is the fused step with the weights of the PREVIOUS backward anticipated, the backward an
+    "only if changed" launch.  Every combination must give the oracle's gradient: first call (nothing anticipated), repeated
+    weights (hit), changed weights (miss), two forwards before two backwards, and a second backward through one graph."""
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200 import ops
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    ops._anticipated_upstream.clear()
+    z0, g0 = make_inputs(6, 3, 64, 31)
+    z0, g0 = z0.cuda(), g0.cuda()
+
+    def ours(z, g, up, retain=False):
+        zz = z.clone().requires_grad_(True)
+        np.random.seed(0)
+        losses = eco.losses_fn(zz, g, True, from_logits=True)
+        return zz, losses, sum(w * l for w, l in zip(up, losses) if w)
+
+    def check(z, g, up):
+        zz, losses, total = ours(z, g, up)
+        total.backward()
+        rl, rg = _oracle(z, g.float(), up)
+        assert_losses_close([float(v) for v in losses], rl, tol=TOL, what=f"drop-in {up}")
+        assert_grad_close(zz.grad.cpu(), rg.cpu(), tol=TOL, what=f"drop-in {up}")
+
+    check(z0, g0, UP)            # nothing anticipated yet: the backward recomputes
+    check(z0, g0, UP)            # hit
+    check(z0 * 0.5, g0, UP)      # hit on other data
+    check(z0, g0, UP_ALL)        # the weights changed: miss, recomputed
+    check(z0, g0.to(torch.uint8), UP_ALL)   # byte masks through the reference signature
+    # two forwards, then two backwards with different weights
+    za, la, ta = ours(z0, g0, UP)
+    zb, lb, tb = ours(z0 * 2.0, g0, UP_ALL)
+    tb.backward()
+    ta.backward()
+    assert_grad_close(za.grad.cpu(), _oracle(z0, g0, UP)[1].cpu(), tol=TOL, what="interleaved a")
+    assert_grad_close(zb.grad.cpu(), _oracle(z0 * 2.0, g0, UP_ALL)[1].cpu(), tol=TOL, what="interleaved b")
+    # a second backward through the same graph with other weights
+    zc, lc, _ = ours(z0, g0, UP)
+    sum(w * l for w, l in zip(UP, lc) if w).backward(retain_graph=True)
+    first = zc.grad.clone()
+    zc.grad = None
+    sum(w * l for w, l in zip(UP_ALL, lc) if w).backward()
+    assert_grad_close(first.cpu(), _oracle(z0, g0, UP)[1].cpu(), tol=TOL, what="retain 1")
+    assert_grad_close(zc.grad.cpu(), _oracle(z0, g0, UP_ALL)[1].cpu(), tol=TOL, what="retain 2")
