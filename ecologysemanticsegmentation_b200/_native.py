@@ -90,6 +90,8 @@ SIGNATURES = {
     "eco_xch_free": (C.c_int, [_vp, C.c_int]),
     "eco_dice_ws_bytes": (_i64, [_i32, _i32]),
     "eco_dice_counts": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp, C.c_int, _vp]),
+    "eco_dice_counts_ex": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp, C.c_int, _vp]),
+    "eco_dice_finalize_ex": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),
     "eco_dice_finalize": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),
     "eco_masks_u8": (C.c_int, [_VIEW, _i32, _i32, _i64, C.c_float, _i32, _i32, _vp, C.c_int, _vp]),
     "eco_union_sets": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i64, _i64, C.c_uint64, _i32, C.c_int, _vp]),

@@ -26,7 +26,27 @@ struct EvalArgs {
 // ws: counters u32[C] (padded to 256 B) | int64 partial counts [C][kEvMaxCtas][NT][2] ... laid out
 // generically as: per (c, cta): long long cnt[2*NT + 1] (last = label count), double soft[3].
 __host__ __device__ inline int64_t eval_rec_words(int nt) { return 2 * (int64_t)nt + 1 + 3; }  // 8-byte words
-__host__ __device__ inline int64_t eval_ws_off(int C) { return ((int64_t)C * 4 + 255) / 256 * 256; }
+__host__ __device__ inline int64_t eval_ws_off(int C) { return ((int64_t)C * 8 + 255) / 256 * 256; }   // counters u32[C] | non-binary flags u32[C]
+
+// Labels other than exactly 0 / 1 (the datasets that resize their masks produce fractions, ess/dataset/fish/fish_suim.py:60-74):
+// the reference's thresholded Dice is 2 sum(out * lab) / (sum out + sum lab^2) with the REAL label values
+// (ess/test_multiclass.py:80 -> ess/loss_functions.py:55-57), which integer counts cannot express.  The counting kernels
+// count a label only where it is exactly 1, so sum lab^2 == count holds iff every label of the class is 0 or 1 (all terms
+// are non-negative: no cancellation).  The last CTA of a class checks that, publishes the per-threshold intersections as
+// float64 (= the integer counts for binary labels) and raises the class's flag otherwise; dice_exact_kernel, launched
+// after every thresholded scoring call, returns at once unless a flag is up and then re-reads the class for the exact sums.
+__device__ __forceinline__ void publish_intersections(int c, int C, int n_thr, long long* counts_out, const double* soft_out,
+                                                      double* thr_inter_out, unsigned int* flags) {
+    if (n_thr <= 0) { flags[c] = 0u; return; }
+    const long long lab_cnt = counts_out[(int64_t)c * 3 + 2];
+    const bool nb = soft_out[c * 3 + 2] != (double)lab_cnt;
+    flags[c] = (nb && thr_inter_out) ? 1u : 0u;
+    for (int k = 0; k < n_thr; ++k) {
+        long long* r = counts_out + ((int64_t)k * C + c) * 3;
+        if (thr_inter_out) thr_inter_out[(int64_t)k * C + c] = nb ? 0.0 : (double)r[0];
+        else if (nb) r[2] = -1;   // no place for the exact sums: mark the class, eco_dice_finalize turns it into NaN
+    }
+}
 
 // Per-thread counters are packed: low 16 bits = |out| count, high 16 bits = intersection count of one threshold
 // (one FSETP + one predicated IADD per threshold and element); a thread folds them into 32-bit counters before
@@ -39,7 +59,7 @@ template <typename TZ, typename TL, int VEC, int NT>
 __global__ void __launch_bounds__(kEvThreads, NT > 4 ? 2 : kEvCtasPerSm)
 dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
                    long long* __restrict__ partials, long long* __restrict__ counts_out,
-                   double* __restrict__ soft_out) {
+                   double* __restrict__ soft_out, double* __restrict__ thr_inter_out) {
     constexpr int kTile = kEvThreads * VEC * kEvUnroll;
     constexpr int NTA = NT > 0 ? NT : 1;
     const int c = blockIdx.y;
@@ -108,7 +128,7 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
                     }
                 }
                 const float lab = lv[u][v];
-                const int li = fabsf(lab) >= 1.0f ? 1 : 0;
+                const int li = lab == 1.0f ? 1 : 0;
                 const unsigned int inc = 1u + ((unsigned int)li << 16);
                 s0 = fmaf(pr, lab, s0);
                 s1 += pr;
@@ -209,7 +229,11 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
             if (lane == 0) soft_out[c * 3 + s] = v;
         }
     }
-    if (threadIdx.x == 0) counters[c] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        publish_intersections(c, p.C, p.n_thr, counts_out, soft_out, thr_inter_out, counters + p.C);
+        counters[c] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,7 +294,7 @@ __device__ __forceinline__ int beam_bin(float p, const BeamSmem& sm, float t15, 
 template <typename TZ, typename TL, int VEC>
 __global__ void __launch_bounds__(kBeamThreads, kBeamCtasPerSm)
 dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
-                 long long* __restrict__ partials, long long* __restrict__ counts_out, double* __restrict__ soft_out) {
+                 long long* __restrict__ partials, long long* __restrict__ counts_out, double* __restrict__ soft_out, double* __restrict__ thr_inter_out) {
     constexpr int kTile = kBeamThreads * VEC * kEvUnroll;
     constexpr int NTA = kBeamMax;
     __shared__ BeamSmem sm;
@@ -431,7 +455,7 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
             if (!ok[u]) continue;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const unsigned int li = fabsf(lv[u][v]) >= 1.0f ? 0x10000u : 0u;
+                const unsigned int li = lv[u][v] == 1.0f ? 0x10000u : 0u;
                 sm.hist[bins[u][v]][tid] += 1u + li;   // thread-private slot: plain LDS / IADD / STS
             }
         }
@@ -532,19 +556,72 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
             if (lane == 0) soft_out[c * 3 + sidx] = v;
         }
     }
-    if (tid == 0) counters[c] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        publish_intersections(c, p.C, p.n_thr, counts_out, soft_out, thr_inter_out, counters + p.C);
+        counters[c] = 0;
+    }
+}
+
+// Rare exact pass for classes whose labels are not all 0 / 1 (see publish_intersections): sum out * lab per threshold.
+template <typename TZ, typename TL>
+__global__ void __launch_bounds__(256)
+dice_exact_kernel(EvalArgs p, const float* __restrict__ thresholds, const unsigned int* __restrict__ flags,
+                  double* __restrict__ thr_inter_out) {
+    const int c = blockIdx.y;
+    if (!flags[c]) return;
+    __shared__ float thr[kBeamMax];
+    __shared__ double red[8][kBeamMax];
+    if (threadIdx.x < kBeamMax) thr[threadIdx.x] = threadIdx.x < p.n_thr ? thresholds[threadIdx.x] : __int_as_float(0x7f800000);
+    __syncthreads();
+    const TZ* zbase = reinterpret_cast<const TZ*>(p.z) + (int64_t)c * p.z_sc;
+    const TL* lbase = reinterpret_cast<const TL*>(p.l) + (int64_t)c * p.l_sc;
+    double acc[kBeamMax];
+#pragma unroll
+    for (int k = 0; k < kBeamMax; ++k) acc[k] = 0.0;
+    const int64_t total = (int64_t)p.N * p.HW;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = e / p.HW, i = e - n * p.HW;
+        const float zv = Vec4<TZ>::load1(zbase + n * p.z_sn + i);
+        const float lab = Vec4<TL>::load1(lbase + n * p.l_sn + i);
+        const float pr = p.probs ? zv : sigmoid_exact(zv);
+#pragma unroll
+        for (int k = 0; k < kBeamMax; ++k)
+            if (pr > thr[k]) acc[k] += (double)lab;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kBeamMax; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < p.n_thr) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        atomicAdd(&thr_inter_out[(int64_t)threadIdx.x * p.C + c], v);
+    }
 }
 
 struct DiceFinArgs {
     int C, n_thr;
 };
 __global__ void dice_finalize_kernel(const long long* __restrict__ counts, const double* __restrict__ soft,
-                                     DiceFinArgs a, float* __restrict__ dice_out, float* __restrict__ soft_out) {
+                                     const double* __restrict__ thr_inter, DiceFinArgs a, float* __restrict__ dice_out,
+                                     float* __restrict__ soft_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const double eps = 1e-7;
     if (dice_out && counts && i < a.n_thr * a.C) {
         const long long* r = counts + (int64_t)i * 3;
-        dice_out[i] = (float)((2.0 * (double)r[0] + eps) / ((double)r[1] + (double)r[2] + eps));
+        if (thr_inter && soft) {
+            // the reference's formula with the real label values: 2 sum(out*lab) / (sum out + sum lab^2); for 0/1 labels
+            // these are the integer counts
+            dice_out[i] = (float)((2.0 * thr_inter[i] + eps) / ((double)r[1] + soft[(int64_t)(i % a.C) * 3 + 2] + eps));
+        } else if (r[2] < 0) {
+            dice_out[i] = __int_as_float(0x7fc00000);   // labels other than 0/1 and no exact sums were requested
+        } else {
+            dice_out[i] = (float)((2.0 * (double)r[0] + eps) / ((double)r[1] + (double)r[2] + eps));
+        }
     }
     if (soft_out && soft && i < a.C) {
         const double* r = soft + (int64_t)i * 3;
@@ -559,8 +636,8 @@ static bool ev_aligned(const EcoView* v, int64_t HW) {
 
 template <int NT>
 static void launch_nt(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cudaStream_t st, const float* thr,
-                      unsigned int* counters, long long* partials, long long* counts_out, double* soft_out) {
-#define ECO_EV(TZ, TL, V) dice_counts_kernel<TZ, TL, V, NT><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out)
+                      unsigned int* counters, long long* partials, long long* counts_out, double* soft_out, double* inter) {
+#define ECO_EV(TZ, TL, V) dice_counts_kernel<TZ, TL, V, NT><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out, inter)
     if (ld == ECO_U8) {
         if (vec == 4) { if (zd == ECO_F32) ECO_EV(float, uint8_t, 4); else ECO_EV(__nv_bfloat16, uint8_t, 4); }
         else { if (zd == ECO_F32) ECO_EV(float, uint8_t, 1); else ECO_EV(__nv_bfloat16, uint8_t, 1); }
@@ -579,8 +656,8 @@ static void launch_nt(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cud
 }
 
 static void launch_beam(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cudaStream_t st, const float* thr,
-                        unsigned int* counters, long long* partials, long long* counts_out, double* soft_out) {
-#define ECO_BM(TZ, TL, V) dice_beam_kernel<TZ, TL, V><<<grid, kBeamThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out)
+                        unsigned int* counters, long long* partials, long long* counts_out, double* soft_out, double* inter) {
+#define ECO_BM(TZ, TL, V) dice_beam_kernel<TZ, TL, V><<<grid, kBeamThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out, inter)
     if (ld == ECO_U8) {
         if (vec == 4) { if (zd == ECO_F32) ECO_BM(float, uint8_t, 4); else ECO_BM(__nv_bfloat16, uint8_t, 4); }
         else { if (zd == ECO_F32) ECO_BM(float, uint8_t, 1); else ECO_BM(__nv_bfloat16, uint8_t, 1); }
@@ -598,6 +675,18 @@ static void launch_beam(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, c
 #undef ECO_BM
 }
 
+static void launch_exact(const EvalArgs& p, int zd, int ld, int sms, cudaStream_t st, const float* thr, const unsigned int* flags,
+                         double* inter) {
+    dim3 grid((unsigned)(sms * 4 / p.C > 0 ? sms * 4 / p.C : 1), (unsigned)p.C, 1);
+#define ECO_EX(TZ, TL) dice_exact_kernel<TZ, TL><<<grid, 256, 0, st>>>(p, thr, flags, inter)
+    if (zd == ECO_F32) {
+        if (ld == ECO_F32) ECO_EX(float, float); else if (ld == ECO_BF16) ECO_EX(float, __nv_bfloat16); else ECO_EX(float, uint8_t);
+    } else {
+        if (ld == ECO_F32) ECO_EX(__nv_bfloat16, float); else if (ld == ECO_BF16) ECO_EX(__nv_bfloat16, __nv_bfloat16); else ECO_EX(__nv_bfloat16, uint8_t);
+    }
+#undef ECO_EX
+}
+
 static int nt_bucket(int n_thr) { return n_thr == 0 ? 0 : n_thr == 1 ? 1 : n_thr <= 4 ? 4 : 20; }
 
 }  // namespace eco
@@ -610,9 +699,10 @@ extern "C" int64_t eco_dice_ws_bytes(int32_t C, int32_t n_thr) {
     return eval_ws_off(C) + (int64_t)C * kEvMaxCtas * eval_rec_words(nta) * 8;
 }
 
-extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
-                               const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws,
-                               int64_t ws_bytes, int64_t* counts_out, double* soft_out, int device, void* stream) {
+extern "C" int eco_dice_counts_ex(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
+                                  const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws,
+                                  int64_t ws_bytes, int64_t* counts_out, double* soft_out, double* thr_inter_out, int device,
+                                  void* stream) {
     if (N <= 0 || C <= 0 || HW <= 0) { set_error("empty input (N=%d C=%d HW=%lld)", N, C, (long long)HW); return -2; }
     if (!logits || !labels || !logits->ptr || !labels->ptr) { set_error("null input view"); return -1; }
     if (C > 65535) { set_error("C too large"); return -3; }
@@ -649,22 +739,38 @@ extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     long long* co = reinterpret_cast<long long*>(counts_out);
     switch (nt_bucket(n_thr)) {
-        case 0: launch_nt<0>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
-        case 1: launch_nt<1>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
-        case 4: launch_nt<4>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
-        default: launch_beam(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out); break;
+        case 0: launch_nt<0>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
+        case 1: launch_nt<1>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
+        case 4: launch_nt<4>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
+        default: launch_beam(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
     }
-    return check_cuda(cudaGetLastError(), "dice_counts_kernel launch");
+    int rc = check_cuda(cudaGetLastError(), "dice_counts_kernel launch");
+    if (rc || n_thr == 0 || !thr_inter_out) return rc;
+    // exact sums for classes whose labels are not all 0/1: returns at once unless the counting kernel raised a flag
+    launch_exact(p, logits->dtype, labels->dtype, sms, st, thresholds, counters + C, thr_inter_out);
+    return check_cuda(cudaGetLastError(), "dice_exact_kernel launch");
 }
 
-extern "C" int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
-                                 float* soft_dice_out, int device, void* stream) {
+extern "C" int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
+                               const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws,
+                               int64_t ws_bytes, int64_t* counts_out, double* soft_out, int device, void* stream) {
+    return eco_dice_counts_ex(logits, labels, N, C, HW, thresholds, n_thr, logits_are_probs, ws, ws_bytes, counts_out, soft_out,
+                              nullptr, device, stream);
+}
+
+extern "C" int eco_dice_finalize_ex(const int64_t* counts, const double* soft, const double* thr_inter, int32_t C, int32_t n_thr,
+                                    float* dice_out, float* soft_dice_out, int device, void* stream) {
     if (C <= 0 || n_thr < 0) { set_error("bad C/n_thr"); return -1; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     DiceFinArgs a{C, n_thr};
     const int total = (n_thr > 0 ? n_thr : 1) * C;
     dice_finalize_kernel<<<(total + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const long long*>(counts), soft, a, dice_out, soft_dice_out);
+        reinterpret_cast<const long long*>(counts), soft, thr_inter, a, dice_out, soft_dice_out);
     return check_cuda(cudaGetLastError(), "dice_finalize_kernel launch");
+}
+
+extern "C" int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
+                                 float* soft_dice_out, int device, void* stream) {
+    return eco_dice_finalize_ex(counts, soft, nullptr, C, n_thr, dice_out, soft_dice_out, device, stream);
 }

@@ -162,7 +162,16 @@ def composite3_grad(x, g, from_logits, jac, upstream, out=None):
 def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False, out_counts=None, out_soft=None):
     """One pass over logits+labels -> (counts int64 [T,C,3] = (I, |out|, |lab|) per threshold,
     soft float64 [C,3] = (sum p*lab, sum p, sum lab^2)).  thresholds: float32 CUDA tensor [T] or None.
-    ``out_counts`` / ``out_soft``: optional contiguous destinations of those shapes (e.g. one slot of a stream buffer)."""
+    ``out_counts`` / ``out_soft``: optional contiguous destinations of those shapes (e.g. one slot of a stream buffer).
+    Labels are expected to be 0/1 here (a class with other values gets |lab| = -1); ``dice_counts_ex`` serves any labels."""
+    return dice_counts_ex(logits, labels, thresholds, inputs_are_probs, out_counts, out_soft, want_inter=False)[:2]
+
+
+def dice_counts_ex(logits, labels, thresholds=None, inputs_are_probs=False, out_counts=None, out_soft=None, out_inter=None,
+                   want_inter=True):
+    """``dice_counts`` plus inter float64 [T,C] = sum out*lab per threshold with the REAL label values (the integer
+    intersection for 0/1 labels, an exact second pass over a class that holds anything else): what the reference's
+    thresholded Dice (test_multiclass.py:80) needs when the dataset resized its masks."""
     nat.require_cuda(logits, labels)
     if logits.shape != labels.shape or logits.dim() != 4:
         raise ValueError("dice_counts expects two [N,C,H,W] tensors of equal shape")
@@ -192,21 +201,32 @@ def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False, out_cou
         soft = out_soft
         if soft.dtype != torch.float64 or soft.numel() != c * 3 or not soft.is_contiguous():
             raise ValueError("out_soft must be a contiguous float64 tensor of C*3 elements")
+    inter = None
+    if want_inter and nthr:
+        if out_inter is None:
+            inter = torch.empty((nthr, c), dtype=torch.float64, device=logits.device)
+        else:
+            inter = out_inter
+            if inter.dtype != torch.float64 or inter.numel() != nthr * c or not inter.is_contiguous():
+                raise ValueError("out_inter must be a contiguous float64 tensor of T*C elements")
     vz, vl = nat.view_of(logits, z_sn, z_sc), nat.view_of(labels, l_sn, l_sc, allow_u8=True)
-    rc = L.eco_dice_counts(C.byref(vz), C.byref(vl), n, c, h * w, thresholds.data_ptr() if nthr else None, nthr,
-                           int(inputs_are_probs), ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),
-                           _dev(logits), nat.current_stream_ptr(logits.device))
+    rc = L.eco_dice_counts_ex(C.byref(vz), C.byref(vl), n, c, h * w, thresholds.data_ptr() if nthr else None, nthr,
+                              int(inputs_are_probs), ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),
+                              inter.data_ptr() if inter is not None else None, _dev(logits),
+                              nat.current_stream_ptr(logits.device))
     nat.check(rc, "eco_dice_counts")
-    return counts, soft
+    return counts, soft, inter
 
 
-def dice_finalize(counts, soft, nthr):
+def dice_finalize(counts, soft, nthr, inter=None):
+    """counts / soft (/ inter, see dice_counts_ex) -> (thresholded Dice f32 [T,C] or None, soft Dice f32 [C])."""
     c = soft.shape[0]
     dev = soft.device
     dice = torch.empty((max(nthr, 1), c), dtype=torch.float32, device=dev) if nthr else None
     sdice = torch.empty((c,), dtype=torch.float32, device=dev)
-    rc = nat.lib().eco_dice_finalize(counts.data_ptr(), soft.data_ptr(), c, nthr, dice.data_ptr() if nthr else None,
-                                     sdice.data_ptr(), _dev(soft), nat.current_stream_ptr(dev))
+    rc = nat.lib().eco_dice_finalize_ex(counts.data_ptr(), soft.data_ptr(), inter.data_ptr() if inter is not None else None,
+                                        c, nthr, dice.data_ptr() if nthr else None, sdice.data_ptr(), _dev(soft),
+                                        nat.current_stream_ptr(dev))
     nat.check(rc, "eco_dice_finalize")
     return dice, sdice
 

@@ -45,11 +45,13 @@ def score_batch(logits, labels, threshold=None, *, group=None, inputs_are_probs=
             many = hasattr(threshold, "__len__")
             vals = list(threshold) if many else [threshold]
             thr_t = torch.tensor([float(v) for v in vals], dtype=torch.float32, device=logits.device)
-    counts, soft = ops.dice_counts(logits, labels, thr_t, inputs_are_probs=inputs_are_probs)
+    counts, soft, inter = ops.dice_counts_ex(logits, labels, thr_t, inputs_are_probs=inputs_are_probs)
     counts = dist_.allreduce_sums_(counts, group)
     soft = dist_.allreduce_sums_(soft, group)
+    if inter is not None:
+        inter = dist_.allreduce_sums_(inter, group)
     nthr = 0 if thr_t is None else thr_t.numel()
-    dice, sdice = ops.dice_finalize(counts, soft, nthr)
+    dice, sdice = ops.dice_finalize(counts, soft, nthr, inter)
     out = sdice if thr_t is None else (dice if many else dice[0])
     if return_counts:
         return out, counts, soft
@@ -94,6 +96,7 @@ class StreamScorer:
         self.thr = None if threshold is None else torch.tensor([float(threshold)], dtype=torch.float32, device=device)
         self.counts = torch.zeros((self.capacity, self.c, 3), dtype=torch.int64, device=device)
         self.soft = torch.zeros((self.capacity, self.c, 3), dtype=torch.float64, device=device)
+        self.inter = torch.zeros((self.capacity, self.c), dtype=torch.float64, device=device)   # sum out*lab, real label values
         self.n = 0
 
     def reset(self):
@@ -104,21 +107,25 @@ class StreamScorer:
             raise IndexError(f"StreamScorer holds {self.capacity} batches")
         if logits.shape[1] != self.c:
             raise ValueError(f"expected {self.c} classes, got {logits.shape[1]}")
-        ops.dice_counts(logits, labels, self.thr, inputs_are_probs=inputs_are_probs,
-                        out_counts=self.counts[self.n], out_soft=self.soft[self.n])
+        ops.dice_counts_ex(logits, labels, self.thr, inputs_are_probs=inputs_are_probs,
+                           out_counts=self.counts[self.n], out_soft=self.soft[self.n],
+                           out_inter=self.inter[self.n] if self.thr is not None else None)
         self.n += 1
 
     def per_batch(self):
         """float32 [batches, C]: the Dice of every batch scored so far (all-reduced over ``group`` first)."""
         if self.n == 0:
             raise ValueError("no batch scored yet")
-        counts, soft = self.counts[:self.n], self.soft[:self.n]
+        counts, soft, inter = self.counts[:self.n], self.soft[:self.n], self.inter[:self.n]
         if dist_.world_size(self.group) > 1:
             counts = dist_.allreduce_sums_(counts.clone(), self.group)
             soft = dist_.allreduce_sums_(soft.clone(), self.group)
+            inter = dist_.allreduce_sums_(inter.clone(), self.group)
         if self.thr is not None:
-            dice, _ = ops.dice_finalize(counts, soft[0], self.n)       # batches ride on the threshold axis: [n, C]
-            return dice
+            # (2 sum out*lab + eps) / (sum out + sum lab^2 + eps) per batch and class, float64 like the closed form of
+            # eco_dice_finalize_ex: a handful of [batches, C] element-wise ops at the end of the stream
+            eps = 1e-7
+            return ((2.0 * inter + eps) / (counts[..., 1].double() + soft[..., 2] + eps)).float()
         _, sdice = ops.dice_finalize(counts, soft.reshape(self.n * self.c, 3), 0)   # ... or on the class axis
         return sdice.reshape(self.n, self.c)
 

@@ -250,7 +250,7 @@ int eco_xch_free(void* ptr, int device);
  * Evaluation scoring: ess/test_multiclass.py:58 (sigmoid), :68-69 (threshold rule, strict '>' in fp32),
  * :80-81 (per-class dice_loss(out_c, lab_c, background_weight=0)).
  * counts_out: int64[C][3] = (sum out*lab, sum out, sum lab) over pixels with out = (sigmoid(z) > T) and
- *             lab counted where lab != 0 after truncation to integer (exact);
+ *             lab counted where it is exactly 1 (exact integers; see the _ex forms below for other label values);
  * soft_out:   float64[C][3] = (sum p*lab, sum p, sum lab^2) with p = sigmoid(z), the un-thresholded live path.
  * Both additive across shards.  thresholds: float32[n_thr] device (n_thr may be 0); counts_out is then
  * int64[n_thr][C][3] -- one read of logits+labels serves every threshold of the beam search (:64-77).
@@ -259,6 +259,20 @@ int64_t eco_dice_ws_bytes(int32_t C, int32_t n_thr);
 int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
                     const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws, int64_t ws_bytes,
                     int64_t* counts_out, double* soft_out, int device, void* stream);
+/* Labels other than exactly 0 / 1 (masks resized by the dataset, ess/dataset/fish/fish_suim.py:60-74): the reference's
+ * thresholded Dice is 2 sum(out*lab) / (sum out + sum lab^2) with the real label values, which integer counts cannot
+ * express.  The `_ex` forms carry the per-threshold intersections as float64 next to the counts:
+ *   thr_inter_out: float64[n_thr][C] = sum out*lab -- equal to the integer count for 0/1 labels; for a class with any other
+ *   label value a second, exact pass over that class fills it (the counting kernel detects the case: a label is counted
+ *   only where it is exactly 1, so sum lab^2 == count iff all labels are 0/1).  counts_out then holds (count of pixels
+ *   with out = 1 and lab = 1, sum out, count of lab = 1) and eco_dice_finalize_ex evaluates the reference's formula from
+ *   thr_inter, counts[.][1] and soft[.][2].  Without thr_inter_out (the plain forms) such a class gets counts_out[.][2] = -1
+ *   and a NaN Dice from eco_dice_finalize -- loud, not silently different from the reference. */
+int eco_dice_counts_ex(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
+                       const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws, int64_t ws_bytes,
+                       int64_t* counts_out, double* soft_out, double* thr_inter_out, int device, void* stream);
+int eco_dice_finalize_ex(const int64_t* counts, const double* soft, const double* thr_inter, int32_t C, int32_t n_thr,
+                         float* dice_out, float* soft_dice_out, int device, void* stream);
 /* dice_out: float32[n_thr][C] thresholded and soft_dice_out: float32[C], each (2I+eps)/(U+eps); either may be NULL. */
 int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
                       float* soft_dice_out, int device, void* stream);

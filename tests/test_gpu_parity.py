@@ -166,3 +166,30 @@ def test_fused_single_launch_matches_split_path(shape):
     _combine(ref, UP).backward()
     assert_losses_close(losses, ref, tol=1e-6, what="fused vs split")
     assert_grad_close(dz.cpu(), z2.grad.cpu(), tol=1e-6, what="fused vs split")
+
+
+@pytest.mark.parametrize("nthr", [1, 3, 19])
+def test_thresholded_dice_with_fractional_labels_matches_reference(nthr):
+    """Masks resized by the dataset are not 0/1 (ess/dataset/fish/fish_suim.py:60-74, fish_deepfish_segment.py:71-84).  The
+    reference's thresholded Dice uses the real label values, 2 sum(out*lab) / (sum out + sum lab^2)
+    (ess/test_multiclass.py:68-69,80 -> ess/loss_functions.py:55-57); so must the scoring here -- class 1 has fractional
+    labels (the exact second pass), classes 0 and 2 stay binary (integer counts), in one call."""
+    from ecologysemanticsegmentation_b200 import ops, test_multiclass as tmc
+    from oracle import torch_port as tp
+    torch.manual_seed(21)
+    z = (torch.randn(3, 3, 40, 52) * 2.5).cuda()
+    lab = (torch.rand(3, 3, 40, 52) > 0.5).float()
+    frac = torch.rand(3, 40, 52)
+    lab[:, 1] = torch.where(frac < 0.2, torch.round(frac * 5 * 255) / 255, lab[:, 1])   # k/255 values among the 0/1
+    lab[0, 1, 0, 0] = -1.0 / 255                                                       # the datasets' "missing organ" value
+    lab = lab.cuda()
+    thrs = [0.8] if nthr == 1 else list(np.arange(0.8, 0.99, 0.01)[:nthr])
+    got = tmc.score_batch(z, lab, thrs if nthr > 1 else thrs[0])
+    got = got.reshape(nthr, 3).cpu().numpy()
+    for k, t in enumerate(thrs):
+        ref = [float(v) for v in tp.eval_batch_dice(z, lab, float(np.float32(t)))]
+        assert_losses_close(got[k], ref, what=f"fractional labels, T={t:.2f}")
+    # the plain (integer-only) entry point marks the class instead of returning a silently different number
+    counts, _ = ops.dice_counts(z, lab, torch.tensor(thrs, dtype=torch.float32, device="cuda"))
+    c = counts.cpu().numpy()
+    assert (c[:, 1, 2] == -1).all() and (c[:, 0, 2] >= 0).all() and (c[:, 2, 2] >= 0).all()
