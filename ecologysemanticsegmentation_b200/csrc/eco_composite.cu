@@ -656,7 +656,6 @@ static int ensure_packed_smem() {
     ECO_SMEM_ALL(float)
     ECO_SMEM_ALL(__nv_bfloat16)
 #undef ECO_SMEM_ALL
-    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, fused v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<float>::kSmem), "cudaFuncSetAttribute(smem, fused v3 f32 labels)");

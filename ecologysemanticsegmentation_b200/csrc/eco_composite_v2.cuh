@@ -1,6 +1,10 @@
-// Second-generation 3-organ composite kernels (fp32, from-logits, 16-byte aligned planes).
-// Included by eco_composite.cu after eco_composite_packed.cuh; other inputs (bf16, probabilities, ragged planes) keep
-// the first-generation kernels.
+// Second-generation 3-organ composite building blocks (fp32, from-logits, 16-byte aligned planes): the TMA tile pipeline,
+// the scalar pass-1 statistics, the packed pass-2 gradient, the integer grid sums, and the stand-alone gradient kernel
+// composite3_grad_v2_kernel.  Included by eco_composite.cu after eco_composite_packed.cuh; the fused step built from these
+// blocks is composite3_fused_v3_kernel (eco_composite_v3.cuh) -- its predecessor composite3_fused_v2_kernel, which took the
+// linear BCE / focal sums in pass 2 and finished them with a second reduction at the kernel's tail, was removed in round 2
+// (78 -> 72 us at cfg2, one NVLink exchange instead of two).  Other inputs (bf16, probabilities, ragged planes) keep the
+// first-generation kernels.
 //
 // Design notes (all numbers measured on B200; profiles/microbench/regbw2.cu, profiles/README.md):
 //   * An SM sub-partition issues one warp instruction per clock and an instruction holds the issue path for
@@ -13,17 +17,16 @@
 //   * Pass 1 is SCALAR and not role-split: one thread owns all 55 sums of its pixels, so each sigmoid is computed
 //     once (the role-split packed kernel computes it twice) and the float2 packing, which buys no issue cycles,
 //     is dropped where it would cost 2x the accumulator registers.
-//   * BCE and focal are LINEAR in their per-pixel sums, so those sums do not feed the gradient coefficients: they
-//     are accumulated in pass 2, where the union operands u_k and their squares are formed anyway, as two scalars
-//     already weighted by the leaf scales (folded into the polynomial coefficients and into the focal base).  CTAs
-//     that wait for the grid-wide sums already take these sums of their first pass-2 tiles (pre-pass).
+//   * BCE and focal are LINEAR in their per-pixel sums, so those sums do not feed the gradient coefficients: they are
+//     taken apart from the statistics (pixel_pair_tr: two scalars already weighted by the leaf scales, folded into the
+//     polynomial coefficients and into the focal base) by the fused kernel's dedicated warps.
 //   * Both passes read their input through a ring of shared-memory stages filled by 1-D TMA bulk copies
 //     (cp.async.bulk + mbarrier complete_tx) issued by a dedicated producer warp that runs ahead from pass 1 into
 //     pass 2; 16 consumer warps (4 per sub-partition, 96 registers) do nothing but math.  Pass 2 walks the CTA's tiles
 //     backwards so that it starts on the lines pass 1 left in L2.
 //   * Grid-wide sums are 64-bit INTEGER atomics (exact to 2^-62, order-independent => deterministic, no serial
 //     "last CTA adds everything"); every CTA polls the arrival counter itself (cooperative launch: co-resident) and
-//     derives the closed forms; the two sums of pass 2 travel as one word each that carries value and arrival count.
+//     derives the closed forms.
 //   * Sharded (one process per GPU): the rank totals cross NVLink as self-validating 16-byte stores (NCCL LL style),
 //     sent by the CTA that completes the rank's sums and received by every CTA of every rank.
 //   * Tied pixels (|x_i - x_j| < 4e-6, ~2e-5 of all pixels) are recomputed in pass 2 by a scalar slow path with
@@ -195,8 +198,6 @@ enum : int {
     F_NACC = 55
 };
 constexpr int kFlushTiles = 16;    // 32 pixels per fp32 accumulator between folds into fp64
-constexpr int kPrepassTiles = 2;   // < kStages: tiles whose linear sums are taken while waiting for the grid sums (0/2/3/4
-                                   // measured: 81.3 / 80.2 / 80.4 / 80.7 us on one box)
 
 struct StatsSmem {
     double warp_slots[kCWarps][64];
@@ -365,45 +366,6 @@ constexpr int kMaxGrid = 192;   // CTAs of one cooperative launch (one per SM)
 // starts `xch_ll_offset_bytes(world)` into the buffer, after the first-generation slots.  Every rank adds the `world`
 // contributions in rank order, so all ranks hold bit-identical totals.  Called by all CONSUMER threads of ONE CTA.
 __host__ __device__ inline size_t xch_ll_offset_bytes(int world) { return xch_flags_offset_doubles(world) * 8 + 512; }
-// sender half: thread i < count stores `mine` into slot slot0 + i of this rank's row in EVERY rank's buffer (own too)
-__device__ inline void ll_send(const XchArgs& x, double mine, int slot0, int count) {
-    const int par = x.epoch & 1u;
-    if ((int)threadIdx.x < count) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
-        const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
-        for (int r = 0; r < x.world; ++r) {
-            char* dst = reinterpret_cast<char*>(x.peers[r]) + xch_ll_offset_bytes(x.world) +
-                        ((size_t)(par * x.world + x.rank)) * (128 * 16) + (size_t)(slot0 + threadIdx.x) * 16;
-            asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(lo), "r"(x.epoch), "r"(hi), "r"(x.epoch) : "memory");
-        }
-    }
-}
-// receiver half: thread i < count waits for slot slot0 + i of every rank's row in the OWN buffer and returns the sum in
-// rank order; any number of CTAs of a rank may receive the same rows.  A dead peer poisons the result (NaN) after seconds.
-__device__ inline double ll_recv_sum(const XchArgs& x, int slot0, int count) {
-    const int par = x.epoch & 1u;
-    double tot = 0.0;
-    if ((int)threadIdx.x < count) {
-        const char* own = reinterpret_cast<const char*>(x.peers[x.rank]) + xch_ll_offset_bytes(x.world) +
-                          ((size_t)(par * x.world)) * (128 * 16) + (size_t)(slot0 + threadIdx.x) * 16;
-        for (int r = 0; r < x.world; ++r) {
-            unsigned int lo, f0, hi, f1, spins = 0;
-            while (true) {
-                asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(own + (size_t)r * (128 * 16)) : "memory");
-                if (f0 == x.epoch && f1 == x.epoch) break;
-                if (++spins > (1u << 24)) {
-                    *x.status = 1u;
-                    lo = 0u; hi = 0x7ff80000u;   // NaN
-                    break;
-                }
-                __nanosleep(20);
-            }
-            tot += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
-        }
-    }
-    return tot;
-}
-
 // Deterministic grid-wide sums without a serial "last CTA adds everything" phase: every CTA adds its partial into
 // two 64-bit INTEGER accumulators per sum (v * 2^30 rounded to an integer, and the rounding remainder * 2^32), so the
 // total does not depend on the order of the atomics (integer addition is associative) and is exact to 2^-62.
@@ -429,17 +391,14 @@ __device__ __forceinline__ double fix_get(const unsigned long long* slot2, int r
     return ((double)(long long)hi + (double)(long long)lo * (1.0 / kFixLo)) * (1.0 / kFixHi);
 }
 
-// workspace words of the v2 kernels (all zero between launches)
+// workspace words of multiclass3_fused_v2_kernel (all zero between launches)
 // fix1 is double buffered by step parity: step k adds into buffer k & 1 while CTA 0 clears buffer (k + 1) & 1 for the
-// next step, so nobody waits for the clearing.  tr2: the two sums of pass 2, each ONE word that carries the sum
-// (value * 2^16, shifted left by 8) and, in its low 8 bits, the number of CTAs that have added to it -- the atomicAdd
-// that delivers a CTA's share also tells it whether it was the last one, without a fence / arrival counter / re-read.
+// next step, so nobody waits for the clearing.  tr2[0] counts the CTAs that have finished pass 2.
 struct V2Ws {
     unsigned int arrive1, step, _pad0, _pad1;
     unsigned long long tr2[2];
     unsigned long long fix1[2][kFixRep][2 * kNAcc];   // pass-1 sums
 };
-constexpr double kTr2Scale = 65536.0;   // 2^16
 
 // CTA-level tail of pass 1 (all CONSUMER threads): rare slow pass, then this CTA's 100 partial sums go into the
 // integer accumulators and the CTA arrives.  Returns true in the last CTA to arrive.
@@ -703,31 +662,6 @@ __device__ __forceinline__ void pixel_pair_tr(const f2 (&x)[3], const Coef2& c2,
     }
 }
 
-// Pre-pass: while a CTA waits for the grid-wide sums it already takes the linear sums of the first `count` tiles of
-// its pass 2 -- they sit in the ring (the producer runs ahead) and do not depend on the coefficients.  The stages are
-// NOT handed back; pass 2 proper consumes them again without the sums.  Same values, same order as in pass 2.
-template <bool POSW>
-__device__ __forceinline__ void tr_prepass(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem& ps, int k0,
-                                           int count, const Coef2& c2, TrState& st) {
-    int t = tr.t_hi - 1;
-    int kk = t % tr.tpp;
-    const uint32_t my = stage_base + threadIdx.x * 8;
-    const int pix = 2 * (int)threadIdx.x;
-    for (int k = 0; k < count; ++k) {
-        const int kg = k0 + k, s = kg % kStages;
-        mbar_wait(smem_u32(&ps.full[s]), (kg / kStages) & 1);
-        if ((int64_t)kk * kTP + pix < a.HW) {
-            const uint32_t sb = my + (uint32_t)s * kStageBytes;
-            f2 x[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(lds_f2(sb + (uint32_t)c * (kTP * 4)));
-            pixel_pair_tr<POSW>(x, c2, st.sp_acc, st.fl_acc);
-        }
-        if (--kk < 0) kk = tr.tpp - 1;
-        st.tile_done();
-    }
-}
-
 // consumer side of pass 2 over this CTA's tiles [k_first, k_first + k_count) (in walking order).  With TR the linear
 // sums are accumulated into `st`.
 template <bool SIG, bool FL, bool TR, bool POSW>
@@ -816,166 +750,6 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
         st.init(nullptr);
         grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, false, ga, tr, false, sbase, ps, 0, 0, tr.t_hi - tr.t_lo, c2, cf, st);
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// fused step: pass 1 -> grid-wide hand-over of the 100 sums -> closed forms (redundantly per CTA) -> pass 2 (+ the
-// linear BCE / focal sums) -> last CTA adds those sums to the loss totals.  ONE cooperative launch (all CTAs
-// co-resident); the grid-wide wait is a release/acquire flag set by the CTA that formed the totals.
-// ---------------------------------------------------------------------------------------------
-struct FusedSmem {
-    StatsSmem st;
-    LeafCoef cf[ECO_C3_NLEAF];
-    Coef2 c2;
-    double sl[ECO_C3_NLEAF][ECO_NLOSS];
-    double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
-    double tr_warp[kCWarps][2];
-    double tr_thread[kCThreads][2];
-    unsigned long long tr_tot[2];
-    double scale[ECO_C3_NLEAF];
-    double acc[kNAcc];
-    float up[ECO_NLOSS + 1];
-    PipeSmem ps;
-};
-
-__global__ void __launch_bounds__(kThreads, 1)
-composite3_fused_v2_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
-                           V2Ws* __restrict__ ws, double* __restrict__ acc_glob, float* __restrict__ losses_out, XchArgs xch) {
-    extern __shared__ __align__(128) char stage_smem[];
-    __shared__ FusedSmem fs;
-    ECO_TL(0);
-    // the producer must get going first: nothing that waits on global memory sits in front of the first TMA issue
-    stats_smem_init(fs.st);
-    pipe_init(fs.ps);
-    const TileRange tr = tile_range(ga.a);
-    const int ntiles = tr.t_hi - tr.t_lo;
-    const uint32_t sbase = smem_u32(stage_smem);
-    if (threadIdx.x >= kCThreads) {
-        // producer warp: pass 1 forwards, then straight on to pass 2 backwards -- its first tiles land while the
-        // consumers are still exchanging sums
-        if (threadIdx.x == kCThreads) {
-            produce_tiles(ga.a, tr, false, sbase, fs.ps, 0);
-            produce_tiles(ga.a, tr, true, sbase, fs.ps, ntiles);
-        }
-        return;
-    }
-    const int par = (int)(__ldcg(&ws->step) & 1u);   // written only by the last CTA of the previous step
-    if (blockIdx.x == 0)   // clear the other buffer for the next step (nobody touches it during this one)
-        for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kCThreads) (&ws->fix1[par ^ 1][0][0])[i] = 0ull;
-    if (threadIdx.x < ECO_C3_NLEAF) fs.scale[threadIdx.x] = scale_dev[threadIdx.x];
-    if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
-    csync();
-    // focal weights ride on 1 - b when every real-b leaf has a non-negative scale and the focal term carries no gradient
-    bool posw = fs.up[2] == 0.f;
-    for (int t = 0; t < ECO_C3_NLEAF; ++t) posw = posw && (u_leaf_of(t) < 0 || fs.scale[t] >= 0.0);
-    fill_weights(fs.c2, fs.scale, threadIdx.x, posw);   // visible to the consumers after the barriers of stats_finish
-    stats_consume(ga.a, tr, sbase, fs.ps, 0, fs.st);
-    ECO_TL(1);
-    const bool last1 = stats_finish(ga.a, tr, fs.st, ws, par);
-    ECO_TL(2);
-    // every CTA but the one everybody is waiting for uses the wait: linear sums of its first pass-2 tiles
-    TrState st;
-    st.init(&fs.tr_thread[threadIdx.x][0]);
-    // (sharded: the wait also spans an NVLink exchange, so up to a ring's worth of tiles fits)
-    const int n_pre = last1 ? 0 : min(ntiles, xch.world > 1 ? kStages - 1 : kPrepassTiles);
-    if (posw) tr_prepass<true>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
-    else tr_prepass<false>(ga.a, tr, sbase, fs.ps, ntiles, n_pre, fs.c2, st);
-    // grid-wide hand-over of the 100 totals (all CTAs are co-resident: cooperative launch)
-    if (xch.world <= 1) {
-        // every CTA waits until all have arrived and reads the integer accumulators itself
-        if (threadIdx.x == 0) while (ld_acquire_gpu(&ws->arrive1) < gridDim.x) __nanosleep(32);
-        csync();
-        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = fix_get(ws->fix1[par][0] + 2 * threadIdx.x, 2 * kNAcc);
-    } else {
-        // sharded: the last CTA to arrive sends this rank's totals to every rank (its own included); EVERY CTA then
-        // receives the `world` rows itself -- one NVLink hop, no second hand-over inside the GPU
-        if (last1) {
-            __threadfence();
-            double total = 0.0;
-            if (threadIdx.x < kNAcc) total = fix_get(ws->fix1[par][0] + 2 * threadIdx.x, 2 * kNAcc);
-            ll_send(xch, total, 0, kNAcc);
-        }
-        const double all = ll_recv_sum(xch, 0, kNAcc);
-        if (threadIdx.x < kNAcc) fs.acc[threadIdx.x] = all;
-    }
-    csync();
-    ECO_TL(3);
-    // closed forms, redundantly per CTA: one thread per (leaf, loss) row, one WARP per loss so that the switch over
-    // the loss kind does not diverge
-    if (threadIdx.x < ECO_NLOSS * 32 && (threadIdx.x & 31) < ECO_C3_NLEAF) {
-        const int leaf = threadIdx.x & 31, k = threadIdx.x >> 5;
-        double s[ECO_NSTAT];
-        composite_leaf_sums(fs.acc, leaf, s);
-        leaf_closed_form_row(s, 0.0, fs.scale[leaf], k, fs.sl[leaf][k], fs.jac_s[leaf][k]);
-    }
-    csync();
-    ECO_TL(12);
-    if (threadIdx.x < ECO_C3_NLEAF * ECO_NJAC) {
-        // coefficient j of leaf l = sum_k upstream[k] * d loss_k / d stat_j: one thread each (make_coef, in parallel)
-        const int leaf = threadIdx.x / ECO_NJAC, j = threadIdx.x % ECO_NJAC;
-        double c = 0.0;
-#pragma unroll
-        for (int k = 1; k < ECO_NLOSS; ++k)
-            if (fs.up[k] != 0.f) c += (double)fs.up[k] * fs.jac_s[leaf][k][j];   // (an unused loss may have a non-finite Jacobian)
-        reinterpret_cast<float*>(&fs.cf[leaf])[j] = (float)(j == 3 ? 2.0 * c : c);
-    }
-    csync();
-    fill_coef2(fs.c2, fs.cf, threadIdx.x);
-    csync();
-    ECO_TL(4);
-    grad_consume_dispatch<false>(fs.up[1] != 0.f, fs.up[2] != 0.f, posw, ga, tr, true, sbase, fs.ps, ntiles, 0, n_pre, fs.c2, fs.cf, st);
-    grad_consume_dispatch<true>(fs.up[1] != 0.f, fs.up[2] != 0.f, posw, ga, tr, true, sbase, fs.ps, ntiles, n_pre, ntiles - n_pre, fs.c2, fs.cf, st);
-    st.fold();
-    double trs[2] = {warp_sum(st.tot[0]), warp_sum(st.tot[1])};   // (own slots: no barrier needed)
-    if ((threadIdx.x & 31) == 0) { fs.tr_warp[threadIdx.x >> 5][0] = trs[0]; fs.tr_warp[threadIdx.x >> 5][1] = trs[1]; }
-    csync();
-    ECO_TL(5);
-    // second, tiny reduction: the two weighted sums of pass 2.  One atomicAdd per sum delivers this CTA's share and
-    // returns how many CTAs came before it (low 8 bits): the CTA that completes sum 0 finishes the step.
-    if (threadIdx.x < 2) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kCWarps; ++w) v += fs.tr_warp[w][threadIdx.x];
-        const unsigned long long mine = ((unsigned long long)__double2ll_rn(v * kTr2Scale) << 8) + 1ull;
-        const unsigned long long old = atomicAdd(&ws->tr2[threadIdx.x], mine);
-        if (threadIdx.x == 0) {
-            fs.st.flag = ((old & 255ull) == (unsigned long long)(gridDim.x - 1));
-            fs.tr_tot[0] = old + mine;
-        }
-    }
-    csync();
-    if (fs.st.flag) {
-        // last CTA of the step on sum 0: wait (briefly) until sum 1 is complete as well
-        if (threadIdx.x == 1) {
-            unsigned long long t;
-            while (((t = __ldcg(&ws->tr2[1])) & 255ull) != (unsigned long long)gridDim.x) __nanosleep(20);
-            fs.tr_tot[1] = t;
-        }
-        csync();
-        if (threadIdx.x < 2) {
-            const unsigned long long t = fs.tr_tot[threadIdx.x];
-            fs.st.sums[threadIdx.x] = (double)((long long)(t - (t & 255ull)) >> 8) * (1.0 / kTr2Scale);
-        }
-        csync();
-        if (xch.world > 1) {
-            ll_send(xch, threadIdx.x < 2 ? fs.st.sums[threadIdx.x] : 0.0, 100, 2);
-            const double all = ll_recv_sum(xch, 100, 2);
-            csync();
-            if (threadIdx.x < 2) fs.st.sums[threadIdx.x] = all;
-            csync();
-        }
-        if (threadIdx.x < ECO_NLOSS) {
-            double v = 0.0;
-            for (int l = 0; l < ECO_C3_NLEAF; ++l) v += fs.sl[l][threadIdx.x];
-            const double n = fs.acc[A_N];
-            if (threadIdx.x == 1) v += fs.st.sums[0] / n;               // BCE: sum_l scale_l * softplus remainder
-            if (threadIdx.x == 2) v += -kLn2d * fs.st.sums[1] / n;      // focal: sums were taken in log2 units
-            losses_out[threadIdx.x] = (float)v;
-        }
-        // re-arm the workspace for the next step (every CTA has long passed the hand-over of pass 1)
-        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->step = (unsigned int)par + 1u; ws->tr2[0] = 0ull; ws->tr2[1] = 0ull; }
-    }
-    ECO_TL(6);
 }
 
 }  // namespace v2
