@@ -530,6 +530,8 @@ static bool general_focal(const EcoLeafShape* shape, float& gamma_out) {
 
 }  // namespace eco
 
+#include "eco_leaf_resident.cuh"
+
 using namespace eco;
 
 extern "C" int64_t eco_pair_ws_bytes(int32_t C) {
@@ -633,9 +635,11 @@ extern "C" int eco_pair_grad_shaped(const EcoView* a, const EcoView* b, int32_t 
 // ------------------------------------------------------------------------------------------------------------------
 static int64_t fused_ws_offset(int32_t C) { return (eco_pair_ws_bytes(C) + 255) / 256 * 256; }
 
+static int64_t resident_ws_offset(int32_t C) { return (fused_ws_offset(C) + (int64_t)sizeof(FusedWs) + 255) / 256 * 256; }
+
 extern "C" int64_t eco_pair_fused_ws_bytes(int32_t C) {
     if (C <= 0 || C > 64) return -1;
-    return fused_ws_offset(C) + (int64_t)sizeof(FusedWs);
+    return resident_ws_offset(C) + (int64_t)sizeof(resident::ResidentWs);
 }
 
 extern "C" int eco_pair_fused(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
@@ -677,10 +681,31 @@ extern "C" int eco_pair_fused(const EcoView* a, const EcoView* b, int32_t N, int
         fa.shape.beta = shape_host->tversky_beta;
         fa.shape.fd_gamma = shape_host->focal_dice_gamma;
     }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // one fully contiguous fp32 leaf that fits the GPU's shared memory (cfg1): the resident kernel reads it once
+    const bool flat = C == 1 && vec == 4 && !gen && a->dtype == ECO_F32 && b->dtype == ECO_F32 &&
+                      (N == 1 || (a->sn == HW && b->sn == HW)) && (!want_a || N == 1 || ga->sn == HW) && (!want_b || N == 1 || gb->sn == HW);
+    if (flat) {
+        const int64_t total = (int64_t)N * HW;
+        int rgrid = sms;
+        if ((int64_t)rgrid > total / 4) rgrid = (int)(total / 4);
+        const int smem = resident::resident_smem_bytes(total, rgrid);
+        if (smem > 0) {
+            static thread_local int attr_done[64];
+            if (device >= 0 && device < 64 && !attr_done[device]) {
+                ECO_CUDA(cudaFuncSetAttribute(resident::leaf_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, resident::kRMaxSmem));
+                attr_done[device] = 1;
+            }
+            resident::ResidentWs* rws = reinterpret_cast<resident::ResidentWs*>(reinterpret_cast<char*>(ws) + resident_ws_offset(C));
+            int64_t total_arg = total;
+            void* rargs[] = {&fa, &total_arg, (void*)&upstream, &rws, &sums_out, &losses_out};
+            return check_cuda(cudaLaunchCooperativeKernel((const void*)resident::leaf_resident_kernel, dim3(rgrid), dim3(resident::kRThreads),
+                                                          rargs, smem, st), "leaf_resident_kernel launch");
+        }
+    }
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + pair_ws_partials_offset(C));
     FusedWs* fw = reinterpret_cast<FusedWs*>(reinterpret_cast<char*>(ws) + fused_ws_offset(C));
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     void* args[] = {&fa, (void*)&upstream, &counters, &partials, &fw, &sums_out, &losses_out};
     const void* fn = nullptr;
 #define ECO_PICK(TA, TB, V, G) fn = (const void*)pair_fused_kernel<TA, TB, V, G>
