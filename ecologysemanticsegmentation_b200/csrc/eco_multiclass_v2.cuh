@@ -92,9 +92,13 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         return;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the workspace is double buffered by step parity (integer accumulators in fix1, arrival counter in tr2): step k works
+    // in buffer k & 1 while CTA 0 clears buffer (k + 1) & 1, so there is no re-arming phase at the end of a step
     const int par = (int)(__ldcg(&ws->step) & 1u);
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < kFixRep * 2 * kNAcc; i += kCThreads) (&ws->fix1[par ^ 1][0][0])[i] = 0ull;
+        if (threadIdx.x == 0) ws->tr2[par ^ 1] = 0ull;
+    }
     if (threadIdx.x < ECO_NLOSS) ms.up[threadIdx.x] = upstream[threadIdx.x];
 
     // ---- pass 1: per channel sum g, sum x, sum x^2, sum g x, softplus remainder, focal (log2 units) ----------------
@@ -129,7 +133,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
                 }
             }
             if (++kk == tr.tpp) kk = 0;
-            if (++since_flush == kFlushTiles) { mc_flush(acc, ms.warp_slots[warp], lane); since_flush = 0; }
+            if (++since_flush == 2 * kFlushTiles) { mc_flush(acc, ms.warp_slots[warp], lane); since_flush = 0; }   // packed: 64 values per fp32 lane
         }
         mc_flush(acc, ms.warp_slots[warp], lane);
     }
@@ -159,36 +163,45 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
     }
     csync();
     if (threadIdx.x == 0) {
-        atomicAdd(&ws->arrive1, 1u);
-        while (ld_acquire_gpu(&ws->arrive1) < gridDim.x) __nanosleep(32);
+        atomicAdd(&ws->tr2[par], 1ull);
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&ws->tr2[par]) : "memory");
+            if (seen < gridDim.x) __nanosleep(32);
+        } while (seen < gridDim.x);
     }
     csync();
     if (threadIdx.x < kMcSums) ms.acc[threadIdx.x] = fix_get(ws->fix1[par][0] + 2 * threadIdx.x, 2 * kNAcc);
     csync();
 
-    // ---- closed forms (one warp per loss kind, one lane per channel leaf) and coefficients ----------------------------
+    // ---- closed forms (one warp per loss kind, one lane per channel leaf); every row leaves its Jacobian already weighted
+    //      by its upstream gradient, three threads add the rows in a fixed order into the gradient coefficients -------------
     if (threadIdx.x < ECO_NLOSS * 32 && lane < 3) {
         const double* s6 = ms.acc + 1 + M_PER * lane;
-        double s[ECO_NSTAT];
+        double s[ECO_NSTAT], jrow[ECO_NJAC];
         s[S_N] = ms.acc[0]; s[S_A] = s6[M_G]; s[S_B] = s6[M_X]; s[S_AB] = s6[M_GX]; s[S_BB] = s6[M_XX];
         s[S_SP] = s6[M_R]; s[S_FL] = s6[M_FL]; s[S_FLB] = 0.0;
-        leaf_closed_form_row(s, 0.0, scale, warp, ms.sl[lane][warp], ms.jac_s[lane][warp]);
-    }
-    csync();
-    if (threadIdx.x < 3 * ECO_NJAC) {
-        const int leaf = threadIdx.x / ECO_NJAC, j = threadIdx.x % ECO_NJAC;
-        double c = 0.0;
+        leaf_closed_form_row(s, 0.0, scale, warp, ms.sl[lane][warp], jrow);
+        const float u = warp == 0 ? 0.f : ms.up[warp];
 #pragma unroll
-        for (int k = 1; k < ECO_NLOSS; ++k)
-            if (ms.up[k] != 0.f) c += (double)ms.up[k] * ms.jac_s[leaf][k][j];
-        reinterpret_cast<float*>(&ms.cf[leaf])[j] = (float)(j == 3 ? 2.0 * c : c);
+        for (int j = 0; j < ECO_NJAC; ++j) ms.jac_s[lane][warp][j] = u != 0.f ? (double)u * jrow[j] : 0.0;   // (an unused loss may have a non-finite Jacobian)
     }
     csync();
     if (threadIdx.x < 3) {
-        const LeafCoef c = ms.cf[threadIdx.x];
-        ms.ua[threadIdx.x] = make_float4(c.sb + 0.5f * c.sp, c.sab, c.sbb2, c.sp);
-        ms.ufl[threadIdx.x] = c.fl;
+        float c[ECO_NJAC];
+#pragma unroll
+        for (int j = 0; j < ECO_NJAC; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 1; k < ECO_NLOSS; ++k) v += ms.jac_s[threadIdx.x][k][j];
+            c[j] = (float)(j == 3 ? 2.0 * v : v);
+        }
+        // LeafCoef order: sa, sb, sab, 2 sbb, sp, fl, flb
+        ms.ua[threadIdx.x] = make_float4(c[1] + 0.5f * c[4], c[2], c[3], c[4]);
+        ms.ufl[threadIdx.x] = c[5];
     }
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + ECO_NLOSS)
+        losses_out[threadIdx.x - 32] = (float)(ms.sl[0][threadIdx.x - 32] + ms.sl[1][threadIdx.x - 32] + ms.sl[2][threadIdx.x - 32]);
     csync();
 
     // ---- pass 2: d(sum_k upstream_k loss_k)/d logits, walking this CTA's tiles backwards --------------------------------
@@ -200,16 +213,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         if (need_sig) mc_grad_consume<true, false>(ga, tr, sbase, ms, ntiles);
         else mc_grad_consume<false, false>(ga, tr, sbase, ms, ntiles);
     }
-    csync();
-    if (threadIdx.x == 0) {
-        const unsigned long long old = atomicAdd(&ws->tr2[0], 1ull);
-        ms.flag = (old == (unsigned long long)(gridDim.x - 1));
-    }
-    csync();
-    if (ms.flag) {
-        if (threadIdx.x < ECO_NLOSS) losses_out[threadIdx.x] = (float)(ms.sl[0][threadIdx.x] + ms.sl[1][threadIdx.x] + ms.sl[2][threadIdx.x]);
-        if (threadIdx.x == 0) { ws->arrive1 = 0u; ws->step = (unsigned int)par + 1u; ws->tr2[0] = 0ull; }
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws->step = (unsigned int)par + 1u;   // every CTA read `step` before it arrived
 }
 
 }  // namespace v2
