@@ -658,8 +658,9 @@ static int ensure_packed_smem() {
 #undef ECO_SMEM_ALL
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
-    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<float>::kSmem), "cudaFuncSetAttribute(smem, fused v3 f32 labels)");
-    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<uint8_t>::kSmem), "cudaFuncSetAttribute(smem, fused v3 u8 labels)");
+#define ECO_V3_ATTR(TX, TG) rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<TX, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<TX, TG>::kSmem), "cudaFuncSetAttribute(smem, fused v3)")
+    ECO_V3_ATTR(float, float); ECO_V3_ATTR(float, uint8_t); ECO_V3_ATTR(__nv_bfloat16, float); ECO_V3_ATTR(__nv_bfloat16, uint8_t);
+#undef ECO_V3_ATTR
     if (!rc) done_for_device[dev] = 1;
     return rc;
 }
@@ -679,10 +680,18 @@ static int comp_grid(int device, int64_t units, int ctas_per_sm, int threads_per
 static bool v2_eligible(const EcoView* x, int32_t from_logits, int vec, int32_t N, int64_t HW) {
     return vec == 4 && from_logits != 0 && x->dtype == ECO_F32 && (int64_t)N * HW <= ((int64_t)1 << 31);
 }
-// third-generation fused step: as v2, plus byte labels whose planes and tiles are 16-byte aligned (TMA bulk copies)
-static bool v3_labels_ok(const EcoView* g, int64_t HW) {
-    if (g->dtype == ECO_F32) return true;   // alignment checked by c_aligned
-    return g->dtype == ECO_U8 && reinterpret_cast<uintptr_t>(g->ptr) % 16 == 0 && g->sn % 16 == 0 && g->sc % 16 == 0 && HW % 16 == 0;
+// third-generation fused step: logits (and the gradient) fp32 or bf16, labels fp32 or bytes; every plane and every tile of
+// it must start on a 16-byte boundary and be a multiple of 16 bytes long (1-D TMA bulk copies)
+static bool tma_planes_ok(const void* ptr, int64_t sn, int64_t sc, int dtype, int64_t HW) {
+    const int64_t esz = dtype == ECO_F32 ? 4 : (dtype == ECO_BF16 ? 2 : 1), per16 = 16 / esz;
+    return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && sn % per16 == 0 && sc % per16 == 0 && HW % per16 == 0;
+}
+static bool v3_eligible(const EcoView* x, const EcoView* g, const EcoOut* gx, bool from_logits, int32_t N, int64_t HW) {
+    if (!from_logits || (int64_t)N * HW > ((int64_t)1 << 31)) return false;
+    if (x->dtype != ECO_F32 && x->dtype != ECO_BF16) return false;
+    if (g->dtype != ECO_F32 && g->dtype != ECO_U8) return false;
+    return tma_planes_ok(x->ptr, x->sn, x->sc, x->dtype, HW) && tma_planes_ok(g->ptr, g->sn, g->sc, g->dtype, HW) &&
+           tma_planes_ok(gx->ptr, gx->sn, gx->sc, gx->dtype, HW) && HW % 4 == 0;
 }
 static int v2_grid(int device, int32_t N, int64_t HW) {
     const int sms = sm_count_cached(device);
@@ -813,23 +822,25 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
     double* partials = acc_glob + 128;
     if (!xch.status) xch.status = counter + 32;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (v2_eligible(x, lg ? 1 : 0, vec, N, HW) && v3_labels_ok(g, HW)) {
+    if (v3_eligible(x, g, gx, lg, N, HW)) {
         rc = ensure_packed_smem();
         if (rc) return rc;
         const int g2 = v2_grid(device, N, HW);
         if (g2 < 0) return -10;
         v2::V3Ws* ws3 = reinterpret_cast<v2::V3Ws*>(reinterpret_cast<char*>(ws) + kWsV3Offset);
         void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws3, &losses_out, &flags, &xch, (void*)&upstream_prev};
-        if (g_f32)
-            return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v3_kernel<float>, dim3(g2), dim3(v2::kThreads3), args,
-                                                          v2::Stage3<float>::kSmem, st), "composite3_fused_v3_kernel<f32 labels> launch");
-        return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::composite3_fused_v3_kernel<uint8_t>, dim3(g2), dim3(v2::kThreads3), args,
-                                                      v2::Stage3<uint8_t>::kSmem, st), "composite3_fused_v3_kernel<u8 labels> launch");
+        const void* fn;
+        int smem;
+#define ECO_V3_PICK(TX, TG) do { fn = (const void*)v2::composite3_fused_v3_kernel<TX, TG>; smem = v2::Stage3<TX, TG>::kSmem; } while (0)
+        if (x->dtype == ECO_F32) { if (g_f32) ECO_V3_PICK(float, float); else ECO_V3_PICK(float, uint8_t); }
+        else { if (g_f32) ECO_V3_PICK(__nv_bfloat16, float); else ECO_V3_PICK(__nv_bfloat16, uint8_t); }
+#undef ECO_V3_PICK
+        return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(g2), dim3(v2::kThreads3), args, smem, st), "composite3_fused_v3_kernel launch");
     }
-    if (upstream_prev) { set_error("eco_composite3_step_if_changed needs fp32 logits with 16-byte aligned planes"); return -8; }
+    if (upstream_prev) { set_error("eco_composite3_step_if_changed needs logits with 16-byte aligned planes"); return -8; }
     // everything below: first-generation kernels (bf16 or probability inputs, ragged / unaligned planes), f32 labels only
     if (!g_f32 || (flags & ECO_C3_UNION_LABELS)) {
-        set_error("byte labels / the fused label union need fp32 logits with 16-byte aligned planes (H*W %% 16 == 0 for byte labels, %% 4 otherwise)");
+        set_error("byte labels / the fused label union need logits with 16-byte aligned planes (H*W %% 16 == 0 for byte labels, %% 8 for bf16 logits, %% 4 otherwise)");
         return -8;
     }
     if (xch.world > 1 && vec != 4) { set_error("the peer-exchange fused step needs 16-byte aligned planes with H*W %% 4 == 0"); return -8; }

@@ -1,4 +1,4 @@
-// Third-generation fused 3-organ composite step (fp32 logits; fp32 or uint8 labels; 16-byte aligned planes).
+// Third-generation fused 3-organ composite step (fp32 or bf16 logits; fp32 or uint8 labels; 16-byte aligned planes).
 // Included by eco_composite.cu after eco_composite_v2.cuh, whose tile pipeline, pass-1 / pass-2 math and integer grid sums
 // it reuses.  What changed against composite3_fused_v2_kernel, and why (measurements: profiles/README.md):
 //
@@ -51,7 +51,11 @@ __device__ __forceinline__ void reg_lower48() { asm volatile("setmaxnreg.dec.syn
 __device__ __forceinline__ void reg_lower24() { asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory"); }
 constexpr int kStages3 = 5;
 constexpr int kLinStages = 4;                                 // ring of the linear warps: logit planes only
-constexpr int kLinStageBytes = 3 * kTP * 4;                   // 12 KB
+template <typename TX>
+struct LinStage {
+    static constexpr int kPlane = kTP * (int)sizeof(TX);
+    static constexpr int kBytes = 3 * kPlane;                 // 12 KB (fp32 logits) / 6 KB (bf16)
+};
 constexpr int kLinFlushTiles = 16;                            // 2 pixel pairs per thread and tile -> 64 values per fp32 partial
 constexpr int kFlushTiles3 = 32;                              // 64 pixels per fp32 accumulator between folds into fp64 (cfg2: one fold per CTA)
 constexpr int kNFlat = 72;                                    // 55 flat sums | 15 label corrections | n | (pad)
@@ -59,14 +63,33 @@ constexpr int F_CORR = 55, F_N = 70;
 
 constexpr unsigned int kC3FlagUnionLabels = 1u;               // == ECO_C3_UNION_LABELS
 
-template <typename TG>
+template <typename TX, typename TG>
 struct Stage3 {
-    static constexpr int kXBytes = 3 * kTP * 4;
+    static constexpr int kXPlane = kTP * (int)sizeof(TX);
+    static constexpr int kXBytes = 3 * kXPlane;
     static constexpr int kGPlane = kTP * (int)sizeof(TG);
-    static constexpr int kBytes = kXBytes + 3 * kGPlane;      // 24 KB (fp32 labels) / 15 KB (byte labels)
+    static constexpr int kBytes = kXBytes + 3 * kGPlane;      // 24 KB (fp32 logits + fp32 labels) ... 9 KB (bf16 + byte labels)
     static constexpr int kMain = kStages3 * kBytes;
-    static constexpr int kSmem = kMain + kLinStages * kLinStageBytes;
+    static constexpr int kSmem = kMain + kLinStages * LinStage<TX>::kBytes;
 };
+
+// this thread's pixel pair of a logit plane: fp32 as is, bf16 widened exactly (a bf16 is the top half of an fp32)
+template <typename TX>
+__device__ __forceinline__ f2 lds_x2(uint32_t plane_addr, int pix);
+template <>
+__device__ __forceinline__ f2 lds_x2<float>(uint32_t plane_addr, int pix) { return lds_f2(plane_addr + (uint32_t)pix * 4); }
+template <>
+__device__ __forceinline__ f2 lds_x2<__nv_bfloat16>(uint32_t plane_addr, int pix) {
+    unsigned int w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(plane_addr + (uint32_t)pix * 2));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+// gradient of a pixel pair out: streaming store, bf16 rounded to nearest even
+__device__ __forceinline__ void stg_grad2(float* p, f2 v) { stg_stream_f2(p, v); }
+__device__ __forceinline__ void stg_grad2(__nv_bfloat16* p, f2 v) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(*reinterpret_cast<const unsigned int*>(&h)) : "memory");
+}
 
 struct PipeSmem3 {
     unsigned long long full[kStages3];
@@ -92,10 +115,10 @@ __device__ __forceinline__ void pipe_init3(PipeSmem3& ps) {
     __syncthreads();
 }
 
-template <typename TG>
+template <typename TX, typename TG>
 __device__ __forceinline__ void produce_tiles3(const CompArgs& a, const TileRange& tr, bool reverse, uint32_t stage_base,
                                                PipeSmem3& ps, int k0) {
-    const float* xb = reinterpret_cast<const float*>(a.x);
+    const TX* xb = reinterpret_cast<const TX*>(a.x);
     const TG* gb = reinterpret_cast<const TG*>(a.g);
     const int ntiles = tr.t_hi - tr.t_lo;
     if (ntiles <= 0) return;
@@ -108,15 +131,15 @@ __device__ __forceinline__ void produce_tiles3(const CompArgs& a, const TileRang
         if (kg >= kStages3) mbar_wait(empty, ((kg / kStages3) - 1) & 1);
         const int64_t p0 = (int64_t)kk * kTP;
         const int valid = (int)((a.HW - p0 < kTP) ? (a.HW - p0) : kTP);
-        const uint32_t xbytes = (uint32_t)valid * 4u, gbytes = (uint32_t)valid * (uint32_t)sizeof(TG);
-        const uint32_t dst = stage_base + (uint32_t)s * Stage3<TG>::kBytes;
-        const float* xs = xb + n * a.x_sn + p0;
+        const uint32_t xbytes = (uint32_t)valid * (uint32_t)sizeof(TX), gbytes = (uint32_t)valid * (uint32_t)sizeof(TG);
+        const uint32_t dst = stage_base + (uint32_t)s * Stage3<TX, TG>::kBytes;
+        const TX* xs = xb + n * a.x_sn + p0;
         const TG* gs = gb + n * a.g_sn + p0;
         mbar_expect_tx(full, 3u * (xbytes + gbytes));
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            bulk_g2s(dst + (uint32_t)c * (kTP * 4), xs + c * a.x_sc, xbytes, full);
-            bulk_g2s(dst + Stage3<TG>::kXBytes + (uint32_t)c * Stage3<TG>::kGPlane, gs + c * a.g_sc, gbytes, full);
+            bulk_g2s(dst + (uint32_t)c * Stage3<TX, TG>::kXPlane, xs + c * a.x_sc, xbytes, full);
+            bulk_g2s(dst + Stage3<TX, TG>::kXBytes + (uint32_t)c * Stage3<TX, TG>::kGPlane, gs + c * a.g_sc, gbytes, full);
         }
         if (reverse) { if (--kk < 0) { kk = tr.tpp - 1; --n; } }
         else { if (++kk == tr.tpp) { kk = 0; ++n; } }
@@ -125,15 +148,15 @@ __device__ __forceinline__ void produce_tiles3(const CompArgs& a, const TileRang
 
 // this thread's pixel pair of label plane c of a stage
 template <typename TG>
-__device__ __forceinline__ f2 lds_label2(uint32_t stage_addr, int c);
+__device__ __forceinline__ f2 lds_label2(uint32_t labels_addr, int c);   // labels_addr = first label plane of the stage
 template <>
-__device__ __forceinline__ f2 lds_label2<float>(uint32_t stage_addr, int c) {
-    return lds_f2(stage_addr + Stage3<float>::kXBytes + (uint32_t)c * Stage3<float>::kGPlane + threadIdx.x * 8);
+__device__ __forceinline__ f2 lds_label2<float>(uint32_t labels_addr, int c) {
+    return lds_f2(labels_addr + (uint32_t)c * (kTP * 4) + threadIdx.x * 8);
 }
 template <>
-__device__ __forceinline__ f2 lds_label2<uint8_t>(uint32_t stage_addr, int c) {
+__device__ __forceinline__ f2 lds_label2<uint8_t>(uint32_t labels_addr, int c) {
     unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(stage_addr + Stage3<uint8_t>::kXBytes + (uint32_t)c * Stage3<uint8_t>::kGPlane + threadIdx.x * 2));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(labels_addr + (uint32_t)c * kTP + threadIdx.x * 2));
     // byte -> float without I2F (which shares the XU pipe with the sigmoids): 0x4b000000 | b is 8388608 + b exactly
     const unsigned int w = v;
     return make_float2(__uint_as_float(0x4b000000u | (w & 0xffu)) - 8388608.0f, __uint_as_float(0x4b000000u | (w >> 8)) - 8388608.0f);
@@ -148,15 +171,15 @@ __device__ __forceinline__ void union_labels(f2 (&g)[3]) {
     for (int c = 0; c < 3; ++c) g[c] = make_float2(clamp_above1(g[c].x), clamp_above1(g[c].y));
 }
 
-template <typename TG>
+template <typename TX, typename TG>
 __device__ __forceinline__ void consume_tile3(uint32_t stage_base, PipeSmem3& ps, int kg, int lane, bool uni, f2 (&z)[3], f2 (&g)[3]) {
     const int s = kg % kStages3;
     mbar_wait(smem_u32(&ps.full[s]), (kg / kStages3) & 1);
-    const uint32_t sb = stage_base + (uint32_t)s * Stage3<TG>::kBytes;
+    const uint32_t sb = stage_base + (uint32_t)s * Stage3<TX, TG>::kBytes;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        z[c] = lds_f2(sb + (uint32_t)c * (kTP * 4) + threadIdx.x * 8);
-        g[c] = lds_label2<TG>(sb, c);
+        z[c] = lds_x2<TX>(sb + (uint32_t)c * Stage3<TX, TG>::kXPlane, 2 * (int)threadIdx.x);
+        g[c] = lds_label2<TG>(sb + Stage3<TX, TG>::kXBytes, c);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&ps.empty[s]));
@@ -254,8 +277,9 @@ __device__ __forceinline__ double lin_fix_get(const unsigned long long* slot2, i
 __device__ __forceinline__ void lsync() { asm volatile("bar.sync 2, %0;" ::"n"(kLinWarps * 32) : "memory"); }
 
 // producer of the linear ring: the logit planes of this CTA's tiles, forwards, once
+template <typename TX>
 __device__ __forceinline__ void produce_lin_tiles(const CompArgs& a, const TileRange& tr, uint32_t lin_base, PipeSmem3& ps) {
-    const float* xb = reinterpret_cast<const float*>(a.x);
+    const TX* xb = reinterpret_cast<const TX*>(a.x);
     const int ntiles = tr.t_hi - tr.t_lo;
     if (ntiles <= 0) return;
     int n = tr.t_lo / tr.tpp, kk = tr.t_lo - n * tr.tpp;
@@ -265,18 +289,18 @@ __device__ __forceinline__ void produce_lin_tiles(const CompArgs& a, const TileR
         if (k >= kLinStages) mbar_wait(smem_u32(&ps.lempty[s]), ((k / kLinStages) - 1) & 1);
         const int64_t p0 = (int64_t)kk * kTP;
         const int valid = (int)((a.HW - p0 < kTP) ? (a.HW - p0) : kTP);
-        const uint32_t xbytes = (uint32_t)valid * 4u;
-        const uint32_t dst = lin_base + (uint32_t)s * kLinStageBytes;
-        const float* xs = xb + n * a.x_sn + p0;
+        const uint32_t xbytes = (uint32_t)valid * (uint32_t)sizeof(TX);
+        const uint32_t dst = lin_base + (uint32_t)s * LinStage<TX>::kBytes;
+        const TX* xs = xb + n * a.x_sn + p0;
         mbar_expect_tx(full, 3u * xbytes);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) bulk_g2s(dst + (uint32_t)c * (kTP * 4), xs + c * a.x_sc, xbytes, full);
+        for (int c = 0; c < 3; ++c) bulk_g2s(dst + (uint32_t)c * LinStage<TX>::kPlane, xs + c * a.x_sc, xbytes, full);
         if (++kk == tr.tpp) { kk = 0; ++n; }
     }
 }
 
 // the eight linear warps: BCE / focal linear sums of every tile of this CTA, from their own ring
-template <bool POSW>
+template <typename TX, bool POSW>
 __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& tr, uint32_t lin_base, PipeSmem3& ps,
                                             const Coef2& c2, double (&tot)[2]) {
     const int lane = threadIdx.x & 31, lw = (threadIdx.x >> 5) - kLinWarp0;
@@ -288,7 +312,7 @@ __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& 
     for (int k = 0; k < ntiles; ++k) {
         const int s = k % kLinStages;
         mbar_wait(smem_u32(&ps.lfull[s]), (k / kLinStages) & 1);
-        const uint32_t sb = lin_base + (uint32_t)s * kLinStageBytes;
+        const uint32_t sb = lin_base + (uint32_t)s * LinStage<TX>::kBytes;
         const int64_t p0 = (int64_t)kk * kTP;
 #pragma unroll 1
         for (int q = 0; q < kCWarps / kLinWarps; ++q) {
@@ -297,7 +321,7 @@ __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& 
             if (p0 + pix < a.HW) {
                 f2 x[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(lds_f2(sb + (uint32_t)c * (kTP * 4) + (uint32_t)pix * 4));
+                for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(lds_x2<TX>(sb + (uint32_t)c * LinStage<TX>::kPlane, pix));
                 pixel_pair_tr<POSW>(x, c2, sp_acc, fl_acc);
             }
 #else
@@ -319,7 +343,7 @@ __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& 
 }
 
 // pass 1, statistics warps: as stats_consume of v2 on the v3 stage layout
-template <typename TG>
+template <typename TX, typename TG>
 __device__ __forceinline__ void stats_consume3(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem3& ps,
                                                bool uni, StatsSmem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -332,7 +356,7 @@ __device__ __forceinline__ void stats_consume3(const CompArgs& a, const TileRang
     bool any_nonbinary = false;
     for (int k = 0; k < ntiles; ++k) {
         f2 z[3], g[3];
-        consume_tile3<TG>(stage_base, ps, k, lane, uni, z, g);
+        consume_tile3<TX, TG>(stage_base, ps, k, lane, uni, z, g);
         if ((int64_t)kk * kTP + 2 * (int)threadIdx.x < a.HW) {
             stats_pixel(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, acc);
             stats_pixel(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
@@ -404,11 +428,11 @@ __device__ __forceinline__ bool stats_finish3(const CompArgs& a, const TileRange
 
 // pass 2, gradient warps: grad_consume of v2 on the v3 stage layout, walking this CTA's tiles backwards (the lines pass 1
 // left in L2 come first); no linear sums here any more
-template <typename TG, bool SIG, bool FL>
+template <typename TX, typename TG, bool SIG, bool FL>
 __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const TileRange& tr, uint32_t stage_base, PipeSmem3& ps,
                                               int k0, bool uni, const Coef2& c2, const LeafCoef* cf) {
     const CompArgs& a = ga.a;
-    float* __restrict__ ob = reinterpret_cast<float*>(ga.gx);
+    TX* __restrict__ ob = reinterpret_cast<TX*>(ga.gx);
     const int lane = threadIdx.x & 31;
     const int ntiles = tr.t_hi - tr.t_lo;
     if (ntiles <= 0) return;
@@ -418,7 +442,7 @@ __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const Tile
     f2 sp_dummy = splat(0.f), fl_dummy = splat(0.f);
     for (int k = 0; k < ntiles; ++k) {
         f2 z[3], g[3];
-        consume_tile3<TG>(stage_base, ps, k0 + k, lane, uni, z, g);
+        consume_tile3<TX, TG>(stage_base, ps, k0 + k, lane, uni, z, g);
         const int64_t p0 = (int64_t)kk * kTP;
         if (p0 + pix < a.HW) {
             f2 x[3], gx[3], diffs[3];
@@ -442,9 +466,9 @@ __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const Tile
                     o[0].y = r.x; o[1].y = r.y; o[2].y = r.z;
                 }
             }
-            float* op = ob + n * ga.gx_sn + p0 + pix;
+            TX* op = ob + n * ga.gx_sn + p0 + pix;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) stg_stream_f2(op + c * ga.gx_sc, o[c]);
+            for (int c = 0; c < 3; ++c) stg_grad2(op + c * ga.gx_sc, o[c]);
         }
         if (--kk < 0) { kk = tr.tpp - 1; --n; }
     }
@@ -486,7 +510,7 @@ __device__ inline void flat_leaf_sums(const double* F, int leaf, double* s /*[8]
     }
 }
 
-template <typename TG>
+template <typename TX, typename TG>
 __global__ void __launch_bounds__(kThreads3, 1)
 composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
                            V3Ws* __restrict__ ws, float* __restrict__ losses_out, unsigned int flags, XchArgs xch,
@@ -513,10 +537,10 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         reg_lower24();
         if (threadIdx.x == kProdWarp * 32) {
             // main ring: pass 1 forwards, then straight on to pass 2 backwards
-            produce_tiles3<TG>(ga.a, tr, false, sbase, fs.ps, 0);
-            produce_tiles3<TG>(ga.a, tr, true, sbase, fs.ps, ntiles);
+            produce_tiles3<TX, TG>(ga.a, tr, false, sbase, fs.ps, 0);
+            produce_tiles3<TX, TG>(ga.a, tr, true, sbase, fs.ps, ntiles);
         } else if (threadIdx.x == (kProdWarp + 1) * 32) {
-            produce_lin_tiles(ga.a, tr, sbase + Stage3<TG>::kMain, fs.ps);
+            produce_lin_tiles<TX>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps);
         }
         return;
     }
@@ -533,8 +557,8 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         lsync();
         double tot[2];
         ECO_TLL(8);
-        if (posw) lin_consume<true>(ga.a, tr, sbase + Stage3<TG>::kMain, fs.ps, fs.c2, tot);
-        else lin_consume<false>(ga.a, tr, sbase + Stage3<TG>::kMain, fs.ps, fs.c2, tot);
+        if (posw) lin_consume<TX, true>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
+        else lin_consume<TX, false>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
         ECO_TLL(9);
         tot[0] = warp_sum(tot[0]);
         tot[1] = warp_sum(tot[1]);
@@ -571,7 +595,7 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     }
     if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 32 + ECO_C3_NLEAF) fs.scale_c[threadIdx.x - 32] = scale_dev[threadIdx.x - 32];
-    stats_consume3<TG>(ga.a, tr, sbase, fs.ps, uni, fs.st);
+    stats_consume3<TX, TG>(ga.a, tr, sbase, fs.ps, uni, fs.st);
     ECO_TL(1);
     const bool last1 = stats_finish3<TG>(ga.a, tr, uni, fs.st, ws, par);
     ECO_TL(2);
@@ -625,11 +649,11 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     {
         const bool need_sig = fs.up[1] != 0.f, need_fl = fs.up[2] != 0.f;
         if (need_fl) {
-            if (need_sig) grad_consume3<TG, true, true>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
-            else grad_consume3<TG, false, true>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            if (need_sig) grad_consume3<TX, TG, true, true>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            else grad_consume3<TX, TG, false, true>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
         } else {
-            if (need_sig) grad_consume3<TG, true, false>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
-            else grad_consume3<TG, false, false>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            if (need_sig) grad_consume3<TX, TG, true, false>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            else grad_consume3<TX, TG, false, false>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
         }
     }
     ECO_TL(5);

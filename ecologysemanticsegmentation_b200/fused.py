@@ -107,8 +107,8 @@ class CompositeLossStep:
         return losses, grad
 
     def union_labels_needs_fallback(self, logits):
-        """The fused label union and byte labels exist for fp32 logits only; everything else takes the general path."""
-        return logits.dtype != torch.float32 or not self.from_logits
+        """The prepared launch serves logits (fp32 / bf16); probabilities take the general path."""
+        return logits.dtype not in (torch.float32, torch.bfloat16) or not self.from_logits
 
     def as_losslist(self, losses):
         return LossList(losses.unbind(0))

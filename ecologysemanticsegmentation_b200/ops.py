@@ -483,7 +483,7 @@ def _byte_labels_ok(x, g, from_logits):
     """uint8 / bool masks go to the kernel as bytes when the byte-label kernel serves the case (fp32 logits, planes and
     tiles 16-byte aligned); otherwise they are widened to float32 here, as the reference does (train_multiclass.py:119-123)."""
     n, c, h, w = x.shape
-    return (from_logits and x.dtype == torch.float32 and (h * w) % 16 == 0 and g.is_contiguous()
+    return (from_logits and x.dtype in (torch.float32, torch.bfloat16) and (h * w) % 16 == 0 and g.is_contiguous()
             and g.data_ptr() % 16 == 0)
 
 

@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(up, hup, sizeof(hup), cudaMemcpyHostToDevice));
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     using namespace eco::v2;
-    CK(cudaFuncSetAttribute(composite3_fused_v3_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage3<float>::kSmem));
+    CK(cudaFuncSetAttribute(composite3_fused_v3_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage3<float, float>::kSmem));
     V3Ws* ws3; CK(cudaMalloc(&ws3, sizeof(V3Ws))); CK(cudaMemset(ws3, 0, sizeof(V3Ws)));
     unsigned int* status; CK(cudaMalloc(&status, 4)); CK(cudaMemset(status, 0, 4));
     auto launch = [&](int k) {
@@ -58,8 +58,8 @@ int main(int argc, char** argv) {
         const double* sd = scale_dev; const float* u = up; unsigned int flags = 0;
         const float* prev = nullptr;
         void* args[] = {&ga, (void*)&sd, (void*)&u, &ws3, &losses, &flags, &xch, (void*)&prev};
-        if (argc > 2) composite3_fused_v3_kernel<float><<<sms, kThreads3, Stage3<float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch, nullptr);
-        else CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float>, dim3(sms), dim3(kThreads3), args, Stage3<float>::kSmem, nullptr));
+        if (argc > 2) composite3_fused_v3_kernel<float, float><<<sms, kThreads3, Stage3<float, float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch, nullptr);
+        else CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float, float>, dim3(sms), dim3(kThreads3), args, Stage3<float, float>::kSmem, nullptr));
     };
     for (int i = 0; i < 5; ++i) launch(i % NSETS);
     CK(cudaDeviceSynchronize());

@@ -230,3 +230,26 @@ def test_dropin_autograd_fast_path_anticipates_the_weights():
     sum(w * l for w, l in zip(UP_ALL, lc) if w).backward()
     assert_grad_close(first.cpu(), _oracle(z0, g0, UP)[1].cpu(), tol=TOL, what="retain 1")
     assert_grad_close(zc.grad.cpu(), _oracle(z0, g0, UP_ALL)[1].cpu(), tol=TOL, what="retain 2")
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 32, 40), (54, 3, 256, 256), (2, 3, 6, 6)])
+def test_v3_bf16_logits_within_1e2(shape):
+    """north_star: 1e-2 in bf16.  bf16 logits (bf16 gradient out) go through the same fused kernel (H*W % 8 == 0; the
+    6x6 case falls back to the first-generation kernels); byte masks give bit-identical results there too."""
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from parity import TOL_BF16
+    torch.manual_seed(shape[0] * 100 + shape[2])
+    z16 = torch.randn(shape).to(torch.bfloat16).cuda()
+    u = torch.rand(shape[0], 1, shape[2], shape[3])
+    g = torch.cat([(u < 0.5).float(), (u < 0.22).float(), (u < 0.11).float()], 1).cuda()
+    np.random.seed(0)
+    step = CompositeLossStep(UP)
+    l, d = step(z16, g)
+    assert d.dtype == torch.bfloat16
+    rl, rg = _oracle(z16.float(), g, UP)
+    assert_losses_close(l.cpu().numpy(), rl, tol=TOL_BF16, what=f"bf16 {shape}")
+    dd = (d.float() - rg).double()
+    assert float(dd.abs().max() / rg.abs().max()) <= TOL_BF16 and float(dd.norm() / rg.double().norm()) <= TOL_BF16
+    if (shape[2] * shape[3]) % 16 == 0:
+        l8, d8 = step(z16, g.to(torch.uint8))
+        assert torch.equal(l8, l) and torch.equal(d8, d)
