@@ -265,22 +265,36 @@ struct BeamSmem {
     long long cnt[2 * kBeamMax + 1];
     double soft[kBeamThreads / 32][3];
     bool is_last;
-    // direct lookup (thresholds at least two cells apart, e.g. the reference's np.arange(0.8, 0.99, 0.01)): cell j of a
-    // uniform grid over [T_min, T_max] -> {thresholds in the cells below (as int bits), the cell's own threshold or +inf,
-    // nearest threshold below the cell or -inf, nearest above or +inf}
-    float4 lut[kBeamCells];
+    // direct lookup (finite, distinct thresholds whose cells are at least three apart, e.g. the reference's
+    // np.arange(0.8, 0.99, 0.01)): cell j of a uniform grid over [T_min, T_max] -> {byte offset of histogram row `rank`,
+    // T} where T is THE threshold whose cell is j - 1, j or j + 1 and `rank` the number of thresholds below it; without
+    // such a threshold {row of the thresholds in the cells below, +inf}.  bin = rank + (p > T) either way.
+    uint2 lut[kBeamCells];
     float lut_scale, lut_bias;
     int lut_ok;
-    int cell_owner[kBeamCells];
+    uint32_t lut_adj;            // shared-memory address of lut[] minus (kCellBits0 << 3): entry = lut_adj + (cell bits << 3)
+    int cell_of[32];
 };
 
-// cell of a value: ONE monotone function for thresholds and probabilities alike, so every threshold in a lower cell is
-// below the value and every threshold in a higher cell above it -- the bin is exact whatever the rounding of the FMA.
-// No F2I: the round-down add of 2^23 leaves floor(x) in the low mantissa bits.
-__device__ __forceinline__ int beam_cell(float v, float scale, float bias) {
-    const float x = fminf(fmaxf(fmaf(v, scale, bias), 0.0f), (float)(kBeamCells - 1));
-    return (int)(__float_as_uint(__fadd_rd(x, 8388608.0f)) & (unsigned)(kBeamCells - 1));
+// cell of a value, as the bits 0x4b000000 + cell: ONE monotone function for thresholds and probabilities alike, so every
+// threshold in a lower cell is below the value and every threshold in a higher cell above it, whatever the rounding of the
+// two FMAs.  The saturating FMA clamps (and sends NaN to cell 0); no F2I: adding 2^23 leaves the integer in the mantissa.
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
+constexpr unsigned int kCellBits0 = 0x4b000000u;
+__device__ __forceinline__ unsigned int beam_cell_bits(float v, float scale, float bias) {
+    return __float_as_uint(fmaf(fma_sat(v, scale, bias), (float)(kBeamCells - 1), 8388608.0f));
+}
+__device__ __forceinline__ int beam_cell(float v, float scale, float bias) { return (int)(beam_cell_bits(v, scale, bias) - kCellBits0); }
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+constexpr unsigned int kBeamRow = kBeamThreads * 4;   // bytes per histogram row
 
 __device__ __forceinline__ int beam_bin(float p, const BeamSmem& sm, float t15, float t7, float t23) {
     int b = p > t15 ? 16 : 0;
@@ -291,11 +305,212 @@ __device__ __forceinline__ int beam_bin(float p, const BeamSmem& sm, float t15, 
     return b;   // number of thresholds T with p > T (strict, fp32), 0..n_thr
 }
 
+// One vector of VEC elements on the direct-lookup path: probability -> cell -> {row, T} -> row + (p > T) -> ONE packed
+// counter of the thread's histogram column (a plain LDS / IADD / STS: the column is private).  An element within kThrEps
+// of T is doubtful (the approximate sigmoid may sit on the other side of T than ATen's): then -- rarely -- the vector's
+// rows are redone from the exact sigmoid.  The soft sums of two elements share packed fp32x2 instructions.
+// ~19 instructions per element all told (the first version of the beam: 57).
+__device__ __forceinline__ void hist_bump(uint32_t addr, unsigned int inc) {
+    unsigned int h;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(h) : "r"(addr));
+    h += inc;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(h) : "memory");
+}
+__device__ __forceinline__ float2 sigmoid_fast_pair(float2 z) {
+    const float2 t = __fmul2_rn(z, make_float2(-kLog2e, -kLog2e));
+    const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+    return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+}
+struct BeamSoft {
+    float2 pl, p, ll;   // sum p * lab, sum p, sum lab^2 (two lanes each)
+};
+template <int VEC, bool PROBS>
+__device__ __forceinline__ void beam_group_lut(const float (&z)[VEC], const float (&lab)[VEC], uint32_t lut_adj, float scale,
+                                               float bias, uint32_t hist_tid, BeamSoft& acc) {
+    float pr[VEC];
+    if constexpr (VEC == 4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 zz = make_float2(z[2 * h], z[2 * h + 1]), ll = make_float2(lab[2 * h], lab[2 * h + 1]);
+            const float2 pp = PROBS ? zz : sigmoid_fast_pair(zz);
+            pr[2 * h] = pp.x; pr[2 * h + 1] = pp.y;
+            acc.pl = __ffma2_rn(pp, ll, acc.pl);
+            acc.p = __fadd2_rn(acc.p, pp);
+            acc.ll = __ffma2_rn(ll, ll, acc.ll);
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            pr[v] = PROBS ? z[v] : sigmoid_fast(z[v]);
+            acc.pl.x = fmaf(pr[v], lab[v], acc.pl.x); acc.p.x += pr[v]; acc.ll.x = fmaf(lab[v], lab[v], acc.ll.x);
+        }
+    }
+    uint32_t addr[VEC];   // this thread's counter of the element's bin
+    bool near = false;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        const uint2 e = lds_u2(lut_adj + (beam_cell_bits(pr[v], scale, bias) << 3));
+        // p > T  <=>  T - p is negative: its sign bit (T - p is +0 for p == T, +inf for T = +inf, and a NaN comes out
+        // canonical, i.e. positive: a NaN is never above a threshold, as in the reference's out[out > T] = 1)
+        const float d = __uint_as_float(e.y) - pr[v];
+        addr[v] = hist_tid + e.x + ((__float_as_uint(d) >> 21) & kBeamRow);
+        near = near || fabsf(d) < kThrEps;
+    }
+    if (!PROBS && near) {   // rare: the strict '>' must see ATen's bits
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float pe = sigmoid_exact(z[v]);
+            const uint2 e = lds_u2(lut_adj + (beam_cell_bits(pe, scale, bias) << 3));
+            addr[v] = hist_tid + e.x + (pe > __uint_as_float(e.y) ? kBeamRow : 0u);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) hist_bump(addr[v], lab[v] == 1.0f ? 0x10001u : 1u);
+}
+static_assert(kBeamRow == 1u << 10, "the row select above takes the sign bit down to bit 10");
+
+// search path (any thresholds): the whole tile branch-free first (the MUFU / LDS latencies of its elements overlap), then
+// the rare exact redo, then the histogram
+template <int VEC>
+__device__ __forceinline__ void beam_tile_search(const float (&zv)[kEvUnroll][VEC], const float (&lv)[kEvUnroll][VEC],
+                                                 const bool (&ok)[kEvUnroll], bool probs, BeamSmem& sm, float t15, float t7,
+                                                 float t23, int tid, BeamSoft& acc) {
+    int bins[kEvUnroll][VEC];
+    unsigned int redo = 0u;
+#pragma unroll
+    for (int u = 0; u < kEvUnroll; ++u) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const float pr = probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
+            const int b = beam_bin(pr, sm, t15, t7, t23);
+            bins[u][v] = b;
+            const float2 nb = sm.nbr[b];
+            const bool near = !probs && ((pr - nb.x) < kThrEps || (nb.y - pr) < kThrEps);
+            redo |= near ? (1u << (u * VEC + v)) : 0u;
+            const float lab = lv[u][v];
+            acc.pl.x = fmaf(pr, lab, acc.pl.x);
+            acc.p.x += pr;
+            acc.ll.x = fmaf(lab, lab, acc.ll.x);
+        }
+    }
+    if (redo) {   // rare: the strict '>' must see ATen's bits
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                if (redo & (1u << (u * VEC + v))) bins[u][v] = beam_bin(sigmoid_exact(zv[u][v]), sm, t15, t7, t23);
+    }
+#pragma unroll
+    for (int u = 0; u < kEvUnroll; ++u) {
+        if (!ok[u]) continue;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const unsigned int li = lv[u][v] == 1.0f ? 0x10000u : 0u;
+            sm.hist[bins[u][v]][tid] += 1u + li;   // thread-private slot: plain LDS / IADD / STS
+        }
+    }
+}
+
+// the streaming loop of one CTA; MODE 0 = search path, 1 = direct lookup from logits, 2 = direct lookup from probabilities
+template <typename TZ, typename TL, int VEC, int MODE>
+__device__ __forceinline__ void beam_stream(const EvalArgs& p, const TZ* __restrict__ zbase, const TL* __restrict__ lbase,
+                                            BeamSmem& sm, int tid, double (&dsoft)[3]) {
+    constexpr int kTile = kBeamThreads * VEC * kEvUnroll;
+    constexpr int NTA = kBeamMax;
+    const float lut_scale = sm.lut_scale, lut_bias = sm.lut_bias;
+    const float t15 = sm.sorted[15], t7 = sm.sorted[7], t23 = sm.sorted[23];
+    // shared-memory addresses with the constant parts folded in: table entry = lut_adj + (cell bits << 3) (read back from
+    // shared memory: as a compile-time constant ptxas splits it into two adds per element), histogram column = hist_tid +
+    // row offset
+    const uint32_t lut_adj = sm.lut_adj;
+    const uint32_t hist_tid = (uint32_t)__cvta_generic_to_shared(&sm.hist[0][tid]);
+    int since_fold = 0;
+    int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
+    int64_t tile_end = tile + p.tiles_per_cta;
+    if (tile_end > p.tiles_per_channel) tile_end = p.tiles_per_channel;
+    int64_t n = tile / p.tiles_per_plane;
+    int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
+
+    for (; tile < tile_end; ++tile) {
+        const TZ* zp = zbase + n * p.z_sn;
+        const TL* lp = lbase + n * p.l_sn;
+        const int64_t e0 = (int64_t)t * kTile + (int64_t)tid * VEC;
+        float zv[kEvUnroll][VEC], lv[kEvUnroll][VEC];
+        BeamSoft acc;
+        acc.pl = acc.p = acc.ll = make_float2(0.f, 0.f);
+        if (MODE != 0 && (int64_t)(t + 1) * kTile <= p.HW) {
+            // the whole tile lies inside the plane (all but the last tile of a plane): no per-vector bounds checks
+#pragma unroll
+            for (int u = 0; u < kEvUnroll; ++u) {
+                const int64_t e = e0 + (int64_t)u * kBeamThreads * VEC;
+                if constexpr (VEC == 4) {
+                    Vec4<TZ>::load(zp + e, reinterpret_cast<float(&)[4]>(zv[u]));
+                    Vec4<TL>::load(lp + e, reinterpret_cast<float(&)[4]>(lv[u]));
+                } else {
+                    zv[u][0] = Vec4<TZ>::load1(zp + e);
+                    lv[u][0] = Vec4<TL>::load1(lp + e);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kEvUnroll; ++u)
+                beam_group_lut<VEC, MODE == 2>(zv[u], lv[u], lut_adj, lut_scale, lut_bias, hist_tid, acc);
+        } else {
+        bool ok[kEvUnroll];
+#pragma unroll
+        for (int u = 0; u < kEvUnroll; ++u) {
+            const int64_t e = e0 + (int64_t)u * kBeamThreads * VEC;
+            ok[u] = e < p.HW;
+            if (ok[u]) {
+                if constexpr (VEC == 4) {
+                    Vec4<TZ>::load(zp + e, reinterpret_cast<float(&)[4]>(zv[u]));
+                    Vec4<TL>::load(lp + e, reinterpret_cast<float(&)[4]>(lv[u]));
+                } else {
+                    zv[u][0] = Vec4<TZ>::load1(zp + e);
+                    lv[u][0] = Vec4<TL>::load1(lp + e);
+                }
+            } else if (MODE == 0) {
+                // outside the plane: probability 0 and label 0 add nothing to the soft sums; the bins are not counted
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { zv[u][v] = p.probs ? 0.f : -__int_as_float(0x7f800000); lv[u][v] = 0.f; }
+            }
+        }
+        if constexpr (MODE == 0) {
+            beam_tile_search<VEC>(zv, lv, ok, p.probs != 0, sm, t15, t7, t23, tid, acc);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kEvUnroll; ++u)
+                if (ok[u]) beam_group_lut<VEC, MODE == 2>(zv[u], lv[u], lut_adj, lut_scale, lut_bias, hist_tid, acc);
+        }
+        }
+        dsoft[0] += (double)(acc.pl.x + acc.pl.y);
+        dsoft[1] += (double)(acc.p.x + acc.p.y);
+        dsoft[2] += (double)(acc.ll.x + acc.ll.y);
+        if ((since_fold += kEvUnroll * VEC) >= kPackFlushElems) {   // before a 16-bit half can overflow (huge inputs only)
+#pragma unroll 1
+            for (int b = 0; b < kBeamBins; ++b) {
+                const unsigned int h = sm.hist[b][tid];
+                sm.hist[b][tid] = 0u;
+                if (h == 0u) continue;
+                // bin b counts towards the sorted thresholds r < b; every bin counts towards the label total
+                for (int r = 0; r < b && r < p.n_thr; ++r) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r]), (unsigned long long)(h & 0xffffu));
+                    atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r + 1]), (unsigned long long)(h >> 16));
+                }
+                atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * NTA]), (unsigned long long)(h >> 16));
+            }
+            since_fold = 0;
+        }
+        if (++t == p.tiles_per_plane) {
+            t = 0;
+            ++n;
+        }
+    }
+}
+
 template <typename TZ, typename TL, int VEC>
 __global__ void __launch_bounds__(kBeamThreads, kBeamCtasPerSm)
 dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
                  long long* __restrict__ partials, long long* __restrict__ counts_out, double* __restrict__ soft_out, double* __restrict__ thr_inter_out) {
-    constexpr int kTile = kBeamThreads * VEC * kEvUnroll;
     constexpr int NTA = kBeamMax;
     __shared__ BeamSmem sm;
     const int c = blockIdx.y;
@@ -327,161 +542,36 @@ dice_beam_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int*
     if (tid == 0) {
         const int nt = p.n_thr;
         const float lo = sm.sorted[0], hi = sm.sorted[nt - 1];
-        float dmin = __int_as_float(0x7f800000);
-        for (int r = 0; r + 1 < nt; ++r) dmin = fminf(dmin, sm.sorted[r + 1] - sm.sorted[r]);
-        const float w = (hi - lo) / (float)(kBeamCells - 2);
-        // finite, distinct, and at least two cells apart (cell 0 = everything below T_min, T_min sits in cell 1)
-        const bool ok = nt >= 2 && fabsf(lo) < 1e30f && fabsf(hi) < 1e30f && hi > lo && dmin >= 2.0f * w && w > 0.0f;
+        // finite and spread over more than 4 kThrEps per cell: an element within kThrEps of a threshold then sits in the
+        // threshold's cell or next to it.  [lo, hi] maps to the cells 1 .. 254.
+        const bool ok = nt >= 2 && fabsf(lo) < 1e30f && fabsf(hi) < 1e30f && (hi - lo) > 4.0f * kThrEps * (float)(kBeamCells - 3);
+        const float sc = ok ? ((float)(kBeamCells - 3) / (float)(kBeamCells - 1)) / (hi - lo) : 0.0f;
         sm.lut_ok = ok ? 1 : 0;
-        sm.lut_scale = ok ? 1.0f / w : 0.0f;
-        sm.lut_bias = ok ? 1.0f - lo * (1.0f / w) : 0.0f;
-    }
-    sm.cell_owner[tid] = -1;
-    __syncthreads();
-    const bool lut_candidate = sm.lut_ok != 0;   // CTA-uniform; read by everyone BEFORE any thread may clear the flag below
-    __syncthreads();
-    if (lut_candidate) {
-        if (tid < p.n_thr) {   // tid = position in the sorted order
-            const int cell = beam_cell(sm.sorted[tid], sm.lut_scale, sm.lut_bias);
-            if (cell == 0 || atomicCAS(&sm.cell_owner[cell], -1, tid) != -1) sm.lut_ok = 0;   // never with the spacing above
-        }
-        __syncthreads();
-        if (sm.lut_ok) {
-            // thresholds below cell `tid` = those whose cell is lower; the cell function is monotone, so they are a prefix
-            int below = 0;
-            for (int r = 0; r < p.n_thr; ++r) below += beam_cell(sm.sorted[r], sm.lut_scale, sm.lut_bias) < tid ? 1 : 0;
-            const int own = sm.cell_owner[tid];
-            const int nx = below + (own >= 0 ? 1 : 0);
-            const float inf = __int_as_float(0x7f800000);
-            sm.lut[tid] = make_float4(__int_as_float(below), own >= 0 ? sm.sorted[own] : inf,
-                                      below > 0 ? sm.sorted[below - 1] : -inf, nx < p.n_thr ? sm.sorted[nx] : inf);
-        }
+        sm.lut_scale = sc;
+        sm.lut_bias = ok ? 1.0f / (float)(kBeamCells - 1) - lo * sc : 0.0f;
+        sm.lut_adj = (uint32_t)__cvta_generic_to_shared(&sm.lut[0]) - (kCellBits0 << 3);
     }
     __syncthreads();
-    const bool use_lut = sm.lut_ok != 0;
-    const float lut_scale = sm.lut_scale, lut_bias = sm.lut_bias;
-    const float t15 = sm.sorted[15], t7 = sm.sorted[7], t23 = sm.sorted[23];
-
-    int since_fold = 0;
+    if (tid < 32) sm.cell_of[tid] = tid < p.n_thr ? beam_cell(sm.sorted[tid], sm.lut_scale, sm.lut_bias) : (1 << 20) + 8 * tid;
+    __syncthreads();
+    if (tid + 1 < p.n_thr && sm.cell_of[tid + 1] - sm.cell_of[tid] < 3) sm.lut_ok = 0;   // (also: duplicate thresholds)
+    __syncthreads();
+    if (sm.lut_ok) {
+        int below = 0, own = -1;
+        for (int r = 0; r < p.n_thr; ++r) {
+            const int cr = sm.cell_of[r];
+            below += cr < tid ? 1 : 0;
+            if (cr >= tid - 1 && cr <= tid + 1) own = r;   // at most one: the cells are three apart
+        }
+        // (sorted, distinct: the rank of sorted[own] is own)
+        sm.lut[tid] = own >= 0 ? make_uint2((unsigned)own * kBeamRow, __float_as_uint(sm.sorted[own]))
+                               : make_uint2((unsigned)below * kBeamRow, 0x7f800000u);
+    }
+    __syncthreads();
     double dsoft[3] = {0.0, 0.0, 0.0};
-    int64_t tile = (int64_t)blockIdx.x * p.tiles_per_cta;
-    int64_t tile_end = tile + p.tiles_per_cta;
-    if (tile_end > p.tiles_per_channel) tile_end = p.tiles_per_channel;
-    int64_t n = tile / p.tiles_per_plane;
-    int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
-
-    for (; tile < tile_end; ++tile) {
-        const TZ* zp = zbase + n * p.z_sn;
-        const TL* lp = lbase + n * p.l_sn;
-        const int64_t e0 = (int64_t)t * kTile + (int64_t)tid * VEC;
-        float zv[kEvUnroll][VEC], lv[kEvUnroll][VEC];
-        bool ok[kEvUnroll];
-#pragma unroll
-        for (int u = 0; u < kEvUnroll; ++u) {
-            const int64_t e = e0 + (int64_t)u * kBeamThreads * VEC;
-            ok[u] = e < p.HW;
-            if (ok[u]) {
-                if constexpr (VEC == 4) {
-                    Vec4<TZ>::load(zp + e, reinterpret_cast<float(&)[4]>(zv[u]));
-                    Vec4<TL>::load(lp + e, reinterpret_cast<float(&)[4]>(lv[u]));
-                } else {
-                    zv[u][0] = Vec4<TZ>::load1(zp + e);
-                    lv[u][0] = Vec4<TL>::load1(lp + e);
-                }
-            } else {
-                // outside the plane: probability 0 and label 0 add nothing to the soft sums; the bins are not counted
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { zv[u][v] = p.probs ? 0.f : -__int_as_float(0x7f800000); lv[u][v] = 0.f; }
-            }
-        }
-        // branch-free phase: probability, bin, doubtful flag of all elements (their MUFU / LDS latencies overlap)
-        int bins[kEvUnroll][VEC];
-        unsigned int redo = 0u;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        if (use_lut) {
-#pragma unroll
-            for (int u = 0; u < kEvUnroll; ++u) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const float pr = p.probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
-                    const float4 e = sm.lut[beam_cell(pr, lut_scale, lut_bias)];
-                    bins[u][v] = __float_as_int(e.x) + (pr > e.y ? 1 : 0);
-                    const bool near = !p.probs && fminf(fminf(fabsf(pr - e.y), pr - e.z), e.w - pr) < kThrEps;
-                    redo |= near ? (1u << (u * VEC + v)) : 0u;
-                    const float lab = lv[u][v];
-                    s0 = fmaf(pr, lab, s0);
-                    s1 += pr;
-                    s2 = fmaf(lab, lab, s2);
-                }
-            }
-            if (redo) {   // rare: the strict '>' must see ATen's bits
-#pragma unroll
-                for (int u = 0; u < kEvUnroll; ++u)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (redo & (1u << (u * VEC + v))) {
-                            const float pe = sigmoid_exact(zv[u][v]);
-                            const float4 e = sm.lut[beam_cell(pe, lut_scale, lut_bias)];
-                            bins[u][v] = __float_as_int(e.x) + (pe > e.y ? 1 : 0);
-                        }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kEvUnroll; ++u) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const float pr = p.probs ? zv[u][v] : sigmoid_fast(zv[u][v]);
-                    const int b = beam_bin(pr, sm, t15, t7, t23);
-                    bins[u][v] = b;
-                    const float2 nb = sm.nbr[b];
-                    const bool near = !p.probs && ((pr - nb.x) < kThrEps || (nb.y - pr) < kThrEps);
-                    redo |= near ? (1u << (u * VEC + v)) : 0u;
-                    const float lab = lv[u][v];
-                    s0 = fmaf(pr, lab, s0);
-                    s1 += pr;
-                    s2 = fmaf(lab, lab, s2);
-                }
-            }
-            if (redo) {   // rare: the strict '>' must see ATen's bits
-#pragma unroll
-                for (int u = 0; u < kEvUnroll; ++u)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (redo & (1u << (u * VEC + v))) bins[u][v] = beam_bin(sigmoid_exact(zv[u][v]), sm, t15, t7, t23);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kEvUnroll; ++u) {
-            if (!ok[u]) continue;
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const unsigned int li = lv[u][v] == 1.0f ? 0x10000u : 0u;
-                sm.hist[bins[u][v]][tid] += 1u + li;   // thread-private slot: plain LDS / IADD / STS
-            }
-        }
-        dsoft[0] += (double)s0;
-        dsoft[1] += (double)s1;
-        dsoft[2] += (double)s2;
-        if ((since_fold += kEvUnroll * VEC) >= kPackFlushElems) {   // before a 16-bit half can overflow (huge inputs only)
-#pragma unroll 1
-            for (int b = 0; b < kBeamBins; ++b) {
-                const unsigned int h = sm.hist[b][tid];
-                sm.hist[b][tid] = 0u;
-                if (h == 0u) continue;
-                // bin b counts towards the sorted thresholds r < b; every bin counts towards the label total
-                for (int r = 0; r < b && r < p.n_thr; ++r) {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r]), (unsigned long long)(h & 0xffffu));
-                    atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * r + 1]), (unsigned long long)(h >> 16));
-                }
-                atomicAdd(reinterpret_cast<unsigned long long*>(&sm.cnt[2 * NTA]), (unsigned long long)(h >> 16));
-            }
-            since_fold = 0;
-        }
-        if (++t == p.tiles_per_plane) {
-            t = 0;
-            ++n;
-        }
-    }
+    if (!sm.lut_ok) beam_stream<TZ, TL, VEC, 0>(p, zbase, lbase, sm, tid, dsoft);
+    else if (!p.probs) beam_stream<TZ, TL, VEC, 1>(p, zbase, lbase, sm, tid, dsoft);
+    else beam_stream<TZ, TL, VEC, 2>(p, zbase, lbase, sm, tid, dsoft);
 
     // ---- CTA reduction: per bin over the threads, then suffix sums -> per sorted threshold ----------------------------
     __syncthreads();
