@@ -50,13 +50,13 @@ __device__ __forceinline__ void publish_intersections(int c, int C, int n_thr, l
 
 // Per-thread counters are packed: low 16 bits = |out| count, high 16 bits = intersection count of one threshold
 // (one FSETP + one predicated IADD per threshold and element); a thread folds them into 32-bit counters before
-// either half can overflow.  For NT <= 4 the sigmoid is the 4-instruction MUFU form and the exact
-// (ATen-bit-compatible) one is recomputed only within 4e-6 of a threshold, which keeps the counts bit-exact.
+// either half can overflow.  The sigmoid is the 4-instruction MUFU form and the exact (ATen-bit-compatible) one is
+// recomputed only within 4e-6 of a threshold, which keeps the counts bit-exact.  (0 or 1 threshold; more go to the beam.)
 constexpr int kPackFlushElems = 32768;
 constexpr float kThrEps = 4e-6f;
 
 template <typename TZ, typename TL, int VEC, int NT>
-__global__ void __launch_bounds__(kEvThreads, NT > 4 ? 2 : kEvCtasPerSm)
+__global__ void __launch_bounds__(kEvThreads, kEvCtasPerSm)
 dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
                    long long* __restrict__ partials, long long* __restrict__ counts_out,
                    double* __restrict__ soft_out, double* __restrict__ thr_inter_out) {
@@ -116,8 +116,6 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
                 float pr;
                 if (p.probs) {
                     pr = zv[u][v];
-                } else if (NT > 4) {
-                    pr = sigmoid_exact(zv[u][v]);
                 } else {
                     pr = sigmoid_fast(zv[u][v]);
                     if (NT > 0) {
@@ -237,16 +235,17 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
 }
 
 // ---------------------------------------------------------------------------------------------
-// Threshold beam (5..20 thresholds, ess/test_multiclass.py:64-77) by BINNING instead of one compare per threshold:
+// Threshold beam (2..20 thresholds, ess/test_multiclass.py:64-77) by BINNING instead of one compare per threshold:
 // the thresholds are sorted once per CTA; an element's bin = number of thresholds below its probability and it bumps
 // ONE packed counter {low 16 bits: elements, high 16 bits: elements with label 1} of its thread-private
-// shared-memory histogram (a plain read-modify-write; measured equal to an uncontended shared-memory atomic).
-// counts(T_r) = sum of the bins above r.  The bin comes from a 256-cell direct-lookup table when the thresholds are at
-// least two cells apart (the reference's np.arange(0.8, 0.99, 0.01)), else from a 5-step branch-free search (two
-// levels in registers, three in shared memory).  The sigmoid is the 4-instruction MUFU form; ATen's exact bits are
-// recomputed only for elements within kThrEps of a threshold (the neighbouring thresholds come with the table entry /
-// from one 8-byte load), after the branch-free phase over the thread's 16 elements.  Issue-bound: ~50 instructions
-// per element (profiles/r1v5_dice_beam_ncu_full.json).
+// shared-memory histogram (a plain read-modify-write; a shared-memory atomic costs 2 cycles per lane).
+// counts(T_r) = sum of the bins above r.  The bin comes from a 256-cell direct-lookup table when the thresholds' cells
+// are at least three apart (the reference's np.arange(0.8, 0.99, 0.01)): beam_group_lut, ~19 instructions per element,
+// HBM-bound (19 thresholds at cfg3: 227 us = 93 % of the measured peak; profiles/r2b_dice_beam_ncu_full.json).  Otherwise
+// a 5-step branch-free search (two levels in registers, three in shared memory) over the whole tile first:
+// beam_tile_search, the round-1 form of the kernel (issue-bound at ~57 instructions per element, 374 us).  Either way the
+// sigmoid is the 4-instruction MUFU form and ATen's exact bits are recomputed only for elements within kThrEps of a
+// threshold.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBeamMax = 20;
 constexpr int kBeamBins = kBeamMax + 1;
@@ -777,7 +776,9 @@ static void launch_exact(const EvalArgs& p, int zd, int ld, int sms, cudaStream_
 #undef ECO_EX
 }
 
-static int nt_bucket(int n_thr) { return n_thr == 0 ? 0 : n_thr == 1 ? 1 : n_thr <= 4 ? 4 : 20; }
+// 0 / 1 threshold: the compare kernel; 2..20: the binning kernel (round 1 ran 2..4 thresholds on the compare kernel: 297 us at
+// cfg3 = 71 % of the HBM peak against 222 us = 95 % here)
+static int nt_bucket(int n_thr) { return n_thr == 0 ? 0 : n_thr == 1 ? 1 : 20; }
 
 }  // namespace eco
 
@@ -831,7 +832,6 @@ extern "C" int eco_dice_counts_ex(const EcoView* logits, const EcoView* labels, 
     switch (nt_bucket(n_thr)) {
         case 0: launch_nt<0>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
         case 1: launch_nt<1>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
-        case 4: launch_nt<4>(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
         default: launch_beam(p, logits->dtype, labels->dtype, vec, grid, st, thresholds, counters, partials, co, soft_out, thr_inter_out); break;
     }
     int rc = check_cuda(cudaGetLastError(), "dice_counts_kernel launch");
