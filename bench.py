@@ -342,6 +342,14 @@ def measure_aux(dev):
         gbs = 8.0 * n * c * s * s / t / 1e9
         out["dice_eval_cfg3_" + label] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
                                           "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 8}
+    # the threshold beam search of ess/test_multiclass.py:64-77 (np.arange(0.8, 0.99, 0.01): 19 thresholds) from ONE read
+    import numpy as np
+    thr19 = torch.tensor(np.arange(0.8, 0.99, step=0.01), dtype=torch.float32, device=dev)
+    t = timed(lambda: ops.dice_counts(z, g, thr19), 20)
+    gbs = 8.0 * n * c * s * s / t / 1e9
+    out["dice_eval_cfg3_beam_19_thresholds"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
+                                                "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 8,
+                                                "what": "all 19 thresholds of the beam search in one launch (binning kernel)"}
     del z, g
     # the plain 3-organ multi-class loss step (the loss train_multiclass.py trains with), cfg2's shape, one launch
     from ecologysemanticsegmentation_b200 import fused
@@ -380,7 +388,6 @@ def measure_aux(dev):
                         "what": "cfg1: single-class losses_fn (bce + gdice + twersky) fwd+bwd from logits, 54x1x256x256, one launch"}
     del sets1, outs1
     # ---- the composite step on the other shapes / input forms ------------------------------------------------------
-    import numpy as np
     import ecologysemanticsegmentation_b200 as eco
     w = fused.loss_weights(**WEIGHTS)
     np.random.seed(0)
@@ -399,6 +406,32 @@ def measure_aux(dev):
     out["composite_cfg2_u8_masks"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": 9.0 * n * c * s * s / t / 1e9,
                                       "frac_of_hbm_peak": 9.0 * n * c * s * s / t / 1e9 / peak, "bytes_per_element": 9, "launch": how,
                                       "what": "cfg2 with uint8 masks (ECO_U8), one launch"}
+    # (a2) probabilities in (ECO_C3_PROBS: the reference's own call order, F.sigmoid before losses_fn) and the step without
+    #      gradient (ECO_C3_NO_GRAD: losses_fn under torch.no_grad()), same kernel
+    psets = [torch.sigmoid(zz) for zz, _ in sets]
+    pstep = fused.CompositeLossStep(w, device=dev, from_logits=False)
+
+    def run_probs():
+        k = st8["i"] % 4
+        st8["i"] += 1
+        pstep(psets[k], sets[k][1], out=outs[k])
+
+    t, how = timed_graph(run_probs, 4, 25)
+    out["composite_cfg2_probabilities"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": 12.0 * n * c * s * s / t / 1e9,
+                                           "frac_of_hbm_peak": 12.0 * n * c * s * s / t / 1e9 / peak, "bytes_per_element": 12, "launch": how,
+                                           "what": "cfg2 from probabilities (gradient w.r.t. them), one launch"}
+    ents = [ops.PreparedComposite3(sets[k][0], sets[k][1], cstep.scales, cstep.upstream, True) for k in range(4)]
+
+    def run_nograd():
+        k = st8["i"] % 4
+        st8["i"] += 1
+        ents[k].run(no_grad=True)
+
+    t, how = timed_graph(run_nograd, 4, 25)
+    out["composite_cfg2_no_grad"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": 8.0 * n * c * s * s / t / 1e9,
+                                     "frac_of_hbm_peak": 8.0 * n * c * s * s / t / 1e9 / peak, "bytes_per_element": 8, "launch": how,
+                                     "what": "cfg2 loss values only (validation, no gradient pass), one launch"}
+    del ents, psets
     # (b) the drop-in path through the reference's own signature: losses_fn(...) -> weighted sum -> backward(), exactly as
     #     ess/train_multiclass.py:139-147 calls it (from_logits=True fuses the sigmoid of :134); eager launches
     zs = [zz.clone().requires_grad_(True) for zz, _ in sets]
@@ -458,6 +491,46 @@ def measure_aux(dev):
         del graph
     except Exception as exc:
         out["dropin_autograd_cfg2_graphed"] = {"error": repr(exc)[:300]}
+    # (b2) the reference's training step with NOTHING changed but the import: outputs = F.sigmoid(outputs) (:134), then
+    #      losses_fn on the probabilities (:139), weighted sum (:145), backward (:147); captured in a CUDA graph
+    try:
+        zg = sets[0][0].clone().requires_grad_(True)
+        gg = sets[0][1]
+
+        def unchanged_step():
+            outputs = torch.sigmoid(zg)
+            ce, bce, fl, dice, gdice, tw, fd = eco.losses_fn(outputs, gg, True)
+            loss = 1.0 * fd + 1.0 * bce + 1.0 * (gdice + tw)
+            loss.backward()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                zg.grad = None
+                unchanged_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        zg.grad = None
+        with torch.cuda.graph(graph, stream=side):
+            unchanged_step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(100):
+            graph.replay()
+        ev1.record()
+        torch.cuda.synchronize()
+        t = ev0.elapsed_time(ev1) / 100 * 1e-3
+        out["dropin_unchanged_train_loop_cfg2_graphed"] = {
+            "gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "launch": "one CUDA graph per step",
+            "what": "F.sigmoid(z) -> eco.losses_fn(probabilities, g, True) -> weighted sum -> backward: torch's sigmoid forward "
+                    "and backward kernels around the one-launch composite step on probabilities"}
+        del graph
+    except Exception as exc:
+        out["dropin_unchanged_train_loop_cfg2_graphed"] = {"error": repr(exc)[:300]}
     # (c) the reference's own eager ops on THIS GPU (the like-for-like 'before'): same step, cfg2, oracle port on cuda
     try:
         t = timed(lambda: cpu_reference_step(sets[0][0], sets[0][1], w), 3)

@@ -33,7 +33,7 @@ class EcoPeerExchange(C.Structure):
                 ("_pad", C.c_uint32), ("status", C.c_void_p), ("timeout_ms", C.c_double)]
 
 
-C3_UNION_LABELS, C3_PROBS = 1, 2
+C3_UNION_LABELS, C3_PROBS, C3_NO_GRAD = 1, 2, 4
 
 
 class EcoLeafShape(C.Structure):

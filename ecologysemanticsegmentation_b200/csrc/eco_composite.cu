@@ -658,8 +658,9 @@ static int ensure_packed_smem() {
 #undef ECO_SMEM_ALL
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
-#define ECO_V3_ATTR(TX, TG) rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<TX, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<TX, TG>::kSmem), "cudaFuncSetAttribute(smem, fused v3)")
-    ECO_V3_ATTR(float, float); ECO_V3_ATTR(float, uint8_t); ECO_V3_ATTR(__nv_bfloat16, float); ECO_V3_ATTR(__nv_bfloat16, uint8_t);
+#define ECO_V3_ATTR(TX, TG, PR) rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<TX, TG, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<TX, TG>::kSmem), "cudaFuncSetAttribute(smem, fused v3)")
+    ECO_V3_ATTR(float, float, false); ECO_V3_ATTR(float, uint8_t, false); ECO_V3_ATTR(__nv_bfloat16, float, false); ECO_V3_ATTR(__nv_bfloat16, uint8_t, false);
+    ECO_V3_ATTR(float, float, true); ECO_V3_ATTR(float, uint8_t, true);
 #undef ECO_V3_ATTR
     if (!rc) done_for_device[dev] = 1;
     return rc;
@@ -686,12 +687,13 @@ static bool tma_planes_ok(const void* ptr, int64_t sn, int64_t sc, int dtype, in
     const int64_t esz = dtype == ECO_F32 ? 4 : (dtype == ECO_BF16 ? 2 : 1), per16 = 16 / esz;
     return reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && sn % per16 == 0 && sc % per16 == 0 && HW % per16 == 0;
 }
+// (probabilities -- ECO_C3_PROBS -- in fp32 only; `gx` may be null for a step without gradient)
 static bool v3_eligible(const EcoView* x, const EcoView* g, const EcoOut* gx, bool from_logits, int32_t N, int64_t HW) {
-    if (!from_logits || (int64_t)N * HW > ((int64_t)1 << 31)) return false;
-    if (x->dtype != ECO_F32 && x->dtype != ECO_BF16) return false;
+    if ((int64_t)N * HW > ((int64_t)1 << 31)) return false;
+    if (x->dtype != ECO_F32 && !(x->dtype == ECO_BF16 && from_logits)) return false;
     if (g->dtype != ECO_F32 && g->dtype != ECO_U8) return false;
     return tma_planes_ok(x->ptr, x->sn, x->sc, x->dtype, HW) && tma_planes_ok(g->ptr, g->sn, g->sc, g->dtype, HW) &&
-           tma_planes_ok(gx->ptr, gx->sn, gx->sc, gx->dtype, HW) && HW % 4 == 0;
+           (!gx || tma_planes_ok(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) && HW % 4 == 0;
 }
 static int v2_grid(int device, int32_t N, int64_t HW) {
     const int sms = sm_count_cached(device);
@@ -804,25 +806,23 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
                         const float* upstream_prev = nullptr) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
-    if (!leaf_scale_dev || !upstream || !losses_out || !gx || !gx->ptr) { set_error("null scale/upstream/output"); return -5; }
+    if (flags & ~(uint32_t)(ECO_C3_UNION_LABELS | ECO_C3_PROBS | ECO_C3_NO_GRAD)) { set_error("unknown flags 0x%x", flags); return -3; }
+    const bool no_grad = (flags & ECO_C3_NO_GRAD) != 0;
+    if (no_grad && (!gx || !gx->ptr)) gx = nullptr;
+    if (!leaf_scale_dev || !upstream || !losses_out || (!no_grad && (!gx || !gx->ptr))) { set_error("null scale/upstream/output"); return -5; }
     if (!ws || ws_bytes < eco_composite3_ws_bytes()) { set_error("workspace too small"); return -5; }
-    if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
-    if (flags & ~(uint32_t)(ECO_C3_UNION_LABELS | ECO_C3_PROBS)) { set_error("unknown flags 0x%x", flags); return -3; }
+    if (gx && gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     const bool lg = (flags & ECO_C3_PROBS) == 0;
     const bool g_f32 = g->dtype == ECO_F32;
-    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && (!g_f32 || c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW)) &&
-                     c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
-    CompGradArgs ga{};
-    fill_comp(ga.a, x, g, N, HW, vec);
-    ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
-    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
-    double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
-    double* partials = acc_glob + 128;
-    if (!xch.status) xch.status = counter + 32;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws);
+    if (!xch.status) xch.status = counter + 32;
     if (v3_eligible(x, g, gx, lg, N, HW)) {
+        CompGradArgs ga{};
+        fill_comp(ga.a, x, g, N, HW, 4);
+        if (gx) { ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc; }
         rc = ensure_packed_smem();
         if (rc) return rc;
         const int g2 = v2_grid(device, N, HW);
@@ -831,14 +831,23 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
         void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &ws3, &losses_out, &flags, &xch, (void*)&upstream_prev};
         const void* fn;
         int smem;
-#define ECO_V3_PICK(TX, TG) do { fn = (const void*)v2::composite3_fused_v3_kernel<TX, TG>; smem = v2::Stage3<TX, TG>::kSmem; } while (0)
-        if (x->dtype == ECO_F32) { if (g_f32) ECO_V3_PICK(float, float); else ECO_V3_PICK(float, uint8_t); }
-        else { if (g_f32) ECO_V3_PICK(__nv_bfloat16, float); else ECO_V3_PICK(__nv_bfloat16, uint8_t); }
+#define ECO_V3_PICK(TX, TG, PR) do { fn = (const void*)v2::composite3_fused_v3_kernel<TX, TG, PR>; smem = v2::Stage3<TX, TG>::kSmem; } while (0)
+        if (!lg) { if (g_f32) ECO_V3_PICK(float, float, true); else ECO_V3_PICK(float, uint8_t, true); }
+        else if (x->dtype == ECO_F32) { if (g_f32) ECO_V3_PICK(float, float, false); else ECO_V3_PICK(float, uint8_t, false); }
+        else { if (g_f32) ECO_V3_PICK(__nv_bfloat16, float, false); else ECO_V3_PICK(__nv_bfloat16, uint8_t, false); }
 #undef ECO_V3_PICK
         return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(g2), dim3(v2::kThreads3), args, smem, st), "composite3_fused_v3_kernel launch");
     }
-    if (upstream_prev) { set_error("eco_composite3_step_if_changed needs logits with 16-byte aligned planes"); return -8; }
-    // everything below: first-generation kernels (bf16 or probability inputs, ragged / unaligned planes), f32 labels only
+    if (no_grad) { set_error("ECO_C3_NO_GRAD needs fp32 inputs (or bf16 logits) with 16-byte aligned planes; use eco_composite3_stats + eco_composite3_finalize otherwise"); return -8; }
+    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && (!g_f32 || c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW)) &&
+                     c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
+    CompGradArgs ga{};
+    fill_comp(ga.a, x, g, N, HW, vec);
+    ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
+    double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
+    double* partials = acc_glob + 128;
+    if (upstream_prev) { set_error("eco_composite3_step_if_changed needs 16-byte aligned planes"); return -8; }
+    // everything below: first-generation kernels (bf16 probabilities, ragged / unaligned planes), f32 labels only
     if (!g_f32 || (flags & ECO_C3_UNION_LABELS)) {
         set_error("byte labels / the fused label union need logits with 16-byte aligned planes (H*W %% 16 == 0 for byte labels, %% 8 for bf16 logits, %% 4 otherwise)");
         return -8;

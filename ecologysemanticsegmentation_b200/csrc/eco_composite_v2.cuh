@@ -206,8 +206,11 @@ struct StatsSmem {
     bool flag;
 };
 
+// PROB: the inputs already are probabilities (ECO_C3_PROBS: the reference's own call order, F.sigmoid at
+// ess/train_multiclass.py:134 before losses_fn)
+template <bool PROB = false>
 __device__ __forceinline__ void stats_pixel(float z0, float z1, float z2, float g0, float g1, float g2, float (&acc)[F_NACC]) {
-    const float x[3] = {sigmoid_fast(z0), sigmoid_fast(z1), sigmoid_fast(z2)};
+    const float x[3] = {PROB ? z0 : sigmoid_fast(z0), PROB ? z1 : sigmoid_fast(z1), PROB ? z2 : sigmoid_fast(z2)};
     const float g[3] = {g0, g1, g2};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -612,13 +615,15 @@ __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)
 
 // rare: a pixel whose probabilities tie to within kTieEps -- the sign of the |x_i - x_j| kink (and sign(0) = 0)
 // must come from ATen's exact sigmoid bits.  Scalar path of the first-generation kernel.
+// With `prob` the inputs are the probabilities themselves and the gradient is taken w.r.t. them.
 __device__ __noinline__ float3 tie_pixel_grad(float z0, float z1, float z2, float g0, float g1, float g2,
-                                              const LeafCoef* cf, bool need_sig, bool need_fl) {
-    const float x[3] = {sigmoid_exact(z0), sigmoid_exact(z1), sigmoid_exact(z2)};
+                                              const LeafCoef* cf, bool need_sig, bool need_fl, bool prob = false) {
+    const float x[3] = {prob ? z0 : sigmoid_exact(z0), prob ? z1 : sigmoid_exact(z1), prob ? z2 : sigmoid_exact(z2)};
     const float g[3] = {g0, g1, g2};
     float gx[3];
     pixel_grad(x, g, cf, need_sig, need_fl, gx);
     // returned BY VALUE: taking the address of the caller's outputs would push them through local memory on every tile
+    if (prob) return make_float3(gx[0], gx[1], gx[2]);
     return make_float3(gx[0] * ((1.0f - x[0]) * x[0]), gx[1] * ((1.0f - x[1]) * x[1]), gx[2] * ((1.0f - x[2]) * x[2]));
 }
 

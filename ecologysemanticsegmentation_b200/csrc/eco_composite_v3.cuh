@@ -62,6 +62,7 @@ constexpr int kNFlat = 72;                                    // 55 flat sums | 
 constexpr int F_CORR = 55, F_N = 70;
 
 constexpr unsigned int kC3FlagUnionLabels = 1u;               // == ECO_C3_UNION_LABELS
+constexpr unsigned int kC3FlagNoGrad = 4u;                    // == ECO_C3_NO_GRAD: loss values only (validation), no pass 2
 
 template <typename TX, typename TG>
 struct Stage3 {
@@ -300,7 +301,7 @@ __device__ __forceinline__ void produce_lin_tiles(const CompArgs& a, const TileR
 }
 
 // the eight linear warps: BCE / focal linear sums of every tile of this CTA, from their own ring
-template <typename TX, bool POSW>
+template <typename TX, bool POSW, bool PROB>
 __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& tr, uint32_t lin_base, PipeSmem3& ps,
                                             const Coef2& c2, double (&tot)[2]) {
     const int lane = threadIdx.x & 31, lw = (threadIdx.x >> 5) - kLinWarp0;
@@ -321,7 +322,10 @@ __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& 
             if (p0 + pix < a.HW) {
                 f2 x[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(lds_x2<TX>(sb + (uint32_t)c * LinStage<TX>::kPlane, pix));
+                for (int c = 0; c < 3; ++c) {
+                    const f2 v = lds_x2<TX>(sb + (uint32_t)c * LinStage<TX>::kPlane, pix);
+                    x[c] = PROB ? v : sigmoid_fast2(v);
+                }
                 pixel_pair_tr<POSW>(x, c2, sp_acc, fl_acc);
             }
 #else
@@ -343,7 +347,7 @@ __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& 
 }
 
 // pass 1, statistics warps: as stats_consume of v2 on the v3 stage layout
-template <typename TX, typename TG>
+template <typename TX, typename TG, bool PROB>
 __device__ __forceinline__ void stats_consume3(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem3& ps,
                                                bool uni, StatsSmem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -358,8 +362,8 @@ __device__ __forceinline__ void stats_consume3(const CompArgs& a, const TileRang
         f2 z[3], g[3];
         consume_tile3<TX, TG>(stage_base, ps, k, lane, uni, z, g);
         if ((int64_t)kk * kTP + 2 * (int)threadIdx.x < a.HW) {
-            stats_pixel(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, acc);
-            stats_pixel(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
+            stats_pixel<PROB>(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, acc);
+            stats_pixel<PROB>(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
         }
         if (++kk == tr.tpp) kk = 0;
         if (++since_flush == kFlushTiles3) {
@@ -428,7 +432,7 @@ __device__ __forceinline__ bool stats_finish3(const CompArgs& a, const TileRange
 
 // pass 2, gradient warps: grad_consume of v2 on the v3 stage layout, walking this CTA's tiles backwards (the lines pass 1
 // left in L2 come first); no linear sums here any more
-template <typename TX, typename TG, bool SIG, bool FL>
+template <typename TX, typename TG, bool SIG, bool FL, bool PROB>
 __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const TileRange& tr, uint32_t stage_base, PipeSmem3& ps,
                                               int k0, bool uni, const Coef2& c2, const LeafCoef* cf) {
     const CompArgs& a = ga.a;
@@ -447,22 +451,22 @@ __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const Tile
         if (p0 + pix < a.HW) {
             f2 x[3], gx[3], diffs[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(z[c]);
+            for (int c = 0; c < 3; ++c) x[c] = PROB ? z[c] : sigmoid_fast2(z[c]);
 #pragma unroll
             for (int p = 0; p < 3; ++p) diffs[p] = add2(x[pair_i(p)], neg2(x[pair_j(p)]));
             pixel_pair_grad2<SIG, FL, false, false>(x, g, diffs, c2, gx, sp_dummy, fl_dummy);
             f2 o[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) o[c] = mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
+            for (int c = 0; c < 3; ++c) o[c] = PROB ? gx[c] : mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
             const float dx = fminf(fminf(fabsf(diffs[0].x), fabsf(diffs[1].x)), fabsf(diffs[2].x));
             const float dy = fminf(fminf(fabsf(diffs[0].y), fabsf(diffs[1].y)), fabsf(diffs[2].y));
             if (fminf(dx, dy) < kTieEps) {
                 if (dx < kTieEps) {
-                    const float3 r = tie_pixel_grad(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, cf, SIG, FL);
+                    const float3 r = tie_pixel_grad(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, cf, SIG, FL, PROB);
                     o[0].x = r.x; o[1].x = r.y; o[2].x = r.z;
                 }
                 if (dy < kTieEps) {
-                    const float3 r = tie_pixel_grad(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, cf, SIG, FL);
+                    const float3 r = tie_pixel_grad(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, cf, SIG, FL, PROB);
                     o[0].y = r.x; o[1].y = r.y; o[2].y = r.z;
                 }
             }
@@ -510,7 +514,7 @@ __device__ inline void flat_leaf_sums(const double* F, int leaf, double* s /*[8]
     }
 }
 
-template <typename TX, typename TG>
+template <typename TX, typename TG, bool PROB>
 __global__ void __launch_bounds__(kThreads3, 1)
 composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
                            V3Ws* __restrict__ ws, float* __restrict__ losses_out, unsigned int flags, XchArgs xch,
@@ -532,13 +536,14 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     const int ntiles = tr.t_hi - tr.t_lo;
     const uint32_t sbase = smem_u32(stage_smem);
     const bool uni = (flags & kC3FlagUnionLabels) != 0u;
+    const bool no_grad = (flags & kC3FlagNoGrad) != 0u;
     if (warp >= kProdWarp) {
         // ---- producers (no path from here joins another role's code: the register budgets differ)
         reg_lower24();
         if (threadIdx.x == kProdWarp * 32) {
             // main ring: pass 1 forwards, then straight on to pass 2 backwards
             produce_tiles3<TX, TG>(ga.a, tr, false, sbase, fs.ps, 0);
-            produce_tiles3<TX, TG>(ga.a, tr, true, sbase, fs.ps, ntiles);
+            if (!no_grad) produce_tiles3<TX, TG>(ga.a, tr, true, sbase, fs.ps, ntiles);
         } else if (threadIdx.x == (kProdWarp + 1) * 32) {
             produce_lin_tiles<TX>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps);
         }
@@ -557,8 +562,8 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         lsync();
         double tot[2];
         ECO_TLL(8);
-        if (posw) lin_consume<TX, true>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
-        else lin_consume<TX, false>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
+        if (posw) lin_consume<TX, true, PROB>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
+        else lin_consume<TX, false, PROB>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
         ECO_TLL(9);
         tot[0] = warp_sum(tot[0]);
         tot[1] = warp_sum(tot[1]);
@@ -595,7 +600,7 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     }
     if (threadIdx.x < ECO_NLOSS) fs.up[threadIdx.x] = upstream[threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 32 + ECO_C3_NLEAF) fs.scale_c[threadIdx.x - 32] = scale_dev[threadIdx.x - 32];
-    stats_consume3<TX, TG>(ga.a, tr, sbase, fs.ps, uni, fs.st);
+    stats_consume3<TX, TG, PROB>(ga.a, tr, sbase, fs.ps, uni, fs.st);
     ECO_TL(1);
     const bool last1 = stats_finish3<TG>(ga.a, tr, uni, fs.st, ws, par);
     ECO_TL(2);
@@ -646,14 +651,14 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     }
     csync();
     ECO_TL(4);
-    {
+    if (!no_grad) {
         const bool need_sig = fs.up[1] != 0.f, need_fl = fs.up[2] != 0.f;
         if (need_fl) {
-            if (need_sig) grad_consume3<TX, TG, true, true>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
-            else grad_consume3<TX, TG, false, true>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            if (need_sig) grad_consume3<TX, TG, true, true, PROB>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            else grad_consume3<TX, TG, false, true, PROB>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
         } else {
-            if (need_sig) grad_consume3<TX, TG, true, false>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
-            else grad_consume3<TX, TG, false, false>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            if (need_sig) grad_consume3<TX, TG, true, false, PROB>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
+            else grad_consume3<TX, TG, false, false, PROB>(ga, tr, sbase, fs.ps, ntiles, uni, fs.c2, fs.cf);
         }
     }
     ECO_TL(5);

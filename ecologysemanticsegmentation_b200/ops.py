@@ -346,8 +346,10 @@ def _device_scales(leaf_scales, device):
 
 
 def _fused_dropin_ok(x, g, from_logits, group):
-    """Inputs the third-generation fused kernel serves (so that the backward's "only if changed" launch is valid too)."""
-    if group is not None or not from_logits or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+    """Inputs the third-generation fused kernel serves (so that the backward's "only if changed" launch is valid too):
+    fp32 logits or -- the reference's own call order, F.sigmoid before losses_fn (train_multiclass.py:134) -- fp32
+    probabilities."""
+    if group is not None or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
         return False
     hw = x.shape[2] * x.shape[3]
     if hw % 4 or not x.is_contiguous() or x.data_ptr() % 16 or not g.is_contiguous() or g.data_ptr() % 16:
@@ -377,11 +379,19 @@ class Composite3(torch.autograd.Function):
             if used is None:
                 used = torch.zeros(nat.NLOSS, dtype=torch.float32, device=dev)
             scales = _device_scales(leaf_scales, dev)
-            losses, gx = _dropin_prepared(x, g, scales, used).run(upstream=used, scales=scales)
+            losses, gx = _dropin_prepared(x, g, scales, used, from_logits).run(upstream=used, scales=scales)
             ctx.save_for_backward(x, g, scales, losses, gx)
             ctx.holds = used          # the weights `gx` currently holds the gradient for
             ctx.returned = False
             return tuple(losses.clone().unbind(0))   # (the saved `losses` buffer is rewritten by the backward's launch)
+        if not ctx.needs_input_grad[0] and not ctx.needs_input_grad[1] and _fused_dropin_ok(x, g, from_logits, group):
+            # loss values only (losses_fn under torch.no_grad(), train_multiclass.py:175-198): the statistics pass and the
+            # closed forms of the same kernel, one launch, no gradient pass
+            dev = x.device
+            scales = _device_scales(leaf_scales, dev)
+            zero = _zero_upstream(dev)
+            losses, _ = _dropin_prepared(x, g, scales, zero, from_logits).run(upstream=zero, scales=scales, no_grad=True)
+            return tuple(losses.unbind(0))
         acc = composite3_stats(x.detach(), g.detach(), from_logits)
         acc = dist_.allreduce_sums_(acc, group)
         losses, jac, _ = composite3_finalize(acc, leaf_scales)
@@ -399,7 +409,7 @@ class Composite3(torch.autograd.Function):
             x, g, scales, losses, gx = ctx.saved_tensors
             up = _stack_upstream(grads, x)
             _anticipated_upstream[x.device.index] = up
-            ent = _dropin_prepared(x, g, scales, up)
+            ent = _dropin_prepared(x, g, scales, up, ctx.from_logits)
             if ctx.returned:   # a second backward through the same graph: autograd may own the first buffer by now
                 _, gx = ent.run(upstream=up, scales=scales)
                 return gx, None, None, None, None
@@ -480,11 +490,11 @@ def multiclass3_fused(x, g, leaf_scale, upstream, out=None):
 
 
 def _byte_labels_ok(x, g, from_logits):
-    """uint8 / bool masks go to the kernel as bytes when the byte-label kernel serves the case (fp32 logits, planes and
-    tiles 16-byte aligned); otherwise they are widened to float32 here, as the reference does (train_multiclass.py:119-123)."""
+    """uint8 / bool masks go to the kernel as bytes when the byte-label kernel serves the case (fp32 inputs or bf16 logits,
+    planes and tiles 16-byte aligned); otherwise they are widened to float32 here, as the reference does (train_multiclass.py:119-123)."""
     n, c, h, w = x.shape
-    return (from_logits and x.dtype in (torch.float32, torch.bfloat16) and (h * w) % 16 == 0 and g.is_contiguous()
-            and g.data_ptr() % 16 == 0)
+    return ((x.dtype == torch.float32 or (from_logits and x.dtype == torch.bfloat16)) and (h * w) % 16 == 0
+            and g.is_contiguous() and g.data_ptr() % 16 == 0)
 
 
 def composite3_fused(x, g, leaf_scales, upstream, from_logits=True, out=None, union_labels=False, peers=None,
@@ -576,12 +586,22 @@ class PreparedComposite3:
         self.ws = nat.workspace("comp3", self.L.eco_composite3_ws_bytes(), x.device)
         self.keep = (x, g, gg)
 
-    def run(self, out=None, upstream=None, scales=None, upstream_prev=None, losses=None):
+    def run(self, out=None, upstream=None, scales=None, upstream_prev=None, losses=None, no_grad=False):
         """Launch.  ``upstream`` / ``scales`` override the tensors given at construction; with ``upstream_prev`` the launch is
-        the "only if changed" form (``out`` and ``losses`` then hold the step for ``upstream_prev``)."""
+        the "only if changed" form (``out`` and ``losses`` then hold the step for ``upstream_prev``); ``no_grad``: loss values
+        only (ECO_C3_NO_GRAD), the returned gradient is None."""
         dev = self.dev
         if losses is None:
             losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=dev)
+        if no_grad:
+            self.og.ptr = None
+            rc = self.fn(self.vx, self.vg, self.n, self.hw, self.flags | nat.C3_NO_GRAD,
+                         (self.scales if scales is None else scales).data_ptr(),
+                         (self.upstream if upstream is None else upstream).data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                         losses.data_ptr(), self.og, self.peers, dev.index, torch._C._cuda_getCurrentRawStream(dev.index))
+            if rc:
+                nat.check(rc, "eco_composite3_step")
+            return losses, None
         gx = out if out is not None else torch.empty(self.shape, dtype=self.dtype, device=dev)
         self.og.ptr = gx.data_ptr()
         up = (self.upstream if upstream is None else upstream).data_ptr()
@@ -602,12 +622,22 @@ class PreparedComposite3:
 _dropin_launches = {}
 
 
-def _dropin_prepared(x, g, scales, upstream):
+def _dropin_prepared(x, g, scales, upstream, from_logits=True):
     """Launch block of the drop-in fast path for this pair of buffers (see PreparedComposite3)."""
-    key = (x.data_ptr(), g.data_ptr(), torch._C._cuda_getCurrentRawStream(x.device.index))
+    key = (x.data_ptr(), g.data_ptr(), torch._C._cuda_getCurrentRawStream(x.device.index), bool(from_logits))
     ent = _dropin_launches.get(key)
     if ent is None or ent.sig != PreparedComposite3.signature(x, g):
         if len(_dropin_launches) >= 64:
             _dropin_launches.clear()
-        ent = _dropin_launches[key] = PreparedComposite3(x, g, scales, upstream, True)
+        ent = _dropin_launches[key] = PreparedComposite3(x, g, scales, upstream, bool(from_logits))
     return ent
+
+
+_zero_up = {}
+
+
+def _zero_upstream(device):
+    t = _zero_up.get(device.index)
+    if t is None:
+        t = _zero_up[device.index] = torch.zeros(nat.NLOSS, dtype=torch.float32, device=device)
+    return t

@@ -204,7 +204,12 @@ int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, int32_t N, 
  *     `return_union_sets_descending_order(ann, exclude_indices=[0])` (channel 1 <- channel 1 + channel 2, then everything
  *     above 1 set to 1; called on the labels at ess/train_multiclass.py:110) is applied in registers at load -- g itself is
  *     not modified, the separate in-place sweep (eco_union_sets) is not needed;
- *   - ECO_C3_PROBS: x holds probabilities (gradient w.r.t. them) instead of logits;
+ *   - ECO_C3_PROBS: x holds probabilities (gradient w.r.t. them) instead of logits -- the reference's own call order,
+ *     F.sigmoid at ess/train_multiclass.py:134 and then losses_fn on its output; fp32 with 16-byte aligned planes runs the
+ *     same one-launch kernel as logits do;
+ *   - ECO_C3_NO_GRAD: loss values only (losses_fn under torch.no_grad(), as in the validation loop of ess/train_multiclass.py:175-198): the
+ *     statistics pass and the closed forms of the same kernel, no gradient pass; gx may be NULL.  Needs inputs the
+ *     one-launch kernel serves (-8 otherwise: use eco_composite3_stats + eco_composite3_finalize);
  *   - peers == NULL: one GPU.  Otherwise the batch is sharded over peers->world processes and the per-class partial sums
  *     are all-reduced inside the kernel over NVLink peer memory (see eco_composite3_fused_sharded for the contract).
  *     A wait on a peer that exceeds timeout_ms (<= 0: 30 s) poisons the step's outputs with NaN and sets *status to 1:
@@ -212,6 +217,7 @@ int eco_composite3_fused_sharded(const EcoView* x, const EcoView* g, int32_t N, 
  *     synchronisation -- or NULL for a word inside `ws` (read and cleared by eco_xch_poll_status). */
 #define ECO_C3_UNION_LABELS 1u
 #define ECO_C3_PROBS 2u
+#define ECO_C3_NO_GRAD 4u
 typedef struct EcoPeerExchange {
     void* const* peer_xch_dev; /* device array of `world` exchange-buffer pointers, [rank] = own */
     int32_t rank;

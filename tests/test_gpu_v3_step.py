@@ -253,3 +253,84 @@ def test_v3_bf16_logits_within_1e2(shape):
     if (shape[2] * shape[3]) % 16 == 0:
         l8, d8 = step(z16, g.to(torch.uint8))
         assert torch.equal(l8, l) and torch.equal(d8, d)
+
+
+def _oracle_probs(p, g, up):
+    """gradient w.r.t. the PROBABILITIES, as autograd delivers it to F.sigmoid's backward (train_multiclass.py:134)"""
+    from oracle import torch_port as tp
+    pr = p.clone().requires_grad_(True)
+    np.random.seed(0)
+    ref = tp.losses_composite(pr, g, True)
+    sum(w * l for w, l in zip(up, ref) if w).backward()
+    return [float(v) for v in ref], pr.grad
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (5, 3, 64, 64), (54, 3, 256, 256)])
+@pytest.mark.parametrize("up", [UP, UP_ALL])
+def test_v3_probability_inputs_one_launch(shape, up):
+    """ECO_C3_PROBS on the one-launch kernel: the reference's own call order (F.sigmoid at train_multiclass.py:134, then
+    losses_fn on the probabilities); losses and d/d probabilities against the same-device oracle, byte masks bit-identical.
+    Exactly tied probabilities (|x_i - x_j| = 0: torch's abs backward is 0 there) are planted on purpose."""
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(shape[0], 3, shape[2], 13, nested=True)
+    p = torch.sigmoid(z.cuda())
+    p[0, 1, 0, :5] = p[0, 0, 0, :5]
+    p[1, 2, 1, :3] = p[1, 1, 1, :3]
+    g = g.cuda()
+    np.random.seed(0)
+    step = CompositeLossStep(up, from_logits=False)
+    l32, d32 = step(p, g)
+    rl, rg = _oracle_probs(p, g, up)
+    assert_losses_close(l32.cpu().numpy(), rl, tol=TOL, what=f"v3 probs {shape}")
+    assert_grad_close(d32.cpu(), rg.cpu(), tol=TOL, what=f"v3 probs {shape}")
+    l8, d8 = step(p, g.to(torch.uint8))
+    assert torch.equal(l8, l32) and torch.equal(d8, d32)
+
+
+@pytest.mark.parametrize("from_logits", [True, False])
+def test_v3_no_grad_step_equals_the_full_step(from_logits):
+    """ECO_C3_NO_GRAD (losses_fn under torch.no_grad(), the validation loop of train_multiclass.py:175-198): the same
+    statistics and closed forms without the gradient pass -- bit-identical loss values, several steps in a row (the
+    workspace parity advances the same way), mixed with full steps."""
+    from ecologysemanticsegmentation_b200 import ops
+    from ecologysemanticsegmentation_b200.fused import CompositeLossStep
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(7, 3, 96, 17)
+    x = z.cuda() if from_logits else torch.sigmoid(z.cuda())
+    g = g.cuda()
+    np.random.seed(0)
+    step = CompositeLossStep(UP_ALL, from_logits=from_logits)
+    full_l, full_d = step(x, g)
+    ent = ops.PreparedComposite3(x, g, step.scales, step.upstream, from_logits)
+    for _ in range(3):
+        l, d = ent.run(no_grad=True)
+        assert d is None and torch.equal(l, full_l)
+        l2, d2 = ent.run()
+        assert torch.equal(l2, full_l) and torch.equal(d2, full_d)
+
+
+def test_dropin_unchanged_train_loop_probabilities_and_no_grad():
+    """The reference's training step verbatim (train_multiclass.py:133-147): outputs = F.sigmoid(net(x)); losses =
+    losses_fn(outputs, labels, True); weighted sum; backward -- on the one-launch kernel (gradient w.r.t. the probabilities,
+    torch's sigmoid backward takes it to the logits), and the same call under torch.no_grad()."""
+    from ecologysemanticsegmentation_b200 import loss_composite as lc
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    z, g = make_inputs(6, 3, 64, 5, nested=True)
+    z, g = z.cuda(), g.cuda()
+    rl, rg = _oracle(z, g, UP)
+    for _ in range(3):   # first step: weights not anticipated yet; later steps: one launch + the no-op check
+        zz = z.clone().requires_grad_(True)
+        np.random.seed(0)
+        losses = lc.losses_fn(torch.sigmoid(zz), g, True)
+        sum(w * l for w, l in zip(UP, losses) if w).backward()
+        assert_losses_close([float(v) for v in losses], rl, tol=TOL, what="drop-in probs")
+        assert_grad_close(zz.grad.cpu(), rg.cpu(), tol=TOL, what="drop-in probs")
+    with torch.no_grad():
+        np.random.seed(0)
+        val = lc.losses_fn(torch.sigmoid(z), g, True)
+    assert_losses_close([float(v) for v in val], rl, tol=TOL, what="drop-in no_grad")
+    with torch.no_grad():
+        np.random.seed(0)
+        val = lc.losses_fn(z, g, True, from_logits=True)
+    assert_losses_close([float(v) for v in val], rl, tol=TOL, what="drop-in no_grad from logits")
