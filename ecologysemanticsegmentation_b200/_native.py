@@ -94,6 +94,10 @@ SIGNATURES = {
     "eco_dice_finalize_ex": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),
     "eco_dice_finalize": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, C.c_int, _vp]),
     "eco_masks_u8": (C.c_int, [_VIEW, _i32, _i32, _i64, C.c_float, _i32, _i32, _vp, C.c_int, _vp]),
+    "eco_frames_plan_sizes": (C.c_int, [_i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
+    "eco_frames_plan": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i32), C.POINTER(_i32)]),
+    "eco_frames_preprocess": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
+                                        _vp, _vp, C.c_int, _vp]),
     "eco_union_sets": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i64, _i64, C.c_uint64, _i32, C.c_int, _vp]),
     "eco_softce_ws_bytes": (_i64, []),
     "eco_softce_stats": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _i32, _vp, _i64, _vp, C.c_int, _vp]),

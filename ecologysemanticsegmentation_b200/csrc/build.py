@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["eco_api.cu", "eco_leaf.cu", "eco_composite.cu", "eco_eval.cu", "eco_masks.cu", "eco_softce.cu", "eco_union.cu"]
+SOURCES = ["eco_api.cu", "eco_leaf.cu", "eco_composite.cu", "eco_eval.cu", "eco_masks.cu", "eco_softce.cu", "eco_union.cu", "eco_frames.cu"]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith(".cuh")) + [os.path.join(ROOT, "include", "ecoloss.h")]
 LIB = os.path.join(HERE, "libecoloss.so")
 OBJ_DIR = os.path.join(HERE, "build")
@@ -24,6 +24,7 @@ NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-ffp-contract=off",   # host code restates third-party double arithmetic operation by operation
     "-Xptxas", "-v",
 ]
 

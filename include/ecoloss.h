@@ -283,6 +283,29 @@ int eco_dice_finalize_ex(const int64_t* counts, const double* soft, const double
 int eco_dice_finalize(const int64_t* counts, const double* soft, int32_t C, int32_t n_thr, float* dice_out,
                       float* soft_dice_out, int device, void* stream);
 
+/* Frame pre-processing in front of the network: ess/test_video.py:70-78
+ *     transforms.Resize((256, 256)) -> transforms.ToTensor() -> transforms.Normalize(mean, std)
+ * on RGB frames.  The reference resizes on the host with Pillow (Image.resize, BILINEAR: two 8-bit passes with 22-bit
+ * fixed-point coefficients, horizontal first), divides by 255 and normalises in float32, then copies 4 B/element to the
+ * GPU; here the uint8 frames go to the device as they are and one kernel produces the float32 [N][3][Hout][Wout] tensor,
+ * bit-identical to Pillow + torchvision on the CPU.
+ *   eco_frames_plan_sizes: taps per output column / row (ksx, ksy) for the table sizes below.
+ *   eco_frames_plan (host only, no GPU): fills HOST arrays xbounds int32[Wout][2] = (first input column, tap count),
+ *     kx int32[Wout][ksx], ybounds int32[Hout][2], ky int32[Hout][ksy] (Pillow's precompute_coeffs +
+ *     normalize_coeffs_8bpc), lut float32[3][256] = ((byte / 255) - mean[c]) / std[c], and the largest input patch of
+ *     one 32 x 16 output tile (patch_cols, patch_rows).  The caller copies the five arrays to the device once per size.
+ *   eco_frames_preprocess: frames = uint8 device [N][Hin][Win][3] with the given byte strides between frames / rows;
+ *     out = float32 device [N][3][Hout][Wout] contiguous.  -8 when one tile's input patch exceeds the shared memory
+ *     (down-scaling by more than ~40x). */
+int eco_frames_plan_sizes(int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout, int32_t* ksx, int32_t* ksy);
+int eco_frames_plan(int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout, const float* mean, const float* stdev,
+                    int32_t* xbounds, int32_t* kx, int32_t* ybounds, int32_t* ky, float* lut, int32_t* patch_cols,
+                    int32_t* patch_rows);
+int eco_frames_preprocess(const uint8_t* frames, int32_t N, int32_t Hin, int32_t Win, int64_t frame_stride_bytes,
+                          int64_t row_stride_bytes, const int32_t* xbounds_dev, const int32_t* kx_dev, int32_t ksx,
+                          const int32_t* ybounds_dev, const int32_t* ky_dev, int32_t ksy, int32_t Hout, int32_t Wout,
+                          int32_t patch_cols, int32_t patch_rows, const float* lut_dev, float* out, int device, void* stream);
+
 /* Byte masks for the result dumps that follow the scoring: ess/test_multiclass.py:58 (sigmoid), :68-69 (optional
  * threshold rule), :90-92 `(t.numpy() * 255).astype(np.uint8)` for images / labels / outputs, ess/test_video.py:129-130.
  * out[n][c][i] = uint8(trunc(fp32(q * 255))) with q = x (x_is_prob) or sigmoid(x), then, if use_threshold,
