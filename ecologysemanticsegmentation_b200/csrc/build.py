@@ -45,6 +45,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
+    extra = os.environ.get("ECO_EXTRA_NVCC_FLAGS", "").split()   # experiment switches (-DECO_...), see DESIGN.md section 4
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdrs = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
@@ -56,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(o + ".log", "w") as f:

@@ -90,7 +90,10 @@ __device__ __forceinline__ void stg_stream_f2(float* p, float2 v) {
 // Tile pipeline.  A tile = kTP consecutive pixels of one image x 6 planes (x0 x1 x2 g0 g1 g2); it never straddles
 // two images and the last tile of a plane may be short.  One consumer thread owns one pixel PAIR of a tile.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCWarps = 16;                       // consumer warps (4 per SM sub-partition)
+#ifndef ECO_V2_CWARPS
+#define ECO_V2_CWARPS 16
+#endif
+constexpr int kCWarps = ECO_V2_CWARPS;            // consumer warps (4 per SM sub-partition)
 constexpr int kCThreads = kCWarps * 32;           // 512
 constexpr int kThreads = kCThreads + 32;          // + the producer warp
 constexpr int kTP = kCThreads * 2;                // pixels per tile
@@ -113,9 +116,9 @@ struct TileRange {
     int tpp;         // tiles per plane
     int t_lo, t_hi;  // this CTA's tiles (global tile index = n * tpp + k)
 };
-__device__ __forceinline__ TileRange tile_range(const CompArgs& a) {
+__device__ __forceinline__ TileRange tile_range(const CompArgs& a, int tp = kTP) {
     TileRange r;
-    r.tpp = (int)((a.HW + kTP - 1) / kTP);
+    r.tpp = (int)((a.HW + tp - 1) / tp);
     const int64_t total = (int64_t)a.N * r.tpp;
     r.t_lo = (int)(total * blockIdx.x / gridDim.x);
     r.t_hi = (int)(total * (blockIdx.x + 1) / gridDim.x);

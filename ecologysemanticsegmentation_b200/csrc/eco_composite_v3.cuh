@@ -42,7 +42,13 @@ namespace v2 {
 // thread; the four statistics / gradient warpgroups then raise their budget to 96, the two linear warpgroups lower theirs to
 // 48 and the producers' warpgroup to 24 (setmaxnreg): 16 x 96 + 8 x 48 + 4 x 24 = 2016 = 28 x 72 -- what is released
 // equals what is claimed, the 55 accumulators of pass 1 stay in registers.
-constexpr int kLinWarps = 8;                                  // two per SM sub-partition
+#ifndef ECO_V3_LINWARPS
+#define ECO_V3_LINWARPS 8
+#endif
+constexpr int kLinWarps = ECO_V3_LINWARPS;                    // two per SM sub-partition
+constexpr int kLinQ = 16 / kLinWarps;                         // pixel pairs per thread and linear tile
+constexpr int kLinTP = kLinWarps * 64 * kLinQ;                // pixels per tile of the linear ring (its own partition of the planes)
+static_assert(kLinQ >= 1 && kLinTP == 1024, "linear tile geometry");
 constexpr int kLinWarp0 = kCWarps;                            // warps 16..23
 constexpr int kProdWarp = kCWarps + kLinWarps;                // warp 24: main ring; warp 25: linear ring; 26, 27 exit at once
 constexpr int kThreads3 = (kCWarps + kLinWarps + 4) * 32;     // 896
@@ -53,10 +59,10 @@ constexpr int kStages3 = 5;
 constexpr int kLinStages = 4;                                 // ring of the linear warps: logit planes only
 template <typename TX>
 struct LinStage {
-    static constexpr int kPlane = kTP * (int)sizeof(TX);
+    static constexpr int kPlane = kLinTP * (int)sizeof(TX);
     static constexpr int kBytes = 3 * kPlane;                 // 12 KB (fp32 logits) / 6 KB (bf16)
 };
-constexpr int kLinFlushTiles = 16;                            // 2 pixel pairs per thread and tile -> 64 values per fp32 partial
+constexpr int kLinFlushTiles = 32 / kLinQ;                    // 64 values per fp32 partial between folds into fp64
 constexpr int kFlushTiles3 = 32;                              // 64 pixels per fp32 accumulator between folds into fp64 (cfg2: one fold per CTA)
 constexpr int kNFlat = 72;                                    // 55 flat sums | 15 label corrections | n | (pad)
 constexpr int F_CORR = 55, F_N = 70;
@@ -288,8 +294,8 @@ __device__ __forceinline__ void produce_lin_tiles(const CompArgs& a, const TileR
         const int s = k % kLinStages;
         const uint32_t full = smem_u32(&ps.lfull[s]);
         if (k >= kLinStages) mbar_wait(smem_u32(&ps.lempty[s]), ((k / kLinStages) - 1) & 1);
-        const int64_t p0 = (int64_t)kk * kTP;
-        const int valid = (int)((a.HW - p0 < kTP) ? (a.HW - p0) : kTP);
+        const int64_t p0 = (int64_t)kk * kLinTP;
+        const int valid = (int)((a.HW - p0 < kLinTP) ? (a.HW - p0) : kLinTP);
         const uint32_t xbytes = (uint32_t)valid * (uint32_t)sizeof(TX);
         const uint32_t dst = lin_base + (uint32_t)s * LinStage<TX>::kBytes;
         const TX* xs = xb + n * a.x_sn + p0;
@@ -314,9 +320,9 @@ __device__ __forceinline__ void lin_consume(const CompArgs& a, const TileRange& 
         const int s = k % kLinStages;
         mbar_wait(smem_u32(&ps.lfull[s]), (k / kLinStages) & 1);
         const uint32_t sb = lin_base + (uint32_t)s * LinStage<TX>::kBytes;
-        const int64_t p0 = (int64_t)kk * kTP;
+        const int64_t p0 = (int64_t)kk * kLinTP;
 #pragma unroll 1
-        for (int q = 0; q < kCWarps / kLinWarps; ++q) {
+        for (int q = 0; q < kLinQ; ++q) {
             const int pix = ((q * kLinWarps + lw) * 32 + lane) * 2;
 #ifndef ECO_V3_EXP_LIN_OFF
             if (p0 + pix < a.HW) {
@@ -533,6 +539,7 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
     stats_smem_init(fs.st);
     pipe_init3(fs.ps);
     const TileRange tr = tile_range(ga.a);
+    const TileRange ltr = tile_range(ga.a, kLinTP);   // the linear warps partition the planes on their own
     const int ntiles = tr.t_hi - tr.t_lo;
     const uint32_t sbase = smem_u32(stage_smem);
     const bool uni = (flags & kC3FlagUnionLabels) != 0u;
@@ -545,7 +552,7 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
             produce_tiles3<TX, TG>(ga.a, tr, false, sbase, fs.ps, 0);
             if (!no_grad) produce_tiles3<TX, TG>(ga.a, tr, true, sbase, fs.ps, ntiles);
         } else if (threadIdx.x == (kProdWarp + 1) * 32) {
-            produce_lin_tiles<TX>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps);
+            produce_lin_tiles<TX>(ga.a, ltr, sbase + Stage3<TX, TG>::kMain, fs.ps);
         }
         return;
     }
@@ -562,8 +569,8 @@ composite3_fused_v3_kernel(CompGradArgs ga, const double* __restrict__ scale_dev
         lsync();
         double tot[2];
         ECO_TLL(8);
-        if (posw) lin_consume<TX, true, PROB>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
-        else lin_consume<TX, false, PROB>(ga.a, tr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
+        if (posw) lin_consume<TX, true, PROB>(ga.a, ltr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
+        else lin_consume<TX, false, PROB>(ga.a, ltr, sbase + Stage3<TX, TG>::kMain, fs.ps, fs.c2, tot);
         ECO_TLL(9);
         tot[0] = warp_sum(tot[0]);
         tot[1] = warp_sum(tot[1]);
