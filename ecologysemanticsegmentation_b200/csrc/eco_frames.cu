@@ -21,8 +21,9 @@
 
 namespace eco {
 
-constexpr int kFrTW = 32, kFrTH = 16, kFrThreads = 256;
+constexpr int kFrTW = 32, kFrTH = 16, kFrThreads = 192;   // 192 = 2 x (32 columns x 3 channels) for the horizontal pass
 constexpr int kFrPrecision = 32 - 8 - 2;   // Resample.c: PRECISION_BITS
+constexpr int kFrPadTaps = 17;             // the horizontal pass may read (and multiply by 0) this many pixels past a row
 
 struct FrameArgs {
     const uint8_t* src;
@@ -35,12 +36,12 @@ struct FrameArgs {
     int32_t patch_cols, patch_rows, pitch;   // shared-memory patch: rows x pitch bytes (pitch % 4 == 0)
 };
 
-__host__ __device__ inline int frames_pitch(int patch_cols) { return (patch_cols * 3 + 3 + 3) / 4 * 4; }
+__host__ __device__ inline int frames_pitch(int patch_cols) { return ((patch_cols + kFrPadTaps) * 3 + 3 + 4) / 4 * 4; }
 __host__ __device__ inline size_t frames_smem_bytes(int patch_cols, int patch_rows, int ksx, int ksy) {
     size_t b = (size_t)patch_rows * frames_pitch(patch_cols);           // patch
     b += (size_t)patch_rows * (kFrTW * 3);                              // rows after the horizontal pass
     b = (b + 15) / 16 * 16;
-    b += (size_t)(kFrTW * ksx + kFrTH * ksy + 2 * kFrTW + 2 * kFrTH + patch_rows) * 4;   // coefficient rows, bounds, row offsets
+    b += (size_t)(kFrTW * ksx + kFrTH * ksy + 2 * kFrTW + 2 * kFrTH) * 4;   // coefficient rows, bounds
     b += 3 * 256 * 4;                                                    // byte -> normalised float
     return b;
 }
@@ -50,6 +51,18 @@ __device__ __forceinline__ uint32_t clip8(int v) {   // Resample.c: clip8(in) = 
     return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+// the aligned 4-byte word at q; the first / last word of the whole buffer byte by byte: nothing outside the caller's memory
+__device__ __forceinline__ uint32_t frames_word(const uint8_t* q, const uint8_t* lo, const uint8_t* hi) {
+    if (q >= lo && q + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(q));
+    uint32_t v = 0u;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (q + b >= lo && q + b < hi) v |= (uint32_t)__ldg(q + b) << (8 * b);
+    return v;
+}
+
+// KX: taps of the horizontal pass held in registers (>= ksx; 0 = any number, read from shared memory)
+template <int KX>
 __global__ void __launch_bounds__(kFrThreads)
 frames_preprocess_kernel(FrameArgs p) {
     extern __shared__ __align__(16) unsigned char fr_smem[];
@@ -63,13 +76,12 @@ frames_preprocess_kernel(FrameArgs p) {
     int* kys = kxs + kFrTW * p.ksx;
     int* xbs = kys + kFrTH * p.ksy;
     int* ybs = xbs + 2 * kFrTW;
-    int* row_off = ybs + 2 * kFrTH;
-    float* lut = reinterpret_cast<float*>(row_off + p.patch_rows);
+    float* lut = reinterpret_cast<float*>(ybs + 2 * kFrTH);
     __shared__ int ext[4];   // cx0, ncols, ry0, nrows
 
-    for (int i = tid; i < tw * p.ksx; i += kFrThreads) kxs[i] = p.kx[(size_t)x0 * p.ksx + i];
+    for (int i = tid; i < kFrTW * p.ksx; i += kFrThreads) kxs[i] = i < tw * p.ksx ? p.kx[(size_t)x0 * p.ksx + i] : 0;
     for (int i = tid; i < th * p.ksy; i += kFrThreads) kys[i] = p.ky[(size_t)y0 * p.ksy + i];
-    for (int i = tid; i < 2 * tw; i += kFrThreads) xbs[i] = p.xb[2 * x0 + i];
+    for (int i = tid; i < 2 * kFrTW; i += kFrThreads) xbs[i] = i < 2 * tw ? p.xb[2 * x0 + i] : 0;
     for (int i = tid; i < 2 * th; i += kFrThreads) ybs[i] = p.yb[2 * y0 + i];
     for (int i = tid; i < 3 * 256; i += kFrThreads) lut[i] = p.lut[i];
     __syncthreads();
@@ -84,42 +96,57 @@ frames_preprocess_kernel(FrameArgs p) {
     __syncthreads();
     const int cx0 = ext[0], ncols = ext[1], ry0 = ext[2], nrows = ext[3];
 
-    // ---- input patch -> shared memory: one warp per row, 4-byte loads from the enclosing aligned words ----------------
+    // ---- input patch -> shared memory: one warp per row, aligned 4-byte loads shifted so that every row starts at byte 0 --
     const uint8_t* fbase = p.src + (int64_t)n * p.frame_stride;
     for (int r = warp; r < nrows; r += kFrThreads / 32) {
         const uint8_t* g0 = fbase + (int64_t)(ry0 + r) * p.row_stride + (int64_t)cx0 * 3;
         const int o = (int)(reinterpret_cast<uintptr_t>(g0) & 3);
         const uint8_t* wbase = g0 - o;
-        const int nwords = (o + ncols * 3 + 3) >> 2;
+        const int nwords = (ncols * 3 + 3) >> 2;
         uint32_t* dst = reinterpret_cast<uint32_t*>(patch + (size_t)r * p.pitch);
-        for (int w = lane; w < nwords; w += 32) {
-            const uint8_t* q = wbase + 4 * w;
-            uint32_t v;
-            if (q >= p.src && q + 4 <= p.src_end) {
-                v = __ldg(reinterpret_cast<const uint32_t*>(q));
-            } else {   // the first / last word of the whole buffer: byte by byte, nothing outside the caller's memory
-                v = 0u;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (q + b >= p.src && q + b < p.src_end) v |= (uint32_t)__ldg(q + b) << (8 * b);
-            }
-            dst[w] = v;
+        // (every word of the row and the one after it inside the caller's buffer: plain loads, the neighbour by shuffle)
+        const bool inside = wbase >= p.src && wbase + 4 * (nwords + 1) <= p.src_end;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t a = 0u;
+            if (w <= nwords) a = inside ? __ldg(reinterpret_cast<const uint32_t*>(wbase) + w) : frames_word(wbase + 4 * w, p.src, p.src_end);
+            uint32_t b = __shfl_down_sync(0xffffffffu, a, 1);
+            if (lane == 31 && o && w < nwords) b = inside ? __ldg(reinterpret_cast<const uint32_t*>(wbase) + w + 1) : frames_word(wbase + 4 * w + 4, p.src, p.src_end);
+            if (w < nwords) dst[w] = __funnelshift_r(a, b, 8 * o);
         }
-        if (lane == 0) row_off[r] = o;
     }
     __syncthreads();
 
-    // ---- horizontal pass: (patch row, output column, channel) -> byte ---------------------------------------------------
-    for (int i = tid; i < nrows * (kFrTW * 3); i += kFrThreads) {
-        const int r = i / (kFrTW * 3), xc = i - r * (kFrTW * 3);
+    // ---- horizontal pass: (patch row, output column, channel) -> byte.  A thread keeps ONE (column, channel) and its
+    //      coefficients in registers and walks down the rows of its half of the patch --------------------------------------
+    {
+        const int xc = tid % (kFrTW * 3), half = tid / (kFrTW * 3);
         const int x = xc / 3, c = xc - 3 * x;
-        if (x >= tw) continue;
-        const int first = xbs[2 * x] - cx0, cnt = xbs[2 * x + 1];
-        const unsigned char* prow = patch + (size_t)r * p.pitch + row_off[r] + first * 3 + c;
-        const int* k = kxs + x * p.ksx;
-        int acc = 1 << (kFrPrecision - 1);
-        for (int j = 0; j < cnt; ++j) acc += k[j] * (int)prow[3 * j];
-        hbuf[i] = (unsigned char)clip8(acc);
+        if (x < tw) {
+            const int first = xbs[2 * x] - cx0;
+            const unsigned char* pcol = patch + first * 3 + c;
+            if (KX > 0) {
+                int k[KX > 0 ? KX : 1];
+#pragma unroll
+                for (int j = 0; j < KX; ++j) k[j] = j < p.ksx ? kxs[x * p.ksx + j] : 0;   // (zero beyond the tap count)
+                for (int r = half; r < nrows; r += 2) {
+                    const unsigned char* prow = pcol + (size_t)r * p.pitch;
+                    int acc = 1 << (kFrPrecision - 1);
+#pragma unroll
+                    for (int j = 0; j < KX; ++j) acc += k[j] * (int)prow[3 * j];
+                    hbuf[r * (kFrTW * 3) + xc] = (unsigned char)clip8(acc);
+                }
+            } else {
+                const int cnt = xbs[2 * x + 1];
+                const int* k = kxs + x * p.ksx;
+                for (int r = half; r < nrows; r += 2) {
+                    const unsigned char* prow = pcol + (size_t)r * p.pitch;
+                    int acc = 1 << (kFrPrecision - 1);
+                    for (int j = 0; j < cnt; ++j) acc += k[j] * (int)prow[3 * j];
+                    hbuf[r * (kFrTW * 3) + xc] = (unsigned char)clip8(acc);
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -243,8 +270,12 @@ extern "C" int eco_frames_preprocess(const uint8_t* frames, int32_t N, int32_t H
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     const size_t smem = frames_smem_bytes(patch_cols, patch_rows, ksx, ksy);
     if (smem > 200 * 1024) { set_error("down-scaling factor too large for one tile's input patch (%zu bytes of shared memory)", smem); return -8; }
+    void (*kernel)(FrameArgs) = ksx <= 3 ? frames_preprocess_kernel<3> : ksx <= 5 ? frames_preprocess_kernel<5>
+                              : ksx <= 7 ? frames_preprocess_kernel<7> : ksx <= 9 ? frames_preprocess_kernel<9>
+                              : ksx <= 13 ? frames_preprocess_kernel<13> : ksx <= 17 ? frames_preprocess_kernel<17>
+                              : frames_preprocess_kernel<0>;
     if (smem > 48 * 1024) {
-        int rc = check_cuda(cudaFuncSetAttribute(frames_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(smem, frames)");
         if (rc) return rc;
     }
@@ -256,6 +287,6 @@ extern "C" int eco_frames_preprocess(const uint8_t* frames, int32_t N, int32_t H
     p.xb = xbounds_dev; p.kx = kx_dev; p.yb = ybounds_dev; p.ky = ky_dev; p.lut = lut_dev; p.out = out;
     p.patch_cols = patch_cols; p.patch_rows = patch_rows; p.pitch = frames_pitch(patch_cols);
     dim3 grid((unsigned)((Wout + kFrTW - 1) / kFrTW), (unsigned)((Hout + kFrTH - 1) / kFrTH), (unsigned)N);
-    frames_preprocess_kernel<<<grid, kFrThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    kernel<<<grid, kFrThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return check_cuda(cudaGetLastError(), "frames_preprocess_kernel launch");
 }
