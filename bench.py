@@ -541,6 +541,25 @@ def measure_aux(dev):
         out["reference_eager_same_gpu_cfg2"] = {"error": repr(exc)}
     del sets8, zs, sets, outs
     torch.cuda.empty_cache()
+    # (e) frame pre-processing in front of the network (ess/test_video.py:70-78; upstream of the path, BASELINE configs[4]'s
+    #     "1080p frames resized to 512"): uint8 frames on the device -> normalised float32 batch, one kernel
+    try:
+        from ecologysemanticsegmentation_b200 import test_video as tv
+        nf = 64
+        gen = torch.Generator(device="cpu").manual_seed(105)
+        frames = torch.randint(0, 256, (nf, 1080, 1920, 3), dtype=torch.uint8, generator=gen).to(dev)
+        fout = torch.empty((nf, 3, 512, 512), dtype=torch.float32, device=dev)
+        t = timed(lambda: tv.preprocess_frames(frames, (512, 512), out=fout), 10)
+        nbytes = frames.numel() + 4.0 * fout.numel()
+        out["frames_preprocess_1080p_to_512"] = {"frames_per_s": nf / t, "us": t * 1e6, "gb_per_s": nbytes / t / 1e9,
+                                                 "frac_of_hbm_peak": nbytes / t / 1e9 / peak,
+                                                 "bytes_per_frame": nbytes / nf,
+                                                 "what": "64 uint8 1080p frames -> Pillow-exact bilinear resize to 512x512 + ToTensor + Normalize, "
+                                                         "float32 [64,3,512,512], one launch (3 B per input pixel + 12 B per output pixel)"}
+        del frames, fout
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["frames_preprocess_1080p_to_512"] = {"error": repr(exc)[:300]}
     # (d) cfg4's per-GPU shard (BASELINE configs[3]: 432x3x512x512 over 8 GPUs = 54x3x512x512 per GPU), single GPU
     out["composite_cfg4_shard"] = time_cfg4_shard(dev, cstep, peak)
     return out

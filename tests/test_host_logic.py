@@ -150,3 +150,12 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
                 if f.endswith(".py"):
                     assert "torch_port" not in src and "oracle." not in src, f
+
+
+def test_frame_preprocessing_has_no_cpu_fallback():
+    """test_video.preprocess_frames (ess/test_video.py:70-78) is a CUDA kernel: CPU tensors are refused loudly."""
+    import torch
+    from ecologysemanticsegmentation_b200 import _native as nat
+    from ecologysemanticsegmentation_b200 import test_video as tv
+    with pytest.raises(nat.EcoLossError):
+        tv.preprocess_frames(torch.zeros(8, 8, 3, dtype=torch.uint8), (4, 4))
