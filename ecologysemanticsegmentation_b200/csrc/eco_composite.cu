@@ -574,38 +574,6 @@ composite3_grad_packed_kernel(CompGradArgs ga, const double* __restrict__ jac, c
     grad_dispatch_packed<TX, LOGITS, kGThreads>(ga, cf, pc, stage_smem, upstream, false);
 }
 
-template <typename TX, bool LOGITS>
-__global__ void __launch_bounds__(kPThreads, 1)
-composite3_fused_packed_kernel(CompGradArgs ga, const double* __restrict__ scale_dev, const float* __restrict__ upstream,
-                               unsigned int* __restrict__ counter, double* __restrict__ partials,
-                               double* __restrict__ acc_glob, float* __restrict__ losses_out, XchArgs xch) {
-    extern __shared__ __align__(16) char stage_smem[];
-    __shared__ PStatsSmem sm;
-    __shared__ LeafCoef cf[ECO_C3_NLEAF];
-    __shared__ PCoef pc;
-    __shared__ double sl[ECO_C3_NLEAF][ECO_NLOSS];
-    __shared__ double jac_s[ECO_C3_NLEAF][ECO_NLOSS][ECO_NJAC];
-    stats_phase_packed<TX, LOGITS>(ga.a, sm, stage_smem, counter, partials, acc_glob, &xch);
-    __threadfence();
-    cooperative_groups::this_grid().sync();
-    // closed forms, redundantly per CTA (no second grid barrier): one thread per (leaf, loss) row
-    if (threadIdx.x < ECO_C3_NLEAF * ECO_NLOSS) {
-        const int leaf = threadIdx.x / ECO_NLOSS, k = threadIdx.x % ECO_NLOSS;
-        double s[ECO_NSTAT];
-        composite_leaf_sums_ldcg(acc_glob, leaf, s);
-        leaf_closed_form_row(s, 0.0, scale_dev[leaf], k, sl[leaf][k], jac_s[leaf][k]);
-    }
-    __syncthreads();
-    if (threadIdx.x < ECO_C3_NLEAF) cf[threadIdx.x] = make_coef(&jac_s[threadIdx.x][0][0], upstream);
-    if (blockIdx.x == 0 && threadIdx.x >= 32 && threadIdx.x < 32 + ECO_NLOSS) {
-        double v = 0.0;
-        for (int l = 0; l < ECO_C3_NLEAF; ++l) v += sl[l][threadIdx.x - 32];
-        losses_out[threadIdx.x - 32] = (float)v;
-    }
-    __syncthreads();
-    grad_dispatch_packed<TX, LOGITS, kPThreads>(ga, cf, pc, stage_smem, upstream, true);
-}
-
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
@@ -650,9 +618,7 @@ static int ensure_packed_smem() {
     rc = rc ? rc : set_smem_attr(composite3_stats_packed_kernel<TX, true>);                        \
     rc = rc ? rc : set_smem_attr(composite3_stats_packed_kernel<TX, false>);                       \
     rc = rc ? rc : set_smem_attr(composite3_grad_packed_kernel<TX, true>);                         \
-    rc = rc ? rc : set_smem_attr(composite3_grad_packed_kernel<TX, false>);                        \
-    rc = rc ? rc : set_smem_attr(composite3_fused_packed_kernel<TX, true>);                        \
-    rc = rc ? rc : set_smem_attr(composite3_fused_packed_kernel<TX, false>);
+    rc = rc ? rc : set_smem_attr(composite3_grad_packed_kernel<TX, false>);
     ECO_SMEM_ALL(float)
     ECO_SMEM_ALL(__nv_bfloat16)
 #undef ECO_SMEM_ALL
@@ -839,31 +805,21 @@ static int launch_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t H
         return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(g2), dim3(v2::kThreads3), args, smem, st), "composite3_fused_v3_kernel launch");
     }
     if (no_grad) { set_error("ECO_C3_NO_GRAD needs fp32 inputs (or bf16 logits) with 16-byte aligned planes; use eco_composite3_stats + eco_composite3_finalize otherwise"); return -8; }
-    const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && (!g_f32 || c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW)) &&
-                     c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
     CompGradArgs ga{};
-    fill_comp(ga.a, x, g, N, HW, vec);
     ga.gx = gx->ptr; ga.gx_sn = gx->sn; ga.gx_sc = gx->sc;
     double* acc_glob = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 256);
     double* partials = acc_glob + 128;
     if (upstream_prev) { set_error("eco_composite3_step_if_changed needs 16-byte aligned planes"); return -8; }
-    // everything below: first-generation kernels (bf16 probabilities, ragged / unaligned planes), f32 labels only
+    // everything below: the scalar first-generation kernel (bf16 probabilities, ragged / unaligned planes), f32 labels only
     if (!g_f32 || (flags & ECO_C3_UNION_LABELS)) {
         set_error("byte labels / the fused label union need logits with 16-byte aligned planes (H*W %% 16 == 0 for byte labels, %% 8 for bf16 logits, %% 4 otherwise)");
         return -8;
     }
-    if (xch.world > 1 && vec != 4) { set_error("the peer-exchange fused step needs 16-byte aligned planes with H*W %% 4 == 0"); return -8; }
-    const int grid = comp_grid(device, ga.a.units_total, 1, vec == 4 ? kRoleThreads : kCThreads);  // one CTA per SM: co-resident
+    if (xch.world > 1) { set_error("the peer-exchange fused step needs fp32 / bf16 logits or fp32 probabilities with 16-byte aligned planes"); return -8; }
+    // scalar kernel: any alignment, any supported dtype (one thread = one pixel)
+    fill_comp(ga.a, x, g, N, HW, 1);
+    const int grid = comp_grid(device, ga.a.units_total, 1, kCThreads);  // one CTA per SM: co-resident
     if (grid < 0) return -10;
-    if (vec == 4) {
-        rc = ensure_packed_smem();
-        if (rc) return rc;
-        void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out, &xch};
-        const void* fn;
-        if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_packed_kernel<float, true> : (const void*)composite3_fused_packed_kernel<float, false>;
-        else fn = lg ? (const void*)composite3_fused_packed_kernel<__nv_bfloat16, true> : (const void*)composite3_fused_packed_kernel<__nv_bfloat16, false>;
-        return check_cuda(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kPThreads), args, kStageBytes, st), "composite3_fused_packed_kernel launch");
-    }
     void* args[] = {&ga, (void*)&leaf_scale_dev, (void*)&upstream, &counter, &partials, &acc_glob, &losses_out};
     const void* fn;
     if (x->dtype == ECO_F32) fn = lg ? (const void*)composite3_fused_kernel<float, 1, true> : (const void*)composite3_fused_kernel<float, 1, false>;

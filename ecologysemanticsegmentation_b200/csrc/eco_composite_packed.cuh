@@ -1,5 +1,8 @@
-// Packed-fp32x2 (FFMA2/FADD2/FMUL2) implementation of the 3-organ composite kernels for the aligned
-// 128-bit path.  Included by eco_composite.cu after the shared layout / helper definitions.
+// Packed-fp32x2 (FFMA2/FADD2/FMUL2) implementation of the two SEPARATE passes of the 3-organ composite loss for the aligned
+// 128-bit path: composite3_stats_packed_kernel / composite3_grad_packed_kernel (statistics -> all-reduce by NCCL -> gradient,
+// and the autograd path on inputs the one-launch kernel does not serve).  Included by eco_composite.cu after the shared
+// layout / helper definitions.  (The one-launch kernel of this generation was removed in round 2: eco_composite_v3.cuh
+// serves fp32 / bf16 logits and fp32 probabilities, the scalar kernel everything else.)
 //
 // Why this shape (measured on B200, profiles/microbench/pipes.cu): the FMA pipe sustains 128 fp32 lanes
 // /clk/SM with scalar FFMA *or* with FFMA2, but FFMA2 needs half the issue slots, and MUFU (16 lanes/clk/SM)
@@ -133,12 +136,10 @@ __device__ __forceinline__ bool flush_role_acc(f2 (&acc)[kRAcc], double* warp_sl
     return nonbinary;
 }
 
-// In-kernel all-reduce of the 100 sums over NVLink peer memory (sharded fused step).  Every rank owns an
-// exchange buffer mapped into all peers (CUDA IPC): double slots[2 parities][world][128] then u32 flags[world].
-// The last CTA of rank r stores its sums into slot [epoch&1][r] of EVERY rank's buffer, fences system-wide,
-// publishes flag[r] = epoch on every rank, waits until all flags of its own buffer have reached `epoch`, then
-// adds the `world` slots in rank order (identical, deterministic result on every rank).  Parity double-buffering
-// is enough: a rank cannot run two steps ahead because it needs every peer's flag of the step in between.
+// Arguments of the in-kernel all-reduce over NVLink peer memory (the sharded fused step, eco_composite_v3.cuh).  Every rank
+// owns an exchange buffer mapped into all peers (CUDA IPC).  The buffer starts with the slots of the first-generation
+// protocol (double slots[2 parities][world][128], then u32 flags[world]; the kernel that used them was removed in round 2,
+// the layout is kept so that buffers stay interchangeable); the LL rows of the current protocol follow.
 struct XchArgs {
     double* const* peers;  // device array [world] of peer-mapped exchange buffers ([rank] = own)
     int rank, world;
@@ -147,54 +148,7 @@ struct XchArgs {
     unsigned long long timeout_ns;  // v3 kernels: wall-clock limit of one wait on a peer
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
 __host__ __device__ inline size_t xch_flags_offset_doubles(int world) { return (size_t)2 * world * 128; }
-
-// called by all threads of ONE CTA; `mine` = this rank's value of sum `threadIdx.x` (threads < kNAcc)
-__device__ inline double peer_allreduce(const XchArgs& x, double mine, double* bcast /* smem [>= 1] */) {
-    const int par = x.epoch & 1u;
-    if (threadIdx.x < kNAcc) {
-        for (int r = 0; r < x.world; ++r) {
-            double* slot = x.peers[r] + ((size_t)(par * x.world + x.rank)) * 128;
-            slot[threadIdx.x] = mine;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < x.world) {
-        unsigned int* flag = reinterpret_cast<unsigned int*>(x.peers[threadIdx.x] + xch_flags_offset_doubles(x.world)) + x.rank;
-        st_release_sys(flag, x.epoch);
-        const unsigned int* own = reinterpret_cast<const unsigned int*>(x.peers[x.rank] + xch_flags_offset_doubles(x.world)) + threadIdx.x;
-        unsigned int spins = 0;
-        while ((int)(ld_acquire_sys(own) - x.epoch) < 0) {
-            __nanosleep(40);
-            if (++spins > (1u << 26)) {  // seconds: a peer is gone; poison instead of hanging the GPU
-                *x.status = 1u;
-                bcast[0] = __longlong_as_double(0x7ff8000000000000ll);
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    double tot = 0.0;
-    if (threadIdx.x < kNAcc) {
-        const double* own = x.peers[x.rank] + (size_t)(par * x.world) * 128;
-        for (int r = 0; r < x.world; ++r) tot += ld_volatile_f64(own + (size_t)r * 128 + threadIdx.x);
-    }
-    return tot;
-}
 
 struct PStatsSmem {
     double warp_slots[kPWarps][32];
@@ -388,7 +342,7 @@ struct UnitWalker {
 template <typename TX, bool LOGITS>
 __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem& sm, char* stage_smem,
                                                    unsigned int* __restrict__ counter, double* __restrict__ partials,
-                                                   double* __restrict__ acc_out, const XchArgs* xch = nullptr) {
+                                                   double* __restrict__ acc_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int role = warp / kRoleWarps;
     const int rtid = threadIdx.x - role * kRoleThreads;
@@ -531,13 +485,6 @@ __device__ __forceinline__ void stats_phase_packed(const CompArgs& a, PStatsSmem
         __syncthreads();
         double total = 0.0;
         if (threadIdx.x < kNAcc) total = scratch[3 * threadIdx.x] + scratch[3 * threadIdx.x + 1] + scratch[3 * threadIdx.x + 2];
-        if (xch != nullptr && xch->world > 1) {
-            __syncthreads();
-            if (threadIdx.x == 0) sm.corr[0] = 0.0;  // reused as the poison broadcast cell
-            __syncthreads();
-            total = peer_allreduce(*xch, total, sm.corr);
-            if (threadIdx.x < kNAcc) total += sm.corr[0];
-        }
         if (threadIdx.x < kNAcc) acc_out[threadIdx.x] = total;
         if (threadIdx.x == 0) *counter = 0;
     }

@@ -3,7 +3,7 @@
 // composite3_grad_v2_kernel.  Included by eco_composite.cu after eco_composite_packed.cuh; the fused step built from these
 // blocks is composite3_fused_v3_kernel (eco_composite_v3.cuh) -- its predecessor composite3_fused_v2_kernel, which took the
 // linear BCE / focal sums in pass 2 and finished them with a second reduction at the kernel's tail, was removed in round 2
-// (78 -> 72 us at cfg2, one NVLink exchange instead of two).  Other inputs (bf16, probabilities, ragged planes) keep the
+// (78 -> 72 us at cfg2, one NVLink exchange instead of two).  Ragged / unaligned planes and bf16 probabilities keep the
 // first-generation kernels.
 //
 // Design notes (all numbers measured on B200; profiles/microbench/regbw2.cu, profiles/README.md):
@@ -273,45 +273,6 @@ __device__ __forceinline__ bool flush_flat_acc(float (&acc)[F_NACC], double* war
     return nonbinary;
 }
 
-// flat sums -> the shared 100-slot layout of eco_composite.cu.  The SP slots of the real-b leaves hold only the
-// algebraic part n ln2 + sum b / 2 + sum b^2 / 8 and their FL slots are 0: the fused kernel adds the weighted
-// remainder / focal sums of pass 2 to the loss totals.
-__device__ inline double flat_to_layout(const double* S, const double* corr, int idx, double n_blk) {
-    auto sp_of = [&](double sb, double sbb) { return n_blk * kLn2d + 0.5 * sb + 0.125 * sbb; };
-    if (idx == A_N) return n_blk;
-    if (idx < A_GD) return S[F_G + idx - A_G];
-    if (idx < A_CH) return S[F_PAIR + 14 * (idx - A_GD) + 0];
-    if (idx < A_PAIR) {
-        const int c = (idx - A_CH) / 5, k = (idx - A_CH) % 5;
-        switch (k) {
-            case 0: return S[F_X + c];
-            case 1: return S[F_XX + c];
-            case 2: return S[F_GX + c];
-            case 3: return sp_of(S[F_X + c], S[F_XX + c]);
-            default: return 0.0;
-        }
-    }
-    if (idx < A_CORR) {
-        const int p = (idx - A_PAIR) / 21, k = (idx - A_PAIR) % 21;
-        const double* r = S + F_PAIR + 14 * p;
-        const int i = pair_i(p), j = pair_j(p);
-        const int grp = k / 7, kk = k % 7;
-        const double m = r[2 + 2 * grp], mg = r[3 + 2 * grp];
-        const double psum = grp == 0 ? S[F_X + j] : (grp == 1 ? r[1] : r[4]);
-        const double usum = S[F_X + i] + 0.5 * (psum - m);
-        switch (kk) {
-            case 0: return m;
-            case 1: return mg;
-            case 2: return usum;
-            case 3: return r[8 + 2 * grp];
-            case 4: return r[9 + 2 * grp];
-            case 5: return sp_of(usum, r[8 + 2 * grp]);
-            default: return 0.0;
-        }
-    }
-    return corr[idx - A_CORR];   // label-b corrections (non-binary labels only), all from the slow pass
-}
-
 // rare path: exact corrections of the label-b sums of one pixel whose labels are not all 0/1 (double math, shared
 // atomics).  Slots 3L + {0 sum(b^2 - b), 1 softplus, 2 focal} for L = g1, g2, gd01, gd02, gd12 (eco_composite.cu).
 __device__ __noinline__ void label_corrections_v2(float g0, float g1, float g2, double* corr) {
@@ -332,34 +293,6 @@ __device__ __forceinline__ void stats_smem_init(StatsSmem& sm) {
     for (int i = threadIdx.x; i < kCWarps * 64; i += blockDim.x) (&sm.warp_slots[0][0])[i] = 0.0;
     if (threadIdx.x < 15) sm.corr[threadIdx.x] = 0.0;
     if (threadIdx.x == 0) sm.flag = false;
-}
-
-__device__ __forceinline__ void stats_consume(const CompArgs& a, const TileRange& tr, uint32_t stage_base, PipeSmem& ps,
-                                              int k0, StatsSmem& sm) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ntiles = tr.t_hi - tr.t_lo;
-    int kk = ntiles > 0 ? tr.t_lo % tr.tpp : 0;
-    float acc[F_NACC];
-#pragma unroll
-    for (int k = 0; k < F_NACC; ++k) acc[k] = 0.f;
-    int since_flush = 0;
-    bool any_nonbinary = false;
-    const uint32_t my = stage_base + threadIdx.x * 8;
-    for (int k = 0; k < ntiles; ++k) {
-        f2 z[3], g[3];
-        consume_tile(my, ps, k0 + k, lane, z, g);
-        if ((int64_t)kk * kTP + 2 * (int)threadIdx.x < a.HW) {
-            stats_pixel(z[0].x, z[1].x, z[2].x, g[0].x, g[1].x, g[2].x, acc);
-            stats_pixel(z[0].y, z[1].y, z[2].y, g[0].y, g[1].y, g[2].y, acc);
-        }
-        if (++kk == tr.tpp) kk = 0;
-        if (++since_flush == kFlushTiles) {
-            any_nonbinary |= flush_flat_acc(acc, sm.warp_slots[warp], lane);
-            since_flush = 0;
-        }
-    }
-    any_nonbinary |= flush_flat_acc(acc, sm.warp_slots[warp], lane);
-    if (any_nonbinary) sm.flag = true;
 }
 
 constexpr int kMaxGrid = 192;   // CTAs of one cooperative launch (one per SM)
@@ -405,55 +338,6 @@ struct V2Ws {
     unsigned long long tr2[2];
     unsigned long long fix1[2][kFixRep][2 * kNAcc];   // pass-1 sums
 };
-
-// CTA-level tail of pass 1 (all CONSUMER threads): rare slow pass, then this CTA's 100 partial sums go into the
-// integer accumulators and the CTA arrives.  Returns true in the last CTA to arrive.
-__device__ __forceinline__ bool stats_finish(const CompArgs& a, const TileRange& tr, StatsSmem& sm, V2Ws* ws, int par) {
-    csync();
-    if (sm.flag) {
-        // some label is not exactly 0 or 1: exact transcendental corrections for this CTA's tiles (rare)
-        const float* gb = reinterpret_cast<const float*>(a.g);
-        for (int t = tr.t_lo; t < tr.t_hi; ++t) {
-            const int n = t / tr.tpp, kk = t - n * tr.tpp;
-            const int64_t p0 = (int64_t)kk * kTP;
-            for (int e = threadIdx.x; e < kTP && p0 + e < a.HW; e += kCThreads) {
-                const float* gp = gb + n * a.g_sn + p0 + e;
-                const float g0 = gp[0], g1 = gp[a.g_sc], g2 = gp[2 * a.g_sc];
-                if ((g0 != 0.f && g0 != 1.f) || (g1 != 0.f && g1 != 1.f) || (g2 != 0.f && g2 != 1.f))
-                    label_corrections_v2(g0, g1, g2, sm.corr);
-            }
-        }
-        csync();
-    }
-    if (threadIdx.x < 64) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kCWarps; ++w) v += sm.warp_slots[w][threadIdx.x];
-        sm.sums[threadIdx.x] = v;
-    }
-    csync();
-    int64_t npix = 0;
-    {
-        const int64_t last = a.HW - (int64_t)(tr.tpp - 1) * kTP;   // pixels of the (possibly short) last tile of a plane
-        const int ntiles = tr.t_hi - tr.t_lo;
-        const int n_last = ntiles > 0 ? (tr.t_hi / tr.tpp - tr.t_lo / tr.tpp) : 0;   // tiles with k == tpp - 1
-        npix = (int64_t)(ntiles - n_last) * kTP + (int64_t)n_last * last;
-    }
-    ECO_TL(7);
-    if (threadIdx.x < kNAcc) {
-        fix_add(ws->fix1[par][blockIdx.x % kFixRep] + 2 * threadIdx.x, flat_to_layout(sm.sums, sm.corr, threadIdx.x, (double)npix));
-        __threadfence();
-    }
-    csync();
-    ECO_TL(8);
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(&ws->arrive1, 1u);
-        sm.flag = (prev == gridDim.x - 1);
-    }
-    csync();
-    ECO_TL(9);
-    return sm.flag;
-}
 
 // ---------------------------------------------------------------------------------------------
 // pass 2
@@ -530,12 +414,11 @@ __device__ __forceinline__ void leaf_tr(const float4 cw, f2 b, f2 t, f2& sp_acc,
     leaf_tr_fl<POSW>(cw, om, sq, lg, fl_acc);
 }
 
-// dT/db of a U-type leaf at b (a = label); SIG: the BCE term carries gradient; FL: the focal term carries gradient;
-// TR: also accumulate the leaf's weighted softplus-remainder and focal sums
-template <bool SIG, bool FL, bool TR, bool POSW>
-__device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, const float cfl, f2 a, f2 b, f2& sp_acc, f2& fl_acc) {
+// dT/db of a U-type leaf at b (a = label); SIG: the BCE term carries gradient; FL: the focal term carries gradient
+template <bool SIG, bool FL>
+__device__ __forceinline__ f2 leaf_g(const float4 ca, const float cfl, f2 a, f2 b) {
     f2 t;
-    if (SIG || TR) t = mul2(b, b);
+    if (SIG) t = mul2(b, b);
     const f2 k = fma2(a, splat(ca.y), splat(ca.x));   // c_Sab a + c0'
     f2 r;
     if (SIG) {
@@ -547,17 +430,12 @@ __device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, const flo
     } else {
         r = fma2(b, splat(ca.z), k);
     }
-    if (TR && !FL) leaf_tr<POSW>(cw, b, t, sp_acc, fl_acc);
     if (FL) {
         const f2 om = fma2(b, splat(-1.0f), splat(1.0f));
         const f2 sq = make_float2(sqrt_approx(om.x), sqrt_approx(om.y));
         const f2 be = add2(b, splat(kEps));
         const f2 lg = make_float2(lg2_approx(be.x), lg2_approx(be.y));
         const f2 w15 = mul2(om, sq);
-        if (TR) {   // (the focal-gradient variants always run with POSW = false: cw.w is the plain leaf scale)
-            leaf_tr_sp(cw, t, sp_acc);
-            leaf_tr_fl<false>(cw, om, sq, lg, fl_acc);
-        }
         // + c_FL d/db[-(1-b)^1.5 log(b+eps)] = c_FL (1.5 ln2 sqrt(1-b) lg2(b+eps) - (1-b)^1.5 / (b+eps))
         const f2 rc = make_float2(rcp_approx(be.x), rcp_approx(be.y));
         const f2 v = fma2(mul2(sq, splat(1.5f * kLn2)), lg, neg2(mul2(w15, rc)));
@@ -567,11 +445,11 @@ __device__ __forceinline__ f2 leaf_g(const float4 ca, const float4 cw, const flo
 }
 
 // the whole gradient of one pixel pair: x = probabilities, g = labels, diffs[p] = x_i - x_j
-template <bool SIG, bool FL, bool TR, bool POSW>
+template <bool SIG, bool FL>
 __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)[3], const f2 (&diffs)[3],
-                                                 const Coef2& c2, f2 (&gx)[3], f2& sp_acc, f2& fl_acc) {
+                                                 const Coef2& c2, f2 (&gx)[3]) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) gx[c] = leaf_g<SIG, FL, TR, POSW>(c2.ua[c], c2.uw[c], c2.ufl[c], g[c], x[c], sp_acc, fl_acc);
+    for (int c = 0; c < 3; ++c) gx[c] = leaf_g<SIG, FL>(c2.ua[c], c2.ufl[c], g[c], x[c]);
     f2 hh[2];
     hh[0] = fma2(x[0], splat(-0.5f), splat(0.5f));
     hh[1] = fma2(x[1], splat(-0.5f), splat(0.5f));
@@ -586,9 +464,9 @@ __device__ __forceinline__ void pixel_pair_grad2(const f2 (&x)[3], const f2 (&g)
         const f2 u1 = fma2(xj, h, xi);
         const f2 u2 = fma2(d, h, xi);
         const f2 u3 = fma2(q, h, xi);
-        const f2 G1 = leaf_g<SIG, FL, TR, POSW>(c2.ua[3 + 3 * p + 0], c2.uw[3 + 3 * p + 0], c2.ufl[3 + 3 * p + 0], gi, u1, sp_acc, fl_acc);
-        const f2 G2 = leaf_g<SIG, FL, TR, POSW>(c2.ua[3 + 3 * p + 1], c2.uw[3 + 3 * p + 1], c2.ufl[3 + 3 * p + 1], gi, u2, sp_acc, fl_acc);
-        const f2 G3 = leaf_g<SIG, FL, TR, POSW>(c2.ua[3 + 3 * p + 2], c2.uw[3 + 3 * p + 2], c2.ufl[3 + 3 * p + 2], gi, u3, sp_acc, fl_acc);
+        const f2 G1 = leaf_g<SIG, FL>(c2.ua[3 + 3 * p + 0], c2.ufl[3 + 3 * p + 0], gi, u1);
+        const f2 G2 = leaf_g<SIG, FL>(c2.ua[3 + 3 * p + 1], c2.ufl[3 + 3 * p + 1], gi, u2);
+        const f2 G3 = leaf_g<SIG, FL>(c2.ua[3 + 3 * p + 2], c2.ufl[3 + 3 * p + 2], gi, u3);
         const float2 k1 = c2.ia[3 * p + 0], k2 = c2.ia[3 * p + 1], k3 = c2.ia[3 * p + 2];
         const f2 A1 = fma2(gj, splat(k1.y), splat(k1.x));
         const f2 A2 = fma2(gd, splat(k2.y), splat(k2.x));
@@ -630,26 +508,6 @@ __device__ __noinline__ float3 tie_pixel_grad(float z0, float z1, float z2, floa
     return make_float3(gx[0] * ((1.0f - x[0]) * x[0]), gx[1] * ((1.0f - x[1]) * x[1]), gx[2] * ((1.0f - x[2]) * x[2]));
 }
 
-// per-thread state of the two linear sums: fp32 partials folded into float64 every kFlushTiles accumulated tiles
-struct TrState {
-    f2 sp_acc, fl_acc;
-    int since_flush;
-    double* tot;   // this thread's two float64 totals: in SHARED memory (touched once per kFlushTiles tiles; pass 2 has no
-                   // register to spare under the 96-register cap of 17 warps)
-    __device__ __forceinline__ void init(double* tot_smem) {
-        sp_acc = splat(0.f); fl_acc = splat(0.f); since_flush = 0;
-        tot = tot_smem;
-        if (tot) tot[0] = tot[1] = 0.0;
-    }
-    __device__ __forceinline__ void fold() {
-        tot[0] += (double)(sp_acc.x + sp_acc.y);
-        tot[1] += (double)(fl_acc.x + fl_acc.y);
-        sp_acc = splat(0.f); fl_acc = splat(0.f);
-        since_flush = 0;
-    }
-    __device__ __forceinline__ void tile_done() { if (++since_flush == kFlushTiles) fold(); }
-};
-
 // only the linear sums of one pixel pair, in the leaf order of pixel_pair_grad2
 template <bool POSW>
 __device__ __forceinline__ void pixel_pair_tr(const f2 (&x)[3], const Coef2& c2, f2& sp_acc, f2& fl_acc) {
@@ -670,23 +528,21 @@ __device__ __forceinline__ void pixel_pair_tr(const f2 (&x)[3], const Coef2& c2,
     }
 }
 
-// consumer side of pass 2 over this CTA's tiles [k_first, k_first + k_count) (in walking order).  With TR the linear
-// sums are accumulated into `st`.
-template <bool SIG, bool FL, bool TR, bool POSW>
-__device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileRange& tr, bool reverse, uint32_t stage_base,
-                                             PipeSmem& ps, int k0, int k_first, int k_count, const Coef2& c2,
-                                             const LeafCoef* cf, TrState& st) {
+// consumer side of pass 2 over this CTA's tiles, forwards (the stand-alone gradient kernel)
+template <bool SIG, bool FL>
+__device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileRange& tr, uint32_t stage_base, PipeSmem& ps,
+                                             const Coef2& c2, const LeafCoef* cf) {
     const CompArgs& a = ga.a;
     float* __restrict__ ob = reinterpret_cast<float*>(ga.gx);
     const int lane = threadIdx.x & 31;
-    if (k_count <= 0) return;
-    int t = reverse ? tr.t_hi - 1 - k_first : tr.t_lo + k_first;
-    int n = t / tr.tpp, kk = t - n * tr.tpp;
+    const int ntiles = tr.t_hi - tr.t_lo;
+    if (ntiles <= 0) return;
+    int n = tr.t_lo / tr.tpp, kk = tr.t_lo - n * tr.tpp;
     const uint32_t my = stage_base + threadIdx.x * 8;
     const int pix = 2 * (int)threadIdx.x;
-    for (int k = k_first; k < k_first + k_count; ++k) {
+    for (int k = 0; k < ntiles; ++k) {
         f2 z[3], g[3];
-        consume_tile(my, ps, k0 + k, lane, z, g);
+        consume_tile(my, ps, k, lane, z, g);
         const int64_t p0 = (int64_t)kk * kTP;
         if (p0 + pix < a.HW) {
             f2 x[3], gx[3], diffs[3];
@@ -694,7 +550,7 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
             for (int c = 0; c < 3; ++c) x[c] = sigmoid_fast2(z[c]);
 #pragma unroll
             for (int p = 0; p < 3; ++p) diffs[p] = add2(x[pair_i(p)], neg2(x[pair_j(p)]));
-            pixel_pair_grad2<SIG, FL, TR, POSW>(x, g, diffs, c2, gx, st.sp_acc, st.fl_acc);
+            pixel_pair_grad2<SIG, FL>(x, g, diffs, c2, gx);
             f2 o[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) o[c] = mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));
@@ -714,27 +570,7 @@ __device__ __forceinline__ void grad_consume(const CompGradArgs& ga, const TileR
 #pragma unroll
             for (int c = 0; c < 3; ++c) stg_stream_f2(op + c * ga.gx_sc, o[c]);
         }
-        if (reverse) { if (--kk < 0) { kk = tr.tpp - 1; --n; } }
-        else { if (++kk == tr.tpp) { kk = 0; ++n; } }
-        if (TR) st.tile_done();
-    }
-}
-
-// block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0/1) and on
-// whether the focal weights ride on 1 - b (posw; only the variants that form the linear sums without the focal gradient)
-template <bool TR>
-__device__ __forceinline__ void grad_consume_dispatch(bool need_sig, bool need_fl, bool posw, const CompGradArgs& ga,
-                                                      const TileRange& tr, bool reverse, uint32_t stage_base, PipeSmem& ps, int k0,
-                                                      int k_first, int k_count, const Coef2& c2, const LeafCoef* cf, TrState& st) {
-    if (need_fl) {
-        if (need_sig) grad_consume<true, true, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-        else grad_consume<false, true, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-    } else if (TR && posw) {
-        if (need_sig) grad_consume<true, false, TR, true>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-        else grad_consume<false, false, TR, true>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-    } else {
-        if (need_sig) grad_consume<true, false, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
-        else grad_consume<false, false, TR, false>(ga, tr, reverse, stage_base, ps, k0, k_first, k_count, c2, cf, st);
+        if (++kk == tr.tpp) { kk = 0; ++n; }
     }
 }
 
@@ -754,9 +590,15 @@ composite3_grad_v2_kernel(CompGradArgs ga, const double* __restrict__ jac, const
     if (threadIdx.x >= kCThreads) {
         if (threadIdx.x == kCThreads) produce_tiles(ga.a, tr, false, sbase, ps, 0);
     } else {
-        TrState st;
-        st.init(nullptr);
-        grad_consume_dispatch<false>(upstream[1] != 0.f, upstream[2] != 0.f, false, ga, tr, false, sbase, ps, 0, 0, tr.t_hi - tr.t_lo, c2, cf, st);
+        // block-uniform dispatch on which of the 7 outputs carry gradient (train_multiclass.py:145 weights them 0 / 1)
+        const bool need_sig = upstream[1] != 0.f, need_fl = upstream[2] != 0.f;
+        if (need_fl) {
+            if (need_sig) grad_consume<true, true>(ga, tr, sbase, ps, c2, cf);
+            else grad_consume<false, true>(ga, tr, sbase, ps, c2, cf);
+        } else {
+            if (need_sig) grad_consume<true, false>(ga, tr, sbase, ps, c2, cf);
+            else grad_consume<false, false>(ga, tr, sbase, ps, c2, cf);
+        }
     }
 }
 

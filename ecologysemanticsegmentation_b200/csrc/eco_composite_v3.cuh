@@ -449,7 +449,6 @@ __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const Tile
     int t = tr.t_hi - 1;
     int n = t / tr.tpp, kk = t - n * tr.tpp;
     const int pix = 2 * (int)threadIdx.x;
-    f2 sp_dummy = splat(0.f), fl_dummy = splat(0.f);
     for (int k = 0; k < ntiles; ++k) {
         f2 z[3], g[3];
         consume_tile3<TX, TG>(stage_base, ps, k0 + k, lane, uni, z, g);
@@ -460,7 +459,7 @@ __device__ __forceinline__ void grad_consume3(const CompGradArgs& ga, const Tile
             for (int c = 0; c < 3; ++c) x[c] = PROB ? z[c] : sigmoid_fast2(z[c]);
 #pragma unroll
             for (int p = 0; p < 3; ++p) diffs[p] = add2(x[pair_i(p)], neg2(x[pair_j(p)]));
-            pixel_pair_grad2<SIG, FL, false, false>(x, g, diffs, c2, gx, sp_dummy, fl_dummy);
+            pixel_pair_grad2<SIG, FL>(x, g, diffs, c2, gx);
             f2 o[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) o[c] = PROB ? gx[c] : mul2(gx[c], mul2(x[c], fma2(x[c], splat(-1.0f), splat(1.0f))));

@@ -38,12 +38,9 @@ __device__ __forceinline__ void mc_flush(f2 (&acc)[M_NACC], double* warp_slot /*
     for (int k = 0; k < M_NACC; ++k) acc[k] = splat(0.f);
 }
 
-// gradient-side leaf: dT/db at b = x_c with a = g_c (see leaf_g of the composite kernel; no linear sums here)
+// gradient-side leaf: dT/db at b = x_c with a = g_c (leaf_g of the composite kernel)
 template <bool SIG, bool FL>
-__device__ __forceinline__ f2 mc_leaf_g(const float4 ca, const float cfl, f2 a, f2 b) {
-    f2 dummy_sp = splat(0.f), dummy_fl = splat(0.f);
-    return leaf_g<SIG, FL, false, false>(ca, make_float4(0.f, 0.f, 0.f, 0.f), cfl, a, b, dummy_sp, dummy_fl);
-}
+__device__ __forceinline__ f2 mc_leaf_g(const float4 ca, const float cfl, f2 a, f2 b) { return leaf_g<SIG, FL>(ca, cfl, a, b); }
 
 template <bool SIG, bool FL>
 __device__ __forceinline__ void mc_grad_consume(const CompGradArgs& ga, const TileRange& tr, uint32_t stage_base, McSmem& ms,
