@@ -89,6 +89,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         return;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ECO_TL(0);
     // the workspace is double buffered by step parity (integer accumulators in fix1, arrival counter in tr2): step k works
     // in buffer k & 1 while CTA 0 clears buffer (k + 1) & 1, so there is no re-arming phase at the end of a step
     const int par = (int)(__ldcg(&ws->step) & 1u);
@@ -134,6 +135,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         }
         mc_flush(acc, ms.warp_slots[warp], lane);
     }
+    ECO_TL(1);
     csync();
     if (threadIdx.x < 32) {
         double v = 0.0;
@@ -159,6 +161,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         __threadfence();
     }
     csync();
+    ECO_TL(2);
     if (threadIdx.x == 0) {
         atomicAdd(&ws->tr2[par], 1ull);
         unsigned long long seen;
@@ -168,6 +171,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         } while (seen < gridDim.x);
     }
     csync();
+    ECO_TL(3);
     if (threadIdx.x < kMcSums) ms.acc[threadIdx.x] = fix_get(ws->fix1[par][0] + 2 * threadIdx.x, 2 * kNAcc);
     csync();
 
@@ -201,6 +205,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         losses_out[threadIdx.x - 32] = (float)(ms.sl[0][threadIdx.x - 32] + ms.sl[1][threadIdx.x - 32] + ms.sl[2][threadIdx.x - 32]);
     csync();
 
+    ECO_TL(4);
     // ---- pass 2: d(sum_k upstream_k loss_k)/d logits, walking this CTA's tiles backwards --------------------------------
     const bool need_sig = ms.up[1] != 0.f, need_fl = ms.up[2] != 0.f;
     if (need_fl) {
@@ -210,6 +215,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
         if (need_sig) mc_grad_consume<true, false>(ga, tr, sbase, ms, ntiles);
         else mc_grad_consume<false, false>(ga, tr, sbase, ms, ntiles);
     }
+    ECO_TL(5);
     if (blockIdx.x == 0 && threadIdx.x == 0) ws->step = (unsigned int)par + 1u;   // every CTA read `step` before it arrived
 }
 
