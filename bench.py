@@ -342,6 +342,25 @@ def measure_aux(dev):
         gbs = 8.0 * n * c * s * s / t / 1e9
         out["dice_eval_cfg3_" + label] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
                                           "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 8}
+    # the sequential model's test (ess/test_multiclass_sequential_densenetloss.py:62,66,97-99): sigmoid -> prediction un-union
+    # -> soft Dice, fused into the one scoring read, against the same result from the stand-alone steps
+    from ecologysemanticsegmentation_b200 import subsets_union
+    t = timed(lambda: ops.dice_counts_ex(z, g, None, ununion_preds=True), 20)
+    pbuf = torch.empty_like(z)
+
+    def unfused():
+        torch.sigmoid(z, out=pbuf)
+        subsets_union.return_union_sets_descending_order(pbuf, reverse=True)
+        ops.dice_counts_ex(pbuf, g, None, inputs_are_probs=True)
+    t_unfused = timed(unfused, 10)
+    del pbuf
+    gbs = 8.0 * n * c * s * s / t / 1e9
+    out["dice_eval_cfg3_soft_ununion"] = {"gpixel_per_s": n * s * s / t / 1e9, "us": t * 1e6, "gb_per_s": gbs,
+                                          "frac_of_hbm_peak": gbs / peak, "bytes_per_element": 8,
+                                          "us_unfused": t_unfused * 1e6,
+                                          "what": "sigmoid -> |p1 - p2| un-union -> soft Dice in ONE read (the channel-1 CTAs read "
+                                                  "plane 2 as well: L2 hits); unfused = torch.sigmoid + the in-place un-union kernel "
+                                                  "+ scoring of the probabilities"}
     # the threshold beam search of ess/test_multiclass.py:64-77 (np.arange(0.8, 0.99, 0.01): 19 thresholds) from ONE read
     import numpy as np
     thr19 = torch.tensor(np.arange(0.8, 0.99, step=0.01), dtype=torch.float32, device=dev)

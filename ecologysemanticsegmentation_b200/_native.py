@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libecoloss.so")
 
 ECO_F32, ECO_BF16, ECO_U8 = 0, 1, 2
+EVAL_PROBS, EVAL_UNUNION = 1, 2   # flag word of eco_dice_counts (ECO_EVAL_*)
 NSTAT, NLOSS, NJAC = 8, 7, 7
 C3_NLEAF, C3_NACC = 21, 100
 FLAG_A_LOGIT, FLAG_B_LOGIT, FLAG_NEED_BG = 1, 2, 4

@@ -21,6 +21,7 @@ struct EvalArgs {
     int32_t tiles_per_cta;
     int32_t n_thr;
     int32_t probs;  // inputs already are probabilities
+    int32_t unun;   // soft Dice only: the prediction un-union is applied at load (see dice_counts_kernel)
 };
 
 // ws: counters u32[C] (padded to 256 B) | int64 partial counts [C][kEvMaxCtas][NT][2] ... laid out
@@ -55,8 +56,15 @@ __device__ __forceinline__ void publish_intersections(int c, int C, int n_thr, l
 constexpr int kPackFlushElems = 32768;
 constexpr float kThrEps = 4e-6f;
 
-template <typename TZ, typename TL, int VEC, int NT>
-__global__ void __launch_bounds__(kEvThreads, kEvCtasPerSm)
+//
+// UNUN (soft Dice only, NT == 0): the prediction un-union of the sequential model's test
+// (ess/test_multiclass_sequential_densenetloss.py:66 -> ess/utils/subsets_union.py:21-27, reverse=True with
+// exclude_indices=[0]: for idx = C-2 .. 1, out[:, idx] = |out[:, idx] - out[:, idx + 1]| in place, i.e. the recursion
+// p'_c = |p_c - p'_{c+1}|, p'_{C-1} = p_{C-1}) is taken in registers at load: a CTA of channel c in 1 .. C-2 also reads
+// the planes c+1 .. C-1 of its elements (L2 hits: the CTAs of those channels stream the same lines) instead of a
+// separate in-place sweep over the predictions.  Channels 0 and C-1 run the plain code.
+template <typename TZ, typename TL, int VEC, int NT, bool UNUN = false>
+__global__ void __launch_bounds__(kEvThreads, UNUN ? kEvCtasPerSm - 1 : kEvCtasPerSm)   // (the running p' costs 16 registers)
 dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned int* __restrict__ counters,
                    long long* __restrict__ partials, long long* __restrict__ counts_out,
                    double* __restrict__ soft_out, double* __restrict__ thr_inter_out) {
@@ -65,6 +73,8 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
     const int c = blockIdx.y;
     const TZ* __restrict__ zbase = reinterpret_cast<const TZ*>(p.z) + (int64_t)c * p.z_sc;
     const TL* __restrict__ lbase = reinterpret_cast<const TL*>(p.l) + (int64_t)c * p.l_sc;
+    static_assert(!UNUN || NT == 0, "the un-union is fused for the soft Dice only");
+    const bool uu = UNUN && c >= 1 && c <= p.C - 2;
 
     float thr[NTA];
 #pragma unroll
@@ -107,6 +117,25 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
                 }
             }
         }
+        float below[UNUN ? kEvUnroll : 1][VEC];   // p'_{c+1} of this thread's elements
+        if (UNUN && uu) {
+            for (int k = p.C - 1; k > c; --k) {
+                const TZ* zk = zp + (int64_t)(k - c) * p.z_sc;
+#pragma unroll
+                for (int u = 0; u < kEvUnroll; ++u) {
+                    if (!ok[u]) continue;
+                    const int64_t e = e0 + (int64_t)u * kEvThreads * VEC;
+                    float t4[VEC];
+                    if constexpr (VEC == 4) Vec4<TZ>::load(zk + e, reinterpret_cast<float(&)[4]>(t4));
+                    else t4[0] = Vec4<TZ>::load1(zk + e);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float pk = p.probs ? t4[v] : sigmoid_fast(t4[v]);
+                        below[UNUN ? u : 0][v] = (k == p.C - 1) ? pk : fabsf(pk - below[UNUN ? u : 0][v]);
+                    }
+                }
+            }
+        }
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int u = 0; u < kEvUnroll; ++u) {
@@ -125,6 +154,7 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
                         if (near) pr = sigmoid_exact(zv[u][v]);  // rare: the strict '>' must see ATen's bits
                     }
                 }
+                if (UNUN && uu) pr = fabsf(pr - below[UNUN ? u : 0][v]);
                 const float lab = lv[u][v];
                 const int li = lab == 1.0f ? 1 : 0;
                 const unsigned int inc = 1u + ((unsigned int)li << 16);
@@ -726,7 +756,13 @@ static bool ev_aligned(const EcoView* v, int64_t HW) {
 template <int NT>
 static void launch_nt(const EvalArgs& p, int zd, int ld, int vec, dim3 grid, cudaStream_t st, const float* thr,
                       unsigned int* counters, long long* partials, long long* counts_out, double* soft_out, double* inter) {
-#define ECO_EV(TZ, TL, V) dice_counts_kernel<TZ, TL, V, NT><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out, inter)
+#define ECO_EV(TZ, TL, V)                                                                                                       \
+    do {                                                                                                                        \
+        if constexpr (NT == 0) {                                                                                                \
+            if (p.unun) { dice_counts_kernel<TZ, TL, V, 0, true><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out, inter); break; } \
+        }                                                                                                                       \
+        dice_counts_kernel<TZ, TL, V, NT><<<grid, kEvThreads, 0, st>>>(p, thr, counters, partials, counts_out, soft_out, inter); \
+    } while (0)
     if (ld == ECO_U8) {
         if (vec == 4) { if (zd == ECO_F32) ECO_EV(float, uint8_t, 4); else ECO_EV(__nv_bfloat16, uint8_t, 4); }
         else { if (zd == ECO_F32) ECO_EV(float, uint8_t, 1); else ECO_EV(__nv_bfloat16, uint8_t, 1); }
@@ -804,13 +840,19 @@ extern "C" int eco_dice_counts_ex(const EcoView* logits, const EcoView* labels, 
         set_error("dice_counts: logits must be f32/bf16, labels f32/bf16/u8");
         return -4;
     }
+    if (logits_are_probs & ~(ECO_EVAL_PROBS | ECO_EVAL_UNUNION)) { set_error("dice_counts: unknown flag bits 0x%x", logits_are_probs); return -4; }
+    if ((logits_are_probs & ECO_EVAL_UNUNION) && n_thr > 0) {
+        set_error("dice_counts: the prediction un-union is fused for the soft Dice only (n_thr = 0); un-union in place first (eco_union_sets)");
+        return -4;
+    }
     if (!ws || ws_bytes < eco_dice_ws_bytes(C, n_thr) || !counts_out || !soft_out) { set_error("workspace too small or null output"); return -5; }
     DeviceGuard guard(device);
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     EvalArgs p{};
     p.z = logits->ptr; p.l = labels->ptr;
     p.z_sn = logits->sn; p.z_sc = logits->sc; p.l_sn = labels->sn; p.l_sc = labels->sc;
-    p.N = N; p.C = C; p.HW = HW; p.n_thr = n_thr; p.probs = logits_are_probs;
+    p.N = N; p.C = C; p.HW = HW; p.n_thr = n_thr; p.probs = (logits_are_probs & ECO_EVAL_PROBS) ? 1 : 0;
+    p.unun = ((logits_are_probs & ECO_EVAL_UNUNION) && C >= 3) ? 1 : 0;
     const int vec = (ev_aligned(logits, HW) && ev_aligned(labels, HW)) ? 4 : 1;
     const int tile = kEvThreads * vec * kEvUnroll;
     p.tiles_per_plane = (int32_t)((HW + tile - 1) / tile);

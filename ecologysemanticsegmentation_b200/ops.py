@@ -168,10 +168,12 @@ def dice_counts(logits, labels, thresholds=None, inputs_are_probs=False, out_cou
 
 
 def dice_counts_ex(logits, labels, thresholds=None, inputs_are_probs=False, out_counts=None, out_soft=None, out_inter=None,
-                   want_inter=True):
+                   want_inter=True, ununion_preds=False):
     """``dice_counts`` plus inter float64 [T,C] = sum out*lab per threshold with the REAL label values (the integer
     intersection for 0/1 labels, an exact second pass over a class that holds anything else): what the reference's
-    thresholded Dice (test_multiclass.py:80) needs when the dataset resized its masks."""
+    thresholded Dice (test_multiclass.py:80) needs when the dataset resized its masks.
+    ``ununion_preds`` (soft Dice only): score ``return_union_sets_descending_order(sigmoid(logits), reverse=True)``
+    (test_multiclass_sequential_densenetloss.py:66) -- the un-union happens in registers at load, ``logits`` stay as they are."""
     nat.require_cuda(logits, labels)
     if logits.shape != labels.shape or logits.dim() != 4:
         raise ValueError("dice_counts expects two [N,C,H,W] tensors of equal shape")
@@ -211,7 +213,8 @@ def dice_counts_ex(logits, labels, thresholds=None, inputs_are_probs=False, out_
                 raise ValueError("out_inter must be a contiguous float64 tensor of T*C elements")
     vz, vl = nat.view_of(logits, z_sn, z_sc), nat.view_of(labels, l_sn, l_sc, allow_u8=True)
     rc = L.eco_dice_counts_ex(C.byref(vz), C.byref(vl), n, c, h * w, thresholds.data_ptr() if nthr else None, nthr,
-                              int(inputs_are_probs), ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),
+                              (nat.EVAL_PROBS if inputs_are_probs else 0) | (nat.EVAL_UNUNION if ununion_preds else 0),
+                              ws.data_ptr(), ws.numel(), counts.data_ptr(), soft.data_ptr(),
                               inter.data_ptr() if inter is not None else None, _dev(logits),
                               nat.current_stream_ptr(logits.device))
     nat.check(rc, "eco_dice_counts")

@@ -27,7 +27,7 @@ def get_env_variable(name, default_value):
 ORGANS = [o for o in get_env_variable("ORGANS", "whole_body").split(",")]
 
 
-def score_batch(logits, labels, threshold=None, *, group=None, inputs_are_probs=False, return_counts=False):
+def score_batch(logits, labels, threshold=None, *, group=None, inputs_are_probs=False, return_counts=False, ununion=False):
     """Per-class Dice of one batch, float32 [C] on the device.
 
     threshold=None: the live path of the reference -- soft Dice ``(2 sum p*lab + eps) / (sum (p + lab^2) + eps)``.
@@ -45,7 +45,10 @@ def score_batch(logits, labels, threshold=None, *, group=None, inputs_are_probs=
             many = hasattr(threshold, "__len__")
             vals = list(threshold) if many else [threshold]
             thr_t = torch.tensor([float(v) for v in vals], dtype=torch.float32, device=logits.device)
-    counts, soft, inter = ops.dice_counts_ex(logits, labels, thr_t, inputs_are_probs=inputs_are_probs)
+    if ununion and thr_t is not None:
+        raise ValueError("ununion=True is the soft-Dice path of the sequential test; un-union in place "
+                         "(subsets_union.return_union_sets_descending_order) before a thresholded score")
+    counts, soft, inter = ops.dice_counts_ex(logits, labels, thr_t, inputs_are_probs=inputs_are_probs, ununion_preds=ununion)
     counts = dist_.allreduce_sums_(counts, group)
     soft = dist_.allreduce_sums_(soft, group)
     if inter is not None:
@@ -143,7 +146,7 @@ def score_stream(batches, threshold=None, *, group=None):
 
 
 def test(net, dataloader, models_dir="models/vgg", results_dir="test_results/", batch_size=1, saved_epoch=-1,
-         single_model=False, threshold=None):
+         single_model=False, threshold=None, ununion=False):
     """Same call signature and return value as the reference ``test()`` (test_multiclass.py:30): a float32
     CPU tensor [C] with the mean per-batch Dice per organ, or None when the results directory of this epoch
     already exists.  ``net`` maps images to logits; the sigmoid is fused into the scoring kernel.  Image dumping
@@ -163,7 +166,7 @@ def test(net, dataloader, models_dir="models/vgg", results_dir="test_results/", 
             test_images, test_labels, image_ids = batch
             test_images = test_images.cuda()
             test_labels = test_labels.cuda()
-            acc.update(score_batch(net(test_images), test_labels, threshold))
+            acc.update(score_batch(net(test_images), test_labels, threshold, ununion=ununion))
     dice_loss_val = acc.mean().cpu()
     print("Epoch %d: \n\t Test Dice Score: " % saved_epoch, dice_loss_val)
     print('Finished Testing')

@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(up, hup, sizeof(hup), cudaMemcpyHostToDevice));
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     using namespace eco::v2;
-    CK(cudaFuncSetAttribute(composite3_fused_v3_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage3<float, float>::kSmem));
+    CK(cudaFuncSetAttribute(composite3_fused_v3_kernel<float, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Stage3<float, float>::kSmem));
     V3Ws* ws3; CK(cudaMalloc(&ws3, sizeof(V3Ws))); CK(cudaMemset(ws3, 0, sizeof(V3Ws)));
     unsigned int* status; CK(cudaMalloc(&status, 4)); CK(cudaMemset(status, 0, 4));
     auto launch = [&](int k) {
@@ -58,8 +58,8 @@ int main(int argc, char** argv) {
         const double* sd = scale_dev; const float* u = up; unsigned int flags = 0;
         const float* prev = nullptr;
         void* args[] = {&ga, (void*)&sd, (void*)&u, &ws3, &losses, &flags, &xch, (void*)&prev};
-        if (argc > 2) composite3_fused_v3_kernel<float, float><<<sms, kThreads3, Stage3<float, float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch, nullptr);
-        else CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float, float>, dim3(sms), dim3(kThreads3), args, Stage3<float, float>::kSmem, nullptr));
+        if (argc > 2) composite3_fused_v3_kernel<float, float, false><<<sms, kThreads3, Stage3<float, float>::kSmem>>>(ga, sd, u, ws3, losses, flags, xch, nullptr);
+        else CK(cudaLaunchCooperativeKernel((const void*)composite3_fused_v3_kernel<float, float, false>, dim3(sms), dim3(kThreads3), args, Stage3<float, float>::kSmem, nullptr));
     };
     for (int i = 0; i < 5; ++i) launch(i % NSETS);
     CK(cudaDeviceSynchronize());
@@ -77,13 +77,13 @@ int main(int argc, char** argv) {
     static unsigned long long tl[1024 * 16];
     CK(cudaMemcpyFromSymbol(tl, g_timeline, sizeof(tl)));
     unsigned long long t0 = ~0ull; for (int b = 0; b < sms; ++b) t0 = tl[b * 16] < t0 ? tl[b * 16] : t0;
-    const int order[14] = {0, 8, 1, 14, 15, 2, 3, 13, 12, 4, 5, 9, 10, 6};
-    const char* nm[16] = {"start", "pass1 loop end", "stats_finish end", "sums received", "coef ready", "pass2 loop end", "cta0 end", "", "lin start", "lin loop end", "lin arrived", "", "closed forms done", "layout done", "flush done", "sums in L2"};
-    for (int oi = 0; oi < 14; ++oi) {
+    const int order[15] = {0, 8, 1, 14, 15, 2, 7, 3, 13, 12, 4, 5, 9, 10, 6};
+    const char* nm[16] = {"start", "pass1 loop end", "stats_finish end", "sums received", "coef ready", "pass2 loop end", "cta0 end", "extra lin tiles done", "lin start", "lin loop end", "lin arrived", "", "closed forms done", "layout done", "flush done", "sums in L2"};
+    for (int oi = 0; oi < 15; ++oi) {
         const int sl = order[oi];
         double mn = 1e30, mxv = 0, av = 0; int cnt = 0;
         for (int b = 0; b < sms; ++b) { if (tl[b * 16 + sl] < t0) continue; const double v = (double)(tl[b * 16 + sl] - t0) * 1e-3; mn = fmin(mn, v); mxv = fmax(mxv, v); av += v; ++cnt; }
-        printf("  timeline %-18s min %7.2f  avg %7.2f  max %7.2f us  (%d CTAs)\n", nm[sl], mn, av / (cnt ? cnt : 1), mxv, cnt);
+        printf("  timeline %-22s min %7.2f  avg %7.2f  max %7.2f us  (%d CTAs)\n", nm[sl], mn, av / (cnt ? cnt : 1), mxv, cnt);
     }
     return 0;
 }

@@ -260,7 +260,15 @@ int eco_xch_free(void* ptr, int device);
  * soft_out:   float64[C][3] = (sum p*lab, sum p, sum lab^2) with p = sigmoid(z), the un-thresholded live path.
  * Both additive across shards.  thresholds: float32[n_thr] device (n_thr may be 0); counts_out is then
  * int64[n_thr][C][3] -- one read of logits+labels serves every threshold of the beam search (:64-77).
+ * `logits_are_probs` is a flag word: ECO_EVAL_PROBS = the inputs already are probabilities (no sigmoid);
+ * ECO_EVAL_UNUNION (soft Dice only, n_thr = 0; refused with -4 otherwise) = the prediction un-union of the sequential
+ * model's test, ess/test_multiclass_sequential_densenetloss.py:66 -> ess/utils/subsets_union.py:21-27
+ * (`return_union_sets_descending_order(out, reverse=True)`, exclude_indices=[0]: p_c <- |p_c - p_{c+1}| for
+ * c = C-2 .. 1, in that order), taken in registers at load instead of a separate in-place sweep (eco_union_sets);
+ * the predictions themselves are left untouched.
  * ------------------------------------------------------------------------------------------ */
+#define ECO_EVAL_PROBS 1
+#define ECO_EVAL_UNUNION 2
 int64_t eco_dice_ws_bytes(int32_t C, int32_t n_thr);
 int eco_dice_counts(const EcoView* logits, const EcoView* labels, int32_t N, int32_t C, int64_t HW,
                     const float* thresholds, int32_t n_thr, int32_t logits_are_probs, void* ws, int64_t ws_bytes,

@@ -47,6 +47,12 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc < 0 and b"empty" in L.eco_last_error()
     rc = L.eco_dice_counts(ctypes.byref(v), ctypes.byref(v), 1, 1, 16, None, 25, 0, None, 0, None, None, 0, None)
     assert rc < 0 and b"n_thr" in L.eco_last_error()
+    # flag word of the scoring call: unknown bits, and the fused prediction un-union together with thresholds
+    thr = (ctypes.c_float * 1)(0.8)
+    rc = L.eco_dice_counts(ctypes.byref(v), ctypes.byref(v), 1, 3, 16, None, 0, 8, None, 0, None, None, 0, None)
+    assert rc < 0 and b"flag" in L.eco_last_error()
+    rc = L.eco_dice_counts(ctypes.byref(v), ctypes.byref(v), 1, 3, 16, thr, 1, _native.EVAL_UNUNION, None, 0, None, None, 0, None)
+    assert rc < 0 and b"un-union" in L.eco_last_error()
 
 
 def test_new_entry_points_validate_arguments_without_gpu():

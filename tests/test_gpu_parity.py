@@ -193,3 +193,88 @@ def test_thresholded_dice_with_fractional_labels_matches_reference(nthr):
     counts, _ = ops.dice_counts(z, lab, torch.tensor(thrs, dtype=torch.float32, device="cuda"))
     c = counts.cpu().numpy()
     assert (c[:, 1, 2] == -1).all() and (c[:, 0, 2] >= 0).all() and (c[:, 2, 2] >= 0).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# the sequential model's test: sigmoid -> prediction un-union -> soft Dice in ONE read
+# (ess/test_multiclass_sequential_densenetloss.py:62,66,97-99)
+# ----------------------------------------------------------------------------------------------
+def _ununion_reference(zc, lc, probs=False):
+    """The reference's own sequence on the same device: F.sigmoid, the in-place un-union, then dice_loss's sums per class
+    (float64 here so that the comparison is about the per-element values, not the summation order)."""
+    from oracle import torch_port as tp
+    out = zc.float().clone() if probs else torch.sigmoid(zc.float())
+    out = tp.union_sets_descending(out, reverse=True).double()
+    lab = lc.double()
+    C = lab.shape[1]
+    sums = np.array([[float((out[:, c] * lab[:, c]).sum()), float(out[:, c].sum()), float((lab[:, c] ** 2).sum())] for c in range(C)])
+    dice = torch.stack([-tp.pair_dice(out[:, c:c + 1].float(), lc[:, c:c + 1].float(), background_weight=0) for c in range(C)])
+    return sums, dice
+
+
+@pytest.mark.parametrize("labels_dtype", [torch.float32, torch.uint8])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 3, 17, 19), (2, 4, 32, 32), (2, 5, 9, 7), (3, 2, 16, 16), (2, 1, 16, 16),
+                                   (8, 3, 256, 256)])
+def test_sequential_test_ununion_fused_into_soft_dice(shape, labels_dtype):
+    from ecologysemanticsegmentation_b200 import ops, test_multiclass_sequential_densenetloss as seq
+    torch.manual_seed(11)
+    z = (torch.randn(shape) * 2).cuda()
+    lab = (torch.rand(shape) > 0.6).to(labels_dtype).cuda()
+    keep = z.clone()
+    _, soft, _ = ops.dice_counts_ex(z, lab, None, ununion_preds=True)
+    assert torch.equal(z, keep)                                     # the predictions are not rewritten
+    ref_sums, ref_dice = _ununion_reference(z, lab)
+    np.testing.assert_allclose(soft.cpu().numpy(), ref_sums, rtol=2e-6, atol=1e-9)
+    d = seq.score_batch(z, lab)
+    np.testing.assert_allclose(d.cpu().numpy(), ref_dice.cpu().numpy(), rtol=1e-5)
+    # ... and it is the same thing as un-unioning in place first (the stand-alone kernel) and scoring the probabilities
+    from ecologysemanticsegmentation_b200 import subsets_union
+    pr = subsets_union.return_union_sets_descending_order(torch.sigmoid(z), reverse=True)
+    _, soft2, _ = ops.dice_counts_ex(pr, lab, None, inputs_are_probs=True)
+    np.testing.assert_allclose(soft.cpu().numpy(), soft2.cpu().numpy(), rtol=2e-6, atol=1e-9)
+
+
+def test_sequential_test_ununion_on_probabilities_and_bf16():
+    from ecologysemanticsegmentation_b200 import ops
+    torch.manual_seed(12)
+    p = torch.rand(3, 4, 24, 24).cuda()
+    lab = (torch.rand(3, 4, 24, 24) > 0.5).float().cuda()
+    _, soft, _ = ops.dice_counts_ex(p, lab, None, inputs_are_probs=True, ununion_preds=True)
+    ref_sums, _ = _ununion_reference(p, lab, probs=True)
+    np.testing.assert_allclose(soft.cpu().numpy(), ref_sums, rtol=2e-6, atol=1e-9)
+    zb = (torch.randn(2, 3, 32, 32) * 2).cuda().bfloat16()
+    labb = (torch.rand(2, 3, 32, 32) > 0.5).float().cuda()
+    _, softb, _ = ops.dice_counts_ex(zb, labb, None, ununion_preds=True)
+    ref_b, _ = _ununion_reference(zb, labb)                          # the oracle on the widened bf16 logits
+    np.testing.assert_allclose(softb.cpu().numpy(), ref_b, rtol=2e-6, atol=1e-9)
+
+
+def test_sequential_test_ununion_refuses_thresholds():
+    from ecologysemanticsegmentation_b200 import ops, test_multiclass
+    from ecologysemanticsegmentation_b200._native import EcoLossError
+    z = torch.randn(2, 3, 16, 16).cuda()
+    lab = (torch.rand(2, 3, 16, 16) > 0.5).float().cuda()
+    thr = torch.tensor([0.8], dtype=torch.float32, device="cuda")
+    with pytest.raises(EcoLossError):
+        ops.dice_counts_ex(z, lab, thr, ununion_preds=True)
+    with pytest.raises(ValueError):
+        test_multiclass.score_batch(z, lab, 0.8, ununion=True)
+
+
+def test_sequential_test_function_matches_reference_loop(tmp_path):
+    """test() of the sequential module against the reference's batch loop (:50-99, :137-140 mean of per-batch Dice)."""
+    from ecologysemanticsegmentation_b200 import test_multiclass_sequential_densenetloss as seq
+    from oracle import torch_port as tp
+    torch.manual_seed(13)
+    batches = [(torch.randn(2, 3, 32, 32), (torch.rand(2, 3, 32, 32) > 0.5).float(), [0, 1]) for _ in range(3)]
+
+    class Net(torch.nn.Module):
+        def forward(self, x):
+            return x * 1.5
+    got = seq.test(Net(), batches, results_dir=str(tmp_path / "r"), saved_epoch=3)
+    acc = torch.zeros(3, dtype=torch.float64)
+    for x, lab, _ in batches:
+        out = tp.union_sets_descending(torch.sigmoid(x.cuda() * 1.5), reverse=True)
+        acc += torch.stack([-tp.pair_dice(out[:, c:c + 1], lab.cuda()[:, c:c + 1], background_weight=0) for c in range(3)]).double().cpu()
+    np.testing.assert_allclose(got.numpy(), (acc / 3).float().numpy(), rtol=1e-5)
+    assert seq.test(Net(), batches, results_dir=str(tmp_path / "r"), saved_epoch=3) is None   # "Test already done"
