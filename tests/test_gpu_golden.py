@@ -282,3 +282,16 @@ def test_sequential_variant_losses_fn_vs_reference_outputs():
     assert_grad_close(gr.cpu(), G["seq_c1_grad"], what="sequential C=1")
     with pytest.raises(ValueError):
         seq.losses_fn(_c("p")[:, :1], _c("g_iid")[:, :1], True)
+
+
+def test_sequential_test_scoring_vs_reference_outputs():
+    """ess/test_multiclass_sequential_densenetloss.py:62,66,97-99 -- the fused sigmoid -> un-union -> soft Dice read against
+    outputs of the reference's own functions (tests/golden/make_golden_seqtest.py), 1e-5 relative (CPU vs CUDA sigmoid)."""
+    from ecologysemanticsegmentation_b200 import test_multiclass_sequential_densenetloss as seq
+    S = np.load(os.path.join(HERE, "golden", "golden_seqtest.npz"))
+    for tag in ("c3", "c4", "c2"):
+        z, lab = torch.from_numpy(S[f"{tag}_z"]).cuda(), torch.from_numpy(S[f"{tag}_lab"]).cuda()
+        d = seq.score_batch(z, lab)
+        np.testing.assert_allclose(d.cpu().numpy(), S[f"{tag}_dice"], rtol=1e-5)
+        d8 = seq.score_batch(z, lab.to(torch.uint8))
+        assert torch.equal(d8, d)

@@ -185,3 +185,17 @@ def test_masks_u8_known_answers():
     m = oc.masks_u8(out)
     assert set(np.unique(m).tolist()) <= {0, 255}
     assert int((m == 255).sum()) == int(G["eval_counts_0.8"][:, 1].sum())   # |out| counts of the golden file
+
+
+def test_sequential_test_scoring_against_golden():
+    """ess/test_multiclass_sequential_densenetloss.py:62,66,97-99 (sigmoid -> prediction un-union -> per-class soft Dice): the
+    oracle's restatement against outputs of the reference's own functions (tests/golden/make_golden_seqtest.py)."""
+    import os
+    from oracle import torch_port as tp
+    S = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_seqtest.npz"))
+    for tag in ("c3", "c4", "c2"):
+        z, lab = torch.from_numpy(S[f"{tag}_z"]), torch.from_numpy(S[f"{tag}_lab"])
+        out = tp.union_sets_descending(torch.sigmoid(z), reverse=True)
+        assert np.array_equal(out.numpy(), S[f"{tag}_out"])
+        dice = [-float(tp.pair_dice(out[:, c:c + 1], lab[:, c:c + 1], background_weight=0)) for c in range(lab.shape[1])]
+        np.testing.assert_allclose(dice, S[f"{tag}_dice"], rtol=1e-7)
