@@ -550,6 +550,62 @@ def measure_aux(dev):
         del graph
     except Exception as exc:
         out["dropin_unchanged_train_loop_cfg2_graphed"] = {"error": repr(exc)[:300]}
+    # (b3) the call the reference's train() REALLY makes (ess/train_multiclass.py:134,139-141,145,147: composite_set_theory is
+    #      hard-wired to False there): F.sigmoid -> the plain 3-organ losses_fn on the probabilities -> weighted sum -> backward,
+    #      with nothing changed but the import; one launch of the plain fused step on probabilities (+ the backward's
+    #      "only if changed" check) against the three pair-leaf launches the same call took before
+    try:
+        from ecologysemanticsegmentation_b200 import train_multiclass as tmod
+        zg = sets[0][0].clone().requires_grad_(True)
+        gg = sets[0][1]
+
+        def live_step():
+            outputs = torch.sigmoid(zg)
+            ce, bce, fl, dice, gdice, tw, fd = tmod.losses_fn(outputs, gg, composite_set_theory=False, background_weight=0,
+                                                              early_stopped=False)
+            loss = 1.0 * fd + 1.0 * bce + 1.0 * (gdice + tw)
+            loss.backward()
+
+        def graphed_us():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    zg.grad = None
+                    live_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            zg.grad = None
+            with torch.cuda.graph(graph, stream=side):
+                live_step()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(100):
+                graph.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            del graph
+            return ev0.elapsed_time(ev1) / 100 * 1e3
+
+        us_fast = graphed_us()
+        grad_fast = zg.grad.clone()
+        ops.PLAIN_FAST_PATH = False
+        try:
+            us_three = graphed_us()
+        finally:
+            ops.PLAIN_FAST_PATH = True
+        err = float((grad_fast - zg.grad).abs().max() / zg.grad.abs().max())
+        out["dropin_live_train_loop_plain_cfg2_shape_graphed"] = {
+            "gpixel_per_s": n * s * s / (us_fast * 1e-6) / 1e9, "us": us_fast, "us_three_launch_path": us_three,
+            "grad_vs_three_launch_path_maxnorm": err, "launch": "one CUDA graph per step",
+            "what": "F.sigmoid(z) -> train_multiclass.losses_fn(probabilities, g, composite_set_theory=False) -> weighted sum -> "
+                    "backward, 54x3x256x256: torch's sigmoid forward / backward around ONE launch of the plain fused step on "
+                    "probabilities; before: statistics + closed forms + gradient launches of the pair-leaf kernels"}
+    except Exception as exc:
+        out["dropin_live_train_loop_plain_cfg2_shape_graphed"] = {"error": repr(exc)[:300]}
     # (c) the reference's own eager ops on THIS GPU (the like-for-like 'before'): same step, cfg2, oracle port on cuda
     try:
         t = timed(lambda: cpu_reference_step(sets[0][0], sets[0][1], w), 3)

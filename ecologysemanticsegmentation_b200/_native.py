@@ -78,6 +78,7 @@ SIGNATURES = {
     "eco_composite3_grad": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _OUT, C.c_int, _vp]),
     "eco_composite3_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
     "eco_multiclass3_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i64, C.c_double, _vp, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
+    "eco_multiclass3_step": (C.c_int, [_VIEW, _VIEW, _i32, _i64, C.c_double, _vp, _vp, _u32, _vp, _i64, _vp, _OUT, C.c_int, _vp]),
     "eco_composite3_fused_sharded": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _OUT, _vp, _i32, _i32,
                                                _u32, C.c_int, _vp]),
     "eco_composite3_step": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _u32, _vp, _vp, _vp, _i64, _vp, _OUT, C.POINTER(EcoPeerExchange),

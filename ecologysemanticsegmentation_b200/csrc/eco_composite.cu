@@ -622,7 +622,8 @@ static int ensure_packed_smem() {
     ECO_SMEM_ALL(float)
     ECO_SMEM_ALL(__nv_bfloat16)
 #undef ECO_SMEM_ALL
-    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2)");
+    rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::multiclass3_fused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, multiclass v2 probs)");
     rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_grad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes), "cudaFuncSetAttribute(smem, grad v2)");
 #define ECO_V3_ATTR(TX, TG, PR) rc = rc ? rc : check_cuda(cudaFuncSetAttribute(v2::composite3_fused_v3_kernel<TX, TG, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::Stage3<TX, TG>::kSmem), "cudaFuncSetAttribute(smem, fused v3)")
     ECO_V3_ATTR(float, float, false); ECO_V3_ATTR(float, uint8_t, false); ECO_V3_ATTR(__nv_bfloat16, float, false); ECO_V3_ATTR(__nv_bfloat16, uint8_t, false);
@@ -901,12 +902,13 @@ extern "C" int eco_xch_poll_status(void* ws, int64_t ws_bytes, uint32_t* status_
     return 0;
 }
 
-extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
-                                     const float* upstream, void* ws, int64_t ws_bytes, float* losses_out,
-                                     const EcoOut* gx, int device, void* stream) {
+extern "C" int eco_multiclass3_step(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
+                                    const float* upstream, const float* upstream_prev, uint32_t flags, void* ws,
+                                    int64_t ws_bytes, float* losses_out, const EcoOut* gx, int device, void* stream) {
     int rc = check_comp(x, g, N, HW);
     if (rc) return rc;
-    if ((rc = need_f32_labels(g, "eco_multiclass3_fused"))) return rc;
+    if ((rc = need_f32_labels(g, "eco_multiclass3_step"))) return rc;
+    if (flags & ~(uint32_t)ECO_C3_PROBS) { set_error("eco_multiclass3_step: unknown flag bits 0x%x", flags); return -4; }
     if (!upstream || !losses_out || !gx || !gx->ptr) { set_error("null upstream/output"); return -5; }
     if (!ws || ws_bytes < eco_composite3_ws_bytes()) { set_error("workspace too small"); return -5; }
     if (gx->dtype != x->dtype) { set_error("gx dtype must match x"); return -7; }
@@ -915,7 +917,7 @@ extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t
     const int vec = (c_aligned(x->ptr, x->sn, x->sc, x->dtype, HW) && c_aligned(g->ptr, g->sn, g->sc, g->dtype, HW) &&
                      c_aligned(gx->ptr, gx->sn, gx->sc, gx->dtype, HW)) ? 4 : 1;
     if (!v2_eligible(x, 1, vec, N, HW)) {
-        set_error("eco_multiclass3_fused serves fp32 logits with 16-byte aligned planes (H*W %% 4 == 0); use eco_pair_* otherwise");
+        set_error("eco_multiclass3_step serves fp32 logits / probabilities with 16-byte aligned planes (H*W %% 4 == 0); use eco_pair_* otherwise");
         return -8;
     }
     CompGradArgs ga{};
@@ -926,10 +928,18 @@ extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t
     const int grid = v2_grid(device, N, HW);
     if (grid < 0) return -10;
     v2::V2Ws* ws2 = reinterpret_cast<v2::V2Ws*>(reinterpret_cast<char*>(ws) + kWsV2Offset);
-    void* args[] = {&ga, &leaf_scale, (void*)&upstream, &ws2, &losses_out};
-    return check_cuda(cudaLaunchCooperativeKernel((const void*)v2::multiclass3_fused_v2_kernel, dim3(grid), dim3(v2::kThreads), args,
-                                                  v2::kSmemBytes, reinterpret_cast<cudaStream_t>(stream)),
+    void* args[] = {&ga, &leaf_scale, (void*)&upstream, &ws2, &losses_out, (void*)&upstream_prev};
+    const void* kernel = (flags & ECO_C3_PROBS) ? (const void*)v2::multiclass3_fused_v2_kernel<true>
+                                                : (const void*)v2::multiclass3_fused_v2_kernel<false>;
+    return check_cuda(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(v2::kThreads), args, v2::kSmemBytes,
+                                                  reinterpret_cast<cudaStream_t>(stream)),
                       "multiclass3_fused_v2_kernel launch");
+}
+
+extern "C" int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
+                                     const float* upstream, void* ws, int64_t ws_bytes, float* losses_out,
+                                     const EcoOut* gx, int device, void* stream) {
+    return eco_multiclass3_step(x, g, N, HW, leaf_scale, upstream, nullptr, 0u, ws, ws_bytes, losses_out, gx, device, stream);
 }
 
 // ---- peer exchange buffers (CUDA IPC).  The one place the library allocates: IPC needs a cudaMalloc base pointer. ----

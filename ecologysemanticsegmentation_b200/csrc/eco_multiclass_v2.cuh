@@ -42,7 +42,9 @@ __device__ __forceinline__ void mc_flush(f2 (&acc)[M_NACC], double* warp_slot /*
 template <bool SIG, bool FL>
 __device__ __forceinline__ f2 mc_leaf_g(const float4 ca, const float cfl, f2 a, f2 b) { return leaf_g<SIG, FL>(ca, cfl, a, b); }
 
-template <bool SIG, bool FL>
+// PROB: the inputs already are probabilities (the reference's own call order, F.sigmoid at ess/train_multiclass.py:134
+// before losses_fn) and the gradient is taken w.r.t. them; torch's sigmoid backward carries it on to the logits
+template <bool SIG, bool FL, bool PROB>
 __device__ __forceinline__ void mc_grad_consume(const CompGradArgs& ga, const TileRange& tr, uint32_t stage_base, McSmem& ms,
                                                 int k0) {
     const CompArgs& a = ga.a;
@@ -61,20 +63,29 @@ __device__ __forceinline__ void mc_grad_consume(const CompGradArgs& ga, const Ti
             float* op = ob + n * ga.gx_sn + p0 + pix;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const f2 x = sigmoid_fast2(z[c]);
+                const f2 x = PROB ? z[c] : sigmoid_fast2(z[c]);
                 const f2 G = mc_leaf_g<SIG, FL>(ms.ua[c], ms.ufl[c], g[c], x);
-                stg_stream_f2(op + c * ga.gx_sc, mul2(G, mul2(x, fma2(x, splat(-1.0f), splat(1.0f)))));
+                stg_stream_f2(op + c * ga.gx_sc, PROB ? G : mul2(G, mul2(x, fma2(x, splat(-1.0f), splat(1.0f)))));
             }
         }
         if (--kk < 0) { kk = tr.tpp - 1; --n; }
     }
 }
 
+// upstream_prev != nullptr: the "only if changed" form of the drop-in autograd path -- the outputs already hold the step for
+// the weights `upstream_prev`; if `upstream` is the same vector the whole grid leaves before it touches anything.
+template <bool PROB>
 __global__ void __launch_bounds__(kThreads, 1)
 multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restrict__ upstream, V2Ws* __restrict__ ws,
-                            float* __restrict__ losses_out) {
+                            float* __restrict__ losses_out, const float* __restrict__ upstream_prev) {
     extern __shared__ __align__(128) char stage_smem[];
     __shared__ McSmem ms;
+    if (upstream_prev) {
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < ECO_NLOSS; ++k) same = same && (__float_as_uint(upstream[k]) == __float_as_uint(upstream_prev[k]));
+        if (same) return;
+    }
     for (int i = threadIdx.x; i < kCWarps * 32; i += kThreads) (&ms.warp_slots[0][0])[i] = 0.0;
     pipe_init(ms.ps);
     const CompArgs& a = ga.a;
@@ -114,7 +125,7 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     f2* ac = &acc[M_PER * c];
-                    const f2 x = sigmoid_fast2(z[c]);
+                    const f2 x = PROB ? z[c] : sigmoid_fast2(z[c]);
                     const f2 t = mul2(x, x);
                     ac[M_G] = add2(ac[M_G], g[c]);
                     ac[M_X] = add2(ac[M_X], x);
@@ -209,11 +220,11 @@ multiclass3_fused_v2_kernel(CompGradArgs ga, double scale, const float* __restri
     // ---- pass 2: d(sum_k upstream_k loss_k)/d logits, walking this CTA's tiles backwards --------------------------------
     const bool need_sig = ms.up[1] != 0.f, need_fl = ms.up[2] != 0.f;
     if (need_fl) {
-        if (need_sig) mc_grad_consume<true, true>(ga, tr, sbase, ms, ntiles);
-        else mc_grad_consume<false, true>(ga, tr, sbase, ms, ntiles);
+        if (need_sig) mc_grad_consume<true, true, PROB>(ga, tr, sbase, ms, ntiles);
+        else mc_grad_consume<false, true, PROB>(ga, tr, sbase, ms, ntiles);
     } else {
-        if (need_sig) mc_grad_consume<true, false>(ga, tr, sbase, ms, ntiles);
-        else mc_grad_consume<false, false>(ga, tr, sbase, ms, ntiles);
+        if (need_sig) mc_grad_consume<true, false, PROB>(ga, tr, sbase, ms, ntiles);
+        else mc_grad_consume<false, false, PROB>(ga, tr, sbase, ms, ntiles);
     }
     ECO_TL(5);
     if (blockIdx.x == 0 && threadIdx.x == 0) ws->step = (unsigned int)par + 1u;   // every CTA read `step` before it arrived

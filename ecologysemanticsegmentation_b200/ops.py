@@ -309,23 +309,64 @@ class PairLeaves(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b, background_weight, scale, flags, group, shape):
         c = a.shape[1]
+        ctx.set_materialize_grads(False)
+        ctx.fast = (PLAIN_FAST_PATH and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0]
+                    and _plain3_dropin_ok(a, b, background_weight, flags, group, shape))
+        if ctx.fast:
+            # The live call of the reference's training loop (train_multiclass.py:139-141 with three organs: labels in the
+            # gt slot, predictions in the pred slot): ONE launch of the fused plain step with the upstream weights anticipated
+            # from the previous backward; the backward only confirms them (see Composite3).
+            dev = b.device
+            used = _anticipated_upstream.get(("plain", dev.index))
+            if used is None:
+                used = _zero_upstream(dev)
+            probs = not (flags & nat.FLAG_B_LOGIT)
+            losses, gb = multiclass3_fused(b.detach(), a.detach(), scale, used, probs=probs)
+            ctx.save_for_backward(a, b, losses, gb)
+            ctx.holds, ctx.returned, ctx.scale, ctx.probs = used, False, float(scale), probs
+            return tuple(losses.clone().unbind(0))   # (the saved `losses` buffer is rewritten by the backward's launch)
         sums = pair_stats(a.detach(), b.detach(), flags | (nat.FLAG_NEED_BG if background_weight != 0 else 0), shape)
         sums = dist_.allreduce_sums_(sums, group)
         _, total, jac = pair_finalize(sums, background_weight, [scale] * c, shape)
         ctx.save_for_backward(a, b, jac)
         ctx.flags, ctx.shape = flags, shape
-        ctx.set_materialize_grads(False)
         return tuple(total.unbind(0))
 
     @staticmethod
     def backward(ctx, *grads):
-        a, b, jac = ctx.saved_tensors
         want_a, want_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (want_a or want_b) or all(g is None for g in grads):
             return None, None, None, None, None, None, None
+        if ctx.fast:
+            a, b, losses, gb = ctx.saved_tensors
+            up = _stack_upstream(grads, b)
+            _anticipated_upstream[("plain", b.device.index)] = up
+            if ctx.returned:   # a second backward through the same graph: autograd may own the first buffer by now
+                _, gb = multiclass3_fused(b.detach(), a.detach(), ctx.scale, up, probs=ctx.probs)
+                return None, gb, None, None, None, None, None
+            multiclass3_fused(b.detach(), a.detach(), ctx.scale, up, out=gb, probs=ctx.probs, upstream_prev=ctx.holds,
+                              losses=losses)
+            ctx.holds, ctx.returned = up, True
+            return None, gb, None, None, None, None, None
+        a, b, jac = ctx.saved_tensors
         up = _stack_upstream(grads, a)
         ga, gb = pair_grad(a.detach(), b.detach(), ctx.flags, jac, up, want_a, want_b, ctx.shape)
         return ga, gb, None, None, None, None, None
+
+
+PLAIN_FAST_PATH = True   # (switch for measurements: False sends the plain 3-organ call through the three pair-leaf launches)
+
+
+def _plain3_dropin_ok(a, b, background_weight, flags, group, shape):
+    """Calls the one-launch plain 3-organ step serves: three channels, labels (a) and fp32 predictions (b: probabilities, or
+    logits with FLAG_B_LOGIT) contiguous with 16-byte aligned planes, the default leaf shape, no background term, one GPU."""
+    if group is not None or shape is not None or background_weight != 0 or (flags & ~nat.FLAG_B_LOGIT):
+        return False
+    if b.dim() != 4 or b.shape[1] != 3 or a.shape != b.shape or b.dtype != torch.float32 or a.dtype != torch.float32:
+        return False
+    hw = b.shape[2] * b.shape[3]
+    return (hw % 4 == 0 and a.is_contiguous() and b.is_contiguous() and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+            and b.shape[0] * hw <= 2 ** 31)
 
 
 # Anticipated upstream weights of the drop-in composite path, per device: the float32 [7] vector dT/dloss_k that the LAST
@@ -465,10 +506,12 @@ def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None, shape=Non
     return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group, shape)
 
 
-def multiclass3_fused(x, g, leaf_scale, upstream, out=None):
+def multiclass3_fused(x, g, leaf_scale, upstream, out=None, probs=False, upstream_prev=None, losses=None):
     """ONE cooperative launch for the plain 3-organ multi-class loss (train_multiclass.py:253-274, C == 3): losses of
     the three (g_c, sigmoid(x_c)) leaves summed over channels, each times ``leaf_scale``, and the gradient of
-    sum_k upstream[k] * loss_k w.r.t. the LOGITS x.  Returns (losses f32 [7], grad)."""
+    sum_k upstream[k] * loss_k w.r.t. the LOGITS x.  Returns (losses f32 [7], grad).
+    ``probs``: x already are probabilities (F.sigmoid at train_multiclass.py:134 ran before), gradient w.r.t. them.
+    ``upstream_prev`` (+ ``out`` / ``losses`` holding that step): only recompute if the weights differ from it."""
     nat.require_cuda(x, g, upstream)
     if x.shape != g.shape or x.dim() != 4 or x.shape[1] != 3:
         raise ValueError(f"multiclass3 expects two [N,3,H,W] tensors, got {tuple(x.shape)} and {tuple(g.shape)}")
@@ -481,14 +524,18 @@ def multiclass3_fused(x, g, leaf_scale, upstream, out=None):
     n, c, h, w = x.shape
     L = nat.lib()
     ws = nat.workspace("mc3", L.eco_composite3_ws_bytes(), x.device)
-    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
+    if upstream_prev is not None and (out is None or losses is None):
+        raise ValueError("upstream_prev needs the `out` and `losses` buffers of the step it describes")
+    if losses is None:
+        losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=x.device)
     gx = out if out is not None else torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
     vx, vg = nat.view_of(x, x_sn, x_sc), nat.view_of(g, g_sn, g_sc)
     og = nat.out_of(gx, c * h * w, h * w)
-    rc = L.eco_multiclass3_fused(C.byref(vx), C.byref(vg), n, h * w, float(leaf_scale), upstream.data_ptr(),
-                                 ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og), _dev(x),
-                                 nat.current_stream_ptr(x.device))
-    nat.check(rc, "eco_multiclass3_fused")
+    rc = L.eco_multiclass3_step(C.byref(vx), C.byref(vg), n, h * w, float(leaf_scale), upstream.data_ptr(),
+                                upstream_prev.data_ptr() if upstream_prev is not None else None,
+                                nat.C3_PROBS if probs else 0, ws.data_ptr(), ws.numel(), losses.data_ptr(), C.byref(og),
+                                _dev(x), nat.current_stream_ptr(x.device))
+    nat.check(rc, "eco_multiclass3_step")
     return losses, gx
 
 

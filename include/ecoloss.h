@@ -183,6 +183,16 @@ int eco_composite3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t 
 int eco_multiclass3_fused(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
                           const float* upstream, void* ws, int64_t ws_bytes, float* losses_out, const EcoOut* gx,
                           int device, void* stream);
+/* General form of the call above (which is this one with flags = 0 and upstream_prev = NULL):
+ *   - flags & ECO_C3_PROBS: x holds probabilities instead of logits and gx = d(...)/d probabilities -- the reference's own
+ *     call order, `outputs = F.sigmoid(net(x))` at ess/train_multiclass.py:134 BEFORE `losses_fn(outputs, labels,
+ *     composite_set_theory=False, ...)` at :139-141, so an unchanged training loop runs on this kernel;
+ *   - upstream_prev (device float32[7] or NULL): "only if changed" -- losses_out / gx already hold the step for the weights
+ *     upstream_prev; the kernel compares the two vectors on the device and returns at once when they are equal (the
+ *     backward half of the drop-in autograd path: the forward anticipated the weights of ess/train_multiclass.py:145). */
+int eco_multiclass3_step(const EcoView* x, const EcoView* g, int32_t N, int64_t HW, double leaf_scale,
+                         const float* upstream, const float* upstream_prev, uint32_t flags, void* ws, int64_t ws_bytes,
+                         float* losses_out, const EcoOut* gx, int device, void* stream);
 
 /* Sharded flavour of eco_composite3_fused: one process per GPU, each with its batch shard; the 100 sums are
  * all-reduced INSIDE the kernel over NVLink peer memory (P2P stores + release/acquire flags), so the whole

@@ -334,3 +334,72 @@ def test_dropin_unchanged_train_loop_probabilities_and_no_grad():
         np.random.seed(0)
         val = lc.losses_fn(z, g, True, from_logits=True)
     assert_losses_close([float(v) for v in val], rl, tol=TOL, what="drop-in no_grad from logits")
+
+
+def _oracle_plain(z, g, up, fn="losses_train_multiclass"):
+    from oracle import torch_port as tp
+    zr = z.clone().requires_grad_(True)
+    ref = getattr(tp, fn)(torch.sigmoid(zr), g, False, 0, False)
+    sum(w * l for w, l in zip(up, ref) if w).backward()
+    return [float(v) for v in ref], zr.grad
+
+
+def test_dropin_live_train_loop_plain_three_organs_one_launch():
+    """The call the reference's train() really makes (ess/train_multiclass.py:134,139-141,145,147): outputs = F.sigmoid(net(x));
+    losses_fn(outputs, labels, composite_set_theory=False, ...) with three organs; weighted sum; backward -- on ONE launch of
+    the plain fused step on probabilities with anticipated weights.  First call, hit, miss, other data, interleaved forwards,
+    a second backward through one graph, the doubled flavour of loss_composite.losses_fn, logits in (from_logits=True), and
+    the three-launch path (labels that require grad, unaligned shapes) next to it."""
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200 import ops, train_multiclass as tm
+    from ecologysemanticsegmentation_b200.synthetic import make_inputs
+    ops._anticipated_upstream.clear()
+    z0, g0 = make_inputs(6, 3, 64, 77)
+    z0, g0 = z0.cuda(), g0.cuda()
+
+    def ours(z, g, up, fn=tm.losses_fn, **kw):
+        zz = z.clone().requires_grad_(True)
+        x = zz if kw.get("from_logits") else torch.sigmoid(zz)
+        losses = fn(x, g, False, 0, False, **kw)
+        return zz, losses, sum(w * l for w, l in zip(up, losses) if w)
+
+    def check(z, g, up, fn=tm.losses_fn, ref="losses_train_multiclass", **kw):
+        zz, losses, total = ours(z, g, up, fn, **kw)
+        total.backward()
+        rl, rg = _oracle_plain(z, g, up, ref)
+        assert_losses_close([float(v) for v in losses], rl, tol=TOL, what=f"live plain {up}")
+        assert_grad_close(zz.grad.cpu(), rg.cpu(), tol=TOL, what=f"live plain {up}")
+
+    check(z0, g0, UP)                       # nothing anticipated yet: the backward recomputes
+    check(z0, g0, UP)                       # hit
+    check(z0 * 0.5, g0, UP)                 # hit on other data
+    check(z0, g0, UP_ALL)                   # the weights changed: miss, recomputed
+    check(z0, g0, UP_ALL, from_logits=True)
+    check(z0, g0, UP, fn=eco.losses_fn, ref="losses_composite")     # loss_composite.losses_fn: every leaf doubled
+    za, la, ta = ours(z0, g0, UP)
+    zb, lb, tb = ours(z0 * 2.0, g0, UP_ALL)
+    tb.backward()
+    ta.backward()
+    assert_grad_close(za.grad.cpu(), _oracle_plain(z0, g0, UP)[1].cpu(), tol=TOL, what="interleaved a")
+    assert_grad_close(zb.grad.cpu(), _oracle_plain(z0 * 2.0, g0, UP_ALL)[1].cpu(), tol=TOL, what="interleaved b")
+    zc, lc, _ = ours(z0, g0, UP)
+    sum(w * l for w, l in zip(UP, lc) if w).backward(retain_graph=True)
+    first = zc.grad.clone()
+    zc.grad = None
+    sum(w * l for w, l in zip(UP_ALL, lc) if w).backward()
+    assert_grad_close(first.cpu(), _oracle_plain(z0, g0, UP)[1].cpu(), tol=TOL, what="retain 1")
+    assert_grad_close(zc.grad.cpu(), _oracle_plain(z0, g0, UP_ALL)[1].cpu(), tol=TOL, what="retain 2")
+    # the same call with the fast path switched off gives the same numbers (three pair-leaf launches)
+    ops.PLAIN_FAST_PATH = False
+    try:
+        zs, ls, ts = ours(z0, g0, UP)
+        ts.backward()
+    finally:
+        ops.PLAIN_FAST_PATH = True
+    zf, lf, tf = ours(z0, g0, UP)
+    tf.backward()
+    assert_losses_close([float(v) for v in lf], [float(v) for v in ls], tol=1e-6, what="fast vs three-launch")
+    assert_grad_close(zf.grad.cpu(), zs.grad.cpu(), tol=1e-6, what="fast vs three-launch")
+    # full cfg2 shape
+    z2, g2 = make_inputs(54, 3, 256, 102)
+    check(z2.cuda(), g2.cuda(), UP)
