@@ -551,19 +551,22 @@ def measure_aux(dev):
     except Exception as exc:
         out["dropin_unchanged_train_loop_cfg2_graphed"] = {"error": repr(exc)[:300]}
     # (b3) the call the reference's train() REALLY makes (ess/train_multiclass.py:134,139-141,145,147: composite_set_theory is
-    #      hard-wired to False there): F.sigmoid -> the plain 3-organ losses_fn on the probabilities -> weighted sum -> backward,
-    #      with nothing changed but the import; one launch of the plain fused step on probabilities (+ the backward's
+    #      hard-wired to False there): F.sigmoid -> the plain losses_fn on the probabilities -> weighted sum -> backward, with
+    #      nothing changed but the import -- for three organs (cfg2's shape) and for ORGANS=whole_body (cfg1, the reference's
+    #      default): one launch of the fused plain / leaf step on probabilities with anticipated weights (+ the backward's
     #      "only if changed" check) against the three pair-leaf launches the same call took before
-    try:
-        from ecologysemanticsegmentation_b200 import train_multiclass as tmod
-        zg = sets[0][0].clone().requires_grad_(True)
-        gg = sets[0][1]
+    from ecologysemanticsegmentation_b200 import train_multiclass as tmod
+
+    def live_loop(zsrc, gsrc, with_fd):
+        zg = zsrc.clone().requires_grad_(True)
 
         def live_step():
             outputs = torch.sigmoid(zg)
-            ce, bce, fl, dice, gdice, tw, fd = tmod.losses_fn(outputs, gg, composite_set_theory=False, background_weight=0,
+            ce, bce, fl, dice, gdice, tw, fd = tmod.losses_fn(outputs, gsrc, composite_set_theory=False, background_weight=0,
                                                               early_stopped=False)
-            loss = 1.0 * fd + 1.0 * bce + 1.0 * (gdice + tw)
+            loss = 1.0 * bce + 1.0 * (gdice + tw)          # :145 with the epoch < 1000 weights (:92-100) ...
+            if with_fd:
+                loss = 1.0 * fd + loss                      # ... and with focal_dice_w = 1
             loss.backward()
 
         def graphed_us():
@@ -598,14 +601,23 @@ def measure_aux(dev):
         finally:
             ops.PLAIN_FAST_PATH = True
         err = float((grad_fast - zg.grad).abs().max() / zg.grad.abs().max())
-        out["dropin_live_train_loop_plain_cfg2_shape_graphed"] = {
-            "gpixel_per_s": n * s * s / (us_fast * 1e-6) / 1e9, "us": us_fast, "us_three_launch_path": us_three,
-            "grad_vs_three_launch_path_maxnorm": err, "launch": "one CUDA graph per step",
-            "what": "F.sigmoid(z) -> train_multiclass.losses_fn(probabilities, g, composite_set_theory=False) -> weighted sum -> "
-                    "backward, 54x3x256x256: torch's sigmoid forward / backward around ONE launch of the plain fused step on "
-                    "probabilities; before: statistics + closed forms + gradient launches of the pair-leaf kernels"}
-    except Exception as exc:
-        out["dropin_live_train_loop_plain_cfg2_shape_graphed"] = {"error": repr(exc)[:300]}
+        return us_fast, us_three, err
+
+    for name, zsrc, gsrc, with_fd, what in (
+            ("dropin_live_train_loop_plain_cfg2_shape_graphed", sets[0][0], sets[0][1], True,
+             "54x3x256x256, three organs: ONE launch of the plain fused step on probabilities"),
+            ("dropin_live_train_loop_cfg1_graphed", sets[0][0][:, :1].contiguous(), sets[0][1][:, :1].contiguous(), False,
+             "cfg1 (ORGANS=whole_body, 54x1x256x256, loss = bce + gdice + twersky): ONE launch of the resident leaf step on "
+             "probabilities")):
+        try:
+            us_fast, us_three, err = live_loop(zsrc, gsrc, with_fd)
+            out[name] = {"gpixel_per_s": n * s * s / (us_fast * 1e-6) / 1e9, "us": us_fast, "us_three_launch_path": us_three,
+                         "grad_vs_three_launch_path_maxnorm": err, "launch": "one CUDA graph per step",
+                         "what": "F.sigmoid(z) -> train_multiclass.losses_fn(probabilities, g, composite_set_theory=False) -> "
+                                 "weighted sum -> backward; " + what + "; torch's sigmoid forward / backward around it; before: "
+                                 "statistics + closed forms + gradient launches of the pair-leaf kernels"}
+        except Exception as exc:
+            out[name] = {"error": repr(exc)[:300]}
     # (c) the reference's own eager ops on THIS GPU (the like-for-like 'before'): same step, cfg2, oracle port on cuda
     try:
         t = timed(lambda: cpu_reference_step(sets[0][0], sets[0][1], w), 3)

@@ -72,6 +72,8 @@ SIGNATURES = {
     "eco_pair_fused_ws_bytes": (_i64, [_i32]),
     "eco_pair_fused": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _u32, _f64, _f64, _SHAPE, _vp, _vp, _i64, _vp, _vp, _OUT, _OUT,
                                  C.c_int, _vp]),
+    "eco_pair_fused_ex": (C.c_int, [_VIEW, _VIEW, _i32, _i32, _i64, _u32, _f64, _f64, _SHAPE, _vp, _vp, _vp, _i64, _vp, _vp, _OUT,
+                                    _OUT, C.c_int, _vp]),
     "eco_composite3_ws_bytes": (_i64, []),
     "eco_composite3_stats": (C.c_int, [_VIEW, _VIEW, _i32, _i64, _i32, _vp, _i64, _vp, C.c_int, _vp]),
     "eco_composite3_finalize": (C.c_int, [_vp, C.POINTER(_f64), _vp, _vp, _vp, _vp, C.c_int, _vp]),

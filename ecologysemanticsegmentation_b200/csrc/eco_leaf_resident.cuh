@@ -85,6 +85,7 @@ leaf_resident_kernel(FusedArgs fa, int64_t total, const float* __restrict__ upst
                      double* __restrict__ sums_out, float* __restrict__ losses_out) {
     extern __shared__ __align__(128) char tile_smem[];
     __shared__ ResidentSmem rs;
+    if (upstream_unchanged(upstream, fa.upstream_prev)) return;
     const PairArgs& p = fa.g.p;
     const bool a_logit = p.flags & ECO_A_LOGIT, b_logit = p.flags & ECO_B_LOGIT, need_bg = p.flags & ECO_NEED_BG;
     const int64_t units = total / 4;

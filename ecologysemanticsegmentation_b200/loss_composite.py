@@ -55,15 +55,15 @@ def composite3_leaf_scales(pair_weights, doubling=2.0):
     return scales
 
 
-def _per_channel(x, g, doubling, group=None, from_logits=False):
+def _per_channel(x, g, doubling, group=None, from_logits=False, key=None):
     """C>1 recursion (loss_composite.py:28-30): leaf(a = g_c, b = x_c) summed over channels;
     ``background_weight`` is dropped there."""
     flags = ops.nat.FLAG_B_LOGIT if from_logits else 0
-    return LossList(ops.PairLeaves.apply(g, x, 0.0, float(doubling), flags, group, None))
+    return LossList(ops.PairLeaves.apply(g, x, 0.0, float(doubling), flags, group, None, key))
 
 
 def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopped=False,
-              relative_set_ratios=DEFAULT_RATIOS, *, group=None, from_logits=False):
+              relative_set_ratios=DEFAULT_RATIOS, *, group=None, from_logits=False, _site="lc"):
     """loss_composite.py:21-84.  Returns ``LossList[ce, bce, focal, dice, generalized_dice, twersky, focal_dice]``.
 
     Extensions (keyword-only, default to the reference behaviour): ``group`` shards the batch over a
@@ -85,12 +85,17 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
         # require grad): one explicit sigmoid, exactly the reference's F.sigmoid at train_multiclass.py:134
         x, from_logits = torch.sigmoid(x), False
 
+    # A top-level call of the plain loss runs as one launch with the upstream weights of the previous step anticipated
+    # (ops.PairLeaves, `key`); the pair-by-pair composition below makes 1 + 6 * pairs leaf calls whose upstream weights differ
+    # from call to call (intersection_loss / union_loss pass _site=None), so it keeps the three pair-leaf launches per leaf.
+    key = None if (composite_set_theory or _site is None) else _site
     if C > 1:
-        return_losses = _per_channel(x, g, 2.0, group, from_logits)
+        return_losses = _per_channel(x, g, 2.0, group, from_logits, key)
     else:
         # single channel: prediction goes in the gt slot, background_weight is honoured, result doubled (:32-40)
         flags = ops.nat.FLAG_A_LOGIT if from_logits else 0
-        return_losses = LossList(ops.leaf7(x, g, background_weight, scale=2.0, flags=flags, group=group))
+        return_losses = LossList(ops.leaf7(x, g, background_weight, scale=2.0, flags=flags, group=group,
+                                           key=None if key is None else key + "1"))
 
     if composite_set_theory:
         # generic organ count (and labels that require grad): the reference's own composition, each leaf one
@@ -109,10 +114,10 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
 
 def intersection_loss(superset_p, set_p, set_g, *, group=None):
     """loss_composite.py:87-88 -- ``losses_fn(superset_p * set_p, set_g)``."""
-    return LossList(losses_fn(superset_p * set_p, set_g, composite_set_theory=False, group=group))
+    return LossList(losses_fn(superset_p * set_p, set_g, composite_set_theory=False, group=group, _site=None))
 
 
 def union_loss(superset_p, set_p, superset_g, *, group=None):
     """loss_composite.py:92-94 -- ``losses_fn(superset_g, u)`` with u evaluated in the reference's op order."""
     return LossList(losses_fn(superset_g, (superset_p * (1 - set_p) + (superset_p * set_p + set_p) * 0.5),
-                              composite_set_theory=False, group=group))
+                              composite_set_theory=False, group=group, _site=None))

@@ -79,10 +79,12 @@ def pair_grad(a, b, flags, jac, upstream, want_a, want_b, shape=None):
 
 
 def pair_fused(a, b, flags, background_weight, scale, upstream, want_a=False, want_b=True, out_a=None, out_b=None,
-               shape=None):
+               shape=None, upstream_prev=None, losses=None, sums=None):
     """ONE cooperative launch for a step of C independent leaves (eco_pair_fused): sums -> closed forms -> gradient of
     sum_k upstream[k] * loss_k w.r.t. slot a and/or slot b (w.r.t. the logits where a slot is flagged as logits).
-    Returns (losses f32 [7] summed over the channels, ga, gb, sums f64 [C, 8])."""
+    Returns (losses f32 [7] summed over the channels, ga, gb, sums f64 [C, 8]).
+    ``upstream_prev`` (with the ``losses`` / ``sums`` / ``out_*`` buffers of the step it describes): only recompute if the
+    weights differ from it -- decided on the device, no host synchronisation."""
     nat.require_cuda(a, b, upstream)
     if a.shape != b.shape or a.dim() != 4:
         raise ValueError(f"pair_fused expects two [N,C,H,W] tensors of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
@@ -96,15 +98,21 @@ def pair_fused(a, b, flags, background_weight, scale, upstream, want_a=False, wa
     if nbytes < 0:
         raise ValueError(f"pair_fused serves at most 64 leaves per launch (got {c})")
     ws = nat.workspace("pairfused", nbytes, a.device)
-    sums = torch.empty((c, nat.NSTAT), dtype=torch.float64, device=a.device)
-    losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=a.device)
+    if upstream_prev is not None and (losses is None or sums is None or (want_a and out_a is None) or (want_b and out_b is None)):
+        raise ValueError("upstream_prev needs the losses / sums / gradient buffers of the step it describes")
+    if sums is None:
+        sums = torch.empty((c, nat.NSTAT), dtype=torch.float64, device=a.device)
+    if losses is None:
+        losses = torch.empty((nat.NLOSS,), dtype=torch.float32, device=a.device)
     ga = (out_a if out_a is not None else torch.empty((n, c, h, w), dtype=a.dtype, device=a.device)) if want_a else None
     gb = (out_b if out_b is not None else torch.empty((n, c, h, w), dtype=b.dtype, device=b.device)) if want_b else None
     va, vb = nat.view_of(a, a_sn, a_sc), nat.view_of(b, b_sn, b_sc)
     oa, ob = nat.out_of(ga, c * h * w, h * w), nat.out_of(gb, c * h * w, h * w)
-    rc = L.eco_pair_fused(C.byref(va), C.byref(vb), n, c, h * w, int(flags), float(background_weight), float(scale),
-                          _shape_ref(shape), upstream.data_ptr(), ws.data_ptr(), ws.numel(), sums.data_ptr(),
-                          losses.data_ptr(), C.byref(oa), C.byref(ob), _dev(a), nat.current_stream_ptr(a.device))
+    rc = L.eco_pair_fused_ex(C.byref(va), C.byref(vb), n, c, h * w, int(flags), float(background_weight), float(scale),
+                             _shape_ref(shape), upstream.data_ptr(),
+                             upstream_prev.data_ptr() if upstream_prev is not None else None, ws.data_ptr(), ws.numel(),
+                             sums.data_ptr(), losses.data_ptr(), C.byref(oa), C.byref(ob), _dev(a),
+                             nat.current_stream_ptr(a.device))
     nat.check(rc, "eco_pair_fused")
     return losses, ga, gb, sums
 
@@ -307,17 +315,20 @@ class PairLeaves(torch.autograd.Function):
     per-leaf sums are all-reduced before the closed forms."""
 
     @staticmethod
-    def forward(ctx, a, b, background_weight, scale, flags, group, shape):
+    def forward(ctx, a, b, background_weight, scale, flags, group, shape, key):
+        # key: None, or a name for the call site -- a top-level losses_fn whose upstream weights repeat from step to step
+        # (train_multiclass.py:145): the step then runs as ONE launch with the weights of that site's previous backward
         c = a.shape[1]
         ctx.set_materialize_grads(False)
-        ctx.fast = (PLAIN_FAST_PATH and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0]
+        ctx.fast = (PLAIN_FAST_PATH and key is not None and ctx.needs_input_grad[1] and not ctx.needs_input_grad[0]
                     and _plain3_dropin_ok(a, b, background_weight, flags, group, shape))
+        ctx.key = key
         if ctx.fast:
             # The live call of the reference's training loop (train_multiclass.py:139-141 with three organs: labels in the
             # gt slot, predictions in the pred slot): ONE launch of the fused plain step with the upstream weights anticipated
             # from the previous backward; the backward only confirms them (see Composite3).
             dev = b.device
-            used = _anticipated_upstream.get(("plain", dev.index))
+            used = _anticipated_upstream.get((key, dev.index))
             if used is None:
                 used = _zero_upstream(dev)
             probs = not (flags & nat.FLAG_B_LOGIT)
@@ -325,6 +336,27 @@ class PairLeaves(torch.autograd.Function):
             ctx.save_for_backward(a, b, losses, gb)
             ctx.holds, ctx.returned, ctx.scale, ctx.probs = used, False, float(scale), probs
             return tuple(losses.clone().unbind(0))   # (the saved `losses` buffer is rewritten by the backward's launch)
+        want_a, want_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if PLAIN_FAST_PATH and key is not None and group is None and c <= 64 and (want_a or want_b) and a.dim() == 4:
+            # Any other top-level leaf call (one organ -- cfg1, ORGANS=whole_body: the prediction sits in the gt slot and
+            # background_weight counts --, organ counts other than three, bf16, strided slices, both slots with gradient): the
+            # one-launch step of eco_pair_fused, the same way.  (The stand-alone primitives and the inner leaves of the
+            # pair-by-pair composite pass no key: their upstream weights differ from call to call.)
+            dev = a.device
+            used = _anticipated_upstream.get((key, dev.index))
+            if used is None:
+                used = _zero_upstream(dev)
+            try:
+                losses, ga, gb, sums = pair_fused(a.detach(), b.detach(), flags, background_weight, scale, used, want_a, want_b,
+                                                  shape=shape)
+            except nat.EcoLossError:
+                losses = None   # (more leaves than one resident wave holds: the three launches below)
+            if losses is not None:
+                ctx.fast = 2
+                ctx.save_for_backward(a, b, losses, sums, ga, gb)
+                ctx.holds, ctx.returned = used, False
+                ctx.call = (flags, float(background_weight), float(scale), shape)
+                return tuple(losses.clone().unbind(0))
         sums = pair_stats(a.detach(), b.detach(), flags | (nat.FLAG_NEED_BG if background_weight != 0 else 0), shape)
         sums = dist_.allreduce_sums_(sums, group)
         _, total, jac = pair_finalize(sums, background_weight, [scale] * c, shape)
@@ -336,25 +368,37 @@ class PairLeaves(torch.autograd.Function):
     def backward(ctx, *grads):
         want_a, want_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (want_a or want_b) or all(g is None for g in grads):
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
+        if ctx.fast == 2:
+            a, b, losses, sums, ga, gb = ctx.saved_tensors
+            up = _stack_upstream(grads, a)
+            _anticipated_upstream[(ctx.key, a.device.index)] = up
+            flags, bw, scale, shape = ctx.call
+            if ctx.returned:   # a second backward through the same graph: autograd may own the first buffers by now
+                _, ga, gb, _ = pair_fused(a.detach(), b.detach(), flags, bw, scale, up, want_a, want_b, shape=shape)
+                return ga, gb, None, None, None, None, None, None
+            pair_fused(a.detach(), b.detach(), flags, bw, scale, up, want_a, want_b, out_a=ga, out_b=gb, shape=shape,
+                       upstream_prev=ctx.holds, losses=losses, sums=sums)
+            ctx.holds, ctx.returned = up, True
+            return ga, gb, None, None, None, None, None, None
         if ctx.fast:
             a, b, losses, gb = ctx.saved_tensors
             up = _stack_upstream(grads, b)
-            _anticipated_upstream[("plain", b.device.index)] = up
+            _anticipated_upstream[(ctx.key, b.device.index)] = up
             if ctx.returned:   # a second backward through the same graph: autograd may own the first buffer by now
                 _, gb = multiclass3_fused(b.detach(), a.detach(), ctx.scale, up, probs=ctx.probs)
-                return None, gb, None, None, None, None, None
+                return None, gb, None, None, None, None, None, None
             multiclass3_fused(b.detach(), a.detach(), ctx.scale, up, out=gb, probs=ctx.probs, upstream_prev=ctx.holds,
                               losses=losses)
             ctx.holds, ctx.returned = up, True
-            return None, gb, None, None, None, None, None
+            return None, gb, None, None, None, None, None, None
         a, b, jac = ctx.saved_tensors
         up = _stack_upstream(grads, a)
         ga, gb = pair_grad(a.detach(), b.detach(), ctx.flags, jac, up, want_a, want_b, ctx.shape)
-        return ga, gb, None, None, None, None, None
+        return ga, gb, None, None, None, None, None, None
 
 
-PLAIN_FAST_PATH = True   # (switch for measurements: False sends the plain 3-organ call through the three pair-leaf launches)
+PLAIN_FAST_PATH = True   # (switch for measurements: False sends the plain leaf calls through the three pair-leaf launches)
 
 
 def _plain3_dropin_ok(a, b, background_weight, flags, group, shape):
@@ -499,11 +543,11 @@ def as_single_leaf(a, b):
     return a.contiguous().view(1, 1, 1, -1), b.contiguous().view(1, 1, 1, -1)
 
 
-def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None, shape=None):
+def leaf7(a, b, background_weight=0.0, scale=1.0, flags=0, group=None, shape=None, key=None):
     """The 7 losses of ONE leaf over all elements of (a, b), each times ``scale``.  ``shape``: optional
     (focal_gamma, tversky_alpha, tversky_beta, focal_dice_gamma) when a primitive is called with its own keywords."""
     a4, b4 = as_single_leaf(a, b)
-    return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group, shape)
+    return PairLeaves.apply(a4, b4, float(background_weight), float(scale), int(flags), group, shape, key)
 
 
 def multiclass3_fused(x, g, leaf_scale, upstream, out=None, probs=False, upstream_prev=None, losses=None):

@@ -30,7 +30,7 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
         ops.nat.require_cuda(x, g)
     if not isinstance(g, list) and g.shape[CLASS_INDEX] > 1:
         flags = ops.nat.FLAG_B_LOGIT if from_logits else 0
-        return list(ops.PairLeaves.apply(g, x, 0.0, 1.0, flags, group, None))
+        return list(ops.PairLeaves.apply(g, x, 0.0, 1.0, flags, group, None, "tm"))
 
     if isinstance(x, list):
         # deep-supervision branch (:264-267): binary_cross_entropy_list works, the next helper raises
@@ -41,7 +41,7 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
         return [ce_loss, bce_loss, fl_loss, dice, generalized_dice, twersky_dice, focal_dice]
 
     flags = ops.nat.FLAG_A_LOGIT if from_logits else 0
-    return_losses = list(ops.leaf7(x, g, background_weight, scale=1.0, flags=flags, group=group))
+    return_losses = list(ops.leaf7(x, g, background_weight, scale=1.0, flags=flags, group=group, key="tm1"))
     if composite_set_theory:
         # :276-301 slices channels 1 and 2 of a 1-channel tensor and zips three lists into two names
         raise ValueError("too many values to unpack (expected 2)")

@@ -12,12 +12,12 @@ def losses_fn(x, g, composite_set_theory=False, background_weight=0, early_stopp
     CLASS_INDEX = 1
     ops.nat.require_cuda(x, g)
     if g.shape[CLASS_INDEX] > 1:
-        per_channel = ops.PairLeaves.apply(g, x, 0.0, 1.0, 0, group, None)
+        per_channel = ops.PairLeaves.apply(g, x, 0.0, 1.0, 0, group, None, "seq")
         # direct optimisation of the target objective: superset 1 minus subset 2 (:283-285)
         extra = ops.leaf7(g[:, 1:2, :, :] - g[:, 2:3, :, :], torch.abs(x[:, 1:2, :, :] - x[:, 2:3, :, :]), 0.0, 1.0,
-                          group=group)
+                          group=group, key="seq_extra")
         return [a + b for a, b in zip(per_channel, extra)]
-    return_losses = list(ops.leaf7(x, g, background_weight, scale=1.0, group=group))
+    return_losses = list(ops.leaf7(x, g, background_weight, scale=1.0, group=group, key="seq1"))
     if composite_set_theory:
         # :304-320 slice channels 1 and 2 of a 1-channel tensor; the reference fails inside BCEWithLogits
         raise ValueError("Target size (%s) must be the same as input size (%s)"

@@ -140,6 +140,13 @@ int eco_pair_fused(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int
                    double background_weight, double scale, const EcoLeafShape* shape_host, const float* upstream,
                    void* ws, int64_t ws_bytes, double* sums_out, float* losses_out, const EcoOut* ga, const EcoOut* gb,
                    int device, void* stream);
+/* The same with the "only if changed" form of the drop-in autograd path: upstream_prev (device float32[7] or NULL) are the
+ * weights the output buffers already hold the step for; the kernel compares the two vectors on the device and returns at
+ * once when they are equal (the backward of a step whose forward anticipated the weights of ess/train_multiclass.py:145). */
+int eco_pair_fused_ex(const EcoView* a, const EcoView* b, int32_t N, int32_t C, int64_t HW, uint32_t flags,
+                      double background_weight, double scale, const EcoLeafShape* shape_host, const float* upstream,
+                      const float* upstream_prev, void* ws, int64_t ws_bytes, double* sums_out, float* losses_out,
+                      const EcoOut* ga, const EcoOut* gb, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3-organ composite loss: ess/loss_composite.py:21-94 `losses_fn(x, g, composite_set_theory=True)`

@@ -403,3 +403,57 @@ def test_dropin_live_train_loop_plain_three_organs_one_launch():
     # full cfg2 shape
     z2, g2 = make_inputs(54, 3, 256, 102)
     check(z2.cuda(), g2.cuda(), UP)
+
+
+@pytest.mark.parametrize("shape", [(6, 1, 64, 64), (54, 1, 256, 256), (3, 1, 17, 19), (4, 2, 32, 32), (2, 5, 8, 24)])
+def test_dropin_live_train_loop_other_organ_counts_one_launch(shape):
+    """The same for every other organ count -- cfg1 (ORGANS=whole_body, the reference's default: C == 1, prediction in the gt
+    slot, background_weight honoured) and plain C != 3 -- on the one-launch leaf step (eco_pair_fused_ex) with anticipated
+    weights: first call, hit, miss, interleaved forwards, second backward through one graph, both losses_fn flavours."""
+    import ecologysemanticsegmentation_b200 as eco
+    from ecologysemanticsegmentation_b200 import ops, train_multiclass as tm
+    from oracle import torch_port as tp
+    ops._anticipated_upstream.clear()
+    n, c, h, w = shape
+    torch.manual_seed(500 + c + h)
+    z0 = torch.randn(n, c, h, w).cuda()
+    g0 = (torch.rand(n, c, h, w) > 0.5).float().cuda()
+    bw = 0.5 if c == 1 else 0
+
+    def oracle(z, up, fn):
+        zr = z.clone().requires_grad_(True)
+        ref = getattr(tp, fn)(torch.sigmoid(zr), g0, False, bw, False)
+        sum(wk * l for wk, l in zip(up, ref) if wk).backward()
+        return [float(v) for v in ref], zr.grad
+
+    def ours(z, up, fn):
+        zz = z.clone().requires_grad_(True)
+        losses = fn(torch.sigmoid(zz), g0, False, bw, False)
+        return zz, losses, sum(wk * l for wk, l in zip(up, losses) if wk)
+
+    def check(z, up, fn=tm.losses_fn, ref="losses_train_multiclass"):
+        zz, losses, total = ours(z, up, fn)
+        total.backward()
+        rl, rg = oracle(z, up, ref)
+        assert_losses_close([float(v) for v in losses], rl, tol=TOL, what=f"live {shape} {up}")
+        assert_grad_close(zz.grad.cpu(), rg.cpu(), tol=TOL, what=f"live {shape} {up}")
+
+    check(z0, UP)
+    check(z0, UP)
+    check(z0 * 0.5, UP)
+    check(z0, UP_ALL)
+    check(z0, UP, fn=eco.losses_fn, ref="losses_composite")
+    check(z0, UP, fn=eco.losses_fn, ref="losses_composite")
+    za, la, ta = ours(z0, UP, tm.losses_fn)
+    zb, lb, tb = ours(z0 * 2.0, UP_ALL, tm.losses_fn)
+    tb.backward()
+    ta.backward()
+    assert_grad_close(za.grad.cpu(), oracle(z0, UP, "losses_train_multiclass")[1].cpu(), tol=TOL, what="interleaved a")
+    assert_grad_close(zb.grad.cpu(), oracle(z0 * 2.0, UP_ALL, "losses_train_multiclass")[1].cpu(), tol=TOL, what="interleaved b")
+    zc, lc_, _ = ours(z0, UP, tm.losses_fn)
+    sum(wk * l for wk, l in zip(UP, lc_) if wk).backward(retain_graph=True)
+    first = zc.grad.clone()
+    zc.grad = None
+    sum(wk * l for wk, l in zip(UP_ALL, lc_) if wk).backward()
+    assert_grad_close(first.cpu(), oracle(z0, UP, "losses_train_multiclass")[1].cpu(), tol=TOL, what="retain 1")
+    assert_grad_close(zc.grad.cpu(), oracle(z0, UP_ALL, "losses_train_multiclass")[1].cpu(), tol=TOL, what="retain 2")
