@@ -1148,6 +1148,23 @@ def _run(args):
                     "traffic": traffic, "peak_source": peak_src,
                     "kernel": "composite3_fused_v3_kernel" if (world == 1 or args.exchange == "p2p") else "composite3_stats_packed+allreduce+finalize+composite3_grad_v2",
                     "algorithmic_bytes_per_launch": alg_bytes}
+        if args.workload == "cfg2" and (world == 1 or args.exchange == "p2p"):
+            # what really bounds this kernel: its instruction stream.  Warp instructions per launch are a
+            # property of the code and the shape (ncu smsp__inst_executed.sum of the committed capture); the issue peak is one
+            # warp instruction per clock and SM sub-partition at the clock sampled during the timed region.
+            try:
+                ncu = json.load(open(os.path.join(ROOT, "profiles", "r2c_fused_v3_ncu_full.json")))["launches"][0]
+                inst = float(ncu["smsp__inst_executed.sum"]["value"])
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                peak_issue = 4.0 * sms * mhz * 1e6
+                roofline["instruction_stream"] = {
+                    "warp_instructions_per_launch": inst, "achieved_ginst_per_s": inst / (ms_per_step * 1e-3) / 1e9,
+                    "peak_ginst_per_s": peak_issue / 1e9, "frac": inst / (ms_per_step * 1e-3) / peak_issue,
+                    "note": "informational: the step is bound by its issue + XU work (FFMA2 holds an issue slot for 2-3 cycles), "
+                            "not by HBM; source of the count: profiles/r2c_fused_v3_ncu_full.json"}
+            except Exception:
+                pass
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             res = time_cpu_baseline(args.workload, budget_s=15.0)
