@@ -13,8 +13,11 @@
 // Pillow's operation order) and the per-channel map byte -> (byte / 255 - mean) / std is a 3 x 256 table of IEEE
 // float32 operations (torchvision F.to_tensor / F.normalize on the CPU: true division, no reciprocal).
 //
-// One CTA = one 32 x 16 tile of one output frame: input patch -> shared memory (4-byte loads, whatever the alignment of the
-// rows), horizontal pass into a byte buffer in shared memory, vertical pass + table look-up, coalesced 128-byte stores.
+// One CTA = one 32 x 16 tile of one output frame: input patch -> shared memory by ONE 1-D TMA bulk copy per patch row
+// (cp.async.bulk from the 16-byte aligned superset of the row; the row then starts `o` bytes into its shared-memory line),
+// horizontal pass into a byte buffer in shared memory, vertical pass (taps unrolled, one coefficient fetch per output row for
+// its three channels) + table look-up, coalesced 128-byte stores.  Rows whose aligned superset would leave the caller's
+// buffer (first / last rows of the whole batch) are fetched word by word into the same layout.
 #include <cmath>
 
 #include "eco_common.cuh"
@@ -36,13 +39,14 @@ struct FrameArgs {
     int32_t patch_cols, patch_rows, pitch;   // shared-memory patch: rows x pitch bytes (pitch % 4 == 0)
 };
 
-__host__ __device__ inline int frames_pitch(int patch_cols) { return ((patch_cols + kFrPadTaps) * 3 + 3 + 4) / 4 * 4; }
+// a patch row in shared memory: up to 15 bytes in front of the row (16-byte aligned source), the row, the horizontal pass's
+// read-ahead, rounded up to the 16-byte granule of the bulk copy
+__host__ __device__ inline int frames_pitch(int patch_cols) { return (15 + (patch_cols + kFrPadTaps) * 3 + 15) / 16 * 16; }
 __host__ __device__ inline size_t frames_smem_bytes(int patch_cols, int patch_rows, int ksx, int ksy) {
     size_t b = (size_t)patch_rows * frames_pitch(patch_cols);           // patch
-    b += (size_t)patch_rows * (kFrTW * 3);                              // rows after the horizontal pass
+    b += (size_t)(patch_rows + kFrPadTaps) * (kFrTW * 3);               // rows after the horizontal pass (+ the vertical pass's zero-weighted read-ahead)
     b = (b + 15) / 16 * 16;
     b += (size_t)(kFrTW * ksx + kFrTH * ksy + 2 * kFrTW + 2 * kFrTH) * 4;   // coefficient rows, bounds
-    b += 3 * 256 * 4;                                                    // byte -> normalised float
     return b;
 }
 
@@ -52,7 +56,7 @@ __device__ __forceinline__ uint32_t clip8(int v) {   // Resample.c: clip8(in) = 
 }
 
 // the aligned 4-byte word at q; the first / last word of the whole buffer byte by byte: nothing outside the caller's memory
-__device__ __forceinline__ uint32_t frames_word(const uint8_t* q, const uint8_t* lo, const uint8_t* hi) {
+__device__ __noinline__ uint32_t frames_word(const uint8_t* q, const uint8_t* lo, const uint8_t* hi) {
     if (q >= lo && q + 4 <= hi) return __ldg(reinterpret_cast<const uint32_t*>(q));
     uint32_t v = 0u;
 #pragma unroll
@@ -61,8 +65,10 @@ __device__ __forceinline__ uint32_t frames_word(const uint8_t* q, const uint8_t*
     return v;
 }
 
-// KX: taps of the horizontal pass held in registers (>= ksx; 0 = any number, read from shared memory)
-template <int KX>
+__device__ __forceinline__ uint32_t fr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// KX / KY: taps of the horizontal / vertical pass held in registers (>= ksx / ksy; 0 = any number, read from shared memory)
+template <int KX, int KY>
 __global__ void __launch_bounds__(kFrThreads)
 frames_preprocess_kernel(FrameArgs p) {
     extern __shared__ __align__(16) unsigned char fr_smem[];
@@ -71,51 +77,86 @@ frames_preprocess_kernel(FrameArgs p) {
     const int tw = min(kFrTW, p.Wout - x0), th = min(kFrTH, p.Hout - y0);
     unsigned char* patch = fr_smem;
     unsigned char* hbuf = patch + (size_t)p.patch_rows * p.pitch;
-    size_t off = ((size_t)p.patch_rows * p.pitch + (size_t)p.patch_rows * (kFrTW * 3) + 15) / 16 * 16;
+    size_t off = ((size_t)p.patch_rows * p.pitch + (size_t)(p.patch_rows + kFrPadTaps) * (kFrTW * 3) + 15) / 16 * 16;
     int* kxs = reinterpret_cast<int*>(fr_smem + off);
     int* kys = kxs + kFrTW * p.ksx;
     int* xbs = kys + kFrTH * p.ksy;
     int* ybs = xbs + 2 * kFrTW;
-    float* lut = reinterpret_cast<float*>(ybs + 2 * kFrTH);
+    const float* __restrict__ lut = p.lut;   // 3 KB, read through L1 (a copy per CTA cost more than its 1536 look-ups)
     __shared__ int ext[4];   // cx0, ncols, ry0, nrows
 
     for (int i = tid; i < kFrTW * p.ksx; i += kFrThreads) kxs[i] = i < tw * p.ksx ? p.kx[(size_t)x0 * p.ksx + i] : 0;
     for (int i = tid; i < th * p.ksy; i += kFrThreads) kys[i] = p.ky[(size_t)y0 * p.ksy + i];
     for (int i = tid; i < 2 * kFrTW; i += kFrThreads) xbs[i] = i < 2 * tw ? p.xb[2 * x0 + i] : 0;
     for (int i = tid; i < 2 * th; i += kFrThreads) ybs[i] = p.yb[2 * y0 + i];
-    for (int i = tid; i < 3 * 256; i += kFrThreads) lut[i] = p.lut[i];
     __syncthreads();
-    if (tid == 0) {
-        int lo = xbs[0], hi = xbs[0] + xbs[1];
-        for (int x = 1; x < tw; ++x) { lo = min(lo, xbs[2 * x]); hi = max(hi, xbs[2 * x] + xbs[2 * x + 1]); }
-        ext[0] = lo; ext[1] = min(hi - lo, p.patch_cols);   // (eco_frames_plan sized the patch for every tile)
-        lo = ybs[0]; hi = ybs[0] + ybs[1];
-        for (int y = 1; y < th; ++y) { lo = min(lo, ybs[2 * y]); hi = max(hi, ybs[2 * y] + ybs[2 * y + 1]); }
-        ext[2] = lo; ext[3] = min(hi - lo, p.patch_rows);
+    if (warp == 0) {   // extent of the input patch: min / max over the tile's columns and rows (kFrTW == 32 lanes)
+        const bool hx = lane < tw, hy = lane < th;
+        const int xlo = __reduce_min_sync(0xffffffffu, hx ? xbs[2 * lane] : 0x7fffffff);
+        const int xhi = __reduce_max_sync(0xffffffffu, hx ? xbs[2 * lane] + xbs[2 * lane + 1] : -0x7fffffff);
+        const int ylo = __reduce_min_sync(0xffffffffu, hy ? ybs[2 * lane] : 0x7fffffff);
+        const int yhi = __reduce_max_sync(0xffffffffu, hy ? ybs[2 * lane] + ybs[2 * lane + 1] : -0x7fffffff);
+        if (lane == 0) {
+            ext[0] = xlo; ext[1] = min(xhi - xlo, p.patch_cols);   // (eco_frames_plan sized the patch for every tile)
+            ext[2] = ylo; ext[3] = min(yhi - ylo, p.patch_rows);
+        }
     }
     __syncthreads();
     const int cx0 = ext[0], ncols = ext[1], ry0 = ext[2], nrows = ext[3];
 
-    // ---- input patch -> shared memory: one warp per row, aligned 4-byte loads shifted so that every row starts at byte 0 --
+    // ---- input patch -> shared memory.  Row r of the patch starts at fbase + (ry0 + r) * row_stride + cx0 * 3; its 16-byte
+    //      aligned superset goes to patch + r * pitch, so the row itself starts row_off(r) bytes into that line ------------------
     const uint8_t* fbase = p.src + (int64_t)n * p.frame_stride;
-    for (int r = warp; r < nrows; r += kFrThreads / 32) {
-        const uint8_t* g0 = fbase + (int64_t)(ry0 + r) * p.row_stride + (int64_t)cx0 * 3;
-        const int o = (int)(reinterpret_cast<uintptr_t>(g0) & 3);
-        const uint8_t* wbase = g0 - o;
-        const int nwords = (ncols * 3 + 3) >> 2;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(patch + (size_t)r * p.pitch);
-        // (every word of the row and the one after it inside the caller's buffer: plain loads, the neighbour by shuffle)
-        const bool inside = wbase >= p.src && wbase + 4 * (nwords + 1) <= p.src_end;
-        for (int w0 = 0; w0 < nwords; w0 += 32) {
-            const int w = w0 + lane;
-            uint32_t a = 0u;
-            if (w <= nwords) a = inside ? __ldg(reinterpret_cast<const uint32_t*>(wbase) + w) : frames_word(wbase + 4 * w, p.src, p.src_end);
-            uint32_t b = __shfl_down_sync(0xffffffffu, a, 1);
-            if (lane == 31 && o && w < nwords) b = inside ? __ldg(reinterpret_cast<const uint32_t*>(wbase) + w + 1) : frames_word(wbase + 4 * w + 4, p.src, p.src_end);
-            if (w < nwords) dst[w] = __funnelshift_r(a, b, 8 * o);
+    const uint8_t* g00 = fbase + (int64_t)ry0 * p.row_stride + (int64_t)cx0 * 3;
+    const uint32_t a00 = (uint32_t)(reinterpret_cast<uintptr_t>(g00) & 15u), rs15 = (uint32_t)(p.row_stride & 15);
+    auto row_off = [&](int r) { return (int)((a00 + (uint32_t)r * rs15) & 15u); };
+    __shared__ __align__(8) unsigned long long tma_bar;
+    const int row_bytes = ncols * 3;
+    if (warp == 0) {   // the lanes of warp 0 issue the rows' copies side by side
+        const uint32_t bar = fr_smem_u32(&tma_bar);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        uint32_t mine = 0;
+        for (int r = lane; r < nrows; r += 32) {
+            const int o = row_off(r);
+            const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
+            const uint32_t bytes = (uint32_t)((o + row_bytes + 15) & ~15);
+            if (src16 >= p.src && src16 + bytes <= p.src_end) mine += bytes;
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+        __syncwarp();
+        for (int r = lane; r < nrows; r += 32) {
+            const int o = row_off(r);
+            const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
+            const uint32_t bytes = (uint32_t)((o + row_bytes + 15) & ~15);
+            if (src16 >= p.src && src16 + bytes <= p.src_end)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 fr_smem_u32(patch + (size_t)r * p.pitch)), "l"(src16), "r"(bytes), "r"(bar)
+                             : "memory");
         }
     }
-    __syncthreads();
+    // (rare) rows at the very start / end of the caller's buffer: word by word, nothing outside the caller's memory is read
+    for (int r = warp; r < nrows; r += kFrThreads / 32) {
+        const int o = row_off(r);
+        const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
+        const int bytes = (o + row_bytes + 15) & ~15;
+        if (src16 >= p.src && src16 + bytes <= p.src_end) continue;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(patch + (size_t)r * p.pitch);
+        for (int w = lane; w < bytes / 4; w += 32) dst[w] = frames_word(src16 + 4 * w, p.src, p.src_end);
+    }
+    __syncthreads();   // (the barrier's initialisation is visible to every thread; the word-by-word rows are in place)
+    {
+        const uint32_t bar = fr_smem_u32(&tma_bar);
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(ok) : "r"(bar) : "memory");
+        }
+    }
 
     // ---- horizontal pass: (patch row, output column, channel) -> byte.  A thread keeps ONE (column, channel) and its
     //      coefficients in registers and walks down the rows of its half of the patch --------------------------------------
@@ -130,7 +171,7 @@ frames_preprocess_kernel(FrameArgs p) {
 #pragma unroll
                 for (int j = 0; j < KX; ++j) k[j] = j < p.ksx ? kxs[x * p.ksx + j] : 0;   // (zero beyond the tap count)
                 for (int r = half; r < nrows; r += 2) {
-                    const unsigned char* prow = pcol + (size_t)r * p.pitch;
+                    const unsigned char* prow = pcol + r * p.pitch + row_off(r);
                     int acc = 1 << (kFrPrecision - 1);
 #pragma unroll
                     for (int j = 0; j < KX; ++j) acc += k[j] * (int)prow[3 * j];
@@ -140,7 +181,7 @@ frames_preprocess_kernel(FrameArgs p) {
                 const int cnt = xbs[2 * x + 1];
                 const int* k = kxs + x * p.ksx;
                 for (int r = half; r < nrows; r += 2) {
-                    const unsigned char* prow = pcol + (size_t)r * p.pitch;
+                    const unsigned char* prow = pcol + r * p.pitch + row_off(r);
                     int acc = 1 << (kFrPrecision - 1);
                     for (int j = 0; j < cnt; ++j) acc += k[j] * (int)prow[3 * j];
                     hbuf[r * (kFrTW * 3) + xc] = (unsigned char)clip8(acc);
@@ -150,17 +191,33 @@ frames_preprocess_kernel(FrameArgs p) {
     }
     __syncthreads();
 
-    // ---- vertical pass + byte -> normalised float; a warp writes 32 consecutive floats of one (channel, row) -----------
+    // ---- vertical pass + byte -> normalised float; a warp takes whole output rows: the row's coefficients are fetched once
+    //      for its three channels, and the warp writes 32 consecutive floats of one (channel, row) at a time -----------------
     const int x = lane;
     if (x < tw) {
-        for (int yc = warp; yc < th * 3; yc += kFrThreads / 32) {
-            const int y = yc / 3, c = yc - 3 * y;
+        for (int y = warp; y < th; y += kFrThreads / 32) {
             const int first = ybs[2 * y] - ry0, cnt = ybs[2 * y + 1];
-            const unsigned char* col = hbuf + (size_t)first * (kFrTW * 3) + x * 3 + c;
+            const unsigned char* col0 = hbuf + first * (kFrTW * 3) + x * 3;
             const int* k = kys + y * p.ksy;
-            int acc = 1 << (kFrPrecision - 1);
-            for (int j = 0; j < cnt; ++j) acc += k[j] * (int)col[(size_t)j * (kFrTW * 3)];
-            p.out[(((int64_t)n * 3 + c) * p.Hout + (y0 + y)) * p.Wout + (x0 + x)] = lut[c * 256 + clip8(acc)];
+            float* orow = p.out + (((int64_t)n * 3) * p.Hout + (y0 + y)) * p.Wout + (x0 + x);
+            if (KY > 0) {
+                int kk[KY > 0 ? KY : 1];
+#pragma unroll
+                for (int j = 0; j < KY; ++j) kk[j] = j < p.ksy ? k[j] : 0;   // (the table rows are zero beyond the tap count)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    int acc = 1 << (kFrPrecision - 1);
+#pragma unroll
+                    for (int j = 0; j < KY; ++j) acc += kk[j] * (int)col0[j * (kFrTW * 3) + c];
+                    orow[(int64_t)c * p.Hout * p.Wout] = __ldg(lut + c * 256 + clip8(acc));
+                }
+            } else {
+                for (int c = 0; c < 3; ++c) {
+                    int acc = 1 << (kFrPrecision - 1);
+                    for (int j = 0; j < cnt; ++j) acc += k[j] * (int)col0[j * (kFrTW * 3) + c];
+                    orow[(int64_t)c * p.Hout * p.Wout] = __ldg(lut + c * 256 + clip8(acc));
+                }
+            }
         }
     }
 }
@@ -270,10 +327,16 @@ extern "C" int eco_frames_preprocess(const uint8_t* frames, int32_t N, int32_t H
     if (!guard.ok) { set_error("cannot select device %d", device); return -6; }
     const size_t smem = frames_smem_bytes(patch_cols, patch_rows, ksx, ksy);
     if (smem > 200 * 1024) { set_error("down-scaling factor too large for one tile's input patch (%zu bytes of shared memory)", smem); return -8; }
-    void (*kernel)(FrameArgs) = ksx <= 3 ? frames_preprocess_kernel<3> : ksx <= 5 ? frames_preprocess_kernel<5>
-                              : ksx <= 7 ? frames_preprocess_kernel<7> : ksx <= 9 ? frames_preprocess_kernel<9>
-                              : ksx <= 13 ? frames_preprocess_kernel<13> : ksx <= 17 ? frames_preprocess_kernel<17>
-                              : frames_preprocess_kernel<0>;
+    // taps in registers: 3 (up-scaling and no scaling), 5, 7, 9, 13, 17; anything longer reads its taps from shared memory
+    auto bucket = [](int k) { return k <= 3 ? 0 : k <= 5 ? 1 : k <= 7 ? 2 : k <= 9 ? 3 : k <= 13 ? 4 : k <= 17 ? 5 : 6; };
+    static void (*const kernels[7][7])(FrameArgs) = {
+#define ECO_FR_ROW(KX) {frames_preprocess_kernel<KX, 3>, frames_preprocess_kernel<KX, 5>, frames_preprocess_kernel<KX, 7>, \
+                        frames_preprocess_kernel<KX, 9>, frames_preprocess_kernel<KX, 13>, frames_preprocess_kernel<KX, 17>, \
+                        frames_preprocess_kernel<KX, 0>}
+        ECO_FR_ROW(3), ECO_FR_ROW(5), ECO_FR_ROW(7), ECO_FR_ROW(9), ECO_FR_ROW(13), ECO_FR_ROW(17), ECO_FR_ROW(0)
+#undef ECO_FR_ROW
+    };
+    void (*kernel)(FrameArgs) = kernels[bucket(ksx)][bucket(ksy)];
     if (smem > 48 * 1024) {
         int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(smem, frames)");
