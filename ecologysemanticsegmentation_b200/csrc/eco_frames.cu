@@ -85,17 +85,25 @@ frames_preprocess_kernel(FrameArgs p) {
     const float* __restrict__ lut = p.lut;   // 3 KB, read through L1 (a copy per CTA cost more than its 1536 look-ups)
     __shared__ int ext[4];   // cx0, ncols, ry0, nrows
 
-    for (int i = tid; i < kFrTW * p.ksx; i += kFrThreads) kxs[i] = i < tw * p.ksx ? p.kx[(size_t)x0 * p.ksx + i] : 0;
-    for (int i = tid; i < th * p.ksy; i += kFrThreads) kys[i] = p.ky[(size_t)y0 * p.ksy + i];
-    for (int i = tid; i < 2 * kFrTW; i += kFrThreads) xbs[i] = i < 2 * tw ? p.xb[2 * x0 + i] : 0;
-    for (int i = tid; i < 2 * th; i += kFrThreads) ybs[i] = p.yb[2 * y0 + i];
-    __syncthreads();
+    // Tap counts held in registers (the usual case): every thread fetches its own coefficients and bounds straight from the
+    // tables in global memory (L1 / L2 hits, under the patch copies); only the any-number-of-taps instantiations stage the
+    // tile's table rows in shared memory
+    if (KX == 0) {
+        for (int i = tid; i < kFrTW * p.ksx; i += kFrThreads) kxs[i] = i < tw * p.ksx ? p.kx[(size_t)x0 * p.ksx + i] : 0;
+        for (int i = tid; i < 2 * kFrTW; i += kFrThreads) xbs[i] = i < 2 * tw ? p.xb[2 * x0 + i] : 0;
+    }
+    if (KY == 0) {
+        for (int i = tid; i < th * p.ksy; i += kFrThreads) kys[i] = p.ky[(size_t)y0 * p.ksy + i];
+        for (int i = tid; i < 2 * th; i += kFrThreads) ybs[i] = p.yb[2 * y0 + i];
+    }
     if (warp == 0) {   // extent of the input patch: min / max over the tile's columns and rows (kFrTW == 32 lanes)
         const bool hx = lane < tw, hy = lane < th;
-        const int xlo = __reduce_min_sync(0xffffffffu, hx ? xbs[2 * lane] : 0x7fffffff);
-        const int xhi = __reduce_max_sync(0xffffffffu, hx ? xbs[2 * lane] + xbs[2 * lane + 1] : -0x7fffffff);
-        const int ylo = __reduce_min_sync(0xffffffffu, hy ? ybs[2 * lane] : 0x7fffffff);
-        const int yhi = __reduce_max_sync(0xffffffffu, hy ? ybs[2 * lane] + ybs[2 * lane + 1] : -0x7fffffff);
+        const int xb0 = hx ? __ldg(p.xb + 2 * (x0 + lane)) : 0, xb1 = hx ? __ldg(p.xb + 2 * (x0 + lane) + 1) : 0;
+        const int yb0 = hy ? __ldg(p.yb + 2 * (y0 + lane)) : 0, yb1 = hy ? __ldg(p.yb + 2 * (y0 + lane) + 1) : 0;
+        const int xlo = __reduce_min_sync(0xffffffffu, hx ? xb0 : 0x7fffffff);
+        const int xhi = __reduce_max_sync(0xffffffffu, hx ? xb0 + xb1 : -0x7fffffff);
+        const int ylo = __reduce_min_sync(0xffffffffu, hy ? yb0 : 0x7fffffff);
+        const int yhi = __reduce_max_sync(0xffffffffu, hy ? yb0 + yb1 : -0x7fffffff);
         if (lane == 0) {
             ext[0] = xlo; ext[1] = min(xhi - xlo, p.patch_cols);   // (eco_frames_plan sized the patch for every tile)
             ext[2] = ylo; ext[3] = min(yhi - ylo, p.patch_rows);
@@ -112,6 +120,15 @@ frames_preprocess_kernel(FrameArgs p) {
     auto row_off = [&](int r) { return (int)((a00 + (uint32_t)r * rs15) & 15u); };
     __shared__ __align__(8) unsigned long long tma_bar;
     const int row_bytes = ncols * 3;
+    auto row_fast = [&](int r) {   // the row's 16-byte aligned superset lies inside the caller's buffer
+        const int o = row_off(r);
+        const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
+        return src16 >= p.src && src16 + ((o + row_bytes + 15) & ~15) <= p.src_end;
+    };
+    // Rows lie row_stride >= row_bytes apart, so when the patch's first and last row are inside by this test and a row holds
+    // at least the 15 bytes a superset can stick out, every row in between is inside too: one CTA-uniform test instead of one
+    // per row (only tiles on the first / last rows of the whole batch fail it)
+    const bool all_fast = nrows > 0 && row_bytes >= 16 && row_fast(0) && row_fast(nrows - 1);
     if (warp == 0) {   // the lanes of warp 0 issue the rows' copies side by side
         const uint32_t bar = fr_smem_u32(&tma_bar);
         if (lane == 0) {
@@ -119,33 +136,31 @@ frames_preprocess_kernel(FrameArgs p) {
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         uint32_t mine = 0;
-        for (int r = lane; r < nrows; r += 32) {
-            const int o = row_off(r);
-            const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
-            const uint32_t bytes = (uint32_t)((o + row_bytes + 15) & ~15);
-            if (src16 >= p.src && src16 + bytes <= p.src_end) mine += bytes;
-        }
+        for (int r = lane; r < nrows; r += 32)
+            if (all_fast || row_fast(r)) mine += (uint32_t)((row_off(r) + row_bytes + 15) & ~15);
         const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
         if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
         __syncwarp();
         for (int r = lane; r < nrows; r += 32) {
+            if (!all_fast && !row_fast(r)) continue;
             const int o = row_off(r);
             const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
             const uint32_t bytes = (uint32_t)((o + row_bytes + 15) & ~15);
-            if (src16 >= p.src && src16 + bytes <= p.src_end)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 fr_smem_u32(patch + (size_t)r * p.pitch)), "l"(src16), "r"(bytes), "r"(bar)
-                             : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             fr_smem_u32(patch + (size_t)r * p.pitch)), "l"(src16), "r"(bytes), "r"(bar)
+                         : "memory");
         }
     }
-    // (rare) rows at the very start / end of the caller's buffer: word by word, nothing outside the caller's memory is read
-    for (int r = warp; r < nrows; r += kFrThreads / 32) {
-        const int o = row_off(r);
-        const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
-        const int bytes = (o + row_bytes + 15) & ~15;
-        if (src16 >= p.src && src16 + bytes <= p.src_end) continue;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(patch + (size_t)r * p.pitch);
-        for (int w = lane; w < bytes / 4; w += 32) dst[w] = frames_word(src16 + 4 * w, p.src, p.src_end);
+    if (!all_fast) {
+        // (rare) rows at the very start / end of the caller's buffer: word by word, nothing outside the caller's memory is read
+        for (int r = warp; r < nrows; r += kFrThreads / 32) {
+            if (row_fast(r)) continue;
+            const int o = row_off(r);
+            const uint8_t* src16 = g00 + (int64_t)r * p.row_stride - o;
+            const int bytes = (o + row_bytes + 15) & ~15;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(patch + (size_t)r * p.pitch);
+            for (int w = lane; w < bytes / 4; w += 32) dst[w] = frames_word(src16 + 4 * w, p.src, p.src_end);
+        }
     }
     __syncthreads();   // (the barrier's initialisation is visible to every thread; the word-by-word rows are in place)
     {
@@ -164,18 +179,26 @@ frames_preprocess_kernel(FrameArgs p) {
         const int xc = tid % (kFrTW * 3), half = tid / (kFrTW * 3);
         const int x = xc / 3, c = xc - 3 * x;
         if (x < tw) {
-            const int first = xbs[2 * x] - cx0;
+            const int first = (KX > 0 ? __ldg(p.xb + 2 * (x0 + x)) : xbs[2 * x]) - cx0;
             const unsigned char* pcol = patch + first * 3 + c;
             if (KX > 0) {
                 int k[KX > 0 ? KX : 1];
+                const int32_t* kg = p.kx + (size_t)(x0 + x) * p.ksx;
 #pragma unroll
-                for (int j = 0; j < KX; ++j) k[j] = j < p.ksx ? kxs[x * p.ksx + j] : 0;   // (zero beyond the tap count)
+                for (int j = 0; j < KX; ++j) k[j] = j < p.ksx ? __ldg(kg + j) : 0;   // (zero beyond the tap count)
+                // (row pointer, row offset and output pointer advance incrementally: two rows per step)
+                const unsigned char* pline = pcol + half * p.pitch;
+                unsigned char* hout = hbuf + half * (kFrTW * 3) + xc;
+                uint32_t o = a00 + (uint32_t)half * rs15;
+                const uint32_t o_step = 2u * rs15;
+                const int line_step = 2 * p.pitch;
                 for (int r = half; r < nrows; r += 2) {
-                    const unsigned char* prow = pcol + r * p.pitch + row_off(r);
+                    const unsigned char* prow = pline + (o & 15u);
                     int acc = 1 << (kFrPrecision - 1);
 #pragma unroll
                     for (int j = 0; j < KX; ++j) acc += k[j] * (int)prow[3 * j];
-                    hbuf[r * (kFrTW * 3) + xc] = (unsigned char)clip8(acc);
+                    *hout = (unsigned char)clip8(acc);
+                    pline += line_step; hout += 2 * (kFrTW * 3); o += o_step;
                 }
             } else {
                 const int cnt = xbs[2 * x + 1];
@@ -196,14 +219,15 @@ frames_preprocess_kernel(FrameArgs p) {
     const int x = lane;
     if (x < tw) {
         for (int y = warp; y < th; y += kFrThreads / 32) {
-            const int first = ybs[2 * y] - ry0, cnt = ybs[2 * y + 1];
+            const int first = (KY > 0 ? __ldg(p.yb + 2 * (y0 + y)) : ybs[2 * y]) - ry0;
+            const int cnt = KY > 0 ? 0 : ybs[2 * y + 1];
             const unsigned char* col0 = hbuf + first * (kFrTW * 3) + x * 3;
-            const int* k = kys + y * p.ksy;
+            const int* k = KY > 0 ? p.ky + (size_t)(y0 + y) * p.ksy : kys + y * p.ksy;
             float* orow = p.out + (((int64_t)n * 3) * p.Hout + (y0 + y)) * p.Wout + (x0 + x);
             if (KY > 0) {
                 int kk[KY > 0 ? KY : 1];
 #pragma unroll
-                for (int j = 0; j < KY; ++j) kk[j] = j < p.ksy ? k[j] : 0;   // (the table rows are zero beyond the tap count)
+                for (int j = 0; j < KY; ++j) kk[j] = j < p.ksy ? __ldg(k + j) : 0;   // (the table rows are zero beyond the tap count)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     int acc = 1 << (kFrPrecision - 1);
