@@ -278,3 +278,52 @@ def test_sequential_test_function_matches_reference_loop(tmp_path):
         acc += torch.stack([-tp.pair_dice(out[:, c:c + 1], lab.cuda()[:, c:c + 1], background_weight=0) for c in range(3)]).double().cpu()
     np.testing.assert_allclose(got.numpy(), (acc / 3).float().numpy(), rtol=1e-5)
     assert seq.test(Net(), batches, results_dir=str(tmp_path / "r"), saved_epoch=3) is None   # "Test already done"
+
+
+# ----------------------------------------------------------------------------------------------
+# soft-label cross entropy over the channel dim (loss_functions.py:26-30,44), every kernel variant: 128-bit kernels for 2..4
+# channels on aligned planes, the generic kernel otherwise (other channel counts, H*W % 4 != 0, strided slices)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bw", [0, 0.3])
+@pytest.mark.parametrize("shape", [(2, 2, 16, 16), (3, 3, 32, 40), (2, 4, 8, 24), (2, 5, 16, 16), (3, 3, 17, 19), (2, 7, 5, 3),
+                                   (54, 3, 256, 256)])
+def test_soft_label_cross_entropy_value_and_both_gradients(shape, bw):
+    import ecologysemanticsegmentation_b200 as eco
+    from oracle import torch_port as tp
+    torch.manual_seed(90 + shape[1])
+    a0 = torch.rand(shape).cuda()
+    b0 = (torch.randn(shape) * 2).cuda()
+    ar, br = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    ref = tp.pair_soft_ce(ar, br, bw)
+    ref.backward()
+    ao, bo = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    got = eco.loss_functions.cross_entropy_loss(ao, bo, background_weight=bw)
+    got.backward()
+    assert abs(float(got) - float(ref)) <= TOL * abs(float(ref))
+    assert_grad_close(ao.grad.cpu(), ar.grad.cpu(), what=f"soft CE d/dgt {shape} bw={bw}")
+    assert_grad_close(bo.grad.cpu(), br.grad.cpu(), what=f"soft CE d/dpred {shape} bw={bw}")
+
+
+def test_soft_label_cross_entropy_slices_and_bf16():
+    import ecologysemanticsegmentation_b200 as eco
+    from oracle import torch_port as tp
+    torch.manual_seed(91)
+    a0 = torch.rand(3, 6, 16, 24).cuda()
+    b0 = (torch.randn(3, 6, 16, 24) * 2).cuda()
+    # channel slices of a larger tensor: strided planes, three channels -> the 128-bit kernels on non-contiguous input
+    ar, br = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    tp.pair_soft_ce(ar[:, 1:4], br[:, 1:4], 0.3).backward()
+    ao, bo = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    eco.loss_functions.cross_entropy_loss(ao[:, 1:4], bo[:, 1:4], background_weight=0.3).backward()
+    assert_grad_close(bo.grad.cpu(), br.grad.cpu(), what="soft CE on channel slices")
+    assert_grad_close(ao.grad.cpu(), ar.grad.cpu(), what="soft CE on channel slices (gt)")
+    # bf16 predictions
+    bb = b0[:, :3].bfloat16()
+    brf = bb.float().requires_grad_(True)
+    ref = tp.pair_soft_ce(a0[:, :3], brf, 0.0)
+    ref.backward()
+    bq = bb.clone().requires_grad_(True)
+    got = eco.loss_functions.cross_entropy_loss(a0[:, :3].contiguous(), bq, background_weight=0.0)
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 1e-2 * abs(float(ref))
+    assert_grad_close(bq.grad.float().cpu(), brf.grad.cpu(), tol=1e-2, what="soft CE bf16")
