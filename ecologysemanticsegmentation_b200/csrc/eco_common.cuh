@@ -158,6 +158,34 @@ __device__ __forceinline__ float focal_bg_log2(float b) { return (b * sqrt_appro
 
 __device__ __forceinline__ float sigmoid_fast(float b) { return rcp_approx(1.0f + ex2_approx(-b * kLog2e)); }
 
+// The BCE terms see probabilities and labels, i.e. arguments in [0, 1], where softplus and sigmoid are polynomials in
+// t = b^2 (both remainders are even / odd functions, so the fits hold on [-1, 1]):
+//   softplus(-b) = ln2 - b/2 + t/8 + t^2 r(t)   (max abs err 7e-9)      sigmoid(b) = 1/2 + b s(t)   (max abs err 7e-8)
+constexpr float kSpR0 = -5.2077806842e-03f, kSpR1 = 3.4455654967e-04f, kSpR2 = -2.2275527791e-05f;
+constexpr float kSgS0 = 2.4999950727e-01f, kSgS1 = -2.0825986369e-02f, kSgS2 = 2.054964847e-03f,
+                kSgS3 = -1.6997672007e-04f;
+// softplus(b) = max(b, 0) + log(1 + exp(-|b|)) and sigmoid(b) of an arbitrary slot value: the polynomial inside [-1, 1]
+// (two MUFU operations per element less, the pair-leaf kernels are XU-limited), the MUFU form outside
+__device__ __forceinline__ float softplus_slot(float b) {
+    if (fabsf(b) <= 1.0f) {
+        const float t = b * b;
+        float r = fmaf(kSpR2, t, kSpR1);
+        r = fmaf(r, t, kSpR0);
+        return fmaf(t * t, r, fmaf(0.125f, t, fmaf(0.5f, b, kLn2)));
+    }
+    return fmaf(softplus_neg_abs_log2(b), kLn2, fmaxf(b, 0.f));
+}
+__device__ __forceinline__ float sigmoid_slot(float b) {
+    if (fabsf(b) <= 1.0f) {
+        const float t = b * b;
+        float s = fmaf(kSgS3, t, kSgS2);
+        s = fmaf(s, t, kSgS1);
+        s = fmaf(s, t, kSgS0);
+        return fmaf(b, s, 0.5f);
+    }
+    return sigmoid_fast(b);
+}
+
 // d/db [ -(1-b)^1.5 log(b+eps) ] = 1.5 sqrt(1-b) log(b+eps) - (1-b)^1.5/(b+eps)
 __device__ __forceinline__ float dfocal_fg(float b) {
     float t = 1.0f - b;

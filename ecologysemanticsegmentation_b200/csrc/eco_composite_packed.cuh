@@ -44,11 +44,7 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ f2 abs2(f2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
 
-// softplus(-b) = ln2 - b/2 + t/8 + t^2 r(t), t = b^2, b in [0,1]   (max abs err 7e-9)
-constexpr float kSpR0 = -5.2077806842e-03f, kSpR1 = 3.4455654967e-04f, kSpR2 = -2.2275527791e-05f;
-// sigmoid(b) = 1/2 + b s(t), b in [0,1]                               (max abs err 7e-8)
-constexpr float kSgS0 = 2.4999950727e-01f, kSgS1 = -2.0825986369e-02f, kSgS2 = 2.054964847e-03f,
-                kSgS3 = -1.6997672007e-04f;
+// (kSpR0..2, kSgS0..3: the softplus / sigmoid polynomials on [-1, 1], eco_common.cuh)
 
 __device__ __forceinline__ f2 sigmoid_fast2(f2 z) {
     const f2 t = mul2(z, splat(-kLog2e));

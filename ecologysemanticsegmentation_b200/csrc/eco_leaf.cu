@@ -110,7 +110,7 @@ __device__ __forceinline__ bool pair_stats_cta(const PairArgs& p, unsigned int* 
                     acc[1] += b;
                     acc[2] = fmaf(a, b, acc[2]);
                     acc[3] = fmaf(b, b, acc[3]);
-                    acc[4] += fmaf(softplus_neg_abs_log2(b), kLn2, fmaxf(b, 0.f));
+                    acc[4] += softplus_slot(b);
                     if constexpr (GEN) {
                         acc[5] -= focal_fg_log2_gen(b, p.focal_gamma);
                         if (need_bg) acc[6] -= focal_bg_log2_gen(b, p.focal_gamma);
@@ -284,7 +284,7 @@ __device__ __forceinline__ void pair_grad_cta(const GradArgs& g, const LeafCoef 
                 if (b_logit) b = sigmoid_fast(b);
                 float da = fmaf(cf.sab, b, cf.sa);
                 float db = fmaf(cf.sab, a, fmaf(cf.sbb2, b, cf.sb));
-                if (need_sig) db = fmaf(cf.sp, sigmoid_fast(b), db);
+                if (need_sig) db = fmaf(cf.sp, sigmoid_slot(b), db);
                 if constexpr (GEN) {
                     if (need_fl) db = fmaf(cf.fl, dfocal_fg_gen(b, p.focal_gamma), db);
                     if (need_flb) db = fmaf(cf.flb, dfocal_bg_gen(b, p.focal_gamma), db);
