@@ -145,7 +145,7 @@ leaf_resident_kernel(FusedArgs fa, int64_t total, const float* __restrict__ upst
                 acc[1] += b;
                 acc[2] = fmaf(a, b, acc[2]);
                 acc[3] = fmaf(b, b, acc[3]);
-                acc[4] += softplus_slot(b);
+                acc[4] += fmaf(softplus_neg_abs_log2(b), kLn2, fmaxf(b, 0.f));   // (MUFU form: this kernel is a latency chain, not XU-limited -- the polynomial of the pair-leaf kernels costs it 1 us at cfg1)
                 acc[5] -= focal_fg_log2(b);
                 if (need_bg) acc[6] -= focal_bg_log2(b);
             }
@@ -222,7 +222,7 @@ leaf_resident_kernel(FusedArgs fa, int64_t total, const float* __restrict__ upst
             const float a = ap[v], b = bp[v];   // probabilities where the slot held logits
             float da = fmaf(cf.sab, b, cf.sa);
             float db = fmaf(cf.sab, a, fmaf(cf.sbb2, b, cf.sb));
-            if (need_sig) db = fmaf(cf.sp, sigmoid_slot(b), db);
+            if (need_sig) db = fmaf(cf.sp, sigmoid_fast(b), db);
             if (need_fl) db = fmaf(cf.fl, dfocal_fg(b), db);
             if (need_flb) db = fmaf(cf.flb, dfocal_bg(b), db);
             if (a_logit) da *= (1.0f - a) * a;
