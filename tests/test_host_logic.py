@@ -159,3 +159,26 @@ def test_frame_preprocessing_has_no_cpu_fallback():
     from ecologysemanticsegmentation_b200 import test_video as tv
     with pytest.raises(nat.EcoLossError):
         tv.preprocess_frames(torch.zeros(8, 8, 3, dtype=torch.uint8), (4, 4))
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    """No library, no result: the product path raises instead of falling back to PyTorch or to the oracle."""
+    from ecologysemanticsegmentation_b200 import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "libecoloss.so"))
+    with pytest.raises(_native.EcoLossError, match="is missing.*no CPU or PyTorch fallback"):
+        _native.lib()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (or the C ABI's header) may import or mention it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ecologysemanticsegmentation_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|importlib.*oracle|__import__\(.oracle")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                for i, line in enumerate(open(os.path.join(dirpath, f), encoding="utf-8"), 1):
+                    assert not pat.search(line), f"{f}:{i}: {line.strip()}"
