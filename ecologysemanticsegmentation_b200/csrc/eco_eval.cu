@@ -1,6 +1,8 @@
 // Evaluation scoring: sigmoid -> strict '>' threshold -> exact per-class pixel counts, plus the
 // un-thresholded soft-Dice sums, in ONE read of logits and labels (8 B/element, HBM-bound).
 // Replaces ess/test_multiclass.py:58,68-69,80-81 (see include/ecoloss.h).
+#include <type_traits>
+
 #include "eco_common.cuh"
 
 namespace eco {
@@ -97,23 +99,28 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
     int64_t n = tile / p.tiles_per_plane;
     int32_t t = (int32_t)(tile - n * p.tiles_per_plane);
 
-    for (; tile < tile_end; ++tile) {
-        const TZ* zp = zbase + n * p.z_sn;
-        const TL* lp = lbase + n * p.l_sn;
+    // One tile.  FULL: the tile lies inside its plane (every tile but a plane's last): no bounds checks, and the four loads per
+    // operand are one base pointer + immediate offsets -- with the checks the compiler re-derives the 64-bit image offset for
+    // every load, 8 of the 26-29 instructions per element.  Only the byte-label instantiations get the second copy of the
+    // loop: they are bound by their instruction stream (5 B/element), the others by HBM, and with 16 label registers more the
+    // duplicated loop spills under the 64-register budget.
+    auto tile_body = [&](auto full_c) {
+        constexpr bool FULL = decltype(full_c)::value;
         const int64_t e0 = (int64_t)t * kTile + (int64_t)threadIdx.x * VEC;
+        const TZ* zp = zbase + n * p.z_sn + e0;
+        const TL* lp = lbase + n * p.l_sn + e0;
         float zv[kEvUnroll][VEC], lv[kEvUnroll][VEC];
         bool ok[kEvUnroll];
 #pragma unroll
         for (int u = 0; u < kEvUnroll; ++u) {
-            const int64_t e = e0 + (int64_t)u * kEvThreads * VEC;
-            ok[u] = e < p.HW;
+            ok[u] = FULL || e0 + (int64_t)u * kEvThreads * VEC < p.HW;
             if (ok[u]) {
                 if constexpr (VEC == 4) {
-                    Vec4<TZ>::load(zp + e, reinterpret_cast<float(&)[4]>(zv[u]));
-                    Vec4<TL>::load(lp + e, reinterpret_cast<float(&)[4]>(lv[u]));
+                    Vec4<TZ>::load(zp + u * kEvThreads * VEC, reinterpret_cast<float(&)[4]>(zv[u]));
+                    Vec4<TL>::load(lp + u * kEvThreads * VEC, reinterpret_cast<float(&)[4]>(lv[u]));
                 } else {
-                    zv[u][0] = Vec4<TZ>::load1(zp + e);
-                    lv[u][0] = Vec4<TL>::load1(lp + e);
+                    zv[u][0] = Vec4<TZ>::load1(zp + u * kEvThreads * VEC);
+                    lv[u][0] = Vec4<TL>::load1(lp + u * kEvThreads * VEC);
                 }
             }
         }
@@ -124,10 +131,9 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
 #pragma unroll
                 for (int u = 0; u < kEvUnroll; ++u) {
                     if (!ok[u]) continue;
-                    const int64_t e = e0 + (int64_t)u * kEvThreads * VEC;
                     float t4[VEC];
-                    if constexpr (VEC == 4) Vec4<TZ>::load(zk + e, reinterpret_cast<float(&)[4]>(t4));
-                    else t4[0] = Vec4<TZ>::load1(zk + e);
+                    if constexpr (VEC == 4) Vec4<TZ>::load(zk + u * kEvThreads * VEC, reinterpret_cast<float(&)[4]>(t4));
+                    else t4[0] = Vec4<TZ>::load1(zk + u * kEvThreads * VEC);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         const float pk = p.probs ? t4[v] : sigmoid_fast(t4[v]);
@@ -171,6 +177,11 @@ dice_counts_kernel(EvalArgs p, const float* __restrict__ thresholds, unsigned in
         dsoft[0] += (double)s0;
         dsoft[1] += (double)s1;
         dsoft[2] += (double)s2;
+    };
+
+    for (; tile < tile_end; ++tile) {
+        if (sizeof(TL) == 1 && !UNUN && (int64_t)(t + 1) * kTile <= p.HW) tile_body(std::true_type{});
+        else tile_body(std::false_type{});
         if (NT > 0 && (since_fold += kEvUnroll * VEC) >= kPackFlushElems) {  // rare: before a 16-bit half can overflow
 #pragma unroll
             for (int k = 0; k < NTA; ++k) {
