@@ -284,7 +284,7 @@ __device__ __forceinline__ void pair_grad_cta(const GradArgs& g, const LeafCoef 
                 if (b_logit) b = sigmoid_fast(b);
                 float da = fmaf(cf.sab, b, cf.sa);
                 float db = fmaf(cf.sab, a, fmaf(cf.sbb2, b, cf.sb));
-                if (need_sig) db = fmaf(cf.sp, sigmoid_slot(b), db);
+                if (need_sig) db = fmaf(cf.sp, sigmoid_fast(b), db);
                 if constexpr (GEN) {
                     if (need_fl) db = fmaf(cf.fl, dfocal_fg_gen(b, p.focal_gamma), db);
                     if (need_flb) db = fmaf(cf.flb, dfocal_bg_gen(b, p.focal_gamma), db);
